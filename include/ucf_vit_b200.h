@@ -1,0 +1,120 @@
+/* ucf_vit_b200.h -- C ABI of the B200-native (sm_100a) ViT transformer-block training hot path.
+ *
+ * Drop-in boundary.  The reference (irlyngaas/UCF-VIT) is 100 % Python: its "operator interface"
+ * for this path is the set of torch library calls made by
+ *   src/UCF_VIT/simple/building_blocks.py  (PatchEmbed :30-92, Mlp :94-129, Attention :131-192,
+ *                                           Block :194-239, VariableMapping_Attention :301-373)
+ *   src/UCF_VIT/simple/arch.py             (VIT.forward_features :434-476, _pos_embed :367-393,
+ *                                           MAE.random_masking :663-681)
+ *   src/UCF_VIT/dataloaders/quadtree.py    (FixedQuadTree.serialize/deserialize :144-221)
+ * There is no FFI in the reference; each entry point below names the reference call it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all pointers are DEVICE pointers unless the name ends in _host
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - return 0 on success; <0 = argument/driver error (UCF_ERR_*), >0 = cudaError_t of the launch
+ *   - ucf_last_error() returns a thread-local message for the last non-zero return
+ *   - launchers are re-entrant, hold no mutable global state besides lazily queried device
+ *     attributes, allocate nothing: every workspace is caller-provided
+ *   - bf16 storage is the raw 16-bit pattern (torch.bfloat16 / __nv_bfloat16)
+ */
+#ifndef UCF_VIT_B200_H_
+#define UCF_VIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UCF_ABI_VERSION 1
+
+enum { UCF_DTYPE_F32 = 0, UCF_DTYPE_BF16 = 1 };
+enum { UCF_LAYOUT_K_MAJOR = 0, UCF_LAYOUT_MN_MAJOR = 1 };
+/* GEMM epilogues */
+enum {
+  UCF_EPI_BIAS = 0,          /* C = acc (+ bias)                       bf16 out                    */
+  UCF_EPI_BIAS_RESIDUAL = 1, /* C = acc (+ bias) + aux                 bf16 out, aux bf16 in       */
+  UCF_EPI_BIAS_GELU_AUX = 2, /* aux = acc (+ bias); C = gelu_erf(aux)  bf16 out, aux bf16 out      */
+  UCF_EPI_DGELU = 3,         /* C = acc * gelu_erf'(aux)               bf16 out, aux bf16 in       */
+  UCF_EPI_F32_ADD = 4        /* C += acc   (fp32, split-K capable)     fp32 in/out                 */
+};
+
+int ucf_abi_version(void);
+const char* ucf_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+unsigned long long ucf_launch_count(void);
+
+/* ---- dense contractions: nn.Linear forward / dgrad / wgrad ---------------------------------
+ * replaces torch.nn.Linear.forward + autograd at building_blocks.py:115-128 (Mlp.fc1/act/fc2),
+ * :150,159 (Attention.qkv), :154,189 (Attention.proj), :321-373 (var-agg q/kv/proj) and the
+ * Conv{2,3}d patch projection :58-60,89 once patches are laid out as rows (ucf_patchify_*).
+ *
+ *   C[M,N] = epilogue( A[M,K] * B[N,K]^T ), fp32 accumulation on tcgen05 tensor cores.
+ * a_layout/b_layout: K_MAJOR  = operand stored [rows, K] with K contiguous (pitch ld, elements)
+ *                    MN_MAJOR = operand stored [K, rows] with rows contiguous (pitch ld)
+ * bias: length N, dtype bias_dtype, may be NULL.  splits: split-K factor (UCF_EPI_F32_ADD only).
+ * tile_n: 0 = auto, else 128 or 256.  Pointers and pitches*elemsize must be 16-byte aligned. */
+int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* bias, void* aux,
+                  int M, int N, int K, long long lda, long long ldb, long long ldc, long long ldaux,
+                  int a_layout, int b_layout, int epilogue, int bias_dtype, int splits, int tile_n,
+                  void* stream);
+
+/* ---- LayerNorm (replaces nn.LayerNorm at arch.py:170,266; building_blocks.py:212,226) ------
+ * x: [rows, D] (x_dtype), gamma/beta: [D] (param_dtype, may be NULL = 1/0), y: [rows, D] bf16,
+ * mean/rstd: [rows] fp32 (saved for backward).  D % 8 == 0, D <= 4096 (fwd) / 2048 (bwd). */
+int ucf_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean,
+                      float* rstd, long long rows, int D, float eps, int x_dtype, int param_dtype,
+                      void* stream);
+/* dx = LN'(dy) (+ dres if non-NULL: fuses the residual-branch gradient add); dgamma/dbeta fp32
+ * [D] are ACCUMULATED into (caller zero-fills or carries .grad). x/dy/dres/dx are bf16. */
+int ucf_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
+                      const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                      long long rows, int D, int param_dtype, void* stream);
+
+/* ---- fused scaled-dot-product attention (replaces building_blocks.py:163-187) --------------
+ * q,k,v,o: bf16, element (b, n, h, d) at  ptr[b*sb + n*sn + h*sh + d]  (d contiguous), so the
+ * packed qkv buffer of Attention.qkv is consumed in place and o is written as (B,N,H*hd).
+ * lse: [B,H,N] fp32 log-sum-exp of the scaled scores (saved for backward).  hd in {32,64}.
+ * non-causal, no mask, no dropout (attn_drop = 0 in every reference config). */
+int ucf_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                      int B, int H, int Nq, int Nk, int hd,
+                      long long q_sb, long long q_sn, long long q_sh,
+                      long long k_sb, long long k_sn, long long k_sh,
+                      long long v_sb, long long v_sn, long long v_sh,
+                      long long o_sb, long long o_sn, long long o_sh,
+                      float scale, void* stream);
+/* dq_acc: fp32 workspace [B,Nq,H,hd] (zero-filled by this call), delta: fp32 [B,H,Nq] workspace.
+ * dq/dk/dv: bf16, addressed like q/k/v (may alias a packed dqkv buffer). */
+int ucf_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                      const float* lse, void* dq, void* dk, void* dv, float* dq_acc, float* delta,
+                      int B, int H, int Nq, int Nk, int hd,
+                      long long q_sb, long long q_sn, long long q_sh,
+                      long long k_sb, long long k_sn, long long k_sh,
+                      long long v_sb, long long v_sn, long long v_sh,
+                      long long o_sb, long long o_sn, long long o_sh,
+                      long long dq_sb, long long dq_sn, long long dq_sh,
+                      long long dk_sb, long long dk_sn, long long dk_sh,
+                      long long dv_sb, long long dv_sn, long long dv_sh,
+                      float scale, void* stream);
+
+/* ---- bandwidth-bound helpers ------------------------------------------------------------- */
+/* dst_bf16[i] = (bf16) src_f32[i] */
+int ucf_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+/* dst_f32[i] (+)= (float) src_bf16[i] */
+int ucf_cast_bf16_to_f32(const void* src, float* dst, long long n, int accumulate, void* stream);
+/* out[n] (+)= sum_m x[m, n]   x bf16 [M, N] pitch ld; out fp32 [N]  (bias gradients) */
+int ucf_colsum_bf16(const void* x, float* out, long long M, int N, long long ld, int accumulate,
+                    void* stream);
+/* Conv{2,3}d(k = s = p) input -> GEMM rows (replaces the im2col inside cuDNN, building_blocks.py:89)
+ * x: [B, C, G0*p, G1*p (, G2*p)] of x_dtype (fp32 / bf16), contiguous
+ * out: bf16 [B*G0*G1(*G2), C*p^dims], K ordered (c, p0, p1(, p2)) == conv weight.view(D, -1) */
+int ucf_patchify(const void* x, void* out, int B, int C, int G0, int G1, int G2, int p, int dims,
+                 int x_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UCF_VIT_B200_H_ */

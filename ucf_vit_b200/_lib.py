@@ -1,0 +1,69 @@
+"""ctypes binding of the C-ABI library (include/ucf_vit_b200.h).
+
+The product path has NO fallback: if the shared library is missing, or a launcher returns a
+non-zero code, a RuntimeError is raised.  PyTorch is used only for device memory and streams.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libucfvit_b200.so")
+_lib = None
+
+UCF_DTYPE_F32, UCF_DTYPE_BF16 = 0, 1
+UCF_LAYOUT_K_MAJOR, UCF_LAYOUT_MN_MAJOR = 0, 1
+EPI_BIAS, EPI_BIAS_RESIDUAL, EPI_BIAS_GELU_AUX, EPI_DGELU, EPI_F32_ADD = 0, 1, 2, 3, 4
+
+_LL = c_longlong
+_SIGNATURES = {
+    "ucf_abi_version": (c_int, []),
+    "ucf_last_error": (c_char_p, []),
+    "ucf_launch_count": (c_ulonglong, []),
+    "ucf_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                              _LL, _LL, _LL, _LL, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ucf_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, _LL, c_int,
+                                  c_float, c_int, c_int, c_void_p]),
+    "ucf_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, _LL, c_int, c_int, c_void_p]),
+    "ucf_attention_fwd": (c_int, [c_void_p] * 5 + [c_int] * 5 + [_LL] * 12 + [c_float, c_void_p]),
+    "ucf_attention_bwd": (c_int, [c_void_p] * 11 + [c_int] * 5 + [_LL] * 21 + [c_float, c_void_p]),
+    "ucf_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, _LL, c_void_p]),
+    "ucf_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, _LL, c_int, c_void_p]),
+    "ucf_colsum_bf16": (c_int, [c_void_p, c_void_p, _LL, c_int, _LL, c_int, c_void_p]),
+    "ucf_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_void_p]),
+}
+
+
+def declared_symbols():
+    """Every entry point include/ucf_vit_b200.h declares (checked by tests/test_abi.py)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"ucf_vit_b200: CUDA library {LIB_PATH} is missing. Build it with "
+                "`python -m ucf_vit_b200._build` (or __graft_entry__.build()). There is no CPU fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            if not hasattr(l, name):
+                continue   # tests/test_abi.py reports missing symbols explicitly
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().ucf_last_error()
+        raise RuntimeError(f"ucf_vit_b200.{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(lib().ucf_launch_count())

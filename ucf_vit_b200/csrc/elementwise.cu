@@ -1,0 +1,204 @@
+// Bandwidth-bound helpers around the tensor-core kernels: dtype casts, bias-gradient column sums,
+// and the cast+patchify pass that turns Conv{2,3}d(k=s=p) into a plain GEMM.
+#include "common.cuh"
+#include "ucf_vit_b200.h"
+
+namespace ucf {
+
+__global__ void __launch_bounds__(256)
+cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + i + 4));
+      uint4 o = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+      *reinterpret_cast<uint4*>(dst + i) = o;
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+    }
+  }
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(256)
+cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      const uint4 r = __ldg(reinterpret_cast<const uint4*>(src + i));
+      const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
+      float4 o0 = make_float4(a.x, a.y, b.x, b.y), o1 = make_float4(c.x, c.y, d.x, d.y);
+      if (ACC) {
+        const float4 p0 = *reinterpret_cast<const float4*>(dst + i), p1 = *reinterpret_cast<const float4*>(dst + i + 4);
+        o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
+        o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
+      }
+      *reinterpret_cast<float4*>(dst + i) = o0;
+      *reinterpret_cast<float4*>(dst + i + 4) = o1;
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = (ACC ? dst[j] : 0.f) + __bfloat162float(src[j]);
+    }
+  }
+}
+
+// Column sums of a [M, N] bf16 matrix.  Block = 32 column-pairs x 8 row lanes; each block owns a
+// 64-column strip and a slab of rows, so every warp reads 128 contiguous bytes per row.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long M, int N,
+                   long long ld, int rows_per_block) {
+  __shared__ float2 part[8][32];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 64 + cx * 2;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r1 = min(r0 + rows_per_block, M);
+  float2 acc = make_float2(0.f, 0.f);
+  if (col < N) {   // N is even (16-byte pitch contract)
+    long long r = r0 + ry;
+    for (; r + 24 < r1; r += 32) {
+      uint32_t v0 = __ldg(reinterpret_cast<const uint32_t*>(x + r * ld + col));
+      uint32_t v1 = __ldg(reinterpret_cast<const uint32_t*>(x + (r + 8) * ld + col));
+      uint32_t v2 = __ldg(reinterpret_cast<const uint32_t*>(x + (r + 16) * ld + col));
+      uint32_t v3 = __ldg(reinterpret_cast<const uint32_t*>(x + (r + 24) * ld + col));
+      float2 a = unpack_bf16x2(v0), b = unpack_bf16x2(v1), c = unpack_bf16x2(v2), d = unpack_bf16x2(v3);
+      acc.x += (a.x + b.x) + (c.x + d.x);
+      acc.y += (a.y + b.y) + (c.y + d.y);
+    }
+    for (; r < r1; r += 8) {
+      float2 a = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(x + r * ld + col)));
+      acc.x += a.x; acc.y += a.y;
+    }
+  }
+  part[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && col < N) {
+    float2 s = part[0][cx];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { s.x += part[i][cx].x; s.y += part[i][cx].y; }
+    atomicAdd(&out[col], s.x);
+    if (col + 1 < N) atomicAdd(&out[col + 1], s.y);
+  }
+}
+
+// x [B, C, G0*p, G1*p(, G2*p)] -> out bf16 [B*G0*G1(*G2), C*p^dims].  One thread produces 8
+// consecutive K elements (one 16-byte store); the innermost patch axis (p) is contiguous in x.
+template <bool X_BF16>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int G0, int G1,
+                int G2, int p, int dims, long long total_vec) {
+  const int Kp = (dims == 2) ? p * p : p * p * p;
+  const int K = C * Kp;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total_vec; t += stride) {
+    const long long e = t * 8;
+    const long long row = e / K;
+    int k = static_cast<int>(e - row * K);
+    const int c = k / Kp; k -= c * Kp;
+    long long src;
+    if (dims == 2) {
+      const int p0 = k / p, p1 = k - p0 * p;
+      const int g1 = static_cast<int>(row % G1);
+      const long long r2 = row / G1;
+      const int g0 = static_cast<int>(r2 % G0);
+      const long long b = r2 / G0;
+      const long long W = static_cast<long long>(G1) * p, Hh = static_cast<long long>(G0) * p;
+      src = ((b * C + c) * Hh + (static_cast<long long>(g0) * p + p0)) * W + static_cast<long long>(g1) * p + p1;
+    } else {
+      const int p0 = k / (p * p); k -= p0 * p * p;
+      const int p1 = k / p, p2 = k - p1 * p;
+      const int g2 = static_cast<int>(row % G2);
+      long long r2 = row / G2;
+      const int g1 = static_cast<int>(r2 % G1); r2 /= G1;
+      const int g0 = static_cast<int>(r2 % G0);
+      const long long b = r2 / G0;
+      const long long Z = static_cast<long long>(G2) * p, W = static_cast<long long>(G1) * p, Hh = static_cast<long long>(G0) * p;
+      src = (((b * C + c) * Hh + (static_cast<long long>(g0) * p + p0)) * W + (static_cast<long long>(g1) * p + p1)) * Z +
+            static_cast<long long>(g2) * p + p2;
+    }
+    float f[8];
+    if (X_BF16) {
+      const uint4 r = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + src));
+      *reinterpret_cast<uint4*>(out + e) = r;
+    } else {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + src));
+      const float4 b2 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + src + 4));
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b2.x; f[5] = b2.y; f[6] = b2.z; f[7] = b2.w;
+      uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      *reinterpret_cast<uint4*>(out + e) = o;
+    }
+  }
+}
+
+static int ew_grid(long long work_items, int per_block) {
+  long long blocks = (work_items + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  return static_cast<int>(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace ucf
+
+using namespace ucf;
+
+extern "C" int ucf_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (n <= 0) return UCF_OK;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) {
+    set_last_error("cast_f32_to_bf16: pointers must be 16-byte aligned"); return UCF_ERR_BAD_ARG;
+  }
+  cast_f32_to_bf16_kernel<<<ew_grid((n + 7) / 8, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  return check_launch("cast_f32_to_bf16_kernel");
+}
+
+extern "C" int ucf_cast_bf16_to_f32(const void* src, float* dst, long long n, int accumulate, void* stream) {
+  if (n <= 0) return UCF_OK;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) {
+    set_last_error("cast_bf16_to_f32: pointers must be 16-byte aligned"); return UCF_ERR_BAD_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ew_grid((n + 7) / 8, 256);
+  if (accumulate) cast_bf16_to_f32_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+  else cast_bf16_to_f32_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+  return check_launch("cast_bf16_to_f32_kernel");
+}
+
+extern "C" int ucf_colsum_bf16(const void* x, float* out, long long M, int N, long long ld, int accumulate,
+                               void* stream) {
+  if (M <= 0 || N <= 0) return UCF_OK;
+  if (N % 2 || ld % 2 || (reinterpret_cast<uintptr_t>(x) & 3)) {
+    set_last_error("colsum_bf16: N and ld must be even, x 4-byte aligned"); return UCF_ERR_BAD_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * N, st);
+    if (e != cudaSuccess) { set_last_error("colsum_bf16: memset: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  }
+  const int strips = (N + 63) / 64;
+  // aim for ~8 blocks per SM overall
+  long long want_y = (static_cast<long long>(num_sms()) * 8 + strips - 1) / strips;
+  long long rows_per_block = (M + want_y - 1) / want_y;
+  if (rows_per_block < 64) rows_per_block = 64;
+  const long long gy = (M + rows_per_block - 1) / rows_per_block;
+  dim3 grid(strips, static_cast<unsigned>(gy));
+  colsum_bf16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, M, N, ld,
+                                            static_cast<int>(rows_per_block));
+  return check_launch("colsum_bf16_kernel");
+}
+
+extern "C" int ucf_patchify(const void* x, void* out, int B, int C, int G0, int G1, int G2, int p, int dims,
+                            int x_dtype, void* stream) {
+  if (dims != 2 && dims != 3) { set_last_error("patchify: dims must be 2 or 3"); return UCF_ERR_BAD_ARG; }
+  if (p % 8 != 0) { set_last_error("patchify: patch size %d must be a multiple of 8", p); return UCF_ERR_BAD_ARG; }
+  if (dims == 2) G2 = 1;
+  const long long Kp = (dims == 2) ? 1LL * p * p : 1LL * p * p * p;
+  const long long total = 1LL * B * G0 * G1 * G2 * C * Kp;
+  if (total <= 0) return UCF_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long nvec = total / 8;
+  const int grid = ew_grid(nvec, 256);
+  if (x_dtype == UCF_DTYPE_BF16)
+    patchify_kernel<true><<<grid, 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(out), B, C, G0, G1, G2, p, dims, nvec);
+  else
+    patchify_kernel<false><<<grid, 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(out), B, C, G0, G1, G2, p, dims, nvec);
+  return check_launch("patchify_kernel");
+}

@@ -1,0 +1,445 @@
+// bf16 GEMM with fused epilogues on tcgen05 / TMEM / TMA (sm_100a).
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )        fp32 accumulation in tensor memory
+//
+// This one kernel family serves every dense contraction of the transformer block
+// (/root/reference/src/UCF_VIT/simple/building_blocks.py:115-128,150-191):
+//   forward   x*W^T          A K-major,  B K-major   (nn.Linear weight is [out,in])
+//   dgrad     dY*W           A K-major,  B MN-major  (W read in place, no transpose copy)
+//   wgrad     dY^T*X         A MN-major, B MN-major  (split-K, fp32 TMA reduce-add into dW)
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM
+// alloc), warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store).  The
+// accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "ucf_vit_b200.h"
+
+namespace ucf {
+
+struct GemmParams {
+  int M, N, K;
+  int tiles_m, tiles_n, splits;
+  int kb_total, kb_per_split;
+  const void* bias;   // length N or null
+  int bias_is_bf16;
+};
+
+enum { EPI_BIAS = 0, EPI_BIAS_RESIDUAL = 1, EPI_BIAS_GELU_AUX = 2, EPI_DGELU = 3, EPI_F32_ADD = 4 };
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
+struct GemmCfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr bool HAS_AUX = (EPI == EPI_BIAS_RESIDUAL || EPI == EPI_BIAS_GELU_AUX || EPI == EPI_DGELU);
+  static constexpr bool AUX_IN = (EPI == EPI_BIAS_RESIDUAL || EPI == EPI_DGELU);
+  static constexpr int EPI_STAGE_BYTES = 4 * 2 * 4096;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_STAGE_BYTES +
+                                    (HAS_AUX ? EPI_STAGE_BYTES : 0) + BN * 4 + (2 * STAGES + 4 + 8) * 8 + 16;
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+  static_assert(2 * BN <= 512, "two accumulators must fit in TMEM");
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN, STAGES, A_MN, B_MN, EPI>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK;
+  constexpr int A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* epi_out = smem + STAGES * STAGE_BYTES;
+  uint8_t* epi_aux = epi_out + Cfg::EPI_STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(epi_aux + (Cfg::HAS_AUX ? Cfg::EPI_STAGE_BYTES : 0));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + BN);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* aux_bar = tempty_bar + 2;   // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (Cfg::HAS_AUX) tma_prefetch_desc(&tmAux);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);
+    }
+    for (int i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.tiles_m * p.tiles_n * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t kiter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.tiles_n;
+        const int rest = tile / p.tiles_n;
+        const int m_blk = rest % p.tiles_m;
+        const int split = rest / p.tiles_m;
+        const int m0 = m_blk * BM, n0 = n_blk * BN;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
+          const int s = kiter % STAGES;
+          const uint32_t ph = (kiter / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* a_dst = stage_base + s * STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_BYTES;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+          } else {
+            tma_load_2d(a_dst, &tmA, &full_bar[s], m0, kb * BK);
+            tma_load_2d(a_dst + 8192, &tmA, &full_bar[s], m0 + 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * BK);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      uint32_t kiter = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int rest = tile / p.tiles_n;
+        const int split = rest / p.tiles_m;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        const int buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
+          const int s = kiter % STAGES;
+          const uint32_t ph = (kiter / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(stage_base + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
+                                        : umma_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                        : umma_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);   // smem slot reusable once these MMAs retire
+        }
+        umma_commit(&tfull_bar[buf]);   // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;           // TMEM lane quarter this warp may touch
+    const int ew = warp - 2;          // staging buffer owner index
+    const int etid = threadIdx.x - 64;
+    uint8_t* my_out = epi_out + ew * 8192;
+    uint8_t* my_aux = epi_aux + ew * 8192;
+    uint64_t* my_aux_bar = aux_bar + ew * 2;
+    const uint32_t row_sw = (lane & 7);
+    const uint32_t row_off = lane * 128;
+    constexpr int CW = (EPI == EPI_F32_ADD) ? 32 : 64;   // columns per 128-byte staging row
+    constexpr int NCHUNK = BN / CW;
+    uint32_t cc = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_blk = tile % p.tiles_n;
+      const int rest = tile / p.tiles_n;
+      const int m_blk = rest % p.tiles_m;
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
+      const int buf = it & 1;
+      const int r0 = m0 + q * 32;   // first row of this warp's 32-row slab
+
+      if (EPI != EPI_F32_ADD && EPI != EPI_DGELU) {
+        named_bar_sync(1, 128);
+        for (int i = etid; i < BN; i += 128) {
+          float b = 0.f;
+          if (p.bias != nullptr && n0 + i < p.N)
+            b = p.bias_is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n0 + i])
+                               : reinterpret_cast<const float*>(p.bias)[n0 + i];
+          bias_s[i] = b;
+        }
+        named_bar_sync(1, 128);
+      }
+      if (Cfg::AUX_IN && lane == 0 && r0 < p.M) {
+        mbar_expect_tx(&my_aux_bar[cc & 1], 4096);
+        tma_load_2d(my_aux + (cc & 1) * 4096, &tmAux, &my_aux_bar[cc & 1], n0, r0);
+      }
+      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
+
+      if (r0 < p.M) {
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int col0 = n0 + c * CW;
+          if (col0 >= p.N) break;
+          const uint32_t b = cc & 1;
+          if (Cfg::AUX_IN && lane == 0 && c + 1 < NCHUNK && col0 + CW < p.N) {
+            mbar_expect_tx(&my_aux_bar[b ^ 1], 4096);
+            tma_load_2d(my_aux + (b ^ 1) * 4096, &tmAux, &my_aux_bar[b ^ 1], col0 + CW, r0);
+          }
+          uint32_t v[CW];  // fully unrolled below: stays in registers
+          {
+            uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+            tmem_ld32(t_row + c * CW, v0);
+            if (CW == 64) {
+              uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[CW - 32]);
+              tmem_ld32(t_row + c * CW + 32, v1);
+            }
+          }
+          tmem_wait_ld();
+          if (lane == 0) tma_store_wait_read<1>();   // staging buffer b (2 chunks ago) drained
+          __syncwarp();
+          if (Cfg::AUX_IN) mbar_wait(&my_aux_bar[b], (cc >> 1) & 1);
+          uint8_t* out_row = my_out + b * 4096 + row_off;
+          uint8_t* aux_row = my_aux + b * 4096 + row_off;
+
+          if (EPI == EPI_F32_ADD) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint4 o = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              *reinterpret_cast<uint4*>(out_row + ((j ^ row_sw) << 4)) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+              if (EPI != EPI_DGELU) {
+                const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c * CW + 8 * j]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c * CW + 8 * j + 4]);
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              const uint32_t sw = (j ^ row_sw) << 4;
+              if (EPI == EPI_BIAS_RESIDUAL) {
+                const uint4 r = *reinterpret_cast<const uint4*>(aux_row + sw);
+                const float2 r0f = unpack_bf16x2(r.x), r1f = unpack_bf16x2(r.y);
+                const float2 r2f = unpack_bf16x2(r.z), r3f = unpack_bf16x2(r.w);
+                f[0] += r0f.x; f[1] += r0f.y; f[2] += r1f.x; f[3] += r1f.y;
+                f[4] += r2f.x; f[5] += r2f.y; f[6] += r3f.x; f[7] += r3f.y;
+              } else if (EPI == EPI_DGELU) {
+                const uint4 r = *reinterpret_cast<const uint4*>(aux_row + sw);
+                const float2 z0 = unpack_bf16x2(r.x), z1 = unpack_bf16x2(r.y);
+                const float2 z2 = unpack_bf16x2(r.z), z3 = unpack_bf16x2(r.w);
+                f[0] *= gelu_erf_grad(z0.x); f[1] *= gelu_erf_grad(z0.y);
+                f[2] *= gelu_erf_grad(z1.x); f[3] *= gelu_erf_grad(z1.y);
+                f[4] *= gelu_erf_grad(z2.x); f[5] *= gelu_erf_grad(z2.y);
+                f[6] *= gelu_erf_grad(z3.x); f[7] *= gelu_erf_grad(z3.y);
+              } else if (EPI == EPI_BIAS_GELU_AUX) {
+                // pre-activation is rounded to bf16 first so that backward (which re-reads the
+                // stored bf16 z) differentiates exactly the function forward evaluated.
+                uint4 zq = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                      pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                *reinterpret_cast<uint4*>(aux_row + sw) = zq;
+                const float2 z0 = unpack_bf16x2(zq.x), z1 = unpack_bf16x2(zq.y);
+                const float2 z2 = unpack_bf16x2(zq.z), z3 = unpack_bf16x2(zq.w);
+                f[0] = gelu_erf(z0.x); f[1] = gelu_erf(z0.y); f[2] = gelu_erf(z1.x); f[3] = gelu_erf(z1.y);
+                f[4] = gelu_erf(z2.x); f[5] = gelu_erf(z2.y); f[6] = gelu_erf(z3.x); f[7] = gelu_erf(z3.y);
+              }
+              uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+              *reinterpret_cast<uint4*>(out_row + sw) = o;
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (EPI == EPI_F32_ADD) {
+              tma_reduce_add_2d(&tmC, my_out + b * 4096, col0, r0);
+            } else {
+              tma_store_2d(&tmC, my_out + b * 4096, col0, r0);
+              if (EPI == EPI_BIAS_GELU_AUX) tma_store_2d(&tmAux, my_aux + b * 4096, col0, r0);
+            }
+            tma_store_commit();
+          }
+          ++cc;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
+                       const CUtensorMap& tAux, const GemmParams& p, int max_ctas, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, STAGES, A_MN, B_MN, EPI>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("gemm: cudaFuncSetAttribute(%d B smem): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.splits;
+  int grid = total < num_sms() ? total : num_sms();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(tA, tB, tC, tAux, p);
+  return check_launch("gemm_bf16_kernel");
+}
+
+}  // namespace ucf
+
+using namespace ucf;
+
+extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* bias, void* aux,
+                             int M, int N, int K, long long lda, long long ldb, long long ldc,
+                             long long ldaux, int a_layout, int b_layout, int epilogue,
+                             int bias_dtype, int splits, int tile_n, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) { set_last_error("gemm: empty problem M=%d N=%d K=%d", M, N, K); return UCF_ERR_BAD_ARG; }
+  if (!A || !B || !C) { set_last_error("gemm: null operand"); return UCF_ERR_BAD_ARG; }
+  if (epilogue < 0 || epilogue > 4) { set_last_error("gemm: bad epilogue %d", epilogue); return UCF_ERR_BAD_ARG; }
+  const bool a_mn = a_layout == UCF_LAYOUT_MN_MAJOR, b_mn = b_layout == UCF_LAYOUT_MN_MAJOR;
+  const bool has_aux = epilogue == EPI_BIAS_RESIDUAL || epilogue == EPI_BIAS_GELU_AUX || epilogue == EPI_DGELU;
+  if (has_aux && !aux) { set_last_error("gemm: epilogue %d needs aux", epilogue); return UCF_ERR_BAD_ARG; }
+  const int out_es = (epilogue == EPI_F32_ADD) ? 4 : 2;
+  if ((lda * 2) % 16 || (ldb * 2) % 16 || (ldc * out_es) % 16 || (has_aux && (ldaux * 2) % 16) ||
+      (reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |
+       reinterpret_cast<uintptr_t>(aux)) & 15) {
+    set_last_error("gemm: pointers and row pitches must be 16-byte aligned (lda=%lld ldb=%lld ldc=%lld ldaux=%lld)",
+                   lda, ldb, ldc, ldaux);
+    return UCF_ERR_BAD_ARG;
+  }
+  if (epilogue != EPI_F32_ADD) splits = 1;
+  if (splits < 1) splits = 1;
+
+  int BN = tile_n;
+  if (BN != 128 && BN != 256) BN = (N <= 128 || (N % 256 != 0 && N % 128 == 0 && N < 1024)) ? 128 : 256;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.tiles_m = (M + 127) / 128;
+  p.tiles_n = (N + BN - 1) / BN;
+  p.kb_total = (K + 63) / 64;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.bias = bias;
+  p.bias_is_bf16 = bias_dtype == UCF_DTYPE_BF16;
+
+  CUtensorMap tA, tB, tC, tAux;
+  memset(&tAux, 0, sizeof(tAux));
+  int rc;
+  {
+    // K-major: dims {K, M}, box {64, 128}.  MN-major (stored [K, M]): dims {M, K}, box {64, 64}.
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    if (!a_mn) { dims[0] = K; dims[1] = M; box[0] = 64; box[1] = 128; }
+    else       { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = 64; }
+    strides[0] = static_cast<uint64_t>(lda) * 2;
+    if ((rc = make_tmap(&tA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = BN; }
+    else       { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = 64; }
+    strides[0] = static_cast<uint64_t>(ldb) * 2;
+    if ((rc = make_tmap(&tB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    dims[0] = N; dims[1] = M; box[1] = 32;
+    if (epilogue == EPI_F32_ADD) {
+      box[0] = 32; strides[0] = static_cast<uint64_t>(ldc) * 4;
+      if ((rc = make_tmap(&tC, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    } else {
+      box[0] = 64; strides[0] = static_cast<uint64_t>(ldc) * 2;
+      if ((rc = make_tmap(&tC, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    }
+    if (has_aux) {
+      box[0] = 64; strides[0] = static_cast<uint64_t>(ldaux) * 2;
+      if ((rc = make_tmap(&tAux, aux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    }
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+#define UCF_GEMM_CASE(bn, stg, amn, bmn, epi)                                        \
+  if (BN == bn && a_mn == amn && b_mn == bmn && epilogue == epi)                     \
+    return launch_gemm<bn, stg, amn, bmn, epi>(tA, tB, tC, tAux, p, 0, st);
+
+  // forward
+  UCF_GEMM_CASE(256, 4, false, false, EPI_BIAS)
+  UCF_GEMM_CASE(128, 6, false, false, EPI_BIAS)
+  UCF_GEMM_CASE(256, 3, false, false, EPI_BIAS_RESIDUAL)
+  UCF_GEMM_CASE(128, 4, false, false, EPI_BIAS_RESIDUAL)
+  UCF_GEMM_CASE(256, 3, false, false, EPI_BIAS_GELU_AUX)
+  UCF_GEMM_CASE(128, 4, false, false, EPI_BIAS_GELU_AUX)
+  UCF_GEMM_CASE(256, 4, false, false, EPI_F32_ADD)
+  UCF_GEMM_CASE(128, 6, false, false, EPI_F32_ADD)
+  // dgrad
+  UCF_GEMM_CASE(256, 4, false, true, EPI_BIAS)
+  UCF_GEMM_CASE(128, 6, false, true, EPI_BIAS)
+  UCF_GEMM_CASE(256, 3, false, true, EPI_DGELU)
+  UCF_GEMM_CASE(128, 4, false, true, EPI_DGELU)
+  UCF_GEMM_CASE(256, 3, false, true, EPI_BIAS_RESIDUAL)
+  UCF_GEMM_CASE(128, 4, false, true, EPI_BIAS_RESIDUAL)
+  // wgrad
+  UCF_GEMM_CASE(256, 4, true, true, EPI_F32_ADD)
+  UCF_GEMM_CASE(128, 6, true, true, EPI_F32_ADD)
+  UCF_GEMM_CASE(256, 4, true, true, EPI_BIAS)
+  UCF_GEMM_CASE(128, 6, true, true, EPI_BIAS)
+  UCF_GEMM_CASE(128, 6, true, false, EPI_BIAS)
+  UCF_GEMM_CASE(128, 6, true, false, EPI_F32_ADD)
+#undef UCF_GEMM_CASE
+  set_last_error("gemm: no kernel for a_layout=%d b_layout=%d epilogue=%d tile_n=%d", a_layout, b_layout, epilogue, BN);
+  return UCF_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,139 @@
+"""Thin tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers,
+launch on torch's current stream.  No autograd here (see `functional.py`)."""
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ucf_vit_b200 ops run on CUDA tensors only (sm_100a); there is no CPU fallback")
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return L.UCF_DTYPE_BF16
+    if t.dtype == torch.float32:
+        return L.UCF_DTYPE_F32
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def gemm(a, b, *, M, N, K, a_mn=False, b_mn=False, epilogue=L.EPI_BIAS, bias=None, aux=None, out=None,
+         splits=1, tile_n=0):
+    """C[M,N] = epi(A * B^T).  `a` is stored [M,K] (a_mn=False) or [K,M] (a_mn=True); same for b with N.
+    Only the pitch of dim 0 is free; dim 1 must be contiguous."""
+    _require_cuda(a, b, bias, aux, out)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    assert tuple(a.shape) == ((K, M) if a_mn else (M, K)), (a.shape, M, K, a_mn)
+    assert tuple(b.shape) == ((K, N) if b_mn else (N, K)), (b.shape, N, K, b_mn)
+    if out is None:
+        assert epilogue != L.EPI_F32_ADD, "accumulating epilogue needs an explicit output"
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    assert out.stride(1) == 1 and tuple(out.shape) == (M, N)
+    assert out.dtype == (torch.float32 if epilogue == L.EPI_F32_ADD else torch.bfloat16)
+    if epilogue == L.EPI_BIAS_GELU_AUX and aux is None:
+        aux = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    if aux is not None:
+        assert aux.dtype == torch.bfloat16 and tuple(aux.shape) == (M, N) and aux.stride(1) == 1
+    rc = L.lib().ucf_gemm_bf16(
+        a.data_ptr(), b.data_ptr(), out.data_ptr(), _ptr(bias), _ptr(aux), M, N, K,
+        a.stride(0), b.stride(0), out.stride(0), aux.stride(0) if aux is not None else 0,
+        int(a_mn), int(b_mn), epilogue, _dt(bias) if bias is not None else 0, splits, tile_n, _stream())
+    L.check(rc, "gemm_bf16")
+    return (out, aux) if epilogue == L.EPI_BIAS_GELU_AUX else out
+
+
+def layernorm_fwd(x, gamma, beta, eps):
+    _require_cuda(x, gamma, beta)
+    D = x.shape[-1]
+    x2 = x.reshape(-1, D)
+    assert x2.is_contiguous()
+    rows = x2.shape[0]
+    y = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    pd = _dt(gamma) if gamma is not None else L.UCF_DTYPE_F32
+    rc = L.lib().ucf_layernorm_fwd(x2.data_ptr(), _ptr(gamma), _ptr(beta), y.data_ptr(), mean.data_ptr(),
+                                   rstd.data_ptr(), rows, D, float(eps), _dt(x2), pd, _stream())
+    L.check(rc, "layernorm_fwd")
+    return y.view(*x.shape[:-1], D), mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, dgamma=None, dbeta=None):
+    """Returns dx (bf16).  dgamma/dbeta (fp32 [D]) are accumulated into when given."""
+    _require_cuda(dy, x, gamma, dres)
+    D = x.shape[-1]
+    dy2, x2 = dy.reshape(-1, D), x.reshape(-1, D)
+    assert dy2.is_contiguous() and x2.is_contiguous() and dy2.dtype == torch.bfloat16 and x2.dtype == torch.bfloat16
+    if dres is not None:
+        dres = dres.reshape(-1, D)
+        assert dres.is_contiguous() and dres.dtype == torch.bfloat16
+    dx = torch.empty_like(x2)
+    pd = _dt(gamma) if gamma is not None else L.UCF_DTYPE_F32
+    rc = L.lib().ucf_layernorm_bwd(dy2.data_ptr(), x2.data_ptr(), _ptr(gamma), mean.data_ptr(), rstd.data_ptr(),
+                                   _ptr(dres), dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), x2.shape[0], D, pd,
+                                   _stream())
+    L.check(rc, "layernorm_bwd")
+    return dx.view(x.shape)
+
+
+def cast_to_bf16(x, out=None):
+    _require_cuda(x)
+    if x.dtype == torch.bfloat16:
+        return x
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().ucf_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "cast_f32_to_bf16")
+    return out
+
+
+def cast_to_f32(x, out=None, accumulate=False):
+    _require_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    if out is None:
+        assert not accumulate
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    L.check(L.lib().ucf_cast_bf16_to_f32(x.data_ptr(), out.data_ptr(), x.numel(), int(accumulate), _stream()),
+            "cast_bf16_to_f32")
+    return out
+
+
+def colsum(x, out=None, accumulate=False):
+    """out[n] (+)= sum_m x[m, n]; x bf16 [M, N] (row pitch free), out fp32 [N]."""
+    _require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.bfloat16
+    M, N = x.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=x.device)
+        accumulate = False
+    L.check(L.lib().ucf_colsum_bf16(x.data_ptr(), out.data_ptr(), M, N, x.stride(0), int(accumulate), _stream()),
+            "colsum_bf16")
+    return out
+
+
+def patchify(x, p):
+    """x [B,C,H,W] or [B,C,H,W,Z] (fp32/bf16, contiguous) -> bf16 [B*L, C*p^dims], K order (c,p0,p1[,p2])."""
+    _require_cuda(x)
+    assert x.is_contiguous()
+    dims = x.dim() - 2
+    B, C = x.shape[:2]
+    G = [s // p for s in x.shape[2:]]
+    assert all(g * p == s for g, s in zip(G, x.shape[2:])), "spatial size must be a multiple of the patch size"
+    L_ = 1
+    for g in G:
+        L_ *= g
+    out = torch.empty((B * L_, C * p ** dims), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().ucf_patchify(x.data_ptr(), out.data_ptr(), B, C, G[0], G[1], G[2] if dims == 3 else 1, p, dims,
+                                 _dt(x), _stream()), "patchify")
+    return out
