@@ -1,0 +1,432 @@
+// Fused softmax attention backward on tcgen05 (sm_100a).
+// Gradient of Attention.forward's core (/root/reference/src/UCF_VIT/simple/building_blocks.py:163-187),
+// which the reference leaves to autograd over SDPA / xformers.
+//
+// One CTA per (128-key tile j, head, batch element); it loops over 128-query tiles i:
+//     S  = Q_i K_j^T            dP = dO_i V_j^T                    (tensor core -> TMEM)
+//     P  = exp(S*scale - lse)   dS = scale * P o (dP - delta)      (registers, thread == query row)
+//     dV_j += P^T dO_i          dK_j += dS^T Q_i                   (accumulate in TMEM over i)
+//     dQ_i  = dS K_j  -> fp32 TMA reduce-add into dq_acc           (summed over j by the TMA unit)
+// P and dS are written once, as bf16, into 128B-swizzled shared memory and consumed both as a
+// K-major operand (dS K) and as an MN-major operand (P^T dO, dS^T Q) -- same bytes, two
+// descriptors.  delta = rowsum(dO o O) comes from a small bandwidth-bound pre-pass; dq_acc is
+// converted to bf16 by a post-pass.
+#include "common.cuh"
+#include "ucf_vit_b200.h"
+
+namespace ucf {
+
+int make_bnhd_tmap(CUtensorMap* tm, const void* ptr, int B, int H, int N, int hd, long long sb, long long sn,
+                   long long sh, int box_rows, CUtensorMapDataType dt, int elem_bytes, int box_cols);
+
+struct AttnBwdParams {
+  int B, H, Nq, Nk;
+  float scale, scale_log2;
+  const float* lse;     // [B,H,Nq]
+  const float* delta;   // [B,H,Nq]
+};
+
+template <int HD>
+struct AttnBwdCfg {
+  static constexpr int T = 128;
+  static constexpr int TILE_BYTES = T * HD * 2;       // one Q / K / V / dO tile
+  static constexpr int PS_BYTES = T * T * 2;          // P or dS
+  static constexpr int DQ_STAGE = T * HD * 4;
+  static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES /*K,V*/ + 4 * TILE_BYTES /*Q,dO x2*/ +
+                                    2 * PS_BYTES + DQ_STAGE + 16 * 8 + 16;
+  static constexpr int ROW_BYTES = HD * 2;
+  static constexpr int ATOM_BYTES = 8 * ROW_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "smem");
+};
+
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t bwd_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = umma_smem_desc(saddr, lbo, sbo);
+  if (ROW_BYTES == 64) d = (d & ~(7ull << 61)) | (4ull << 61);   // SWIZZLE_64B
+  return d;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                const __grid_constant__ CUtensorMap tmdQacc, const __grid_constant__ CUtensorMap tmdK,
+                const __grid_constant__ CUtensorMap tmdV, const AttnBwdParams p) {
+  using Cfg = AttnBwdCfg<HD>;
+  constexpr int T = Cfg::T, TB = Cfg::TILE_BYTES, RB = Cfg::ROW_BYTES, AB = Cfg::ATOM_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* k_s = smem;
+  uint8_t* v_s = k_s + TB;
+  uint8_t* q_s = v_s + TB;          // [2]
+  uint8_t* do_s = q_s + 2 * TB;     // [2]
+  uint8_t* p_s = do_s + 2 * TB;
+  uint8_t* ds_s = p_s + Cfg::PS_BYTES;
+  uint8_t* dq_s = ds_s + Cfg::PS_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dq_s + Cfg::DQ_STAGE);
+  uint64_t* kv_full = bars;          // 1
+  uint64_t* qdo_full = bars + 1;     // 2
+  uint64_t* qdo_empty = bars + 3;    // 2
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* sdp_empty = bars + 6;
+  uint64_t* pds_full = bars + 7;
+  uint64_t* dq_full = bars + 8;
+  uint64_t* dq_empty = bars + 9;
+  uint64_t* dkv_full = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * T, h = blockIdx.y, b = blockIdx.z;
+  const int nq = (p.Nq + T - 1) / T;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmdQacc); tma_prefetch_desc(&tmdK); tma_prefetch_desc(&tmdV);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_empty, 128);
+    mbar_init(pds_full, 128);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 128);
+    mbar_init(dkv_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dv = tmem_base + 256, t_dk = tmem_base + 320,
+                 t_dq = tmem_base + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * TB);
+      tma_load_4d(k_s, &tmK, kv_full, 0, h, k0, b);
+      tma_load_4d(v_s, &tmV, kv_full, 0, h, k0, b);
+      for (int i = 0; i < nq; ++i) {
+        const int slot = i & 1;
+        mbar_wait(&qdo_empty[slot], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[slot], 2 * TB);
+        tma_load_4d(q_s + slot * TB, &tmQ, &qdo_full[slot], 0, h, i * T, b);
+        tma_load_4d(do_s + slot * TB, &tmdO, &qdo_full[slot], 0, h, i * T, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(T, T, false, false);     // S, dP
+      constexpr uint32_t idesc_tn = umma_idesc_bf16(T, HD, true, true);      // dV, dK
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(T, HD, false, true);     // dQ
+      const uint32_t k_addr = smem_u32(k_s), v_addr = smem_u32(v_s);
+      const uint32_t p_addr = smem_u32(p_s), ds_addr = smem_u32(ds_s);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < nq; ++i) {
+        const int slot = i & 1;
+        const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
+        mbar_wait(&qdo_full[slot], (i >> 1) & 1);
+        mbar_wait(sdp_empty, (i & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(t_s, bwd_desc<RB>(q_addr + k * 32, 16, AB), bwd_desc<RB>(k_addr + k * 32, 16, AB), idesc_qk, k > 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(t_dp, bwd_desc<RB>(do_addr + k * 32, 16, AB), bwd_desc<RB>(v_addr + k * 32, 16, AB), idesc_qk, k > 0);
+        umma_commit(sdp_full);
+
+        mbar_wait(pds_full, i & 1);
+        mbar_wait(dq_empty, (i & 1) ^ 1);
+        tc_fence_after();
+        // dV += P^T dO_i ; dK += dS^T Q_i   (reduction over the 128 query rows, 16 per MMA)
+#pragma unroll
+        for (int kk = 0; kk < T / 16; ++kk)
+          umma_bf16(t_dv, umma_smem_desc(p_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(do_addr + kk * 2 * AB, 0, AB),
+                    idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < T / 16; ++kk)
+          umma_bf16(t_dk, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(q_addr + kk * 2 * AB, 0, AB),
+                    idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
+        // dQ_i = dS K_j   (reduction over the 128 keys)
+#pragma unroll
+        for (int kk = 0; kk < T / 16; ++kk)
+          umma_bf16(t_dq, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                    bwd_desc<RB>(k_addr + kk * 2 * AB, 0, AB), idesc_dq, kk > 0 ? 1u : 0u);
+        umma_commit(dq_full);
+        umma_commit(&qdo_empty[slot]);
+      }
+      umma_commit(dkv_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t row_sw = row & 7;
+    const uint32_t lrow_sw = lane & 7;
+    uint8_t* p_row = p_s + row * 128;
+    uint8_t* ds_row = ds_s + row * 128;
+    uint8_t* my_dq = dq_s + (warp - 2) * (32 * HD * 4);   // HD/32 boxes of 32 rows x 128 B
+    const long long stat_base = (static_cast<long long>(b) * p.H + h) * p.Nq;
+    const float LOG2E = 1.4426950408889634f;
+
+    for (int i = 0; i < nq; ++i) {
+      const int qrow = i * T + row;
+      float nlse = -INFINITY, delta = 0.f;   // rows past Nq: P = exp2(-inf) = 0
+      if (qrow < p.Nq) {
+        nlse = -p.lse[stat_base + qrow] * LOG2E;
+        delta = p.delta[stat_base + qrow];
+      }
+      mbar_wait(sdp_full, i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < T / 32; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(t_s + lane_addr + c * 32, sv);
+        tmem_ld32(t_dp + lane_addr + c * 32, dv);
+        tmem_wait_ld();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = exp2f(fmaf(__uint_as_float(sv[e]), p.scale_log2, nlse));
+          const float p1 = exp2f(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, nlse));
+          const float d0 = p0 * (__uint_as_float(dv[e]) - delta) * p.scale;
+          const float d1 = p1 * (__uint_as_float(dv[e + 1]) - delta) * p.scale;
+          pk[e >> 1] = pack_bf16x2(p0, p1);
+          dk[e >> 1] = pack_bf16x2(d0, d1);
+        }
+        const int blk = (c >> 1) * 16384;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t off = ((static_cast<uint32_t>((c & 1) * 4 + g)) ^ row_sw) << 4;
+          *reinterpret_cast<uint4*>(p_row + blk + off) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          *reinterpret_cast<uint4*>(ds_row + blk + off) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(sdp_empty);
+      fence_proxy_async_smem();
+      mbar_arrive(pds_full);
+
+      // dQ_i tile -> fp32 staging -> TMA reduce-add
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_dq + lane_addr + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(my_dq + c * 4096 + lane * 128 + ((static_cast<uint32_t>(g) ^ lrow_sw) << 4)) =
+              make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      }
+      tc_fence_before();
+      mbar_arrive(dq_empty);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && i * T + qd * 32 < p.Nq) {
+#pragma unroll
+        for (int c = 0; c < HD / 32; ++c) tma_reduce_add_4d(&tmdQacc, my_dq + c * 4096, c * 32, h, i * T + qd * 32, b);
+        tma_store_commit();
+      }
+    }
+
+    // ---- dK_j, dV_j: TMEM -> bf16 -> staging (P / dS buffers are dead now) -> TMA store
+    mbar_wait(dkv_full, 0);
+    tc_fence_after();
+    uint8_t* st_dv = p_s + (warp - 2) * 4096;
+    uint8_t* st_dk = ds_s + (warp - 2) * 4096;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint8_t* st = which == 0 ? st_dv : st_dk;
+      const uint32_t t_src = which == 0 ? t_dv : t_dk;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_src + lane_addr + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t chunk = static_cast<uint32_t>(c * 4 + g);
+          uint8_t* dst = (RB == 128) ? st + lane * 128 + ((chunk ^ lrow_sw) << 4)
+                                     : st + lane * 64 + ((chunk ^ ((lane >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(dst) =
+              make_uint4(pack_bf16x2(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                         pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                         pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                         pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (k0 + qd * 32 < p.Nk) {
+        tma_store_4d(&tmdV, st_dv, 0, h, k0 + qd * 32, b);
+        tma_store_4d(&tmdK, st_dk, 0, h, k0 + qd * 32, b);
+        tma_store_commit();
+      }
+      tma_store_wait_all<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d]; (HD/8) lanes cooperate on one (b,n,h).
+template <int HD>
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
+                  int B, int H, int N, long long o_sb, long long o_sn, long long o_sh, long long do_sb,
+                  long long do_sn, long long do_sh) {
+  constexpr int G = HD / 8;
+  const long long total = static_cast<long long>(B) * N * H;
+  const long long gstride = (static_cast<long long>(gridDim.x) * blockDim.x) / G;
+  const long long first = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+  const int sub = threadIdx.x % G;
+  const long long iters = (total + gstride - 1) / gstride;   // uniform trip count: shuffles stay converged
+  for (long long it = 0; it < iters; ++it) {
+    const long long item = first + it * gstride;
+    const bool valid = item < total;
+    float s = 0.f;
+    long long bi = 0; int n = 0, hh = 0;
+    if (valid) {
+      hh = static_cast<int>(item % H);
+      const long long r = item / H;
+      n = static_cast<int>(r % N);
+      bi = r / N;
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + bi * o_sb + n * o_sn + hh * o_sh + sub * 8));
+      const uint4 g = __ldg(reinterpret_cast<const uint4*>(d_o + bi * do_sb + n * do_sn + hh * do_sh + sub * 8));
+      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+      const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y), g2 = unpack_bf16x2(g.z), g3 = unpack_bf16x2(g.w);
+      s = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
+    }
+#pragma unroll
+    for (int o2 = G / 2; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+    if (valid && sub == 0) delta[(bi * H + hh) * N + n] = s;
+  }
+}
+
+// dq[b,n,h,:] (bf16, strided) = (bf16) dq_acc[b,n,h,:] (fp32, contiguous [B,N,H,HD])
+__global__ void __launch_bounds__(256)
+attn_dq_cast_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int B, int H, int N, int hd,
+                    long long sb, long long sn, long long sh) {
+  const int per_head = hd / 8;
+  const long long total = static_cast<long long>(B) * N * H * per_head;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int v = static_cast<int>(t % per_head);
+    long long r = t / per_head;
+    const int hh = static_cast<int>(r % H); r /= H;
+    const int n = static_cast<int>(r % N);
+    const long long bi = r / N;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(acc + t * 8));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(acc + t * 8 + 4));
+    *reinterpret_cast<uint4*>(dq + bi * sb + n * sn + hh * sh + v * 8) =
+        make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(c.x, c.y), pack_bf16x2(c.z, c.w));
+  }
+}
+
+}  // namespace ucf
+
+using namespace ucf;
+
+extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                 const float* lse, void* dq, void* dk, void* dv, float* dq_acc, float* delta,
+                                 int B, int H, int Nq, int Nk, int hd,
+                                 long long q_sb, long long q_sn, long long q_sh,
+                                 long long k_sb, long long k_sn, long long k_sh,
+                                 long long v_sb, long long v_sn, long long v_sh,
+                                 long long o_sb, long long o_sn, long long o_sh,
+                                 long long dq_sb, long long dq_sn, long long dq_sh,
+                                 long long dk_sb, long long dk_sn, long long dk_sh,
+                                 long long dv_sb, long long dv_sn, long long dv_sh,
+                                 float scale, void* stream) {
+  if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) { set_last_error("attention_bwd: empty problem"); return UCF_ERR_BAD_ARG; }
+  if (hd != 64 && hd != 32) { set_last_error("attention_bwd: head_dim %d not supported (32 or 64)", hd); return UCF_ERR_UNSUPPORTED; }
+  if (!q || !k || !v || !o || !d_o || !lse || !dq || !dk || !dv || !dq_acc || !delta) {
+    set_last_error("attention_bwd: null pointer"); return UCF_ERR_BAD_ARG;
+  }
+  const long long all_strides[] = {q_sb, q_sn, q_sh, k_sb, k_sn, k_sh, v_sb, v_sn, v_sh, o_sb, o_sn, o_sh,
+                                   dq_sb, dq_sn, dq_sh, dk_sb, dk_sn, dk_sh, dv_sb, dv_sn, dv_sh};
+  for (long long s : all_strides)
+    if (s % 8) { set_last_error("attention_bwd: strides must be multiples of 8 elements"); return UCF_ERR_BAD_ARG; }
+  if (H > 65535 || B > 65535) { set_last_error("attention_bwd: H and B must be <= 65535"); return UCF_ERR_BAD_ARG; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(dq_acc, 0, sizeof(float) * static_cast<size_t>(B) * Nq * H * hd, st);
+  if (e != cudaSuccess) { set_last_error("attention_bwd: memset: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+
+  // d_o is addressed with o's strides (both are (B,N,H*hd) activations produced by this library)
+  const long long items = static_cast<long long>(B) * Nq * H;
+  {
+    const int G = hd / 8;
+    long long threads = items * G;
+    long long blocks = (threads + 255) / 256;
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    if (hd == 64)
+      attn_delta_kernel<64><<<static_cast<int>(blocks), 256, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), delta, B, H, Nq,
+          o_sb, o_sn, o_sh, o_sb, o_sn, o_sh);
+    else
+      attn_delta_kernel<32><<<static_cast<int>(blocks), 256, 0, st>>>(
+          reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), delta, B, H, Nq,
+          o_sb, o_sn, o_sh, o_sb, o_sn, o_sh);
+    int rc = check_launch("attn_delta_kernel");
+    if (rc) return rc;
+  }
+
+  CUtensorMap tQ, tK, tV, tdO, tdQ, tdK, tdV;
+  int rc;
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  if ((rc = make_bnhd_tmap(&tQ, q, B, H, Nq, hd, q_sb, q_sn, q_sh, 128, bf, 2, hd))) return rc;
+  if ((rc = make_bnhd_tmap(&tK, k, B, H, Nk, hd, k_sb, k_sn, k_sh, 128, bf, 2, hd))) return rc;
+  if ((rc = make_bnhd_tmap(&tV, v, B, H, Nk, hd, v_sb, v_sn, v_sh, 128, bf, 2, hd))) return rc;
+  if ((rc = make_bnhd_tmap(&tdO, d_o, B, H, Nq, hd, o_sb, o_sn, o_sh, 128, bf, 2, hd))) return rc;
+  if ((rc = make_bnhd_tmap(&tdQ, dq_acc, B, H, Nq, hd, static_cast<long long>(Nq) * H * hd, static_cast<long long>(H) * hd, hd,
+                           32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 32))) return rc;
+  if ((rc = make_bnhd_tmap(&tdK, dk, B, H, Nk, hd, dk_sb, dk_sn, dk_sh, 32, bf, 2, hd))) return rc;
+  if ((rc = make_bnhd_tmap(&tdV, dv, B, H, Nk, hd, dv_sb, dv_sn, dv_sh, 32, bf, 2, hd))) return rc;
+
+  AttnBwdParams p;
+  p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse = lse; p.delta = delta;
+  dim3 grid((Nk + 127) / 128, H, B);
+  if (hd == 64) {
+    static bool attr = false;
+    if (!attr) {
+      e = cudaFuncSetAttribute(attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwdCfg<64>::SMEM_BYTES);
+      if (e != cudaSuccess) { set_last_error("attention_bwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+      attr = true;
+    }
+    attn_bwd_kernel<64><<<grid, 192, AttnBwdCfg<64>::SMEM_BYTES, st>>>(tQ, tK, tV, tdO, tdQ, tdK, tdV, p);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      e = cudaFuncSetAttribute(attn_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwdCfg<32>::SMEM_BYTES);
+      if (e != cudaSuccess) { set_last_error("attention_bwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+      attr = true;
+    }
+    attn_bwd_kernel<32><<<grid, 192, AttnBwdCfg<32>::SMEM_BYTES, st>>>(tQ, tK, tV, tdO, tdQ, tdK, tdV, p);
+  }
+  if ((rc = check_launch("attn_bwd_kernel"))) return rc;
+
+  {
+    const long long total = static_cast<long long>(B) * Nq * H * (hd / 8);
+    long long blocks = (total + 255) / 256;
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    attn_dq_cast_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(dq_acc, reinterpret_cast<__nv_bfloat16*>(dq), B, H, Nq,
+                                                                  hd, dq_sb, dq_sn, dq_sh);
+    if ((rc = check_launch("attn_dq_cast_kernel"))) return rc;
+  }
+  return UCF_OK;
+}

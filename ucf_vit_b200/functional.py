@@ -1,0 +1,360 @@
+"""Autograd layer over the C-ABI ops: every Function's forward AND backward run hand-written
+sm_100a kernels (ucf_vit_b200/csrc).  Activations are bf16, accumulation fp32, parameter
+gradients are produced in the parameter's dtype (fp32 masters get fp32 grads straight from the
+tensor-memory accumulators through the TMA reduce-add epilogue).
+
+Reference semantics: /root/reference/src/UCF_VIT/simple/building_blocks.py
+  Mlp.forward :122-129, Attention.forward :157-192, Block.forward :236-239.
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter staging: fp32 master -> bf16 compute copy, cached until the parameter is modified
+# ---------------------------------------------------------------------------------------------
+def bf16_param(p: torch.Tensor) -> torch.Tensor:
+    """bf16, contiguous, detached compute copy of a parameter (no copy if it already is bf16)."""
+    if p.dtype == BF16:
+        q = p.detach()
+        return q if q.is_contiguous() else q.contiguous()
+    cached = getattr(p, "_ucf_bf16", None)
+    ver = p._version
+    if cached is not None and cached[0] == ver and cached[1] == p.data_ptr():
+        return cached[2]
+    src = p.detach()
+    if not src.is_contiguous():
+        src = src.contiguous()
+    q = ops.cast_to_bf16(src)
+    try:
+        p._ucf_bf16 = (ver, p.data_ptr(), q)
+    except Exception:  # noqa: BLE001 - tensors that refuse attributes simply are not cached
+        pass
+    return q
+
+
+def _wgrad(dy2, x2, n_out, k_in, like: torch.Tensor):
+    """dW[n_out,k_in] = dy2^T x2 (fp32, split-K TMA reduce-add) returned in `like`'s dtype."""
+    M = dy2.shape[0]
+    dw = torch.zeros((n_out, k_in), dtype=torch.float32, device=dy2.device)
+    tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
+    kb = (M + 63) // 64
+    splits = max(1, min(kb // 8 if kb >= 16 else 1, (2 * 148 + tiles - 1) // tiles, 16))
+    ops.gemm(dy2, x2, M=n_out, N=k_in, K=M, a_mn=True, b_mn=True, epilogue=L.EPI_F32_ADD, out=dw, splits=splits)
+    return dw if like.dtype == torch.float32 else dw.to(like.dtype)
+
+
+def _bgrad(dy2, like):
+    if like is None:
+        return None
+    db = ops.colsum(dy2)
+    return db if like.dtype == torch.float32 else db.to(like.dtype)
+
+
+def _as_bf16_2d(x):
+    D = x.shape[-1]
+    x2 = x.reshape(-1, D)
+    if x2.dtype != BF16:
+        x2 = ops.cast_to_bf16(x2.contiguous()) if x2.dtype == torch.float32 else x2.to(BF16)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    return x2
+
+
+# ---------------------------------------------------------------------------------------------
+# dtype boundary
+# ---------------------------------------------------------------------------------------------
+class _ToBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.src_dtype = x.dtype
+        return ops.cast_to_bf16(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.cast_to_f32(g.contiguous()) if ctx.src_dtype == torch.float32 else g.to(ctx.src_dtype)
+
+
+def to_bf16(x):
+    if x.dtype == BF16:
+        return x
+    if x.dtype != torch.float32:
+        x = x.float()
+    return _ToBF16.apply(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# LayerNorm
+# ---------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        xs = x if x.is_contiguous() else x.contiguous()
+        y, mean, rstd = ops.layernorm_fwd(xs, weight, bias, eps)
+        if xs.dtype != BF16:      # backward kernel reads bf16 activations
+            xs = ops.cast_to_bf16(xs)
+        ctx.save_for_backward(xs, weight, mean, rstd)
+        ctx.has_bias = bias is not None
+        ctx.x_dtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, weight, mean, rstd = ctx.saved_tensors
+        D = xs.shape[-1]
+        dy = dy if dy.is_contiguous() else dy.contiguous()
+        dg = torch.zeros(D, dtype=torch.float32, device=dy.device) if weight is not None else None
+        db = torch.zeros(D, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+        dx = ops.layernorm_bwd(dy, xs, weight, mean, rstd, dgamma=dg, dbeta=db)
+        if ctx.x_dtype != BF16:
+            dx = dx.to(ctx.x_dtype)
+        if dg is not None and weight.dtype != torch.float32:
+            dg = dg.to(weight.dtype)
+            db = db.to(weight.dtype) if db is not None else None
+        return dx, dg, db, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    """nn.LayerNorm over the last dim; returns bf16."""
+    return _LayerNormFn.apply(x, weight, bias, eps)
+
+
+# ---------------------------------------------------------------------------------------------
+# Linear (+bias, +residual)
+# ---------------------------------------------------------------------------------------------
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual):
+        shp = x.shape
+        N, K = weight.shape
+        x2 = _as_bf16_2d(x)
+        M = x2.shape[0]
+        w = bf16_param(weight)
+        if residual is not None:
+            r2 = _as_bf16_2d(residual)
+            y = ops.gemm(x2, w, M=M, N=N, K=K, bias=bias, aux=r2, epilogue=L.EPI_BIAS_RESIDUAL)
+        else:
+            y = ops.gemm(x2, w, M=M, N=N, K=K, bias=bias)
+        ctx.save_for_backward(x2, weight, bias)
+        ctx.has_res = residual is not None
+        ctx.x_dtype = x.dtype
+        ctx.shp = shp
+        return y.view(*shp[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, bias = ctx.saved_tensors
+        N, K = weight.shape
+        dy2 = _as_bf16_2d(dy)
+        M = dy2.shape[0]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dy2, bf16_param(weight), M=M, N=K, K=N, b_mn=True).view(ctx.shp)
+            if ctx.x_dtype != BF16:
+                dx = dx.to(ctx.x_dtype)
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(dy2, x2, N, K, weight)
+        if bias is not None and ctx.needs_input_grad[2]:
+            db = _bgrad(dy2, bias)
+        dres = dy if ctx.has_res else None
+        return dx, dw, db, dres
+
+
+def linear(x, weight, bias=None, residual=None):
+    """y = x W^T + b (+ residual); bf16 out.  weight [out, in] as nn.Linear stores it."""
+    return _LinearFn.apply(x, weight, bias, residual)
+
+
+# ---------------------------------------------------------------------------------------------
+# MLP: fc1 -> GELU(erf) -> fc2 (+residual), GELU fused in fc1's epilogue, GELU' in fc2-dgrad's
+# ---------------------------------------------------------------------------------------------
+class _MlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual):
+        shp = x.shape
+        Hd, K = w1.shape
+        Nout = w2.shape[0]
+        x2 = _as_bf16_2d(x)
+        M = x2.shape[0]
+        u, z = ops.gemm(x2, bf16_param(w1), M=M, N=Hd, K=K, bias=b1, epilogue=L.EPI_BIAS_GELU_AUX)
+        if residual is not None:
+            y = ops.gemm(u, bf16_param(w2), M=M, N=Nout, K=Hd, bias=b2, aux=_as_bf16_2d(residual),
+                         epilogue=L.EPI_BIAS_RESIDUAL)
+        else:
+            y = ops.gemm(u, bf16_param(w2), M=M, N=Nout, K=Hd, bias=b2)
+        ctx.save_for_backward(x2, z, u, w1, b1, w2, b2)
+        ctx.has_res = residual is not None
+        ctx.shp = shp
+        ctx.x_dtype = x.dtype
+        return y.view(*shp[:-1], Nout)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, z, u, w1, b1, w2, b2 = ctx.saved_tensors
+        Hd, K = w1.shape
+        Nout = w2.shape[0]
+        dy2 = _as_bf16_2d(dy)
+        M = dy2.shape[0]
+        dw2 = _wgrad(dy2, u, Nout, Hd, w2)
+        db2 = _bgrad(dy2, b2)
+        dz = ops.gemm(dy2, bf16_param(w2), M=M, N=Hd, K=Nout, b_mn=True, aux=z, epilogue=L.EPI_DGELU)
+        dw1 = _wgrad(dz, x2, Hd, K, w1)
+        db1 = _bgrad(dz, b1)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dz, bf16_param(w1), M=M, N=K, K=Hd, b_mn=True).view(ctx.shp)
+            if ctx.x_dtype != BF16:
+                dx = dx.to(ctx.x_dtype)
+        return dx, dw1, db1, dw2, db2, (dy if ctx.has_res else None)
+
+
+def mlp(x, w1, b1, w2, b2, residual=None):
+    return _MlpFn.apply(x, w1, b1, w2, b2, residual)
+
+
+# ---------------------------------------------------------------------------------------------
+# attention core on a packed qkv projection
+# ---------------------------------------------------------------------------------------------
+class _AttnPackedFn(torch.autograd.Function):
+    """qkv: [B, N, 3, H, hd] bf16 (the raw output of Attention.qkv) -> o: [B, N, H*hd] bf16."""
+
+    @staticmethod
+    def forward(ctx, qkv, scale):
+        B, N, _, H, hd = qkv.shape
+        o, lse = ops.attention_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.scale = scale
+        return o.view(B, N, H * hd)
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse = ctx.saved_tensors
+        B, N, _, H, hd = qkv.shape
+        d_o = d_o.contiguous().view(B, N, H, hd)
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, d_o, lse, ctx.scale,
+                          dq=dqkv[:, :, 0], dk=dqkv[:, :, 1], dv=dqkv[:, :, 2])
+        return dqkv, None
+
+
+def attention_packed(qkv, scale):
+    return _AttnPackedFn.apply(qkv, scale)
+
+
+class _AttnFn(torch.autograd.Function):
+    """q [B,Nq,H,hd], k/v [B,Nk,H,hd] (bf16, last dim contiguous) -> o [B,Nq,H,hd]."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, scale):
+        o, lse = ops.attention_fwd(q, k, v, scale)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.scale = scale
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, k, v, o, lse = ctx.saved_tensors
+        dq, dk, dv = ops.attention_bwd(q, k, v, o, d_o.contiguous(), lse, ctx.scale)
+        return dq, dk, dv, None
+
+
+def attention(q, k, v, scale):
+    return _AttnFn.apply(q, k, v, scale)
+
+
+# ---------------------------------------------------------------------------------------------
+# whole pre-norm transformer block with a hand-scheduled backward
+# ---------------------------------------------------------------------------------------------
+class _BlockFn(torch.autograd.Function):
+    """x + proj(attn(LN1(x))) then + fc2(gelu(fc1(LN2(.))))  (Block.forward, building_blocks.py:236-239)
+    for the configuration every reference driver uses: no qk_norm, no LayerScale, drop rates 0.
+
+    Fusions: bias / bias+GELU(+pre-activation) / bias+residual in GEMM epilogues; GELU' in the
+    fc2-dgrad epilogue; residual-gradient add inside the LayerNorm backward kernel; attention reads
+    the packed qkv projection in place and its backward writes the packed dqkv in place."""
+
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
+                num_heads, eps1, eps2):
+        B, N, D = x.shape
+        M = B * N
+        H = num_heads
+        hd = D // H
+        x2 = x.reshape(M, D)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        h1, mean1, rstd1 = ops.layernorm_fwd(x2, n1w, n1b, eps1)
+        qkv = ops.gemm(h1, bf16_param(qkv_w), M=M, N=3 * D, K=D, bias=qkv_b)
+        qkv5 = qkv.view(B, N, 3, H, hd)
+        o, lse = ops.attention_fwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], hd ** -0.5)
+        o2 = o.view(M, D)
+        x1 = ops.gemm(o2, bf16_param(proj_w), M=M, N=D, K=D, bias=proj_b, aux=x2, epilogue=L.EPI_BIAS_RESIDUAL)
+        h2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b, eps2)
+        Hd = fc1_w.shape[0]
+        u, z = ops.gemm(h2, bf16_param(fc1_w), M=M, N=Hd, K=D, bias=fc1_b, epilogue=L.EPI_BIAS_GELU_AUX)
+        y = ops.gemm(u, bf16_param(fc2_w), M=M, N=D, K=Hd, bias=fc2_b, aux=x1, epilogue=L.EPI_BIAS_RESIDUAL)
+        ctx.save_for_backward(x2, mean1, rstd1, h1, qkv, o, lse, x1, mean2, rstd2, h2, z, u,
+                              n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
+        ctx.dims = (B, N, D, H, hd, Hd)
+        return y.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x2, mean1, rstd1, h1, qkv, o, lse, x1, mean2, rstd2, h2, z, u,
+         n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b) = ctx.saved_tensors
+        B, N, D, H, hd, Hd = ctx.dims
+        M = B * N
+        dev = dy.device
+        dy2 = dy.reshape(M, D)
+        if dy2.dtype != BF16:
+            dy2 = dy2.to(BF16)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        f32 = torch.float32
+
+        def cast_like(g, like):
+            return g if (g is None or like.dtype == f32) else g.to(like.dtype)
+
+        # ---- MLP
+        d_fc2_w = _wgrad(dy2, u, D, Hd, fc2_w)
+        d_fc2_b = _bgrad(dy2, fc2_b)
+        dz = ops.gemm(dy2, bf16_param(fc2_w), M=M, N=Hd, K=D, b_mn=True, aux=z, epilogue=L.EPI_DGELU)
+        d_fc1_w = _wgrad(dz, h2, Hd, D, fc1_w)
+        d_fc1_b = _bgrad(dz, fc1_b)
+        dh2 = ops.gemm(dz, bf16_param(fc1_w), M=M, N=D, K=Hd, b_mn=True)
+        del dz
+        d_n2w = torch.zeros(D, dtype=f32, device=dev)
+        d_n2b = torch.zeros(D, dtype=f32, device=dev) if n2b is not None else None
+        dx1 = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dy2, dgamma=d_n2w, dbeta=d_n2b)
+        del dh2
+        # ---- attention
+        d_proj_w = _wgrad(dx1, o.view(M, D), D, D, proj_w)
+        d_proj_b = _bgrad(dx1, proj_b)
+        d_o = ops.gemm(dx1, bf16_param(proj_w), M=M, N=D, K=D, b_mn=True)
+        dqkv = torch.empty_like(qkv)
+        qkv5 = qkv.view(B, N, 3, H, hd)
+        dqkv5 = dqkv.view(B, N, 3, H, hd)
+        ops.attention_bwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], o, d_o.view(B, N, H, hd), lse, hd ** -0.5,
+                          dq=dqkv5[:, :, 0], dk=dqkv5[:, :, 1], dv=dqkv5[:, :, 2])
+        del d_o
+        d_qkv_w = _wgrad(dqkv, h1, 3 * D, D, qkv_w)
+        d_qkv_b = _bgrad(dqkv, qkv_b)
+        dh1 = ops.gemm(dqkv, bf16_param(qkv_w), M=M, N=D, K=3 * D, b_mn=True)
+        del dqkv
+        d_n1w = torch.zeros(D, dtype=f32, device=dev)
+        d_n1b = torch.zeros(D, dtype=f32, device=dev) if n1b is not None else None
+        dx = ops.layernorm_bwd(dh1, x2, n1w, mean1, rstd1, dres=dx1, dgamma=d_n1w, dbeta=d_n1b)
+        return (dx.view(B, N, D), cast_like(d_n1w, n1w), cast_like(d_n1b, n1b) if n1b is not None else None,
+                d_qkv_w, d_qkv_b, d_proj_w, d_proj_b,
+                cast_like(d_n2w, n2w), cast_like(d_n2b, n2b) if n2b is not None else None,
+                d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, None, None, None)
+
+
+def fused_block(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
+                num_heads, eps1, eps2):
+    return _BlockFn.apply(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
+                          num_heads, eps1, eps2)

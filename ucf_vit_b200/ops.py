@@ -137,3 +137,45 @@ def patchify(x, p):
     L.check(L.lib().ucf_patchify(x.data_ptr(), out.data_ptr(), B, C, G[0], G[1], G[2] if dims == 3 else 1, p, dims,
                                  _dt(x), _stream()), "patchify")
     return out
+
+
+def _bnhd(t):
+    assert t.dim() == 4 and t.stride(3) == 1 and t.dtype == torch.bfloat16, (t.shape, t.stride(), t.dtype)
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+def attention_fwd(q, k, v, scale):
+    """q [B,Nq,H,hd], k/v [B,Nk,H,hd] bf16 views (last dim contiguous; e.g. slices of the packed qkv
+    projection).  Returns o [B,Nq,H,hd] (contiguous) and lse [B,H,Nq] fp32."""
+    _require_cuda(q, k, v)
+    B, Nq, H, hd = q.shape
+    Nk = k.shape[1]
+    o = torch.empty((B, Nq, H, hd), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
+    rc = L.lib().ucf_attention_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
+                                   B, H, Nq, Nk, hd, *_bnhd(q), *_bnhd(k), *_bnhd(v), *_bnhd(o), float(scale), _stream())
+    L.check(rc, "attention_fwd")
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, d_o, lse, scale, dq=None, dk=None, dv=None):
+    """Gradients of attention_fwd.  dq/dk/dv may be views (e.g. into one packed dqkv buffer)."""
+    _require_cuda(q, k, v, o, d_o)
+    B, Nq, H, hd = q.shape
+    Nk = k.shape[1]
+    assert d_o.is_contiguous() and o.is_contiguous() and d_o.shape == o.shape
+    d_o = d_o.view(B, Nq, H, hd)
+    if dq is None:
+        dq = torch.empty((B, Nq, H, hd), dtype=torch.bfloat16, device=q.device)
+    if dk is None:
+        dk = torch.empty((B, Nk, H, hd), dtype=torch.bfloat16, device=q.device)
+    if dv is None:
+        dv = torch.empty((B, Nk, H, hd), dtype=torch.bfloat16, device=q.device)
+    dq_acc = torch.empty((B, Nq, H, hd), dtype=torch.float32, device=q.device)
+    delta = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
+    rc = L.lib().ucf_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),
+                                   lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dq_acc.data_ptr(),
+                                   delta.data_ptr(), B, H, Nq, Nk, hd, *_bnhd(q), *_bnhd(k), *_bnhd(v), *_bnhd(o),
+                                   *_bnhd(dq), *_bnhd(dk), *_bnhd(dv), float(scale), _stream())
+    L.check(rc, "attention_bwd")
+    return dq, dk, dv
