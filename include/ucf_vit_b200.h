@@ -100,6 +100,19 @@ int ucf_attention_bwd(const void* q, const void* k, const void* v, const void* o
                       long long dv_sb, long long dv_sn, long long dv_sh,
                       float scale, void* stream);
 
+/* ---- channel variable-aggregation cross-attention core (replaces the SDPA call inside
+ * VariableMapping_Attention.forward, building_blocks.py:339-367; Nq = Na (1), Nk = V) ---------
+ * q: bf16 [Bq, Na, H, hd] with Bq == rows, or Bq == 1 when q_shared != 0 (one learned query for
+ * every row); kv: bf16 [rows, V, 2, H, hd] (raw output of the kv projection); o: bf16
+ * [rows, Na, H, hd]; lse: fp32 [rows, Na, H].  hd in {32, 64, 128}. */
+int ucf_var_attention_fwd(const void* q, const void* kv, void* o, float* lse, long long rows, int Na,
+                          int V, int H, int hd, int q_shared, float scale, void* stream);
+/* dkv: bf16 like kv (fully written).  dq_acc: fp32 [Bq, Na, H, hd] (zero-filled here and summed
+ * over rows when q_shared, else plainly written). */
+int ucf_var_attention_bwd(const void* q, const void* kv, const void* o, const void* d_o,
+                          const float* lse, void* dkv, float* dq_acc, long long rows, int Na, int V,
+                          int H, int hd, int q_shared, float scale, void* stream);
+
 /* ---- bandwidth-bound helpers ------------------------------------------------------------- */
 /* dst_bf16[i] = (bf16) src_f32[i] */
 int ucf_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);

@@ -1,0 +1,42 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/ucf_vit_b200.h declares
+(no compute calls -- there is no GPU in the build container)."""
+import os
+import re
+
+from ucf_vit_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "ucf_vit_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ucf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    names = _header_functions()
+    assert len(names) >= 12
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+
+
+def test_python_binding_covers_header():
+    assert _header_functions() == _lib.declared_symbols()
+
+
+def test_abi_version_and_error_string():
+    lib = _lib.lib()
+    assert lib.ucf_abi_version() == 1
+    assert isinstance(lib.ucf_last_error(), (bytes, type(None)))
+    assert lib.ucf_launch_count() == 0 or lib.ucf_launch_count() > 0
+
+
+def test_bad_arguments_are_rejected_without_a_device():
+    lib = _lib.lib()
+    # M = 0 is rejected before any CUDA call is made
+    rc = lib.ucf_gemm_bf16(0, 0, 0, 0, 0, 0, 8, 8, 8, 8, 8, 0, 0, 0, 0, 0, 1, 0, None)
+    assert rc == -1 and b"empty problem" in lib.ucf_last_error()
+    rc = lib.ucf_attention_fwd(1, 1, 1, 1, 1, 1, 1, 4, 4, 36, *([8] * 12), 1.0, None)
+    assert rc == -4 and b"head_dim 36" in lib.ucf_last_error()

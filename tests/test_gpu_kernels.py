@@ -1,0 +1,179 @@
+"""GPU (-m gpu): kernel-level parity through the C ABI (ctypes) against fp32 torch math.
+Tolerances: bf16 outputs 1e-2 * max|ref| (one bf16 rounding of an fp32-accumulated result plus
+bf16 inputs), fp32 outputs 2e-3, exact for pure data movement."""
+import pytest
+import torch
+
+from ucf_vit_b200 import _lib as L
+from ucf_vit_b200 import ops
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _ok(got, ref, tol):
+    got, ref = got.float(), ref.float()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err <= tol * (ref.abs().max().item() + 1e-6), (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 192, 192), (1000, 576, 192), (333, 1000, 768), (77, 40, 72),
+                                   (4096, 3072, 768)])
+@pytest.mark.parametrize("tn", [128, 256])
+def test_gemm_family(M, N, K, tn):
+    torch.manual_seed(M + N + K)
+    a, b = bf(torch.randn(M, K, device=dev) * 0.5), bf(torch.randn(N, K, device=dev) * 0.5)
+    bias, res = torch.randn(N, device=dev), bf(torch.randn(M, N, device=dev))
+    ref = a.float() @ b.float().t()
+    _ok(ops.gemm(a, b, M=M, N=N, K=K, bias=bias, tile_n=tn), ref + bias, 1e-2)
+    _ok(ops.gemm(a, b, M=M, N=N, K=K, bias=bf(bias), tile_n=tn), ref + bf(bias).float(), 1e-2)
+    _ok(ops.gemm(a, b, M=M, N=N, K=K, bias=bias, aux=res, epilogue=L.EPI_BIAS_RESIDUAL, tile_n=tn), ref + bias + res.float(), 1e-2)
+    u, z = ops.gemm(a, b, M=M, N=N, K=K, bias=bias, epilogue=L.EPI_BIAS_GELU_AUX, tile_n=tn)
+    _ok(z, ref + bias, 1e-2)
+    _ok(u, torch.nn.functional.gelu(z.float()), 1e-2)
+    dy = bf(torch.randn(M, N, device=dev) * 0.5)
+    dref = dy.float() @ b.float()
+    _ok(ops.gemm(dy, b, M=M, N=K, K=N, b_mn=True, tile_n=tn), dref, 1e-2)
+    zz = bf(torch.randn(M, K, device=dev)).float().requires_grad_(True)
+    g = torch.autograd.grad(torch.nn.functional.gelu(zz).sum(), zz)[0]
+    _ok(ops.gemm(dy, b, M=M, N=K, K=N, b_mn=True, aux=bf(zz.detach()), epilogue=L.EPI_DGELU, tile_n=tn), dref * g, 1e-2)
+    wref = dy.float().t() @ a.float()
+    for splits in (1, 4):
+        dw = torch.ones(N, K, device=dev)
+        ops.gemm(dy, a, M=N, N=K, K=M, a_mn=True, b_mn=True, epilogue=L.EPI_F32_ADD, out=dw, splits=splits, tile_n=tn)
+        _ok(dw, wref + 1.0, 2e-3)
+
+
+def test_gemm_linearity_at_benchmark_size():
+    """ViT-B/16 batch-256 sized GEMM (M = 50432): size-independent property instead of a CPU
+    reference -- (a1 + a2) W == a1 W + a2 W for operands exactly representable in bf16."""
+    M, N, K = 50432, 768, 768
+    a1 = torch.randint(-4, 5, (M, K), device=dev).to(torch.bfloat16)
+    a2 = torch.randint(-4, 5, (M, K), device=dev).to(torch.bfloat16)
+    w = torch.randint(-2, 3, (N, K), device=dev).to(torch.bfloat16)
+    y12 = ops.gemm(a1 + a2, w, M=M, N=N, K=K).float()
+    y1, y2 = ops.gemm(a1, w, M=M, N=N, K=K).float(), ops.gemm(a2, w, M=M, N=N, K=K).float()
+    # small-integer operands: every product and partial sum is exact in fp32; bf16 output rounding
+    # only matters above 256, so compare with one bf16 ulp of slack
+    assert ((y12 - (y1 + y2)).abs() <= 0.01 * (y1 + y2).abs() + 1e-3).all()
+    idx = torch.randint(0, M, (64,), device=dev)
+    ref = (a1[idx].float() @ w.float().t())
+    assert ((y1[idx] - ref).abs() <= 0.005 * ref.abs() + 1e-3).all()
+
+
+@pytest.mark.parametrize("rows,D", [(7, 64), (1000, 192), (3000, 1024), (513, 512), (100, 2048), (50432, 768)])
+def test_layernorm_fwd_bwd(rows, D):
+    torch.manual_seed(rows)
+    x = torch.randn(rows, D, device=dev) * 2 + 0.5
+    g, b = torch.randn(D, device=dev), torch.randn(D, device=dev)
+    for xx in (x, bf(x)):
+        y, mean, rstd = ops.layernorm_fwd(xx, g, b, 1e-6)
+        _ok(y, torch.nn.functional.layer_norm(xx.float(), (D,), g, b, 1e-6), 1e-2)
+        _ok(mean, xx.float().mean(-1), 1e-4)
+    xb = bf(x)
+    y, mean, rstd = ops.layernorm_fwd(xb, g, b, 1e-6)
+    dy, dres = bf(torch.randn(rows, D, device=dev)), bf(torch.randn(rows, D, device=dev))
+    dg, db = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    dx = ops.layernorm_bwd(dy, xb, g, mean, rstd, dres=dres, dgamma=dg, dbeta=db)
+    xf, gf, bfp = xb.float().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xf, (D,), gf, bfp, 1e-6).backward(dy.float())
+    _ok(dx, xf.grad + dres.float(), 1e-2)
+    _ok(dg, gf.grad, 2e-3)
+    _ok(db, bfp.grad, 2e-3)
+
+
+def _ref_attn(q, k, v, scale):
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k) * scale
+    return torch.einsum("bhqk,bkhd->bqhd", s.softmax(-1), v), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,N,H,hd", [(1, 128, 1, 64), (2, 197, 3, 64), (2, 50, 2, 64), (1, 512, 2, 64), (1, 1000, 1, 64),
+                                      (2, 197, 2, 32), (1, 384, 2, 32), (3, 1, 2, 64)])
+def test_attention_fwd_bwd(B, N, H, hd):
+    torch.manual_seed(N)
+    scale = hd ** -0.5
+    qkv = bf(torch.randn(B, N, 3, H, hd, device=dev))
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    o, lse = ops.attention_fwd(q, k, v, scale)
+    qf, kf, vf = [t.float().detach().requires_grad_(True) for t in (q, k, v)]
+    oref, lref = _ref_attn(qf, kf, vf, scale)
+    _ok(o, oref, 1.5e-2)
+    _ok(lse, lref, 1e-3)
+    do = bf(torch.randn(B, N, H, hd, device=dev) * 0.5)
+    dqkv = torch.empty_like(qkv)
+    ops.attention_bwd(q, k, v, o, do, lse, scale, dq=dqkv[:, :, 0], dk=dqkv[:, :, 1], dv=dqkv[:, :, 2])
+    oref.backward(do.float())
+    _ok(dqkv[:, :, 0], qf.grad, 2e-2)
+    _ok(dqkv[:, :, 1], kf.grad, 2e-2)
+    _ok(dqkv[:, :, 2], vf.grad, 2e-2)
+
+
+def test_attention_cross_lengths():
+    """Nq != Nk (decoder-style)."""
+    B, Nq, Nk, H, hd = 2, 70, 300, 2, 64
+    q, k, v = [bf(torch.randn(B, n, H, hd, device=dev)) for n in (Nq, Nk, Nk)]
+    o, lse = ops.attention_fwd(q, k, v, hd ** -0.5)
+    oref, lref = _ref_attn(q.float(), k.float(), v.float(), hd ** -0.5)
+    _ok(o, oref, 1.5e-2)
+    _ok(lse, lref, 1e-3)
+
+
+def test_attention_rows_sum_to_one_at_long_sequence():
+    """N = 4096 (SAP config): with V = 1 every output must be exactly ~1 (softmax rows sum to 1)."""
+    B, N, H, hd = 1, 4096, 2, 64
+    q, k = bf(torch.randn(B, N, H, hd, device=dev)), bf(torch.randn(B, N, H, hd, device=dev))
+    v = torch.ones(B, N, H, hd, device=dev, dtype=torch.bfloat16)
+    o, _ = ops.attention_fwd(q, k, v, hd ** -0.5)
+    assert (o.float() - 1.0).abs().max().item() <= 1e-2
+
+
+@pytest.mark.parametrize("rows,Na,V,H,hd,shared", [(100, 1, 4, 3, 64, True), (37, 1, 7, 2, 32, True), (50, 2, 3, 2, 64, False)])
+def test_var_attention(rows, Na, V, H, hd, shared):
+    torch.manual_seed(V)
+    scale = hd ** -0.5
+    q = bf(torch.randn(1 if shared else rows, Na, H, hd, device=dev))
+    kv = bf(torch.randn(rows, V, 2, H, hd, device=dev))
+    o, lse = ops.var_attention_fwd(q, kv, scale)
+    qf = q.float().detach().requires_grad_(True)
+    kvf = kv.float().detach().requires_grad_(True)
+    s = torch.einsum("rahd,rvhd->rhav", qf.expand(rows, -1, -1, -1), kvf[:, :, 0]) * scale
+    oref = torch.einsum("rhav,rvhd->rahd", s.softmax(-1), kvf[:, :, 1])
+    _ok(o, oref, 1.5e-2)
+    do = bf(torch.randn_like(oref) * 0.5)
+    dq_acc, dkv = ops.var_attention_bwd(q, kv, o, do, lse, scale)
+    oref.backward(do.float())
+    _ok(dkv, kvf.grad, 2e-2)
+    _ok(dq_acc, qf.grad, 2e-2)
+
+
+def test_elementwise_helpers():
+    x = torch.randn(1000000, device=dev)
+    assert torch.equal(ops.cast_to_bf16(x), x.to(torch.bfloat16))
+    xb = bf(torch.randn(5000, 776, device=dev))
+    _ok(ops.colsum(xb), xb.float().sum(0), 1e-4)
+    _ok(ops.colsum(xb[:, 8:520]), xb[:, 8:520].float().sum(0), 1e-4)
+    acc = torch.ones(776, device=dev)
+    _ok(ops.colsum(xb, out=acc, accumulate=True), xb.float().sum(0) + 1, 1e-4)
+    img = torch.randn(3, 3, 32, 48, device=dev)
+    ref = img.reshape(3, 3, 2, 16, 3, 16).permute(0, 2, 4, 1, 3, 5).reshape(18, 768)
+    assert torch.equal(ops.patchify(img, 16), ref.to(torch.bfloat16))
+    vol = torch.randn(2, 2, 16, 32, 16, device=dev)
+    ref = vol.reshape(2, 2, 2, 8, 4, 8, 2, 8).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(32, 1024)
+    assert torch.equal(ops.patchify(vol, 8), ref.to(torch.bfloat16))
+    assert torch.equal(ops.patchify(bf(vol), 8), ref.to(torch.bfloat16))
+
+
+def test_errors_are_loud():
+    a = bf(torch.randn(16, 20, device=dev))
+    with pytest.raises(RuntimeError, match="16-byte"):
+        ops.gemm(a, a, M=16, N=16, K=20)               # K*2 bytes not a multiple of 16
+    with pytest.raises(RuntimeError, match="head_dim"):
+        q = bf(torch.randn(1, 8, 2, 48, device=dev))
+        ops.attention_fwd(q, q, q, 1.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.layernorm_fwd(torch.randn(4, 64), None, None, 1e-5)

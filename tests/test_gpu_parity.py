@@ -1,0 +1,115 @@
+"""GPU (-m gpu): the CUDA path behind the reference's module API vs the fp32 CPU oracle on the
+same deterministic weights and inputs (the golden cases; the oracle itself is pinned to the
+reference by tests/test_oracle_golden.py).
+
+Stated tolerances (bf16 storage/tensor-core inputs, fp32 accumulation, vs an fp32 oracle):
+  activations / outputs : relative L2 error <= 2e-2, max abs error <= 6e-2 * max|ref|
+  loss                  : relative error    <= 2e-2
+  parameter gradients   : relative L2 error <= 6e-2 and cosine similarity >= 0.998 per tensor
+                          (tensors whose reference norm is < 1e-6 of the largest are skipped)
+  integer outputs (MAE mask)  : bit-exact
+"""
+import pytest
+import torch
+
+from tests import _cases as C
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _to_dev(inp):
+    return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+
+
+@pytest.mark.parametrize("name", C.MODEL_CASES)
+def test_model_forward_loss_and_grads_match_oracle(name):
+    cfg, shapes, arrays, sd = C.load(name)
+    inp = C.inputs(cfg, arrays)
+    # ---- oracle (CPU fp32)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    o_out, o_loss = C.run_oracle(cfg, sdg, inp)
+    o_loss.backward()
+    # ---- product (CUDA)
+    model = C.build_product(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    model.train(cfg.get("train", True))
+    p_out, p_loss = C.run_product(cfg, model, _to_dev(inp))
+    p_loss.backward()
+    torch.cuda.synchronize()
+
+    for k, ref in o_out.items():
+        got = p_out[k].detach().float().cpu()
+        ref = ref.detach()
+        assert got.shape == ref.shape, (k, got.shape, ref.shape)
+        if k == "mask":
+            assert torch.equal(got, ref), "MAE keep/remove mask must be bit-exact"
+            continue
+        assert torch.isfinite(got).all()
+        rel, mx = _rel_l2(got, ref), (got - ref).abs().max().item()
+        assert rel <= 2e-2, f"{name}.{k}: rel L2 {rel:.3e}"
+        assert mx <= 6e-2 * ref.abs().max().item() + 1e-6, f"{name}.{k}: max abs {mx:.3e}"
+    assert abs(p_loss.item() - o_loss.item()) <= 2e-2 * abs(o_loss.item()) + 1e-6, (p_loss.item(), o_loss.item())
+
+    named = dict(model.named_parameters())
+    gmax = max(v.grad.norm().item() for v in sdg.values() if v.grad is not None)
+    checked = 0
+    for k, v in sdg.items():
+        if v.grad is None or k not in named:
+            continue
+        if v.grad.norm().item() < 1e-6 * gmax:
+            continue
+        g = named[k].grad
+        assert g is not None, f"{name}: product produced no grad for {k}"
+        g = g.detach().float().cpu()
+        rel = _rel_l2(g, v.grad)
+        cos = torch.nn.functional.cosine_similarity(g.double().flatten(), v.grad.double().flatten(), dim=0).item()
+        assert rel <= 6e-2 and cos >= 0.998, f"{name}: grad {k}: rel L2 {rel:.3e}, cos {cos:.5f}"
+        checked += 1
+    assert checked >= 10
+
+
+def test_block_module_matches_oracle_with_odd_token_count():
+    """Block alone, N = 197 (ViT-B/16 @224 incl. cls token): tail masking in attention, M not a
+    multiple of the GEMM tile."""
+    from oracle import fixtures as fx
+    from oracle import vit_ref as R
+    from ucf_vit_b200.simple.building_blocks import Block
+    from functools import partial
+    D, H, B, N = 192, 3, 3, 197
+    blk = Block(dim=D, num_heads=H, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    sd = fx.det_state_dict({k: tuple(v.shape) for k, v in blk.state_dict().items()}, 9)
+    blk.load_state_dict(sd)
+    x = fx.det_tensor((B, N, D), 91)
+    gy = fx.det_tensor((B, N, D), 92)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.clone().requires_grad_(True)
+    yo = R.block(xo, sdg, "", H)
+    yo.backward(gy)
+    blk = blk.cuda()
+    xp = x.cuda().requires_grad_(True)
+    yp = blk(xp)
+    yp.backward(gy.cuda().to(yp.dtype))
+    assert _rel_l2(yp.float().cpu(), yo.detach()) <= 1e-2
+    assert _rel_l2(xp.grad.float().cpu(), xo.grad) <= 3e-2
+    for k, p in blk.named_parameters():
+        assert _rel_l2(p.grad.float().cpu(), sdg[k].grad) <= 4e-2, k
+
+
+def test_block_general_path_equals_fused_path():
+    """qk_norm / LayerScale / per-op composition must agree with the single fused Block node."""
+    from functools import partial
+    from ucf_vit_b200.simple.building_blocks import Block
+    torch.manual_seed(0)
+    D, H = 128, 2
+    a = Block(dim=D, num_heads=H, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6)).cuda()
+    b = Block(dim=D, num_heads=H, qkv_bias=True, init_values=1.0, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6)).cuda()
+    b.load_state_dict(a.state_dict(), strict=False)       # LayerScale gamma = 1 -> same function
+    x = torch.randn(2, 50, D, device="cuda")
+    ya, yb = a(x), b(x)
+    assert _rel_l2(yb.float(), ya.float()) <= 1e-2

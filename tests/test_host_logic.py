@@ -1,0 +1,93 @@
+"""CPU: host-side logic of the product package against reference-generated vectors, state_dict
+compatibility of every model class, and loud failure without CUDA."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures as fx
+from tests import _cases as C
+from ucf_vit_b200.utils import misc, pos_embed
+from ucf_vit_b200.utils.lr_scheduler import LinearWarmupCosineAnnealingLR
+
+_, _, HOST = fx.load_case(os.path.join(C.GOLDEN, "host_logic.npz"))
+
+
+def test_pos_embed_tables_bit_exact():
+    assert np.array_equal(pos_embed.get_2d_sincos_pos_embed(16, 4, 6), HOST["pe2d_16_4x6"])
+    assert np.array_equal(pos_embed.get_2d_sincos_pos_embed(16, 3, 3, cls_token=True), HOST["pe2d_16_3x3_cls"])
+    assert np.array_equal(pos_embed.get_3d_sincos_pos_embed(12, 2, 3, 2), HOST["pe3d_12_2x3x2"])
+    assert np.array_equal(pos_embed.get_1d_sincos_pos_embed_from_grid(8, np.arange(5)), HOST["pe1d_8"])
+    assert np.array_equal(pos_embed.SinusoidalEmbeddings(10, 8).embeddings.numpy(), HOST["time_table_10x8"])
+
+
+def test_lr_schedule_matches_reference():
+    prm = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([prm], lr=1e-4)
+    sch = LinearWarmupCosineAnnealingLR(opt, 5, 20, 1e-8, 1e-8)
+    lrs = []
+    for _ in range(30):
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sch.step()
+    assert np.allclose(np.array(lrs), HOST["lr_w5_m20"], rtol=1e-12, atol=0)
+
+
+def test_patchify_targets_bit_exact_and_invertible():
+    x2 = fx.det_tensor((2, 3, 8, 12), 71)
+    x3 = fx.det_tensor((1, 2, 4, 8, 4), 72)
+    assert np.array_equal(misc.patchify(x2, 4, True).numpy(), HOST["patchify2d_p4"])
+    assert np.array_equal(misc.patchify(x3, 4, False).numpy(), HOST["patchify3d_p4"])
+    assert torch.equal(misc.unpatchify(misc.patchify(x2, 4, True), x2, 4, True), x2)
+    assert torch.equal(misc.unpatchify(misc.patchify(x3, 4, False), x3, 4, False), x3)
+
+
+def test_configure_optimizer_groups():
+    m = C.build_product(C.load("vit_cls_hd64")[0])
+    opt = misc.configure_optimizer(m, 1e-4, 0.9, 0.95, 1e-5)
+    assert opt.param_groups[0]["weight_decay"] == 1e-5 and opt.param_groups[1]["weight_decay"] == 0
+    assert any(p is m.pos_embed for p in opt.param_groups[1]["params"])
+    assert all(p is not m.pos_embed for p in opt.param_groups[0]["params"])
+
+
+@pytest.mark.parametrize("name", C.MODEL_CASES)
+def test_state_dict_keys_and_shapes_match_reference(name):
+    """Reference checkpoints must load with strict=True (keys incl. token_embeds aliases)."""
+    cfg, shapes, _, sd = C.load(name)
+    model = C.build_product(cfg)
+    got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert got == shapes
+    model.load_state_dict(sd, strict=True)
+
+
+def test_fsdp_surface_accepts_tp_args_and_rejects_tp():
+    from ucf_vit_b200.fsdp import arch as FA
+    from ucf_vit_b200.fsdp.building_blocks import Block
+    cfg = C.load("mae_hd64_dec32")[0]
+    m = FA.MAE(img_size=cfg["img_size"], patch_size=cfg["patch_size"], in_chans=3, embed_dim=cfg["embed_dim"],
+               depth=cfg["depth"], num_heads=cfg["num_heads"], decoder_embed_dim=cfg["decoder_embed_dim"],
+               decoder_depth=cfg["decoder_depth"], decoder_num_heads=cfg["decoder_num_heads"], mlp_ratio=4,
+               mlp_ratio_decoder=4, mask_ratio=0.75, linear_decoder=False, class_token=False, weight_init="skip",
+               twoD=True, default_vars=C.VARS3, tensor_par_size=1, tensor_par_group=None)
+    assert all(isinstance(b, Block) for b in m.blocks)
+    with pytest.raises(NotImplementedError):
+        FA.VIT(img_size=[32, 32], patch_size=8, num_classes=2, embed_dim=64, depth=1, num_heads=2,
+               default_vars=C.VARS3, tensor_par_size=2)
+
+
+def test_product_fails_loudly_without_cuda():
+    """No CPU / oracle fallback in the product path."""
+    cfg, _, arrays, sd = C.load("vit_cls_hd64")
+    model = C.build_product(cfg)
+    model.load_state_dict(sd)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        model(C.inputs(cfg, arrays)["x"], C.VARS3)
+
+
+def test_product_never_imports_oracle():
+    import pathlib
+    root = pathlib.Path(C.GOLDEN).parents[1] / "ucf_vit_b200"
+    for f in root.rglob("*.py"):
+        txt = f.read_text()
+        assert "import oracle" not in txt and "from oracle" not in txt, f

@@ -28,6 +28,9 @@ _SIGNATURES = {
                                   c_void_p, c_void_p, _LL, c_int, c_int, c_void_p]),
     "ucf_attention_fwd": (c_int, [c_void_p] * 5 + [c_int] * 5 + [_LL] * 12 + [c_float, c_void_p]),
     "ucf_attention_bwd": (c_int, [c_void_p] * 11 + [c_int] * 5 + [_LL] * 21 + [c_float, c_void_p]),
+    "ucf_var_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _LL, c_int, c_int, c_int, c_int, c_int,
+                                      c_float, c_void_p]),
+    "ucf_var_attention_bwd": (c_int, [c_void_p] * 7 + [_LL, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "ucf_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, _LL, c_void_p]),
     "ucf_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, _LL, c_int, c_void_p]),
     "ucf_colsum_bf16": (c_int, [c_void_p, c_void_p, _LL, c_int, _LL, c_int, c_void_p]),

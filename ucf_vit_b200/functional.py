@@ -358,3 +358,60 @@ def fused_block(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_
                 num_heads, eps1, eps2):
     return _BlockFn.apply(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
                           num_heads, eps1, eps2)
+
+
+# ---------------------------------------------------------------------------------------------
+# variable-aggregation cross-attention core (Nq = N_a, Nk = V per spatial token)
+# ---------------------------------------------------------------------------------------------
+class _VarAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, kv, scale):
+        q = q.contiguous()
+        kv = kv.contiguous()
+        o, lse = ops.var_attention_fwd(q, kv, scale)
+        ctx.save_for_backward(q, kv, o, lse)
+        ctx.scale = scale
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, kv, o, lse = ctx.saved_tensors
+        dq_acc, dkv = ops.var_attention_bwd(q, kv, o, d_o, lse, ctx.scale)
+        return dq_acc.to(q.dtype), dkv, None
+
+
+def var_attention(q, kv, scale):
+    """q [Bq, N_a, H, hd] (Bq == rows, or 1 = one query shared by all rows), kv [rows, V, 2, H, hd]."""
+    return _VarAttnFn.apply(q, kv, scale)
+
+
+# ---------------------------------------------------------------------------------------------
+# cast + patchify (Conv(k = s = p) input -> GEMM rows)
+# ---------------------------------------------------------------------------------------------
+class _PatchifyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p):
+        ctx.shape, ctx.p, ctx.dt = x.shape, p, x.dtype
+        if x.dtype not in (torch.float32, BF16):
+            x = x.float()
+        return ops.patchify(x.contiguous(), p)
+
+    @staticmethod
+    def backward(ctx, g):
+        # fold back (only reached when the image itself requires grad, which no driver does)
+        shp, p = ctx.shape, ctx.p
+        B, C = shp[:2]
+        G = [s // p for s in shp[2:]]
+        if len(G) == 2:
+            dx = g.view(B, G[0], G[1], C, p, p).permute(0, 3, 1, 4, 2, 5).reshape(shp)
+        else:
+            dx = g.view(B, G[0], G[1], G[2], C, p, p, p).permute(0, 4, 1, 5, 2, 6, 3, 7).reshape(shp)
+        return dx.to(ctx.dt), None
+
+
+def patchify(x, p):
+    """[B,C,H,W(,Z)] -> bf16 [B*L, C*p^d], K ordered (c, p0, p1(, p2)) like conv.weight.view(D,-1)."""
+    if x.requires_grad:
+        return _PatchifyFn.apply(x, p)
+    with torch.no_grad():
+        return _PatchifyFn.apply(x, p)

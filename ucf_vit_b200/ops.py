@@ -179,3 +179,32 @@ def attention_bwd(q, k, v, o, d_o, lse, scale, dq=None, dk=None, dv=None):
                                    *_bnhd(dq), *_bnhd(dk), *_bnhd(dv), float(scale), _stream())
     L.check(rc, "attention_bwd")
     return dq, dk, dv
+
+
+def var_attention_fwd(q, kv, scale):
+    """q [Bq,Na,H,hd] (Bq == rows or 1), kv [rows,V,2,H,hd] -> o [rows,Na,H,hd], lse [rows,Na,H]."""
+    _require_cuda(q, kv)
+    assert q.is_contiguous() and kv.is_contiguous() and q.dtype == torch.bfloat16 and kv.dtype == torch.bfloat16
+    rows, V, _, H, hd = kv.shape
+    Bq, Na = q.shape[0], q.shape[1]
+    assert Bq in (1, rows)
+    shared = int(Bq == 1 and rows != 1) or int(Bq == 1)
+    o = torch.empty((rows, Na, H, hd), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((rows, Na, H), dtype=torch.float32, device=q.device)
+    L.check(L.lib().ucf_var_attention_fwd(q.data_ptr(), kv.data_ptr(), o.data_ptr(), lse.data_ptr(), rows, Na, V, H, hd,
+                                          shared, float(scale), _stream()), "var_attention_fwd")
+    return o, lse
+
+
+def var_attention_bwd(q, kv, o, d_o, lse, scale):
+    _require_cuda(q, kv, o, d_o)
+    rows, V, _, H, hd = kv.shape
+    Bq, Na = q.shape[0], q.shape[1]
+    shared = int(Bq == 1)
+    d_o = d_o.contiguous()
+    dkv = torch.empty_like(kv)
+    dq_acc = torch.empty((Bq, Na, H, hd), dtype=torch.float32, device=q.device)
+    L.check(L.lib().ucf_var_attention_bwd(q.data_ptr(), kv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(),
+                                          dkv.data_ptr(), dq_acc.data_ptr(), rows, Na, V, H, hd, shared, float(scale),
+                                          _stream()), "var_attention_bwd")
+    return dq_acc, dkv

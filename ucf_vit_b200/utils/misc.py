@@ -1,0 +1,48 @@
+"""Host-side helpers of /root/reference/src/UCF_VIT/utils/misc.py that sit next to the hot path:
+patchify / unpatchify (MAE & diffusion targets, :14-56), optimizer / scheduler factories (:58-96).
+Pure index shuffles and host logic -- no kernel."""
+import torch
+
+from .lr_scheduler import LinearWarmupCosineAnnealingLR
+
+
+def patchify(data, patch_size, twoD):
+    """[N,C,X,Y(,Z)] -> [N, L, p^d * C] with the channel FASTEST inside a patch (pixel-major)."""
+    n, c = data.shape[:2]
+    p = patch_size
+    g = [s // p for s in data.shape[2:]]
+    if twoD:
+        t = data.reshape(n, c, g[0], p, g[1], p).permute(0, 2, 4, 3, 5, 1)
+        return t.reshape(n, g[0] * g[1], p * p * c)
+    t = data.reshape(n, c, g[0], p, g[1], p, g[2], p).permute(0, 2, 4, 6, 3, 5, 7, 1)
+    return t.reshape(n, g[0] * g[1] * g[2], p ** 3 * c)
+
+
+def unpatchify(patchified_pixel_values, data, patch_size, twoD):
+    """Inverse of `patchify`; `data` only provides the target shape."""
+    p = patch_size
+    n = patchified_pixel_values.shape[0]
+    c = data.shape[1]
+    g = [s // p for s in data.shape[2:]]
+    if twoD:
+        t = patchified_pixel_values.reshape(n, g[0], g[1], p, p, c).permute(0, 5, 1, 3, 2, 4)
+        return t.reshape(n, c, g[0] * p, g[1] * p)
+    t = patchified_pixel_values.reshape(n, g[0], g[1], g[2], p, p, p, c).permute(0, 7, 1, 4, 2, 5, 3, 6)
+    return t.reshape(n, c, g[0] * p, g[1] * p, g[2] * p)
+
+
+def configure_optimizer(model, lr, beta_1, beta_2, weight_decay, fused=None):
+    """AdamW with two groups: weight decay everywhere except var/pos/time embeddings."""
+    decay, no_decay = [], []
+    for name, prm in model.named_parameters():
+        (no_decay if ("var_embed" in name or "pos_embed" in name or "time_pos_embed" in name) else decay).append(prm)
+    groups = [
+        {"params": decay, "lr": lr, "betas": (beta_1, beta_2), "weight_decay": weight_decay},
+        {"params": no_decay, "lr": lr, "betas": (beta_1, beta_2), "weight_decay": 0},
+    ]
+    kw = {} if fused is None else {"fused": fused}
+    return torch.optim.AdamW(groups, **kw)
+
+
+def configure_scheduler(optimizer, warmup_steps, max_steps, warmup_start_lr, eta_min):
+    return LinearWarmupCosineAnnealingLR(optimizer, warmup_steps, max_steps, warmup_start_lr, eta_min)
