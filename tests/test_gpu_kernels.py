@@ -19,7 +19,7 @@ def _ok(got, ref, tol):
     got, ref = got.float(), ref.float()
     assert torch.isfinite(got).all()
     err = (got - ref).abs().max().item()
-    assert err <= tol * (ref.abs().max().item() + 1e-6), (err, ref.abs().max().item())
+    assert err <= tol * ref.abs().max().item() + 1e-5, (err, ref.abs().max().item())
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 192, 192), (1000, 576, 192), (333, 1000, 768), (77, 40, 72),
@@ -58,9 +58,9 @@ def test_gemm_linearity_at_benchmark_size():
     w = torch.randint(-2, 3, (N, K), device=dev).to(torch.bfloat16)
     y12 = ops.gemm(a1 + a2, w, M=M, N=N, K=K).float()
     y1, y2 = ops.gemm(a1, w, M=M, N=N, K=K).float(), ops.gemm(a2, w, M=M, N=N, K=K).float()
-    # small-integer operands: every product and partial sum is exact in fp32; bf16 output rounding
-    # only matters above 256, so compare with one bf16 ulp of slack
-    assert ((y12 - (y1 + y2)).abs() <= 0.01 * (y1 + y2).abs() + 1e-3).all()
+    # small-integer operands: every product and partial sum is exact in fp32, so the only error is
+    # the final bf16 rounding of each of the three outputs (half an ulp = 2^-9 relative, each)
+    assert ((y12 - (y1 + y2)).abs() <= 2.0 ** -8 * (y1.abs() + y2.abs() + y12.abs()) + 1e-3).all()
     idx = torch.randint(0, M, (64,), device=dev)
     ref = (a1[idx].float() @ w.float().t())
     assert ((y1[idx] - ref).abs() <= 0.005 * ref.abs() + 1e-3).all()
