@@ -31,7 +31,7 @@ extern "C" {
 
 #define UCF_ABI_VERSION 1
 
-enum { UCF_DTYPE_F32 = 0, UCF_DTYPE_BF16 = 1 };
+enum { UCF_DTYPE_F32 = 0, UCF_DTYPE_BF16 = 1, UCF_DTYPE_U8 = 2, UCF_DTYPE_F64 = 3 };
 enum { UCF_LAYOUT_K_MAJOR = 0, UCF_LAYOUT_MN_MAJOR = 1 };
 /* GEMM epilogues */
 enum {
@@ -112,6 +112,32 @@ int ucf_var_attention_fwd(const void* q, const void* kv, void* o, float* lse, lo
 int ucf_var_attention_bwd(const void* q, const void* kv, const void* o, const void* d_o,
                           const float* lse, void* dkv, float* dq_acc, long long rows, int Na, int V,
                           int H, int hd, int q_shared, float scale, void* stream);
+
+/* ---- adaptive patching (SAP) --------------------------------------------------------------
+ * Tree construction (HOST pointers; integer work, bit-exact with the reference's node order):
+ * replaces FixedQuadTree._build_tree (dataloaders/quadtree.py:115-137) and FixedOctTree._build_tree
+ * (dataloaders/octree.py:72-102).  domain: [n0, n1] (2-D: rows, cols) or cubic [n0, n1, n2] edge map
+ * of dtype u8 / f32 / f64; leaf value = int(sum(domain[box]) / norm_factor).  Greedy: split the FIRST
+ * leaf holding the maximum value until fixed_length leaves exist or the chosen leaf is 2 wide.
+ * boxes_host: int32 [fixed_length, 4] (x1,x2,y1,y2) or [fixed_length, 6] (+z1,z2) in list order;
+ * values_host: int64 [fixed_length] or NULL.  Returns the number of leaves (>= 1) or a negative code. */
+int ucf_sap_build_tree_host(const void* domain_host, int domain_dtype, int ndim, int n0, int n1, int n2,
+                            double norm_factor, int fixed_length, int32_t* boxes_host,
+                            long long* values_host);
+/* Gather = FixedQuadTree.serialize (quadtree.py:144-174; cv.resize INTER_CUBIC per leaf) /
+ * FixedOctTree.serialize (octree.py:104-150; align-corners trilinear).  DEVICE pointers.
+ * img: [n0, n1, C] u8|f32 (2-D, HWC) or [n0, n1, n2, C] f32 (3-D, ZYXC); boxes: int32 on device;
+ * seq: f32 [fixed_length, p, p(, p), C]; seq_size: int64 [fixed_length]; seq_pos: f64
+ * [fixed_length, 2|3] box centres.  Slots >= n_leaves are padded: zero patch, size 0, centre -1. */
+int ucf_sap_gather(const void* img, int img_dtype, int ndim, int n0, int n1, int n2, int C,
+                   const int32_t* boxes, int n_leaves, int fixed_length, int p, float* seq,
+                   long long* seq_size, double* seq_pos, void* stream);
+/* Scatter = FixedQuadTree.deserialize + Rect.set_area (quadtree.py:209-221, :25-36) /
+ * FixedOctTree.deserialize + Cube.set_area (octree.py:201-213, :28-55): each patch is resampled
+ * to its leaf box and pasted into mask (f32 [n0, n1(, n2), C], caller zero-fills).
+ * truncate_to_int != 0 reproduces the 2-D reference's `seq.astype(int)` before resizing. */
+int ucf_sap_scatter(const float* seq, int ndim, int n0, int n1, int n2, int C, const int32_t* boxes,
+                    int n_leaves, int p, int truncate_to_int, float* mask, void* stream);
 
 /* ---- bandwidth-bound helpers ------------------------------------------------------------- */
 /* dst_bf16[i] = (bf16) src_f32[i] */

@@ -1,0 +1,141 @@
+"""SAP adaptive patching.
+CPU part : oracle (numpy restatement) and the product's C++ host tree builder against golden
+           vectors produced by the reference FixedQuadTree / FixedOctTree -- node boxes, order,
+           values, sizes and centres are BIT-EXACT.
+GPU part : gather / scatter kernels against the same goldens (pixels: float32 within 2e-5 of
+           OpenCV INTER_CUBIC / scipy linear; uint8 within 1 LSB of OpenCV's fixed-point path)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures as fx
+from oracle import quadtree_np as Q
+from ucf_vit_b200 import ops
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "sap_tree_*.npz")))
+
+
+def _load(name):
+    cfg, _, a = fx.load_case(os.path.join(GOLDEN, name + ".npz"))
+    n = cfg["size"]
+    shape = (n, n) if cfg["kind"] == "quadtree" else (n, n, n)
+    dom = (np.unpackbits(a["domain"])[:int(np.prod(shape))].reshape(shape) * 255).astype(np.uint8)
+    return cfg, a, dom
+
+
+def test_appendix_e_known_answer():
+    dom = np.zeros((16, 16), dtype=np.uint8)
+    for r, c in [(1, 1), (2, 3), (3, 12), (9, 9), (10, 10), (9, 10), (14, 2)]:
+        dom[r, c] = 255
+    want = [(0, 8, 8, 16, 1), (8, 12, 12, 16, 0), (12, 16, 12, 16, 0), (8, 10, 10, 12, 0), (10, 12, 10, 12, 1),
+            (8, 10, 8, 10, 1), (10, 12, 8, 10, 1), (12, 16, 8, 12, 0), (0, 8, 0, 8, 2), (8, 16, 0, 8, 1)]
+    assert Q.build_quadtree(dom, 10) == want
+    boxes, values = ops.sap_build_tree(dom, 10)
+    assert [tuple(b) + (v,) for b, v in zip(boxes.tolist(), values.tolist())] == want
+    img = np.arange(256, dtype=np.float32).reshape(16, 16, 1)
+    seq, size, pos = Q.serialize2d(want, img, 2, 10)
+    assert np.allclose(seq[0, :, :, 0], [[153.5, 157.5], [217.5, 221.5]])
+    assert size.tolist() == [8, 4, 4, 2, 2, 2, 2, 4, 8, 8]
+    assert pos[:3].tolist() == [[4, 12], [10, 14], [14, 14]]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tree_oracle_and_host_builder_bit_exact(name):
+    cfg, a, dom = _load(name)
+    want = [tuple(int(v) for v in row) for row in a["nodes"]]
+    if cfg["kind"] == "quadtree":
+        assert Q.build_quadtree(dom, cfg["L"]) == want
+    else:
+        assert Q.build_octree(dom, cfg["L"]) == want
+    boxes, values = ops.sap_build_tree(dom, cfg["L"])
+    got = [tuple(b) + (v,) for b, v in zip(boxes.tolist(), values.tolist())]
+    assert got == want
+    for dt in (np.float32, np.float64):        # float edge maps take the double-precision SAT path
+        boxes_f, values_f = ops.sap_build_tree(dom.astype(dt), cfg["L"])
+        assert [tuple(b) + (v,) for b, v in zip(boxes_f.tolist(), values_f.tolist())] == want
+
+
+def test_tree_edge_cases():
+    # fixed_length 1: root only; empty edge map: ties resolved in list order; stop rule at 2 px
+    z = np.zeros((8, 8), dtype=np.uint8)
+    b, v = ops.sap_build_tree(z, 1)
+    assert b.tolist() == [[0, 8, 0, 8]] and v.tolist() == [0]
+    assert [tuple(x) for x in ops.sap_build_tree(z, 7)[0].tolist()] == [n[:4] for n in Q.build_quadtree(z, 7)]
+    full = np.full((4, 4), 255, dtype=np.uint8)
+    b, v = ops.sap_build_tree(full, 64)       # splits 4x4 -> four 2x2, then stops at the 2-px rule
+    assert len(b) == 4 and [tuple(x) + (y,) for x, y in zip(b.tolist(), v.tolist())] == Q.build_quadtree(full, 64)
+    with pytest.raises(RuntimeError):
+        ops.sap_build_tree(np.zeros((4, 8, 8), dtype=np.uint8), 8)      # non-cubic octree domain
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if "oct" not in c])
+def test_oracle_serialize_matches_reference_2d(name):
+    cfg, a, dom = _load(name)
+    nodes = [tuple(int(v) for v in row) for row in a["nodes"]]
+    seq, size, pos = Q.serialize2d(nodes, a["img"], cfg["p"], cfg["L"])
+    assert np.array_equal(size, a["seq_size"]) and np.array_equal(pos, a["seq_pos"])
+    tol = 1.0 if cfg["dtype"] == "uint8" else 2e-6
+    assert np.abs(seq - a["seq_img"]).max() <= tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_gather_scatter_kernels(name):
+    cfg, a, dom = _load(name)
+    L, p, C = cfg["L"], cfg["p"], cfg["C"]
+    boxes, _ = ops.sap_build_tree(dom, L)
+    bdev = torch.from_numpy(boxes).cuda()
+    if cfg["kind"] == "quadtree":
+        img = torch.from_numpy(a["img"]).cuda()
+        seq, size, pos = ops.sap_gather(img, bdev, L, p)
+        assert np.array_equal(size.cpu().numpy(), a["seq_size"]), "sizes must be bit-exact"
+        assert np.array_equal(pos.cpu().numpy(), a["seq_pos"]), "centres must be bit-exact"
+        tol = 1.0 if cfg["dtype"] == "uint8" else 2e-5
+        err = np.abs(seq.cpu().numpy() - a["seq_img"]).max()
+        assert err <= tol, err
+        if cfg["dtype"] == "uint8":
+            assert (seq.cpu().numpy() == a["seq_img"]).mean() > 0.999
+        scale = 1.0 if cfg["dtype"] == "uint8" else 255.0
+        back = torch.from_numpy(a["seq_img"] * scale).cuda()
+        mask = ops.sap_scatter(back, bdev, (cfg["size"], cfg["size"]), p, C, truncate_to_int=True)
+        assert np.abs(mask.cpu().numpy() - a["mask"]).max() <= 2e-3
+        # round trip property at leaf resolution == patch resolution: identity
+        same = [i for i, b in enumerate(boxes) if b[1] - b[0] == p]
+        if same and cfg["dtype"] == "float32":
+            i = same[0]
+            x1, x2, y1, y2 = boxes[i]
+            assert np.array_equal(seq[i].cpu().numpy(), a["img"][y1:y2, x1:x2].astype(np.float32))
+    else:
+        vol = torch.from_numpy(a["vol"]).cuda()
+        seq, size, pos = ops.sap_gather(vol, bdev, L, p)
+        assert np.array_equal(size.cpu().numpy(), a["seq_size"]) and np.array_equal(pos.cpu().numpy(), a["seq_pos"])
+        assert np.abs(seq.cpu().numpy() - a["seq_img"].astype(np.float32)).max() <= 1e-3   # fixture stored as fp16
+        nodes = [tuple(int(v) for v in row) for row in a["nodes"]]
+        o_seq, _, _ = Q.serialize3d(nodes, a["vol"], p, L)
+        assert np.abs(seq.cpu().numpy() - o_seq).max() <= 2e-6
+        mask = ops.sap_scatter(seq, bdev, (cfg["size"],) * 3, p, C)
+        o_mask = Q.deserialize3d(nodes, o_seq, p, C, (cfg["size"],) * 3)
+        assert np.abs(mask.cpu().numpy() - o_mask).max() <= 2e-5
+
+
+@pytest.mark.gpu
+def test_quadtree_class_api_and_large_image_partition():
+    """Reference-typed API + size-independent property at the SAP benchmark scale: the leaves of a
+    4096^2 tree tile the image exactly (areas sum to H*W, no overlaps)."""
+    from ucf_vit_b200.dataloaders.quadtree import FixedQuadTree
+    rng = np.random.RandomState(0)
+    dom = (rng.rand(4096, 4096) < 0.002).astype(np.uint8) * 255
+    qt = FixedQuadTree(dom, fixed_length=1024)
+    assert qt.count_patches() == 1024
+    cover = np.zeros((4096, 4096), dtype=np.int32)
+    for r, _ in qt.nodes:
+        cover[r.y1:r.y2, r.x1:r.x2] += 1
+    assert cover.min() == 1 and cover.max() == 1
+    img = rng.randint(0, 256, (4096, 4096, 3)).astype(np.uint8)
+    patches, sizes, centres = qt.serialize(img, size=(16, 16, 3))
+    assert len(patches) == 1024 and patches[0].shape == (16, 16, 3) and sizes[0] == qt.nodes[0][0].get_size()[0]
+    assert centres[0] == qt.nodes[0][0].get_center()

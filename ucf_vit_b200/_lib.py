@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libucfvit_b200.so")
 _lib = None
 
-UCF_DTYPE_F32, UCF_DTYPE_BF16 = 0, 1
+UCF_DTYPE_F32, UCF_DTYPE_BF16, UCF_DTYPE_U8, UCF_DTYPE_F64 = 0, 1, 2, 3
 UCF_LAYOUT_K_MAJOR, UCF_LAYOUT_MN_MAJOR = 0, 1
 EPI_BIAS, EPI_BIAS_RESIDUAL, EPI_BIAS_GELU_AUX, EPI_DGELU, EPI_F32_ADD = 0, 1, 2, 3, 4
 
@@ -31,6 +31,12 @@ _SIGNATURES = {
     "ucf_var_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _LL, c_int, c_int, c_int, c_int, c_int,
                                       c_float, c_void_p]),
     "ucf_var_attention_bwd": (c_int, [c_void_p] * 7 + [_LL, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "ucf_sap_build_tree_host": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_double, c_int, c_void_p,
+                                        c_void_p]),
+    "ucf_sap_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                               c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ucf_sap_scatter": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                c_void_p]),
     "ucf_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, _LL, c_void_p]),
     "ucf_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, _LL, c_int, c_void_p]),
     "ucf_colsum_bf16": (c_int, [c_void_p, c_void_p, _LL, c_int, _LL, c_int, c_void_p]),

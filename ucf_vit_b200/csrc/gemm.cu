@@ -9,7 +9,7 @@
 //   wgrad     dY^T*X         A MN-major, B MN-major  (split-K, fp32 TMA reduce-add into dW)
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM
-// alloc), warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store).  The
+// alloc), warps 2..9 = epilogue (TMEM -> registers -> swizzled smem -> TMA store).  The
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <stdarg.h>
 #include <stdio.h>
@@ -38,16 +38,24 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr bool HAS_AUX = (EPI == EPI_BIAS_RESIDUAL || EPI == EPI_BIAS_GELU_AUX || EPI == EPI_DGELU);
   static constexpr bool AUX_IN = (EPI == EPI_BIAS_RESIDUAL || EPI == EPI_DGELU);
-  static constexpr int EPI_STAGE_BYTES = 4 * 2 * 4096;
+  // 8 epilogue warps (two per TMEM lane quarter, each owning half of the tile's columns) work in
+  // chunks of 32 rows x 32 columns: bf16 -> 64-byte rows (SWIZZLE_64B), fp32 -> 128-byte rows.
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int CW = 32;
+  static constexpr int OUT_BUF = (EPI == EPI_F32_ADD) ? 4096 : 2048;
+  static constexpr int AUX_BUF = 2048;
+  static constexpr int OUT_STAGE_BYTES = EPI_WARPS * 2 * OUT_BUF;
+  static constexpr int AUX_STAGE_BYTES = HAS_AUX ? EPI_WARPS * 2 * AUX_BUF : 0;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_STAGE_BYTES +
-                                    (HAS_AUX ? EPI_STAGE_BYTES : 0) + BN * 4 + (2 * STAGES + 4 + 8) * 8 + 16;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_STAGE_BYTES + AUX_STAGE_BYTES +
+                                    BN * 4 + (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
   static_assert(2 * BN <= 512, "two accumulators must fit in TMEM");
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(64 + 32 * 8, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
                  const GemmParams p) {
@@ -59,14 +67,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
   uint8_t* epi_out = smem + STAGES * STAGE_BYTES;
-  uint8_t* epi_aux = epi_out + Cfg::EPI_STAGE_BYTES;
-  float* bias_s = reinterpret_cast<float*>(epi_aux + (Cfg::HAS_AUX ? Cfg::EPI_STAGE_BYTES : 0));
+  uint8_t* epi_aux = epi_out + Cfg::OUT_STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(epi_aux + Cfg::AUX_STAGE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + BN);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* aux_bar = tempty_bar + 2;   // [4 warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 8);
+  uint64_t* aux_bar = tempty_bar + 2;   // [EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * Cfg::EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -82,9 +90,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);
+      mbar_init(&tempty_bar[b], Cfg::EPI_WARPS);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -167,16 +175,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;           // TMEM lane quarter this warp may touch
-    const int ew = warp - 2;          // staging buffer owner index
+    const int q = warp & 3;             // TMEM lane quarter this warp may touch
+    const int ew = warp - 2;            // 0..7
+    const int half = ew >> 2;           // which half of the tile's columns this warp owns
     const int etid = threadIdx.x - 64;
-    uint8_t* my_out = epi_out + ew * 8192;
-    uint8_t* my_aux = epi_aux + ew * 8192;
+    constexpr int CW = Cfg::CW;
+    constexpr int NCHUNK = BN / 2 / CW;   // chunks per warp
+    constexpr int OUT_BUF = Cfg::OUT_BUF, AUX_BUF = Cfg::AUX_BUF;
+    uint8_t* my_out = epi_out + ew * 2 * OUT_BUF;
+    uint8_t* my_aux = epi_aux + ew * 2 * AUX_BUF;
     uint64_t* my_aux_bar = aux_bar + ew * 2;
-    const uint32_t row_sw = (lane & 7);
-    const uint32_t row_off = lane * 128;
-    constexpr int CW = (EPI == EPI_F32_ADD) ? 32 : 64;   // columns per 128-byte staging row
-    constexpr int NCHUNK = BN / CW;
+    // byte offset of this lane's 16-byte chunk j inside a staging buffer
+    //   bf16: 64-byte rows, SWIZZLE_64B  -> chunk ^= (row >> 1) & 3
+    //   fp32: 128-byte rows, SWIZZLE_128B -> chunk ^= row & 7
+    const uint32_t sw64 = (lane >> 1) & 3, sw128 = lane & 7;
     uint32_t cc = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -185,72 +197,67 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m_blk = rest % p.tiles_m;
       const int m0 = m_blk * BM, n0 = n_blk * BN;
       const int buf = it & 1;
-      const int r0 = m0 + q * 32;   // first row of this warp's 32-row slab
+      const int r0 = m0 + q * 32;             // first row of this warp's 32-row slab
+      const int cbase = half * (BN / 2);      // first column (inside the tile) of this warp's half
 
       if (EPI != EPI_F32_ADD && EPI != EPI_DGELU) {
-        named_bar_sync(1, 128);
-        for (int i = etid; i < BN; i += 128) {
+        named_bar_sync(1, 32 * Cfg::EPI_WARPS);
+        for (int i = etid; i < BN; i += 32 * Cfg::EPI_WARPS) {
           float b = 0.f;
           if (p.bias != nullptr && n0 + i < p.N)
             b = p.bias_is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n0 + i])
                                : reinterpret_cast<const float*>(p.bias)[n0 + i];
           bias_s[i] = b;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 32 * Cfg::EPI_WARPS);
       }
-      if (Cfg::AUX_IN && lane == 0 && r0 < p.M) {
-        mbar_expect_tx(&my_aux_bar[cc & 1], 4096);
-        tma_load_2d(my_aux + (cc & 1) * 4096, &tmAux, &my_aux_bar[cc & 1], n0, r0);
+      const bool active = r0 < p.M && n0 + cbase < p.N;
+      if (Cfg::AUX_IN && lane == 0 && active) {
+        mbar_expect_tx(&my_aux_bar[cc & 1], AUX_BUF);
+        tma_load_2d(my_aux + (cc & 1) * AUX_BUF, &tmAux, &my_aux_bar[cc & 1], n0 + cbase, r0);
       }
       mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t t_row = tmem_base + buf * BN + cbase + (static_cast<uint32_t>(q * 32) << 16);
 
-      if (r0 < p.M) {
+      if (active) {
 #pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
-          const int col0 = n0 + c * CW;
+          const int col0 = n0 + cbase + c * CW;
           if (col0 >= p.N) break;
           const uint32_t b = cc & 1;
           if (Cfg::AUX_IN && lane == 0 && c + 1 < NCHUNK && col0 + CW < p.N) {
-            mbar_expect_tx(&my_aux_bar[b ^ 1], 4096);
-            tma_load_2d(my_aux + (b ^ 1) * 4096, &tmAux, &my_aux_bar[b ^ 1], col0 + CW, r0);
+            mbar_expect_tx(&my_aux_bar[b ^ 1], AUX_BUF);
+            tma_load_2d(my_aux + (b ^ 1) * AUX_BUF, &tmAux, &my_aux_bar[b ^ 1], col0 + CW, r0);
           }
-          uint32_t v[CW];  // fully unrolled below: stays in registers
-          {
-            uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-            tmem_ld32(t_row + c * CW, v0);
-            if (CW == 64) {
-              uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[CW - 32]);
-              tmem_ld32(t_row + c * CW + 32, v1);
-            }
-          }
+          uint32_t v[32];
+          tmem_ld32(t_row + c * CW, v);
           tmem_wait_ld();
           if (lane == 0) tma_store_wait_read<1>();   // staging buffer b (2 chunks ago) drained
           __syncwarp();
           if (Cfg::AUX_IN) mbar_wait(&my_aux_bar[b], (cc >> 1) & 1);
-          uint8_t* out_row = my_out + b * 4096 + row_off;
-          uint8_t* aux_row = my_aux + b * 4096 + row_off;
 
           if (EPI == EPI_F32_ADD) {
+            uint8_t* out_row = my_out + b * OUT_BUF + lane * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint4 o = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              *reinterpret_cast<uint4*>(out_row + ((j ^ row_sw) << 4)) = o;
-            }
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(out_row + ((j ^ sw128) << 4)) =
+                  make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
+            uint8_t* out_row = my_out + b * OUT_BUF + lane * 64;
+            uint8_t* aux_row = my_aux + b * AUX_BUF + lane * 64;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
               if (EPI != EPI_DGELU) {
-                const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c * CW + 8 * j]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c * CW + 8 * j + 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[cbase + c * CW + 8 * j]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[cbase + c * CW + 8 * j + 4]);
                 f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                 f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
               }
-              const uint32_t sw = (j ^ row_sw) << 4;
+              const uint32_t sw = (static_cast<uint32_t>(j) ^ sw64) << 4;
               if (EPI == EPI_BIAS_RESIDUAL) {
                 const uint4 r = *reinterpret_cast<const uint4*>(aux_row + sw);
                 const float2 r0f = unpack_bf16x2(r.x), r1f = unpack_bf16x2(r.y);
@@ -276,19 +283,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 f[0] = gelu_erf(z0.x); f[1] = gelu_erf(z0.y); f[2] = gelu_erf(z1.x); f[3] = gelu_erf(z1.y);
                 f[4] = gelu_erf(z2.x); f[5] = gelu_erf(z2.y); f[6] = gelu_erf(z3.x); f[7] = gelu_erf(z3.y);
               }
-              uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-              *reinterpret_cast<uint4*>(out_row + sw) = o;
+              *reinterpret_cast<uint4*>(out_row + sw) =
+                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                             pack_bf16x2(f[6], f[7]));
             }
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             if (EPI == EPI_F32_ADD) {
-              tma_reduce_add_2d(&tmC, my_out + b * 4096, col0, r0);
+              tma_reduce_add_2d(&tmC, my_out + b * OUT_BUF, col0, r0);
             } else {
-              tma_store_2d(&tmC, my_out + b * 4096, col0, r0);
-              if (EPI == EPI_BIAS_GELU_AUX) tma_store_2d(&tmAux, my_aux + b * 4096, col0, r0);
+              tma_store_2d(&tmC, my_out + b * OUT_BUF, col0, r0);
+              if (EPI == EPI_BIAS_GELU_AUX) tma_store_2d(&tmAux, my_aux + b * AUX_BUF, col0, r0);
             }
             tma_store_commit();
           }
@@ -339,7 +346,7 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   const int total = p.tiles_m * p.tiles_n * p.splits;
   int grid = total < num_sms() ? total : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(tA, tB, tC, tAux, p);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tA, tB, tC, tAux, p);
   return check_launch("gemm_bf16_kernel");
 }
 
@@ -397,17 +404,18 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
     else       { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = 64; }
     strides[0] = static_cast<uint64_t>(ldb) * 2;
     if ((rc = make_tmap(&tB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    dims[0] = N; dims[1] = M; box[1] = 32;
+    // epilogue boxes: 32 rows x 32 columns (fp32: 128-byte rows, bf16: 64-byte rows)
+    dims[0] = N; dims[1] = M; box[0] = 32; box[1] = 32;
     if (epilogue == EPI_F32_ADD) {
-      box[0] = 32; strides[0] = static_cast<uint64_t>(ldc) * 4;
+      strides[0] = static_cast<uint64_t>(ldc) * 4;
       if ((rc = make_tmap(&tC, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     } else {
-      box[0] = 64; strides[0] = static_cast<uint64_t>(ldc) * 2;
-      if ((rc = make_tmap(&tC, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+      strides[0] = static_cast<uint64_t>(ldc) * 2;
+      if ((rc = make_tmap(&tC, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     }
     if (has_aux) {
-      box[0] = 64; strides[0] = static_cast<uint64_t>(ldaux) * 2;
-      if ((rc = make_tmap(&tAux, aux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+      strides[0] = static_cast<uint64_t>(ldaux) * 2;
+      if ((rc = make_tmap(&tAux, aux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     }
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -420,25 +428,25 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
   UCF_GEMM_CASE(256, 4, false, false, EPI_BIAS)
   UCF_GEMM_CASE(128, 6, false, false, EPI_BIAS)
   UCF_GEMM_CASE(256, 3, false, false, EPI_BIAS_RESIDUAL)
-  UCF_GEMM_CASE(128, 4, false, false, EPI_BIAS_RESIDUAL)
+  UCF_GEMM_CASE(128, 5, false, false, EPI_BIAS_RESIDUAL)
   UCF_GEMM_CASE(256, 3, false, false, EPI_BIAS_GELU_AUX)
-  UCF_GEMM_CASE(128, 4, false, false, EPI_BIAS_GELU_AUX)
-  UCF_GEMM_CASE(256, 4, false, false, EPI_F32_ADD)
-  UCF_GEMM_CASE(128, 6, false, false, EPI_F32_ADD)
+  UCF_GEMM_CASE(128, 5, false, false, EPI_BIAS_GELU_AUX)
+  UCF_GEMM_CASE(256, 3, false, false, EPI_F32_ADD)
+  UCF_GEMM_CASE(128, 5, false, false, EPI_F32_ADD)
   // dgrad
   UCF_GEMM_CASE(256, 4, false, true, EPI_BIAS)
   UCF_GEMM_CASE(128, 6, false, true, EPI_BIAS)
   UCF_GEMM_CASE(256, 3, false, true, EPI_DGELU)
-  UCF_GEMM_CASE(128, 4, false, true, EPI_DGELU)
+  UCF_GEMM_CASE(128, 5, false, true, EPI_DGELU)
   UCF_GEMM_CASE(256, 3, false, true, EPI_BIAS_RESIDUAL)
-  UCF_GEMM_CASE(128, 4, false, true, EPI_BIAS_RESIDUAL)
+  UCF_GEMM_CASE(128, 5, false, true, EPI_BIAS_RESIDUAL)
   // wgrad
-  UCF_GEMM_CASE(256, 4, true, true, EPI_F32_ADD)
-  UCF_GEMM_CASE(128, 6, true, true, EPI_F32_ADD)
+  UCF_GEMM_CASE(256, 3, true, true, EPI_F32_ADD)
+  UCF_GEMM_CASE(128, 5, true, true, EPI_F32_ADD)
   UCF_GEMM_CASE(256, 4, true, true, EPI_BIAS)
   UCF_GEMM_CASE(128, 6, true, true, EPI_BIAS)
   UCF_GEMM_CASE(128, 6, true, false, EPI_BIAS)
-  UCF_GEMM_CASE(128, 6, true, false, EPI_F32_ADD)
+  UCF_GEMM_CASE(128, 5, true, false, EPI_F32_ADD)
 #undef UCF_GEMM_CASE
   set_last_error("gemm: no kernel for a_layout=%d b_layout=%d epilogue=%d tile_n=%d", a_layout, b_layout, epilogue, BN);
   return UCF_ERR_UNSUPPORTED;

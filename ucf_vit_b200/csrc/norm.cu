@@ -90,8 +90,15 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
 
 // Backward.  Each warp walks rows with a grid stride, keeps per-lane partial dgamma/dbeta in
 // registers, then the block reduces them through shared memory and issues one atomicAdd per column.
+// The row (dy, x) is held as the RAW 16-byte bf16 vectors between the reduction pass and the
+// write pass (not as 2 x 8 floats): <= 128 registers, so two 256-thread CTAs stay resident per SM.
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
 template <int NCH, bool P_BF16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NCH <= 3 ? 2 : 1))
 layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const void* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const void* __restrict__ dres, void* __restrict__ dx, float* __restrict__ dgamma,
@@ -101,39 +108,56 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const float inv_d = 1.0f / static_cast<float>(D);
+  const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
 
-  float g[NCH][8], dg[NCH][8], db[NCH][8];
+  // gamma is re-read per row (L1-resident, D*4 bytes) instead of pinning 8*NCH registers
+  float dg[NCH][8], db[NCH][8];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    const int col = c * 256 + lane * 8;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { dg[c][e] = 0.f; db[c][e] = 0.f; g[c][e] = 1.f; }
-    if (col < D && gamma) load8<P_BF16>(gamma, col, g[c]);
+    for (int e = 0; e < 8; ++e) { dg[c][e] = 0.f; db[c][e] = 0.f; }
   }
+  auto load_gamma = [&](int col, float (&gv)[8]) {
+    if (gamma) load8<P_BF16>(gamma, col, gv);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gv[e] = 1.f;
+    }
+  };
 
   for (long long row = warp_global; row < rows; row += nwarps) {
+    uint4 dyr[NCH], xr[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < D) {
+        dyr[c] = __ldg(reinterpret_cast<const uint4*>(dyp + row * D + col));
+        xr[c] = __ldg(reinterpret_cast<const uint4*>(xp + row * D + col));
+      } else {
+        dyr[c] = make_uint4(0, 0, 0, 0);
+        xr[c] = make_uint4(0, 0, 0, 0);
+      }
+    }
     const float mu = mean[row], rs = rstd[row];
-    float gy[NCH][8], xh[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < D) {
-        float dyv[8], xv[8];
-        load8<true>(dy, row * D + col, dyv);
-        load8<true>(x, row * D + col, xv);
+        float dyv[8], xv[8], gv[8];
+        unpack8(dyr[c], dyv);
+        unpack8(xr[c], xv);
+        load_gamma(col, gv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          xh[c][e] = (xv[e] - mu) * rs;
-          gy[c][e] = dyv[e] * g[c][e];
-          s1 += gy[c][e];
-          s2 += gy[c][e] * xh[c][e];
-          dg[c][e] += dyv[e] * xh[c][e];
+          const float xh = (xv[e] - mu) * rs;
+          const float gy = dyv[e] * gv[e];
+          s1 += gy;
+          s2 = fmaf(gy, xh, s2);
+          dg[c][e] = fmaf(dyv[e], xh, dg[c][e]);
           db[c][e] += dyv[e];
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { xh[c][e] = 0.f; gy[c][e] = 0.f; }
       }
     }
     s1 = warp_sum(s1) * inv_d;
@@ -142,9 +166,15 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
     for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < D) {
-        float o[8];
+        float dyv[8], xv[8], gv[8], o[8];
+        unpack8(dyr[c], dyv);
+        unpack8(xr[c], xv);
+        load_gamma(col, gv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rs * (gy[c][e] - s1 - xh[c][e] * s2);
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (xv[e] - mu) * rs;
+          o[e] = rs * (dyv[e] * gv[e] - s1 - xh * s2);
+        }
         if (dres) {
           float r[8];
           load8<true>(dres, row * D + col, r);
@@ -232,7 +262,7 @@ extern "C" int ucf_layernorm_bwd(const void* dy, const void* x, const void* gamm
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // fewer, fatter blocks than forward: every block ends with 2*D global atomics
   long long blocks = (rows + 7) / 8;
-  const long long cap = static_cast<long long>(ucf::num_sms()) * 4;
+  const long long cap = static_cast<long long>(ucf::num_sms()) * (D <= 768 ? 2 : 1);   // resident CTAs per SM, persistent
   if (blocks > cap) blocks = cap;
   const int grid = static_cast<int>(blocks < 1 ? 1 : blocks);
   const size_t smem = 2 * static_cast<size_t>(D) * sizeof(float);

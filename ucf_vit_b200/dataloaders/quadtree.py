@@ -1,0 +1,113 @@
+"""Adaptive-patching quadtree with the reference's class API
+(/root/reference/src/UCF_VIT/dataloaders/quadtree.py: Rect :6-82, FixedQuadTree :84-242).
+
+`nodes` keeps the reference's `[[Rect, value], ...]` list (same order, same integers).  The tree
+is built by the C++ host routine `ucf_sap_build_tree_host` (summed-area table + priority queue,
+O(L log L) instead of the reference's O(L^2) Python scans) and `serialize` / `deserialize`
+resample every leaf on the GPU (`ucf_sap_gather` / `ucf_sap_scatter`) instead of one
+`cv.resize` call per leaf.  Drawing helpers (matplotlib) are not part of the hot path and are
+not provided."""
+import numpy as np
+import torch
+
+from .. import ops
+
+
+class Rect:
+    def __init__(self, x1, x2, y1, y2) -> None:
+        assert x1 <= x2, 'x1 > x2, wrong coordinate.'
+        assert y1 <= y2, 'y1 > y2, wrong coordinate.'
+        self.x1, self.x2, self.y1, self.y2 = x1, x2, y1, y2
+
+    def contains(self, domain):
+        return int(np.sum(domain[self.y1:self.y2, self.x1:self.x2]) / 255)
+
+    def get_area(self, img):
+        return img[self.y1:self.y2, self.x1:self.x2, :]
+
+    def get_coord(self):
+        return self.x1, self.x2, self.y1, self.y2
+
+    def get_size(self):
+        return self.x2 - self.x1, self.y2 - self.y1
+
+    def get_center(self):
+        return (self.x2 + self.x1) / 2, (self.y2 + self.y1) / 2
+
+    def __eq__(self, other):
+        return isinstance(other, Rect) and self.get_coord() == other.get_coord()
+
+
+def _as_device_image(img, device):
+    t = torch.from_numpy(np.ascontiguousarray(img)) if isinstance(img, np.ndarray) else img
+    if t.dtype not in (torch.uint8, torch.float32):
+        t = t.float()
+    return t.to(device).contiguous()
+
+
+class FixedQuadTree:
+    def __init__(self, domain, fixed_length=128, build_from_info=False, meta_info=None, device="cuda") -> None:
+        self.domain = domain
+        self.fixed_length = fixed_length
+        self.device = device
+        self._boxes_dev = None
+        if build_from_info:
+            self.nodes = self.decoder_nodes(meta_info=meta_info)
+            self.boxes = np.array([r.get_coord() for r, _ in self.nodes], dtype=np.int32).reshape(-1, 4)
+        else:
+            self._build_tree()
+
+    def _build_tree(self):
+        h, w = self.domain.shape
+        assert h > 0 and w > 0, "Wrong img size."
+        self.boxes, values = ops.sap_build_tree(np.asarray(self.domain), self.fixed_length, 255.0)
+        self.nodes = [[Rect(int(b[0]), int(b[1]), int(b[2]), int(b[3])), int(v)] for b, v in zip(self.boxes, values)]
+
+    # ---- bookkeeping helpers with reference semantics
+    def nodes_value(self):
+        return [[r.get_size()[0] / 8] for r, _ in self.nodes]
+
+    def encode_nodes(self):
+        return [[r.x1, r.x2, r.y1, r.y2] for r, _ in self.nodes]
+
+    def decoder_nodes(self, meta_info):
+        out = []
+        for x1, x2, y1, y2 in meta_info:
+            r = Rect(x1, x2, y1, y2)
+            out.append([r, r.contains(self.domain)])
+        return out
+
+    def count_patches(self):
+        return len(self.nodes)
+
+    def _dev_boxes(self):
+        if self._boxes_dev is None:
+            self._boxes_dev = torch.from_numpy(np.ascontiguousarray(self.boxes, dtype=np.int32)).to(self.device)
+        return self._boxes_dev
+
+    # ---- device path
+    def serialize_device(self, img, size=(8, 8, 3)):
+        """img: numpy / torch [H, W, C] (uint8 or float32).  -> cuda tensors
+        seq [L, p, p, C] f32, seq_size [L] i64, seq_pos [L, 2] f64."""
+        h2, w2, c2 = size
+        assert h2 == w2, "square target patches only"
+        t = _as_device_image(img, self.device)
+        assert t.dim() == 3 and t.shape[2] == c2
+        return ops.sap_gather(t, self._dev_boxes(), self.fixed_length, h2)
+
+    def deserialize_device(self, seq, patch_size, channel):
+        H, W = self.domain.shape
+        s = seq if torch.is_tensor(seq) else torch.from_numpy(np.asarray(seq, dtype=np.float32))
+        s = s.to(self.device).float().reshape(self.fixed_length, patch_size, patch_size, channel)
+        return ops.sap_scatter(s, self._dev_boxes(), (H, W), patch_size, channel, truncate_to_int=True)
+
+    # ---- reference-typed API (lists / numpy back on the host)
+    def serialize(self, img, size=(8, 8, 3)):
+        seq, ssize, spos = self.serialize_device(img, size)
+        c2 = size[2]
+        seq = seq.cpu().numpy()
+        patches = [seq[i] if c2 > 1 else seq[i, :, :, 0] for i in range(self.fixed_length)]
+        return patches, [int(v) for v in ssize.cpu().tolist()], [tuple(p) for p in spos.cpu().tolist()]
+
+    def deserialize(self, seq, patch_size, channel):
+        return self.deserialize_device(seq, patch_size, channel).cpu().numpy().astype(np.float64)

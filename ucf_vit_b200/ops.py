@@ -208,3 +208,62 @@ def var_attention_bwd(q, kv, o, d_o, lse, scale):
                                           dkv.data_ptr(), dq_acc.data_ptr(), rows, Na, V, H, hd, shared, float(scale),
                                           _stream()), "var_attention_bwd")
     return dq_acc, dkv
+
+
+# ---------------------------------------------------------------------------------------------
+# adaptive patching (SAP)
+# ---------------------------------------------------------------------------------------------
+def sap_build_tree(domain, fixed_length, norm_factor=255.0):
+    """Greedy quadtree (2-D numpy array) / octree (3-D cubic array) on the HOST (integer work, no GPU
+    needed).  Returns (boxes int32 [n, 4|6], values int64 [n]) in the reference's list order."""
+    import numpy as np
+    d = np.ascontiguousarray(domain)
+    if d.dtype == np.uint8:
+        dt = L.UCF_DTYPE_U8
+    elif d.dtype == np.float32:
+        dt = L.UCF_DTYPE_F32
+    else:
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        dt = L.UCF_DTYPE_F64
+    nd = d.ndim
+    assert nd in (2, 3)
+    nc = 4 if nd == 2 else 6
+    boxes = np.zeros((fixed_length, nc), dtype=np.int32)
+    values = np.zeros((fixed_length,), dtype=np.int64)
+    shp = list(d.shape) + [0] * (3 - nd)
+    n = L.lib().ucf_sap_build_tree_host(d.ctypes.data, dt, nd, shp[0], shp[1], shp[2], float(norm_factor), fixed_length,
+                                        boxes.ctypes.data, values.ctypes.data)
+    if n < 0:
+        L.check(n, "sap_build_tree_host")
+    return boxes[:n].copy(), values[:n].copy()
+
+
+def sap_gather(img, boxes, fixed_length, p):
+    """img: cuda uint8/float32 [H,W,C] or float32 [Z,Y,X,C]; boxes: cuda int32 [n,4|6].
+    -> seq f32 [L,p,p(,p),C], seq_size int64 [L], seq_pos f64 [L,2|3] (all on the device)."""
+    _require_cuda(img, boxes)
+    assert img.is_contiguous() and boxes.is_contiguous() and boxes.dtype == torch.int32
+    nd = img.dim() - 1
+    C = img.shape[-1]
+    n = boxes.shape[0]
+    dt = L.UCF_DTYPE_U8 if img.dtype == torch.uint8 else L.UCF_DTYPE_F32
+    assert img.dtype in (torch.uint8, torch.float32)
+    seq = torch.empty((fixed_length,) + (p,) * nd + (C,), dtype=torch.float32, device=img.device)
+    size = torch.empty((fixed_length,), dtype=torch.int64, device=img.device)
+    pos = torch.empty((fixed_length, nd), dtype=torch.float64, device=img.device)
+    shp = list(img.shape[:-1]) + [0] * (3 - nd)
+    L.check(L.lib().ucf_sap_gather(img.data_ptr(), dt, nd, shp[0], shp[1], shp[2], C, boxes.data_ptr(), n, fixed_length, p,
+                                   seq.data_ptr(), size.data_ptr(), pos.data_ptr(), _stream()), "sap_gather")
+    return seq, size, pos
+
+
+def sap_scatter(seq, boxes, out_shape, p, C, truncate_to_int=False):
+    """seq f32 [>=n, p, p(, p), C] -> mask f32 [H,W,C] / [Z,Y,X,C] (zero where no leaf writes)."""
+    _require_cuda(seq, boxes)
+    nd = len(out_shape)
+    seq = seq.contiguous().float()
+    mask = torch.zeros(tuple(out_shape) + (C,), dtype=torch.float32, device=seq.device)
+    shp = list(out_shape) + [0] * (3 - nd)
+    L.check(L.lib().ucf_sap_scatter(seq.data_ptr(), nd, shp[0], shp[1], shp[2], C, boxes.data_ptr(), boxes.shape[0], p,
+                                    int(truncate_to_int), mask.data_ptr(), _stream()), "sap_scatter")
+    return mask
