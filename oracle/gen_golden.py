@@ -228,7 +228,7 @@ def case_sap(name):
 
 def case_unetr(name):
     """3-D, patch 16, two variables -> shared patch embed + variable aggregation + conv decoder."""
-    D, H, depth, p, img, V, B, fs, ncls = 96, 3, 4, 16, 32, 2, 1, 4, 3
+    D, H, depth, p, img, V, B, fs, ncls = 96, 3, 4, 16, 64, 2, 1, 4, 3
     vars_ = ["v0", "v1"]
     cfg = dict(kind="unetr", img_size=[img] * 3, patch_size=p, in_chans=V, num_classes=ncls, embed_dim=D, depth=depth,
                num_heads=H, use_varemb=True, feature_size=fs, class_token=False, batch=B, x_seed=61, y_seed=62)
@@ -242,11 +242,11 @@ def case_unetr(name):
 
     def run_ref(model):
         o = model(x, vars_)
-        return {"seg_logits_slice": o[:, :, ::4, ::4, ::4].contiguous(), "seg_mean": o.mean().reshape(1)}, ((o - tgt) ** 2).mean()
+        return {"seg_logits_slice": o[:, :, ::8, ::8, ::8].contiguous(), "seg_mean": o.mean().reshape(1)}, ((o - tgt) ** 2).mean()
 
     def run_oracle(s):
         o = R.unetr_forward(x, s, cfg, var_ids=[0, 1])
-        return {"seg_logits_slice": o[:, :, ::4, ::4, ::4].contiguous(), "seg_mean": o.mean().reshape(1)}, ((o - tgt) ** 2).mean()
+        return {"seg_logits_slice": o[:, :, ::8, ::8, ::8].contiguous(), "seg_mean": o.mean().reshape(1)}, ((o - tgt) ** 2).mean()
 
     _finish(name, cfg, m, sd, run_ref, run_oracle, {})
 

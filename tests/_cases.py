@@ -79,7 +79,7 @@ def run_oracle(cfg, sd, inp):
         return {"mask_logits": o}, ((o - inp["target"]) ** 2).mean()
     if k == "unetr":
         o = R.unetr_forward(inp["x"], sd, cfg, var_ids=[0, 1])
-        return ({"seg_logits_slice": o[:, :, ::4, ::4, ::4].contiguous(), "seg_mean": o.mean().reshape(1)},
+        return ({"seg_logits_slice": o[:, :, ::8, ::8, ::8].contiguous(), "seg_mean": o.mean().reshape(1)},
                 ((o - inp["target"]) ** 2).mean())
     raise KeyError(k)
 
@@ -148,6 +148,6 @@ def run_product(cfg, model, inp):
         return {"mask_logits": o}, ((o.float() - inp["target"]) ** 2).mean()
     if k == "unetr":
         o = model(inp["x"], ["v0", "v1"]).float()
-        return ({"seg_logits_slice": o[:, :, ::4, ::4, ::4].contiguous(), "seg_mean": o.mean().reshape(1)},
+        return ({"seg_logits_slice": o[:, :, ::8, ::8, ::8].contiguous(), "seg_mean": o.mean().reshape(1)},
                 ((o - inp["target"]) ** 2).mean())
     raise KeyError(k)

@@ -21,6 +21,8 @@ int make_bnhd_tmap(CUtensorMap* tm, const void* ptr, int B, int H, int N, int hd
 
 struct AttnBwdParams {
   int B, H, Nq, Nk;
+  int nkt;              // key tiles per (b, h)
+  int items;            // B * H * nkt
   float scale, scale_log2;
   const float* lse;     // [B,H,Nq]
   const float* delta;   // [B,H,Nq]
@@ -32,8 +34,9 @@ struct AttnBwdCfg {
   static constexpr int TILE_BYTES = T * HD * 2;       // one Q / K / V / dO tile
   static constexpr int PS_BYTES = T * T * 2;          // P or dS
   static constexpr int DQ_STAGE = T * HD * 4;
-  static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES /*K,V*/ + 4 * TILE_BYTES /*Q,dO x2*/ +
-                                    2 * PS_BYTES + DQ_STAGE + 16 * 8 + 16;
+  static constexpr int NBAR = 16;
+  static constexpr int SMEM_BYTES = 1024 + 4 * TILE_BYTES /*K,V x2*/ + 4 * TILE_BYTES /*Q,dO x2*/ +
+                                    2 * PS_BYTES + DQ_STAGE + NBAR * 8 + 16;
   static constexpr int ROW_BYTES = HD * 2;
   static constexpr int ATOM_BYTES = 8 * ROW_BYTES;
   static_assert(SMEM_BYTES <= 232448, "smem");
@@ -46,6 +49,9 @@ __device__ __forceinline__ uint64_t bwd_desc(uint32_t saddr, uint32_t lbo, uint3
   return d;
 }
 
+// Persistent: one CTA per SM loops over work items (batch, head, 128-key tile).  K/V are
+// double-buffered across items and Q/dO tiles stream through a 2-slot ring, so the producer is
+// always one item ahead and set-up (TMEM allocation, barrier init, first loads) is paid once.
 template <int HD>
 __global__ void __launch_bounds__(192, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -57,40 +63,43 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* k_s = smem;
-  uint8_t* v_s = k_s + TB;
-  uint8_t* q_s = v_s + TB;          // [2]
+  uint8_t* kv_s = smem;             // [2 buffers][K, V]
+  uint8_t* q_s = kv_s + 4 * TB;     // [2]
   uint8_t* do_s = q_s + 2 * TB;     // [2]
   uint8_t* p_s = do_s + 2 * TB;
   uint8_t* ds_s = p_s + Cfg::PS_BYTES;
   uint8_t* dq_s = ds_s + Cfg::PS_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(dq_s + Cfg::DQ_STAGE);
-  uint64_t* kv_full = bars;          // 1
-  uint64_t* qdo_full = bars + 1;     // 2
-  uint64_t* qdo_empty = bars + 3;    // 2
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* sdp_empty = bars + 6;
-  uint64_t* pds_full = bars + 7;
-  uint64_t* dq_full = bars + 8;
-  uint64_t* dq_empty = bars + 9;
-  uint64_t* dkv_full = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* kv_full = bars;          // [2]
+  uint64_t* kv_empty = bars + 2;     // [2]
+  uint64_t* qdo_full = bars + 4;     // [2]
+  uint64_t* qdo_empty = bars + 6;    // [2]
+  uint64_t* sdp_full = bars + 8;
+  uint64_t* sdp_empty = bars + 9;
+  uint64_t* pds_full = bars + 10;
+  uint64_t* dq_full = bars + 11;
+  uint64_t* dq_empty = bars + 12;
+  uint64_t* dkv_full = bars + 13;
+  uint64_t* dkv_empty = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k0 = blockIdx.x * T, h = blockIdx.y, b = blockIdx.z;
   const int nq = (p.Nq + T - 1) / T;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     tma_prefetch_desc(&tmdQacc); tma_prefetch_desc(&tmdK); tma_prefetch_desc(&tmdV);
-    mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+      mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
+    }
     mbar_init(sdp_full, 1);
     mbar_init(sdp_empty, 128);
     mbar_init(pds_full, 128);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 128);
     mbar_init(dkv_full, 1);
+    mbar_init(dkv_empty, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -101,17 +110,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dv = tmem_base + 256, t_dk = tmem_base + 320,
                  t_dq = tmem_base + 384;
 
+  auto decode = [&](int item, int& b, int& h, int& k0) {
+    const int jt = item % p.nkt;
+    const int bh = item / p.nkt;
+    h = bh % p.H;
+    b = bh / p.H;
+    k0 = jt * T;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(kv_full, 2 * TB);
-      tma_load_4d(k_s, &tmK, kv_full, 0, h, k0, b);
-      tma_load_4d(v_s, &tmV, kv_full, 0, h, k0, b);
-      for (int i = 0; i < nq; ++i) {
-        const int slot = i & 1;
-        mbar_wait(&qdo_empty[slot], ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&qdo_full[slot], 2 * TB);
-        tma_load_4d(q_s + slot * TB, &tmQ, &qdo_full[slot], 0, h, i * T, b);
-        tma_load_4d(do_s + slot * TB, &tmdO, &qdo_full[slot], 0, h, i * T, b);
+      uint32_t it = 0, qr = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        int b, h, k0;
+        decode(item, b, h, k0);
+        const int kb = it & 1;
+        mbar_wait(&kv_empty[kb], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[kb], 2 * TB);
+        tma_load_4d(kv_s + (kb * 2 + 0) * TB, &tmK, &kv_full[kb], 0, h, k0, b);
+        tma_load_4d(kv_s + (kb * 2 + 1) * TB, &tmV, &kv_full[kb], 0, h, k0, b);
+        for (int i = 0; i < nq; ++i, ++qr) {
+          const int slot = qr & 1;
+          mbar_wait(&qdo_empty[slot], ((qr >> 1) & 1) ^ 1);
+          mbar_expect_tx(&qdo_full[slot], 2 * TB);
+          tma_load_4d(q_s + slot * TB, &tmQ, &qdo_full[slot], 0, h, i * T, b);
+          tma_load_4d(do_s + slot * TB, &tmdO, &qdo_full[slot], 0, h, i * T, b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -119,44 +143,50 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_qk = umma_idesc_bf16(T, T, false, false);     // S, dP
       constexpr uint32_t idesc_tn = umma_idesc_bf16(T, HD, true, true);      // dV, dK
       constexpr uint32_t idesc_dq = umma_idesc_bf16(T, HD, false, true);     // dQ
-      const uint32_t k_addr = smem_u32(k_s), v_addr = smem_u32(v_s);
       const uint32_t p_addr = smem_u32(p_s), ds_addr = smem_u32(ds_s);
-      mbar_wait(kv_full, 0);
-      for (int i = 0; i < nq; ++i) {
-        const int slot = i & 1;
-        const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
-        mbar_wait(&qdo_full[slot], (i >> 1) & 1);
-        mbar_wait(sdp_empty, (i & 1) ^ 1);
-        tc_fence_after();
+      uint32_t it = 0, qr = 0, tc = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int kb = it & 1;
+        const uint32_t k_addr = smem_u32(kv_s + (kb * 2 + 0) * TB), v_addr = smem_u32(kv_s + (kb * 2 + 1) * TB);
+        mbar_wait(&kv_full[kb], (it >> 1) & 1);
+        for (int i = 0; i < nq; ++i, ++qr, ++tc) {
+          const int slot = qr & 1;
+          const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
+          mbar_wait(&qdo_full[slot], (qr >> 1) & 1);
+          mbar_wait(sdp_empty, (tc & 1) ^ 1);
+          tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(t_s, bwd_desc<RB>(q_addr + k * 32, 16, AB), bwd_desc<RB>(k_addr + k * 32, 16, AB), idesc_qk, k > 0);
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16(t_s, bwd_desc<RB>(q_addr + k * 32, 16, AB), bwd_desc<RB>(k_addr + k * 32, 16, AB), idesc_qk, k > 0);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(t_dp, bwd_desc<RB>(do_addr + k * 32, 16, AB), bwd_desc<RB>(v_addr + k * 32, 16, AB), idesc_qk, k > 0);
-        umma_commit(sdp_full);
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16(t_dp, bwd_desc<RB>(do_addr + k * 32, 16, AB), bwd_desc<RB>(v_addr + k * 32, 16, AB), idesc_qk, k > 0);
+          umma_commit(sdp_full);
 
-        mbar_wait(pds_full, i & 1);
-        mbar_wait(dq_empty, (i & 1) ^ 1);
-        tc_fence_after();
-        // dV += P^T dO_i ; dK += dS^T Q_i   (reduction over the 128 query rows, 16 per MMA)
+          mbar_wait(pds_full, tc & 1);
+          mbar_wait(dq_empty, (tc & 1) ^ 1);
+          if (i == 0) mbar_wait(dkv_empty, (it & 1) ^ 1);   // previous item's dK/dV have left TMEM
+          tc_fence_after();
+          // dV += P^T dO_i ; dK += dS^T Q_i   (reduction over the 128 query rows, 16 per MMA)
 #pragma unroll
-        for (int kk = 0; kk < T / 16; ++kk)
-          umma_bf16(t_dv, umma_smem_desc(p_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(do_addr + kk * 2 * AB, 0, AB),
-                    idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < T / 16; ++kk)
+            umma_bf16(t_dv, umma_smem_desc(p_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(do_addr + kk * 2 * AB, 0, AB),
+                      idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
 #pragma unroll
-        for (int kk = 0; kk < T / 16; ++kk)
-          umma_bf16(t_dk, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(q_addr + kk * 2 * AB, 0, AB),
-                    idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
-        // dQ_i = dS K_j   (reduction over the 128 keys)
+          for (int kk = 0; kk < T / 16; ++kk)
+            umma_bf16(t_dk, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(q_addr + kk * 2 * AB, 0, AB),
+                      idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
+          // dQ_i = dS K_j   (reduction over the 128 keys)
 #pragma unroll
-        for (int kk = 0; kk < T / 16; ++kk)
-          umma_bf16(t_dq, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                    bwd_desc<RB>(k_addr + kk * 2 * AB, 0, AB), idesc_dq, kk > 0 ? 1u : 0u);
-        umma_commit(dq_full);
-        umma_commit(&qdo_empty[slot]);
+          for (int kk = 0; kk < T / 16; ++kk)
+            umma_bf16(t_dq, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                      bwd_desc<RB>(k_addr + kk * 2 * AB, 0, AB), idesc_dq, kk > 0 ? 1u : 0u);
+          umma_commit(dq_full);
+          umma_commit(&qdo_empty[slot]);
+        }
+        umma_commit(dkv_full);
+        umma_commit(&kv_empty[kb]);
       }
-      umma_commit(dkv_full);
     }
   } else {
     // ------------------------------------------------------------------ compute warps
@@ -168,110 +198,116 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint8_t* p_row = p_s + row * 128;
     uint8_t* ds_row = ds_s + row * 128;
     uint8_t* my_dq = dq_s + (warp - 2) * (32 * HD * 4);   // HD/32 boxes of 32 rows x 128 B
-    const long long stat_base = (static_cast<long long>(b) * p.H + h) * p.Nq;
-    const float LOG2E = 1.4426950408889634f;
-
-    for (int i = 0; i < nq; ++i) {
-      const int qrow = i * T + row;
-      float nlse = -INFINITY, delta = 0.f;   // rows past Nq: P = exp2(-inf) = 0
-      if (qrow < p.Nq) {
-        nlse = -p.lse[stat_base + qrow] * LOG2E;
-        delta = p.delta[stat_base + qrow];
-      }
-      mbar_wait(sdp_full, i & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < T / 32; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(t_s + lane_addr + c * 32, sv);
-        tmem_ld32(t_dp + lane_addr + c * 32, dv);
-        tmem_wait_ld();
-        uint32_t pk[16], dk[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = exp2f(fmaf(__uint_as_float(sv[e]), p.scale_log2, nlse));
-          const float p1 = exp2f(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, nlse));
-          const float d0 = p0 * (__uint_as_float(dv[e]) - delta) * p.scale;
-          const float d1 = p1 * (__uint_as_float(dv[e + 1]) - delta) * p.scale;
-          pk[e >> 1] = pack_bf16x2(p0, p1);
-          dk[e >> 1] = pack_bf16x2(d0, d1);
-        }
-        const int blk = (c >> 1) * 16384;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t off = ((static_cast<uint32_t>((c & 1) * 4 + g)) ^ row_sw) << 4;
-          *reinterpret_cast<uint4*>(p_row + blk + off) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-          *reinterpret_cast<uint4*>(ds_row + blk + off) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(sdp_empty);
-      fence_proxy_async_smem();
-      mbar_arrive(pds_full);
-
-      // dQ_i tile -> fp32 staging -> TMA reduce-add
-      if (lane == 0) tma_store_wait_read<0>();
-      __syncwarp();
-      mbar_wait(dq_full, i & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_dq + lane_addr + c * 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<uint4*>(my_dq + c * 4096 + lane * 128 + ((static_cast<uint32_t>(g) ^ lrow_sw) << 4)) =
-              make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-      }
-      tc_fence_before();
-      mbar_arrive(dq_empty);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0 && i * T + qd * 32 < p.Nq) {
-#pragma unroll
-        for (int c = 0; c < HD / 32; ++c) tma_reduce_add_4d(&tmdQacc, my_dq + c * 4096, c * 32, h, i * T + qd * 32, b);
-        tma_store_commit();
-      }
-    }
-
-    // ---- dK_j, dV_j: TMEM -> bf16 -> staging (P / dS buffers are dead now) -> TMA store
-    mbar_wait(dkv_full, 0);
-    tc_fence_after();
-    uint8_t* st_dv = p_s + (warp - 2) * 4096;
+    uint8_t* st_dv = p_s + (warp - 2) * 4096;             // dK/dV staging reuses this warp's P/dS rows
     uint8_t* st_dk = ds_s + (warp - 2) * 4096;
+    const float LOG2E = 1.4426950408889634f;
+    uint32_t it = 0, tc = 0;
+
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      int b, h, k0;
+      decode(item, b, h, k0);
+      const long long stat_base = (static_cast<long long>(b) * p.H + h) * p.Nq;
+      for (int i = 0; i < nq; ++i, ++tc) {
+        const int qrow = i * T + row;
+        float nlse = -INFINITY, delta = 0.f;   // rows past Nq: P = exp2(-inf) = 0
+        if (qrow < p.Nq) {
+          nlse = -p.lse[stat_base + qrow] * LOG2E;
+          delta = p.delta[stat_base + qrow];
+        }
+        // every earlier TMA store of this warp (dQ staging, dK/dV staging == P/dS rows) has been read
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        mbar_wait(sdp_full, tc & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < T / 32; ++c) {
+          uint32_t sv[32], dv[32];
+          tmem_ld32(t_s + lane_addr + c * 32, sv);
+          tmem_ld32(t_dp + lane_addr + c * 32, dv);
+          tmem_wait_ld();
+          uint32_t pk[16], dk[16];
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      uint8_t* st = which == 0 ? st_dv : st_dk;
-      const uint32_t t_src = which == 0 ? t_dv : t_dk;
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = fast_ex2(fmaf(__uint_as_float(sv[e]), p.scale_log2, nlse));
+            const float p1 = fast_ex2(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, nlse));
+            const float d0 = p0 * (__uint_as_float(dv[e]) - delta) * p.scale;
+            const float d1 = p1 * (__uint_as_float(dv[e + 1]) - delta) * p.scale;
+            pk[e >> 1] = pack_bf16x2(p0, p1);
+            dk[e >> 1] = pack_bf16x2(d0, d1);
+          }
+          const int blk = (c >> 1) * 16384;
 #pragma unroll
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_src + lane_addr + c * 32, v);
-        tmem_wait_ld();
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t off = ((static_cast<uint32_t>((c & 1) * 4 + g)) ^ row_sw) << 4;
+            *reinterpret_cast<uint4*>(p_row + blk + off) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            *reinterpret_cast<uint4*>(ds_row + blk + off) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(sdp_empty);
+        fence_proxy_async_smem();
+        mbar_arrive(pds_full);
+
+        // dQ_i tile -> fp32 staging -> TMA reduce-add
+        mbar_wait(dq_full, tc & 1);
+        tc_fence_after();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t chunk = static_cast<uint32_t>(c * 4 + g);
-          uint8_t* dst = (RB == 128) ? st + lane * 128 + ((chunk ^ lrow_sw) << 4)
-                                     : st + lane * 64 + ((chunk ^ ((lane >> 1) & 3)) << 4);
-          *reinterpret_cast<uint4*>(dst) =
-              make_uint4(pack_bf16x2(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
-                         pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
-                         pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
-                         pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_dq + lane_addr + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(my_dq + c * 4096 + lane * 128 + ((static_cast<uint32_t>(g) ^ lrow_sw) << 4)) =
+                make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
+        tc_fence_before();
+        mbar_arrive(dq_empty);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && i * T + qd * 32 < p.Nq) {
+#pragma unroll
+          for (int c = 0; c < HD / 32; ++c) tma_reduce_add_4d(&tmdQacc, my_dq + c * 4096, c * 32, h, i * T + qd * 32, b);
+          tma_store_commit();
         }
       }
-    }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      if (k0 + qd * 32 < p.Nk) {
+
+      // ---- dK_j, dV_j: TMEM -> bf16 -> staging (this item's P / dS are dead) -> TMA store
+      mbar_wait(dkv_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        uint8_t* st = which == 0 ? st_dv : st_dk;
+        const uint32_t t_src = which == 0 ? t_dv : t_dk;
+#pragma unroll
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_src + lane_addr + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t chunk = static_cast<uint32_t>(c * 4 + g);
+            uint8_t* dst = (RB == 128) ? st + lane * 128 + ((chunk ^ lrow_sw) << 4)
+                                       : st + lane * 64 + ((chunk ^ ((lane >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(dst) =
+                make_uint4(pack_bf16x2(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                           pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                           pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                           pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dkv_empty);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && k0 + qd * 32 < p.Nk) {
         tma_store_4d(&tmdV, st_dv, 0, h, k0 + qd * 32, b);
         tma_store_4d(&tmdK, st_dk, 0, h, k0 + qd * 32, b);
         tma_store_commit();
       }
-      tma_store_wait_all<0>();
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -358,7 +394,6 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
                                    dq_sb, dq_sn, dq_sh, dk_sb, dk_sn, dk_sh, dv_sb, dv_sn, dv_sh};
   for (long long s : all_strides)
     if (s % 8) { set_last_error("attention_bwd: strides must be multiples of 8 elements"); return UCF_ERR_BAD_ARG; }
-  if (H > 65535 || B > 65535) { set_last_error("attention_bwd: H and B must be <= 65535"); return UCF_ERR_BAD_ARG; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(dq_acc, 0, sizeof(float) * static_cast<size_t>(B) * Nq * H * hd, st);
   if (e != cudaSuccess) { set_last_error("attention_bwd: memset: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
@@ -399,7 +434,11 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
   p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse; p.delta = delta;
-  dim3 grid((Nk + 127) / 128, H, B);
+  p.nkt = (Nk + 127) / 128;
+  const long long n_items = static_cast<long long>(B) * H * p.nkt;
+  if (n_items > 0x7fffffffLL) { set_last_error("attention_bwd: too many work items"); return UCF_ERR_BAD_ARG; }
+  p.items = static_cast<int>(n_items);
+  const int grid = p.items < num_sms() ? p.items : num_sms();
   if (hd == 64) {
     static bool attr = false;
     if (!attr) {

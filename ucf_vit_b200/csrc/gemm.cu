@@ -44,7 +44,8 @@ struct GemmCfg {
   static constexpr int CW = 32;
   static constexpr int OUT_BUF = (EPI == EPI_F32_ADD) ? 4096 : 2048;
   static constexpr int AUX_BUF = 2048;
-  static constexpr int OUT_STAGE_BYTES = EPI_WARPS * 2 * OUT_BUF;
+  static constexpr int OUT_NBUF = (EPI == EPI_F32_ADD) ? 1 : 2;   // wgrad: light epilogue, spend smem on stages
+  static constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_NBUF * OUT_BUF;
   static constexpr int AUX_STAGE_BYTES = HAS_AUX ? EPI_WARPS * 2 * AUX_BUF : 0;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -182,7 +183,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int CW = Cfg::CW;
     constexpr int NCHUNK = BN / 2 / CW;   // chunks per warp
     constexpr int OUT_BUF = Cfg::OUT_BUF, AUX_BUF = Cfg::AUX_BUF;
-    uint8_t* my_out = epi_out + ew * 2 * OUT_BUF;
+    uint8_t* my_out = epi_out + ew * Cfg::OUT_NBUF * OUT_BUF;
     uint8_t* my_aux = epi_aux + ew * 2 * AUX_BUF;
     uint64_t* my_aux_bar = aux_bar + ew * 2;
     // byte offset of this lane's 16-byte chunk j inside a staging buffer
@@ -233,18 +234,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t v[32];
           tmem_ld32(t_row + c * CW, v);
           tmem_wait_ld();
-          if (lane == 0) tma_store_wait_read<1>();   // staging buffer b (2 chunks ago) drained
+          if (lane == 0) {                           // staging buffer about to be rewritten is drained
+            if (Cfg::OUT_NBUF == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+          }
           __syncwarp();
           if (Cfg::AUX_IN) mbar_wait(&my_aux_bar[b], (cc >> 1) & 1);
 
+          const uint32_t ob = (Cfg::OUT_NBUF == 2) ? b : 0;
           if (EPI == EPI_F32_ADD) {
-            uint8_t* out_row = my_out + b * OUT_BUF + lane * 128;
+            uint8_t* out_row = my_out + ob * OUT_BUF + lane * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<uint4*>(out_row + ((j ^ sw128) << 4)) =
                   make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            uint8_t* out_row = my_out + b * OUT_BUF + lane * 64;
+            uint8_t* out_row = my_out + ob * OUT_BUF + lane * 64;
             uint8_t* aux_row = my_aux + b * AUX_BUF + lane * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -292,9 +296,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) {
             if (EPI == EPI_F32_ADD) {
-              tma_reduce_add_2d(&tmC, my_out + b * OUT_BUF, col0, r0);
+              tma_reduce_add_2d(&tmC, my_out + ob * OUT_BUF, col0, r0);
             } else {
-              tma_store_2d(&tmC, my_out + b * OUT_BUF, col0, r0);
+              tma_store_2d(&tmC, my_out + ob * OUT_BUF, col0, r0);
               if (EPI == EPI_BIAS_GELU_AUX) tma_store_2d(&tmAux, my_aux + b * AUX_BUF, col0, r0);
             }
             tma_store_commit();
@@ -431,8 +435,8 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
   UCF_GEMM_CASE(128, 5, false, false, EPI_BIAS_RESIDUAL)
   UCF_GEMM_CASE(256, 3, false, false, EPI_BIAS_GELU_AUX)
   UCF_GEMM_CASE(128, 5, false, false, EPI_BIAS_GELU_AUX)
-  UCF_GEMM_CASE(256, 3, false, false, EPI_F32_ADD)
-  UCF_GEMM_CASE(128, 5, false, false, EPI_F32_ADD)
+  UCF_GEMM_CASE(256, 4, false, false, EPI_F32_ADD)
+  UCF_GEMM_CASE(128, 6, false, false, EPI_F32_ADD)
   // dgrad
   UCF_GEMM_CASE(256, 4, false, true, EPI_BIAS)
   UCF_GEMM_CASE(128, 6, false, true, EPI_BIAS)
@@ -441,12 +445,12 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
   UCF_GEMM_CASE(256, 3, false, true, EPI_BIAS_RESIDUAL)
   UCF_GEMM_CASE(128, 5, false, true, EPI_BIAS_RESIDUAL)
   // wgrad
-  UCF_GEMM_CASE(256, 3, true, true, EPI_F32_ADD)
-  UCF_GEMM_CASE(128, 5, true, true, EPI_F32_ADD)
+  UCF_GEMM_CASE(256, 4, true, true, EPI_F32_ADD)
+  UCF_GEMM_CASE(128, 6, true, true, EPI_F32_ADD)
   UCF_GEMM_CASE(256, 4, true, true, EPI_BIAS)
   UCF_GEMM_CASE(128, 6, true, true, EPI_BIAS)
   UCF_GEMM_CASE(128, 6, true, false, EPI_BIAS)
-  UCF_GEMM_CASE(128, 5, true, false, EPI_F32_ADD)
+  UCF_GEMM_CASE(128, 6, true, false, EPI_F32_ADD)
 #undef UCF_GEMM_CASE
   set_last_error("gemm: no kernel for a_layout=%d b_layout=%d epilogue=%d tile_n=%d", a_layout, b_layout, epilogue, BN);
   return UCF_ERR_UNSUPPORTED;
