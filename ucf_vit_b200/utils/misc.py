@@ -46,3 +46,43 @@ def configure_optimizer(model, lr, beta_1, beta_2, weight_decay, fused=None):
 
 def configure_scheduler(optimizer, warmup_steps, max_steps, warmup_start_lr, eta_min):
     return LinearWarmupCosineAnnealingLR(optimizer, warmup_steps, max_steps, warmup_start_lr, eta_min)
+
+
+# ---------------------------------------------------------------------------------------------
+# process groups (reference: utils/misc.py:129-238).  Rank layout: tensor-parallel fastest, then
+# sequence-parallel, then data-parallel; the data-parallel ranks are further cut into contiguous
+# FSDP groups of `fsdp_size` and strided "simple DDP" groups across them.
+# ---------------------------------------------------------------------------------------------
+def par_group_layout(data_par_size, tensor_par_size, seq_par_size, fsdp_size, simple_ddp_size):
+    """Pure function: the rank lists of every group, in the order the groups must be created
+    (identical on all ranks).  Returns a list of (kind, ranks)."""
+    tp, sp, dp = tensor_par_size, seq_par_size, data_par_size
+    out = []
+    for i in range(dp * sp):
+        out.append(("tensor", list(range(i * tp, (i + 1) * tp))))
+    for t in range(dp):
+        for i in range(tp):
+            out.append(("seq", [t * tp * sp + i + j * tp for j in range(sp)]))
+    for i in range(tp * sp):
+        ranks = [i + j * tp * sp for j in range(dp)]
+        for k in range(simple_ddp_size):
+            out.append(("fsdp", ranks[k * fsdp_size:(k + 1) * fsdp_size]))
+        for k in range(fsdp_size):
+            out.append(("simple_ddp", ranks[k:len(ranks):fsdp_size]))
+        out.append(("ddp", ranks))
+    for i in range(tp):
+        out.append(("data_seq_ort", [i + tp * j for j in range(dp * sp)]))
+    return out
+
+
+def init_par_groups(world_rank, data_par_size, tensor_par_size, seq_par_size, fsdp_size, simple_ddp_size):
+    """-> (seq_par_group, ddp_group, tensor_par_group, data_seq_ort_group, fsdp_group, simple_ddp_group),
+    the tuple the reference's FSDP drivers unpack (train_masked_fsdp.py:272)."""
+    import torch.distributed as dist
+    mine = {}
+    for kind, ranks in par_group_layout(data_par_size, tensor_par_size, seq_par_size, fsdp_size, simple_ddp_size):
+        group = dist.new_group(ranks)
+        if world_rank in ranks:
+            mine[kind] = group
+    return (mine.get("seq"), mine.get("ddp"), mine.get("tensor"), mine.get("data_seq_ort"), mine.get("fsdp"),
+            mine.get("simple_ddp"))
