@@ -153,6 +153,14 @@ int ucf_colsum_bf16(const void* x, float* out, long long M, int N, long long ld,
 int ucf_patchify(const void* x, void* out, int B, int C, int G0, int G1, int G2, int p, int dims,
                  int x_dtype, void* stream);
 
+/* class-token concat + position-embedding add (replaces torch.cat + add in VIT._pos_embed,
+ * arch.py:367-393) in one pass: out[b, n] = (n < P ? prefix[n] : tok[b, n - P]) + pos[b * pos_bstride
+ * + (n - pos_off)] for n >= pos_off.  tok/out bf16; prefix [P, D] and pos of param_dtype (f32|bf16);
+ * pos_bstride = 0 for a table shared by the batch, L*D (elements) for per-sample embeddings;
+ * pos_off = 0 when the table has rows for the prefix tokens, P when it has not.  pos may be NULL. */
+int ucf_assemble_tokens(const void* tok, const void* prefix, const void* pos, void* out, int B, int L,
+                        int P, int D, long long pos_bstride, int pos_off, int param_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

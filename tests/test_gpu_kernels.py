@@ -168,6 +168,30 @@ def test_elementwise_helpers():
     assert torch.equal(ops.patchify(bf(vol), 8), ref.to(torch.bfloat16))
 
 
+def test_assemble_tokens_fwd_bwd():
+    from ucf_vit_b200 import functional as UF
+    B, Lp, D = 3, 10, 64
+    tok = bf(torch.randn(B, Lp, D, device=dev)).requires_grad_(True)
+    cls = torch.randn(1, 1, D, device=dev, requires_grad=True)
+    pos = torch.randn(1, Lp + 1, D, device=dev, requires_grad=True)
+    y = UF.assemble_tokens(tok, cls.reshape(1, -1), pos, pos_has_prefix=True)
+    ref = torch.cat([cls.expand(B, -1, -1), tok.float()], 1) + pos
+    _ok(y, ref, 1e-2)
+    g = bf(torch.randn_like(ref))
+    y.backward(g)
+    gt, gc, gp = tok.grad.clone(), cls.grad.clone(), pos.grad.clone()
+    tok.grad = cls.grad = pos.grad = None
+    ref.backward(g.float())
+    _ok(gt, tok.grad, 1e-2); _ok(gc, cls.grad, 1e-2); _ok(gp, pos.grad, 1e-2)
+    # per-sample (adaptive) embedding without a row for the cls token; and no prefix at all
+    pe = torch.randn(B, Lp, D, device=dev)
+    y2 = UF.assemble_tokens(tok.detach(), cls.detach().reshape(1, -1), pe, pos_has_prefix=False)
+    ref2 = torch.cat([cls.detach().expand(B, -1, -1), tok.detach().float() + pe], 1)
+    _ok(y2, ref2, 1e-2)
+    y3 = UF.assemble_tokens(tok.detach(), None, pos.detach()[:, 1:], pos_has_prefix=True)
+    _ok(y3, tok.detach().float() + pos.detach()[:, 1:], 1e-2)
+
+
 def test_errors_are_loud():
     a = bf(torch.randn(16, 20, device=dev))
     with pytest.raises(RuntimeError, match="16-byte"):

@@ -129,6 +129,56 @@ patchify_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int
   }
 }
 
+// x[b, n, :] = (n < P ? prefix[n] : tok[b, n - P, :]) + pos[(pos_bstride ? b : 0), n - pos_off, :]
+// (class-token concat + position-embedding add of VIT._pos_embed, one pass instead of cat + add).
+// tok bf16 [B, L, D]; prefix/pos of dtype f32 or bf16; out bf16 [B, P + L, D]; 8 elements per thread.
+template <bool PRM_BF16>
+__global__ void __launch_bounds__(256)
+assemble_tokens_kernel(const __nv_bfloat16* __restrict__ tok, const void* __restrict__ prefix,
+                       const void* __restrict__ pos, __nv_bfloat16* __restrict__ out, int B, int L, int P, int D,
+                       long long pos_bstride, int pos_off) {
+  const int N = L + P;
+  const int dv = D / 8;
+  const long long total = static_cast<long long>(B) * N * dv;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int d = static_cast<int>(t % dv) * 8;
+    const long long r = t / dv;
+    const int n = static_cast<int>(r % N);
+    const long long b = r / N;
+    float v[8];
+    if (n < P) {
+      if (PRM_BF16) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(prefix) + n * D + d));
+        float2 a = unpack_bf16x2(q.x), c = unpack_bf16x2(q.y), e = unpack_bf16x2(q.z), f = unpack_bf16x2(q.w);
+        v[0] = a.x; v[1] = a.y; v[2] = c.x; v[3] = c.y; v[4] = e.x; v[5] = e.y; v[6] = f.x; v[7] = f.y;
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(prefix) + n * D + d));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(prefix) + n * D + d + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+      }
+    } else {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(tok + (b * L + (n - P)) * D + d));
+      float2 a = unpack_bf16x2(q.x), c = unpack_bf16x2(q.y), e = unpack_bf16x2(q.z), f = unpack_bf16x2(q.w);
+      v[0] = a.x; v[1] = a.y; v[2] = c.x; v[3] = c.y; v[4] = e.x; v[5] = e.y; v[6] = f.x; v[7] = f.y;
+    }
+    if (pos != nullptr && n >= pos_off) {
+      const long long pi = b * pos_bstride + static_cast<long long>(n - pos_off) * D + d;
+      if (PRM_BF16) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(pos) + pi));
+        float2 a = unpack_bf16x2(q.x), c = unpack_bf16x2(q.y), e = unpack_bf16x2(q.z), f = unpack_bf16x2(q.w);
+        v[0] += a.x; v[1] += a.y; v[2] += c.x; v[3] += c.y; v[4] += e.x; v[5] += e.y; v[6] += f.x; v[7] += f.y;
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pos) + pi));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(pos) + pi + 4));
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += c.x; v[5] += c.y; v[6] += c.z; v[7] += c.w;
+      }
+    }
+    *reinterpret_cast<uint4*>(out + r * D + d) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
 static int ew_grid(long long work_items, int per_block) {
   long long blocks = (work_items + per_block - 1) / per_block;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -201,4 +251,22 @@ extern "C" int ucf_patchify(const void* x, void* out, int B, int C, int G0, int 
   else
     patchify_kernel<false><<<grid, 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(out), B, C, G0, G1, G2, p, dims, nvec);
   return check_launch("patchify_kernel");
+}
+
+extern "C" int ucf_assemble_tokens(const void* tok, const void* prefix, const void* pos, void* out, int B, int L, int P,
+                                   int D, long long pos_bstride, int pos_off, int param_dtype, void* stream) {
+  if (B <= 0 || L < 0 || P < 0 || D <= 0) { set_last_error("assemble_tokens: bad shape"); return UCF_ERR_BAD_ARG; }
+  if (D % 8) { set_last_error("assemble_tokens: D=%d must be a multiple of 8", D); return UCF_ERR_BAD_ARG; }
+  if (P > 0 && !prefix) { set_last_error("assemble_tokens: prefix tokens requested but prefix is NULL"); return UCF_ERR_BAD_ARG; }
+  const long long nvec = static_cast<long long>(B) * (L + P) * (D / 8);
+  if (nvec == 0) return UCF_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ew_grid(nvec, 256);
+  if (param_dtype == UCF_DTYPE_BF16)
+    assemble_tokens_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(tok), prefix, pos,
+                                                       reinterpret_cast<__nv_bfloat16*>(out), B, L, P, D, pos_bstride, pos_off);
+  else
+    assemble_tokens_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(tok), prefix, pos,
+                                                        reinterpret_cast<__nv_bfloat16*>(out), B, L, P, D, pos_bstride, pos_off);
+  return check_launch("assemble_tokens_kernel");
 }

@@ -110,6 +110,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
   const float inv_d = 1.0f / static_cast<float>(D);
   const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(dres);
 
   // gamma is re-read per row (L1-resident, D*4 bytes) instead of pinning 8*NCH registers
   float dg[NCH][8], db[NCH][8];
@@ -125,21 +126,36 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
       for (int e = 0; e < 8; ++e) gv[e] = 1.f;
     }
   };
-
-  for (long long row = warp_global; row < rows; row += nwarps) {
-    uint4 dyr[NCH], xr[NCH];
+  auto load_row = [&](long long row, uint4 (&a)[NCH], uint4 (&b)[NCH]) {
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
-      if (col < D) {
-        dyr[c] = __ldg(reinterpret_cast<const uint4*>(dyp + row * D + col));
-        xr[c] = __ldg(reinterpret_cast<const uint4*>(xp + row * D + col));
+      if (col < D && row < rows) {
+        a[c] = __ldg(reinterpret_cast<const uint4*>(dyp + row * D + col));
+        b[c] = __ldg(reinterpret_cast<const uint4*>(xp + row * D + col));
       } else {
-        dyr[c] = make_uint4(0, 0, 0, 0);
-        xr[c] = make_uint4(0, 0, 0, 0);
+        a[c] = make_uint4(0, 0, 0, 0);
+        b[c] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  };
+
+  // software pipeline: the next row's dy / x are in flight while the current row is reduced
+  uint4 dyn[NCH], xn[NCH];
+  load_row(warp_global, dyn, xn);
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    uint4 dyr[NCH], xr[NCH], rr[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { dyr[c] = dyn[c]; xr[c] = xn[c]; }
+    if (dres) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col = c * 256 + lane * 8;
+        rr[c] = (col < D) ? __ldg(reinterpret_cast<const uint4*>(rp + row * D + col)) : make_uint4(0, 0, 0, 0);
       }
     }
     const float mu = mean[row], rs = rstd[row];
+    load_row(row + nwarps, dyn, xn);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
@@ -177,7 +193,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
         }
         if (dres) {
           float r[8];
-          load8<true>(dres, row * D + col, r);
+          unpack8(rr[c], r);
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] += r[e];
         }

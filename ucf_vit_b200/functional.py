@@ -415,3 +415,44 @@ def patchify(x, p):
         return _PatchifyFn.apply(x, p)
     with torch.no_grad():
         return _PatchifyFn.apply(x, p)
+
+
+# ---------------------------------------------------------------------------------------------
+# class-token concat + position-embedding add in one pass
+# ---------------------------------------------------------------------------------------------
+class _AssembleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tok, prefix, pos, pos_has_prefix):
+        tok_c = tok if tok.is_contiguous() else tok.contiguous()
+        pdt = None
+        for t in (prefix, pos):
+            if t is not None:
+                pdt = t.dtype if pdt is None else pdt
+        pf = None if prefix is None else prefix.reshape(-1, prefix.shape[-1]).to(pdt).contiguous()
+        ps = None if pos is None else pos.to(pdt).contiguous()
+        ctx.P = 0 if pf is None else pf.shape[0]
+        ctx.meta = (None if prefix is None else (prefix.shape, prefix.dtype), None if pos is None else (pos.shape, pos.dtype),
+                    pos_has_prefix)
+        return ops.assemble_tokens(tok_c, pf, ps, pos_has_prefix)
+
+    @staticmethod
+    def backward(ctx, g):
+        P = ctx.P
+        pmeta, smeta, has_prefix = ctx.meta
+        d_tok = g[:, P:, :] if ctx.needs_input_grad[0] else None
+        d_prefix = d_pos = None
+        if pmeta is not None and ctx.needs_input_grad[1]:
+            d_prefix = g[:, :P, :].sum(0, dtype=torch.float32).reshape(pmeta[0]).to(pmeta[1])
+        if smeta is not None and ctx.needs_input_grad[2]:
+            gp = g if has_prefix else g[:, P:, :]
+            shp, dt = smeta
+            if len(shp) == 3 and shp[0] == g.shape[0] and shp[0] != 1:
+                d_pos = gp.to(dt)                                      # per-sample embedding
+            else:
+                d_pos = gp.sum(0, dtype=torch.float32).reshape(shp).to(dt)
+        return d_tok, d_prefix, d_pos, None
+
+
+def assemble_tokens(tok, prefix=None, pos=None, pos_has_prefix=True):
+    """concat(prefix tokens, tok) + pos  ->  bf16 [B, P+L, D]  (VIT._pos_embed, arch.py:367-393)."""
+    return _AssembleFn.apply(tok, prefix, pos, pos_has_prefix)

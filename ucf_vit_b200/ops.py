@@ -267,3 +267,27 @@ def sap_scatter(seq, boxes, out_shape, p, C, truncate_to_int=False):
     L.check(L.lib().ucf_sap_scatter(seq.data_ptr(), nd, shp[0], shp[1], shp[2], C, boxes.data_ptr(), boxes.shape[0], p,
                                     int(truncate_to_int), mask.data_ptr(), _stream()), "sap_scatter")
     return mask
+
+
+def assemble_tokens(tok, prefix, pos, pos_has_prefix):
+    """tok bf16 [B,L,D]; prefix [P,D] or None; pos [N or L, D] (shared) / [B, N or L, D] (per sample) or None.
+    -> bf16 [B, P+L, D] = concat(prefix, tok) + pos."""
+    _require_cuda(tok, prefix, pos)
+    B, L_, D = tok.shape
+    assert tok.dtype == torch.bfloat16 and tok.is_contiguous()
+    P = 0 if prefix is None else prefix.shape[0]
+    pd = L.UCF_DTYPE_F32
+    for t in (prefix, pos):
+        if t is not None:
+            assert t.is_contiguous()
+            pd = _dt(t)
+    if prefix is not None and pos is not None:
+        assert prefix.dtype == pos.dtype
+    bstride = 0
+    if pos is not None and pos.dim() == 3 and pos.shape[0] != 1:
+        assert pos.shape[0] == B
+        bstride = pos.shape[1] * D
+    out = torch.empty((B, P + L_, D), dtype=torch.bfloat16, device=tok.device)
+    L.check(L.lib().ucf_assemble_tokens(tok.data_ptr(), _ptr(prefix), _ptr(pos), out.data_ptr(), B, L_, P, D, bstride,
+                                        0 if pos_has_prefix else P, pd, _stream()), "assemble_tokens")
+    return out

@@ -320,17 +320,19 @@ class VIT(nn.Module):
         return self.aggregate_variables(tok)
 
     def _pos_embed(self, x: torch.Tensor, seq_ps) -> torch.Tensor:
+        """cls-token concat + (learned | sin-cos | size/position-dependent) embedding add, one fused
+        pass.  As in the reference, nothing is added (and no cls token is prepended) when the model
+        has no pos_embed parameter."""
         if self.pos_embed is None:
             return x.view(x.shape[0], -1, x.shape[-1])
-        if self.use_adaptive_pos_emb:
-            pe = _torch_head(self.adaptive_pos_dep_emb, seq_ps)
-        else:
-            pe = self.pos_embed
-        if self.cls_token is not None:
-            x = torch.cat([self.cls_token.to(x.dtype).expand(x.shape[0], -1, -1), x], dim=1)
-            if self.use_adaptive_pos_emb:
-                pe = torch.cat([pe.new_zeros(x.shape[0], 1, self.embed_dim), pe], dim=1)
-        x = x + pe.to(x.dtype)
+        adaptive = self.use_adaptive_pos_emb
+        pe = _torch_head(self.adaptive_pos_dep_emb, seq_ps) if adaptive else self.pos_embed
+        if x.dtype != torch.bfloat16 or not x.is_cuda or x.shape[-1] % 8:
+            raise RuntimeError("ucf_vit_b200: tokens must be bf16 CUDA tensors (no CPU fallback)")
+        prefix = self.cls_token.reshape(1, -1) if self.cls_token is not None else None
+        # the learned table has a row for the cls token; the adaptive embedding has not (the
+        # reference concatenates a zero row there, arch.py:377-390)
+        x = UF.assemble_tokens(x, prefix, pe, pos_has_prefix=not adaptive)
         return self.pos_drop(x)
 
     def _final_norm(self, x):
