@@ -219,6 +219,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         mbar_wait(sdp_full, tc & 1);
         tc_fence_after();
+        const float2 sl2 = mk2(p.scale_log2), nlse2 = mk2(nlse), sc2 = mk2(p.scale), nds2 = mk2(-delta * p.scale);
 #pragma unroll 1
         for (int c = 0; c < T / 32; ++c) {
           uint32_t sv[32], dv[32];
@@ -228,12 +229,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           uint32_t pk[16], dk[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const float p0 = fast_ex2(fmaf(__uint_as_float(sv[e]), p.scale_log2, nlse));
-            const float p1 = fast_ex2(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, nlse));
-            const float d0 = p0 * (__uint_as_float(dv[e]) - delta) * p.scale;
-            const float d1 = p1 * (__uint_as_float(dv[e + 1]) - delta) * p.scale;
-            pk[e >> 1] = pack_bf16x2(p0, p1);
-            dk[e >> 1] = pack_bf16x2(d0, d1);
+            const float2 t = __ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2, nlse2);
+            const float2 pp = make_float2(fast_ex2(t.x), fast_ex2(t.y));
+            // dS = scale * P * (dP - delta)
+            const float2 dd = __fmul2_rn(pp, __ffma2_rn(make_float2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), sc2, nds2));
+            pk[e >> 1] = pack_bf16x2(pp.x, pp.y);
+            dk[e >> 1] = pack_bf16x2(dd.x, dd.y);
           }
           const int blk = (c >> 1) * 16384;
 #pragma unroll

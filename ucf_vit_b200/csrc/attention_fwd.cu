@@ -219,9 +219,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       decode(item, b, h, q0);
       const int qt0 = q0 + g * BQ;                  // first query row of this warpgroup's tile
       if (qt0 >= p.Nq) continue;                    // (only warpgroup 1 can be idle)
-      float o_acc[HD];
+      float2 o_acc[HD / 2];
 #pragma unroll
-      for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
+      for (int i = 0; i < HD / 2; ++i) o_acc[i] = make_float2(0.f, 0.f);
       float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
       // the previous item's O tile may still be leaving the staging area (== P buffer)
       if (lane == 0) tma_store_wait_read<0>();
@@ -242,7 +242,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_wait_ld();
           if ((c + 1) * 32 <= nvalid) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) m_tile = fmaxf(m_tile, __uint_as_float(v[e]));
+            for (int e = 0; e < 32; e += 2)      // 3-input max (FMNMX3)
+              m_tile = fmaxf(m_tile, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
           } else {
 #pragma unroll
             for (int e = 0; e < 32; ++e)
@@ -259,12 +260,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             uint32_t v[32];
             tmem_ld32(tmem_pv + lane_addr + c * 32, v);
             tmem_wait_ld();
+            const float2 ap2 = mk2(alpha_prev);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) o_acc[c * 32 + e] = fmaf(o_acc[c * 32 + e], alpha_prev, __uint_as_float(v[e]));
+            for (int e = 0; e < 16; ++e)
+              o_acc[c * 16 + e] = __ffma2_rn(o_acc[c * 16 + e], ap2,
+                                             make_float2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])));
           }
         }
         // pass 2: probabilities -> bf16 -> swizzled smem
-        float l_tile = 0.f;
+        float2 l2 = make_float2(0.f, 0.f);
+        const float2 sc2 = mk2(p.scale_log2), nm2 = mk2(-m_new);
 #pragma unroll 1
         for (int c = 0; c < BKV / 32; ++c) {
           uint32_t pk[16];
@@ -275,14 +280,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const bool full = (c + 1) * 32 <= nvalid;
 #pragma unroll
             for (int e = 0; e < 32; e += 2) {
-              float p0 = fast_ex2(fmaf(__uint_as_float(v[e]), p.scale_log2, -m_new));
-              float p1 = fast_ex2(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -m_new));
+              const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), sc2, nm2);
+              float2 pp = make_float2(fast_ex2(t.x), fast_ex2(t.y));
               if (!full) {
-                if (c * 32 + e >= nvalid) p0 = 0.f;
-                if (c * 32 + e + 1 >= nvalid) p1 = 0.f;
+                if (c * 32 + e >= nvalid) pp.x = 0.f;
+                if (c * 32 + e + 1 >= nvalid) pp.y = 0.f;
               }
-              l_tile += p0 + p1;
-              pk[e >> 1] = pack_bf16x2(p0, p1);
+              l2 = __fadd2_rn(l2, pp);
+              pk[e >> 1] = pack_bf16x2(pp.x, pp.y);
             }
           } else {
 #pragma unroll
@@ -300,7 +305,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_arrive(&s_empty[g]);        // S_g may be overwritten by the next QK^T
         fence_proxy_async_smem();
         mbar_arrive(&p_full[g]);         // P_g(j) visible to the tensor core
-        l_run = fmaf(l_run, alpha, l_tile);
+        l_run = fmaf(l_run, alpha, l2.x + l2.y);
         m_run = m_new;
         alpha_prev = alpha;
       }
@@ -317,8 +322,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int q4 = 0; q4 < 4; ++q4) {
           float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            f[e] = fmaf(o_acc[c * 32 + q4 * 8 + e], alpha_prev, __uint_as_float(v[q4 * 8 + e])) * inv_l;
+          for (int e = 0; e < 4; ++e) {
+            const float2 r = __fmul2_rn(__ffma2_rn(o_acc[c * 16 + q4 * 4 + e], mk2(alpha_prev),
+                                                   make_float2(__uint_as_float(v[q4 * 8 + 2 * e]), __uint_as_float(v[q4 * 8 + 2 * e + 1]))),
+                                        mk2(inv_l));
+            f[2 * e] = r.x; f[2 * e + 1] = r.y;
+          }
           const uint32_t chunk = static_cast<uint32_t>(c * 4 + q4);
           uint8_t* dst = (RB == 128) ? o_stage + lane * 128 + ((chunk ^ lrow_sw) << 4)
                                      : o_stage + lane * 64 + ((chunk ^ ((lane >> 1) & 3)) << 4);

@@ -347,6 +347,35 @@ __device__ __forceinline__ float gelu_erf_grad(float z) {
   const float cdf = z >= 0.f ? 1.0f - q : q;
   return fmaf(z * 0.39894228040143267794f, e, cdf);   // Phi(z) + z * phi(z)
 }
+// ---- packed fp32x2 forms (FFMA2 / FMUL2 / FADD2 process two lanes per instruction; MUFU stays scalar)
+__device__ __forceinline__ float2 mk2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 bf16x2_to_f32x2(uint32_t v) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ void gelu_terms2(float2 z, float2& q, float2& e) {
+  const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+  const float2 d = __ffma2_rn(az, mk2(0.3275911f * 0.70710678118654752440f), mk2(1.0f));
+  const float2 t = make_float2(fast_rcp(d.x), fast_rcp(d.y));
+  const float2 a = __fmul2_rn(__fmul2_rn(z, z), mk2(-0.5f * 1.4426950408889634f));
+  e = make_float2(fast_ex2(a.x), fast_ex2(a.y));
+  float2 p = __ffma2_rn(t, mk2(1.061405429f), mk2(-1.453152027f));
+  p = __ffma2_rn(t, p, mk2(1.421413741f));
+  p = __ffma2_rn(t, p, mk2(-0.284496736f));
+  p = __ffma2_rn(t, p, mk2(0.254829592f));
+  q = __fmul2_rn(__fmul2_rn(p, t), __fmul2_rn(e, mk2(0.5f)));
+}
+__device__ __forceinline__ float2 gelu_erf2(float2 z) {
+  float2 q, e;
+  gelu_terms2(z, q, e);
+  const float2 zq = __fmul2_rn(z, q);                       // z < 0 : z*q ; z >= 0 : z - z*q
+  return make_float2(z.x >= 0.f ? z.x - zq.x : zq.x, z.y >= 0.f ? z.y - zq.y : zq.y);
+}
+__device__ __forceinline__ float2 gelu_erf_grad2(float2 z) {
+  float2 q, e;
+  gelu_terms2(z, q, e);
+  const float2 cdf = make_float2(z.x >= 0.f ? 1.0f - q.x : q.x, z.y >= 0.f ? 1.0f - q.y : q.y);
+  return __ffma2_rn(__fmul2_rn(z, mk2(0.39894228040143267794f)), e, cdf);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -252,44 +252,45 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* aux_row = my_aux + b * AUX_BUF + lane * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float f[8];
+              float2 f[4];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+              for (int e = 0; e < 4; ++e)
+                f[e] = make_float2(__uint_as_float(v[8 * j + 2 * e]), __uint_as_float(v[8 * j + 2 * e + 1]));
               if (EPI != EPI_DGELU) {
                 const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[cbase + c * CW + 8 * j]);
                 const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[cbase + c * CW + 8 * j + 4]);
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                f[0] = __fadd2_rn(f[0], make_float2(b0.x, b0.y));
+                f[1] = __fadd2_rn(f[1], make_float2(b0.z, b0.w));
+                f[2] = __fadd2_rn(f[2], make_float2(b1.x, b1.y));
+                f[3] = __fadd2_rn(f[3], make_float2(b1.z, b1.w));
               }
               const uint32_t sw = (static_cast<uint32_t>(j) ^ sw64) << 4;
               if (EPI == EPI_BIAS_RESIDUAL) {
                 const uint4 r = *reinterpret_cast<const uint4*>(aux_row + sw);
-                const float2 r0f = unpack_bf16x2(r.x), r1f = unpack_bf16x2(r.y);
-                const float2 r2f = unpack_bf16x2(r.z), r3f = unpack_bf16x2(r.w);
-                f[0] += r0f.x; f[1] += r0f.y; f[2] += r1f.x; f[3] += r1f.y;
-                f[4] += r2f.x; f[5] += r2f.y; f[6] += r3f.x; f[7] += r3f.y;
+                f[0] = __fadd2_rn(f[0], bf16x2_to_f32x2(r.x));
+                f[1] = __fadd2_rn(f[1], bf16x2_to_f32x2(r.y));
+                f[2] = __fadd2_rn(f[2], bf16x2_to_f32x2(r.z));
+                f[3] = __fadd2_rn(f[3], bf16x2_to_f32x2(r.w));
               } else if (EPI == EPI_DGELU) {
                 const uint4 r = *reinterpret_cast<const uint4*>(aux_row + sw);
-                const float2 z0 = unpack_bf16x2(r.x), z1 = unpack_bf16x2(r.y);
-                const float2 z2 = unpack_bf16x2(r.z), z3 = unpack_bf16x2(r.w);
-                f[0] *= gelu_erf_grad(z0.x); f[1] *= gelu_erf_grad(z0.y);
-                f[2] *= gelu_erf_grad(z1.x); f[3] *= gelu_erf_grad(z1.y);
-                f[4] *= gelu_erf_grad(z2.x); f[5] *= gelu_erf_grad(z2.y);
-                f[6] *= gelu_erf_grad(z3.x); f[7] *= gelu_erf_grad(z3.y);
+                f[0] = __fmul2_rn(f[0], gelu_erf_grad2(bf16x2_to_f32x2(r.x)));
+                f[1] = __fmul2_rn(f[1], gelu_erf_grad2(bf16x2_to_f32x2(r.y)));
+                f[2] = __fmul2_rn(f[2], gelu_erf_grad2(bf16x2_to_f32x2(r.z)));
+                f[3] = __fmul2_rn(f[3], gelu_erf_grad2(bf16x2_to_f32x2(r.w)));
               } else if (EPI == EPI_BIAS_GELU_AUX) {
                 // pre-activation is rounded to bf16 first so that backward (which re-reads the
                 // stored bf16 z) differentiates exactly the function forward evaluated.
-                uint4 zq = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                      pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                uint4 zq = make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y),
+                                      pack_bf16x2(f[2].x, f[2].y), pack_bf16x2(f[3].x, f[3].y));
                 *reinterpret_cast<uint4*>(aux_row + sw) = zq;
-                const float2 z0 = unpack_bf16x2(zq.x), z1 = unpack_bf16x2(zq.y);
-                const float2 z2 = unpack_bf16x2(zq.z), z3 = unpack_bf16x2(zq.w);
-                f[0] = gelu_erf(z0.x); f[1] = gelu_erf(z0.y); f[2] = gelu_erf(z1.x); f[3] = gelu_erf(z1.y);
-                f[4] = gelu_erf(z2.x); f[5] = gelu_erf(z2.y); f[6] = gelu_erf(z3.x); f[7] = gelu_erf(z3.y);
+                f[0] = gelu_erf2(bf16x2_to_f32x2(zq.x));
+                f[1] = gelu_erf2(bf16x2_to_f32x2(zq.y));
+                f[2] = gelu_erf2(bf16x2_to_f32x2(zq.z));
+                f[3] = gelu_erf2(bf16x2_to_f32x2(zq.w));
               }
               *reinterpret_cast<uint4*>(out_row + sw) =
-                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                             pack_bf16x2(f[6], f[7]));
+                  make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y), pack_bf16x2(f[2].x, f[2].y),
+                             pack_bf16x2(f[3].x, f[3].y));
             }
           }
           fence_proxy_async_smem();

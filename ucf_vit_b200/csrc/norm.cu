@@ -8,22 +8,28 @@
 
 namespace ucf {
 
+// ---- packed fp32x2 helpers (Blackwell FFMA2 / FADD2 / FMUL2: two fp32 lanes per instruction) -------
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t v) {   // bf16x2 -> fp32x2: one shift + one mask
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ void unpack4(const uint4& r, float2 (&f)[4]) {
+  f[0] = bf2_to_f2(r.x); f[1] = bf2_to_f2(r.y); f[2] = bf2_to_f2(r.z); f[3] = bf2_to_f2(r.w);
+}
 template <bool BF16>
-__device__ __forceinline__ void load8(const void* base, long long idx, float (&f)[8]) {
+__device__ __forceinline__ void load4x2(const void* base, long long idx, float2 (&f)[4]) {   // 8 elements
   if (BF16) {
     const uint4 r = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
-    float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
-    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+    unpack4(r, f);
   } else {
     const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx));
     const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx + 4));
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    f[0] = f2(a.x, a.y); f[1] = f2(a.z, a.w); f[2] = f2(b.x, b.y); f[3] = f2(b.z, b.w);
   }
 }
-__device__ __forceinline__ void store8_bf16(void* base, long long idx, const float (&f)[8]) {
-  uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                       pack_bf16x2(f[6], f[7]));
-  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = o;
+__device__ __forceinline__ uint4 pack4(const float2 (&f)[4]) {
+  return make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y), pack_bf16x2(f[2].x, f[2].y),
+                    pack_bf16x2(f[3].x, f[3].y));
 }
 
 // NCH = number of 256-element chunks a warp covers per row (D <= 256*NCH)
@@ -36,33 +42,38 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const float inv_d = 1.0f / static_cast<float>(D);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
 
   for (long long row = warp_global; row < rows; row += nwarps) {
-    float v[NCH][8];
-    float s = 0.f;
+    const long long base = row * D + lane * 8;
+    float2 v[NCH][4];
+    float2 s = f2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (col < D) {
-        load8<X_BF16>(x, row * D + col, v[c]);
+      if (c * 256 + lane * 8 < D) {
+        load4x2<X_BF16>(x, base + c * 256, v[c]);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) s += v[c][e];
+        for (int e = 0; e < 4; ++e) s = __fadd2_rn(s, v[c][e]);
       } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[c][e] = 0.f;
+        for (int e = 0; e < 4; ++e) v[c][e] = f2(0.f, 0.f);
       }
     }
-    const float mu = warp_sum(s) * inv_d;
-    float ss = 0.f;
+    const float mu = warp_sum(s.x + s.y) * inv_d;
+    const float2 nmu = f2(-mu, -mu);
+    float2 ss = f2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (col < D) {
+      if (c * 256 + lane * 8 < D) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { const float d = v[c][e] - mu; ss += d * d; }
+        for (int e = 0; e < 4; ++e) {
+          v[c][e] = __fadd2_rn(v[c][e], nmu);          // centred values are reused by the write pass
+          ss = __ffma2_rn(v[c][e], v[c][e], ss);
+        }
       }
     }
-    const float rs = rsqrtf(warp_sum(ss) * inv_d + eps);
+    const float rs = rsqrtf(warp_sum(ss.x + ss.y) * inv_d + eps);
+    const float2 rs2 = f2(rs, rs);
     if (lane == 0) {
       if (mean_out) mean_out[row] = mu;
       if (rstd_out) rstd_out[row] = rs;
@@ -71,18 +82,17 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
     for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < D) {
-        float g[8], b[8], o[8];
-        if (gamma) load8<P_BF16>(gamma, col, g); else {
+        float2 g[4], b[4], o[4];
+        if (gamma) load4x2<P_BF16>(gamma, col, g);
+        if (beta) load4x2<P_BF16>(beta, col, b);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) g[e] = 1.f;
+        for (int e = 0; e < 4; ++e) {
+          float2 t = __fmul2_rn(v[c][e], rs2);
+          if (gamma) t = beta ? __ffma2_rn(t, g[e], b[e]) : __fmul2_rn(t, g[e]);
+          else if (beta) t = __fadd2_rn(t, b[e]);
+          o[e] = t;
         }
-        if (beta) load8<P_BF16>(beta, col, b); else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) b[e] = 0.f;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = (v[c][e] - mu) * rs * g[e] + b[e];
-        store8_bf16(y, row * D + col, o);
+        *reinterpret_cast<uint4*>(yp + base + c * 256) = pack4(o);
       }
     }
   }
@@ -90,13 +100,12 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
 
 // Backward.  Each warp walks rows with a grid stride, keeps per-lane partial dgamma/dbeta in
 // registers, then the block reduces them through shared memory and issues one atomicAdd per column.
-// The row (dy, x) is held as the RAW 16-byte bf16 vectors between the reduction pass and the
-// write pass (not as 2 x 8 floats): <= 128 registers, so two 256-thread CTAs stay resident per SM.
-__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
-  const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
-
+// Issue-bound before memory-bound (ncu: IPC 2.1, 52 % issue slots at 40 % DRAM), so the math is
+// arranged for the fewest instructions, on packed fp32x2 lanes:
+//   t = dy*g,  s1 = sum t,  s2' = sum t*x            (s2 = rs*(s2' - mu*s1))
+//   dgamma += rs*(dy*x) - (rs*mu)*dy,  dbeta += dy
+//   dx = rs*t + B*x + C   with  B = -rs^2*s2/D,  C = -B*mu - rs*s1/D      (+ dres)
+// The row (dy, x) is held as the RAW 16-byte bf16 vectors between the two passes.
 template <int NCH, bool P_BF16>
 __global__ void __launch_bounds__(256, (NCH <= 3 ? 2 : 1))
 layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const void* __restrict__ gamma,
@@ -111,93 +120,86 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
   const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(dres);
+  __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
 
-  // gamma is re-read per row (L1-resident, D*4 bytes) instead of pinning 8*NCH registers
-  float dg[NCH][8], db[NCH][8];
+  float2 dg[NCH][4], db[NCH][4];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { dg[c][e] = 0.f; db[c][e] = 0.f; }
+    for (int e = 0; e < 4; ++e) { dg[c][e] = f2(0.f, 0.f); db[c][e] = f2(0.f, 0.f); }
   }
-  auto load_gamma = [&](int col, float (&gv)[8]) {
-    if (gamma) load8<P_BF16>(gamma, col, gv);
+  // gamma is re-read per row (L1-resident) instead of pinning 8*NCH registers
+  auto load_gamma = [&](int col, float2 (&gv)[4]) {
+    if (gamma) load4x2<P_BF16>(gamma, col, gv);
     else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) gv[e] = 1.f;
-    }
-  };
-  auto load_row = [&](long long row, uint4 (&a)[NCH], uint4 (&b)[NCH]) {
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (col < D && row < rows) {
-        a[c] = __ldg(reinterpret_cast<const uint4*>(dyp + row * D + col));
-        b[c] = __ldg(reinterpret_cast<const uint4*>(xp + row * D + col));
-      } else {
-        a[c] = make_uint4(0, 0, 0, 0);
-        b[c] = make_uint4(0, 0, 0, 0);
-      }
+      for (int e = 0; e < 4; ++e) gv[e] = f2(1.f, 1.f);
     }
   };
 
-  // software pipeline: the next row's dy / x are in flight while the current row is reduced
-  uint4 dyn[NCH], xn[NCH];
-  load_row(warp_global, dyn, xn);
   for (long long row = warp_global; row < rows; row += nwarps) {
+    const long long base = row * D + lane * 8;
     uint4 dyr[NCH], xr[NCH], rr[NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) { dyr[c] = dyn[c]; xr[c] = xn[c]; }
-    if (dres) {
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int col = c * 256 + lane * 8;
-        rr[c] = (col < D) ? __ldg(reinterpret_cast<const uint4*>(rp + row * D + col)) : make_uint4(0, 0, 0, 0);
+    for (int c = 0; c < NCH; ++c) {
+      if (c * 256 + lane * 8 < D) {
+        dyr[c] = __ldg(reinterpret_cast<const uint4*>(dyp + base + c * 256));
+        xr[c] = __ldg(reinterpret_cast<const uint4*>(xp + base + c * 256));
+        if (dres) rr[c] = __ldg(reinterpret_cast<const uint4*>(rp + base + c * 256));
+      } else {
+        dyr[c] = make_uint4(0, 0, 0, 0);
+        xr[c] = make_uint4(0, 0, 0, 0);
       }
     }
     const float mu = mean[row], rs = rstd[row];
-    load_row(row + nwarps, dyn, xn);
-    float s1 = 0.f, s2 = 0.f;
+    const float2 rs2 = f2(rs, rs), nrm2 = f2(-rs * mu, -rs * mu);
+    float2 s1 = f2(0.f, 0.f), s2 = f2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < D) {
-        float dyv[8], xv[8], gv[8];
-        unpack8(dyr[c], dyv);
-        unpack8(xr[c], xv);
+        float2 dyv[4], xv[4], gv[4];
+        unpack4(dyr[c], dyv);
+        unpack4(xr[c], xv);
         load_gamma(col, gv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float xh = (xv[e] - mu) * rs;
-          const float gy = dyv[e] * gv[e];
-          s1 += gy;
-          s2 = fmaf(gy, xh, s2);
-          dg[c][e] = fmaf(dyv[e], xh, dg[c][e]);
-          db[c][e] += dyv[e];
+        for (int e = 0; e < 4; ++e) {
+          const float2 t = __fmul2_rn(dyv[e], gv[e]);
+          s1 = __fadd2_rn(s1, t);
+          s2 = __ffma2_rn(t, xv[e], s2);
+          const float2 u = __fmul2_rn(dyv[e], xv[e]);
+          dg[c][e] = __ffma2_rn(u, rs2, dg[c][e]);
+          dg[c][e] = __ffma2_rn(dyv[e], nrm2, dg[c][e]);
+          db[c][e] = __fadd2_rn(db[c][e], dyv[e]);
         }
       }
     }
-    s1 = warp_sum(s1) * inv_d;
-    s2 = warp_sum(s2) * inv_d;
+    const float S1 = warp_sum(s1.x + s1.y);
+    const float S2p = warp_sum(s2.x + s2.y);
+    const float S2 = rs * (S2p - mu * S1);           // sum t * xhat
+    const float Bc = -rs * rs * S2 * inv_d;
+    const float Cc = -Bc * mu - rs * S1 * inv_d;
+    const float2 B2 = f2(Bc, Bc), C2 = f2(Cc, Cc);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < D) {
-        float dyv[8], xv[8], gv[8], o[8];
-        unpack8(dyr[c], dyv);
-        unpack8(xr[c], xv);
+        float2 dyv[4], xv[4], gv[4], o[4];
+        unpack4(dyr[c], dyv);
+        unpack4(xr[c], xv);
         load_gamma(col, gv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float xh = (xv[e] - mu) * rs;
-          o[e] = rs * (dyv[e] * gv[e] - s1 - xh * s2);
+        for (int e = 0; e < 4; ++e) {
+          const float2 t = __fmul2_rn(dyv[e], gv[e]);
+          o[e] = __ffma2_rn(t, rs2, __ffma2_rn(xv[e], B2, C2));
         }
         if (dres) {
-          float r[8];
-          unpack8(rr[c], r);
+          float2 r[4];
+          unpack4(rr[c], r);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] += r[e];
+          for (int e = 0; e < 4; ++e) o[e] = __fadd2_rn(o[e], r[e]);
         }
-        store8_bf16(dx, row * D + col, o);
+        *reinterpret_cast<uint4*>(dxp + base + c * 256) = pack4(o);
       }
     }
   }
@@ -212,9 +214,11 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
     const int col = c * 256 + lane * 8;
     if (col < D) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        atomicAdd(&red_g[col + e], dg[c][e]);
-        atomicAdd(&red_b[col + e], db[c][e]);
+      for (int e = 0; e < 4; ++e) {
+        atomicAdd(&red_g[col + 2 * e], dg[c][e].x);
+        atomicAdd(&red_g[col + 2 * e + 1], dg[c][e].y);
+        atomicAdd(&red_b[col + 2 * e], db[c][e].x);
+        atomicAdd(&red_b[col + 2 * e + 1], db[c][e].y);
       }
     }
   }
