@@ -35,7 +35,7 @@ def run_gemm_cases():
         res = torch.randn(M, N, device=dev)
         ab, bb, rb = bf(a), bf(b), bf(res)
         ref = ab.float() @ bb.float().t()
-        for tn in (128, 256):
+        for tn in (128, 256, 512):
             tag = f"M{M} N{N} K{K} tn{tn}"
             try:
                 out = ops.gemm(ab, bb, M=M, N=N, K=K, bias=bias, tile_n=tn)
@@ -120,7 +120,7 @@ def bench_gemm():
                             (50432, 768, 3072, "fwd"), (50432, 768, 3072, "dgrad"), (50432, 3072, 768, "dgrad"),
                             (3072, 768, 50432, "wgrad"), (768, 3072, 50432, "wgrad"), (2304, 768, 50432, "wgrad"),
                             (8192, 8192, 8192, "fwd")]:
-        for tn in (128, 256):
+        for tn in (256, 512):
             if kind == "fwd":
                 a = bf(torch.randn(M, K, device=dev)); b = bf(torch.randn(N, K, device=dev))
                 f = lambda: ops.gemm(a, b, M=M, N=N, K=K, tile_n=tn)

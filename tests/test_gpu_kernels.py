@@ -24,7 +24,7 @@ def _ok(got, ref, tol):
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 192, 192), (1000, 576, 192), (333, 1000, 768), (77, 40, 72),
                                    (4096, 3072, 768)])
-@pytest.mark.parametrize("tn", [128, 256])
+@pytest.mark.parametrize("tn", [128, 256, 512])      # 512 = CTA-pair (cta_group::2) kernel
 def test_gemm_family(M, N, K, tn):
     torch.manual_seed(M + N + K)
     a, b = bf(torch.randn(M, K, device=dev) * 0.5), bf(torch.randn(N, K, device=dev) * 0.5)

@@ -53,7 +53,7 @@ __device__ __forceinline__ uint64_t bwd_desc(uint32_t saddr, uint32_t lbo, uint3
 // double-buffered across items and Q/dO tiles stream through a 2-slot ring, so the producer is
 // always one item ahead and set-up (TMEM allocation, barrier init, first loads) is paid once.
 template <int HD>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                 const __grid_constant__ CUtensorMap tmdQacc, const __grid_constant__ CUtensorMap tmdK,
@@ -94,12 +94,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_empty, 128);
-    mbar_init(pds_full, 128);
+    mbar_init(sdp_empty, 256);
+    mbar_init(pds_full, 256);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 128);
+    mbar_init(dq_empty, 256);
     mbar_init(dkv_full, 1);
-    mbar_init(dkv_empty, 128);
+    mbar_init(dkv_empty, 256);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -190,16 +190,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ------------------------------------------------------------------ compute warps
+    // 8 warps: two per TMEM lane quarter; warp (qd, half) owns rows qd*32.. and the key columns
+    // [half*64, half*64+64) of S / dP, and the head-dim columns [half*HD/2, ...) of dQ / dK / dV.
+    const int cw = warp - 2;
     const int qd = warp & 3;
+    const int half = cw >> 2;
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t row_sw = row & 7;
     const uint32_t lrow_sw = lane & 7;
-    uint8_t* p_row = p_s + row * 128;
-    uint8_t* ds_row = ds_s + row * 128;
-    uint8_t* my_dq = dq_s + (warp - 2) * (32 * HD * 4);   // HD/32 boxes of 32 rows x 128 B
-    uint8_t* st_dv = p_s + (warp - 2) * 4096;             // dK/dV staging reuses this warp's P/dS rows
-    uint8_t* st_dk = ds_s + (warp - 2) * 4096;
+    constexpr int HH = HD / 2;                                // head-dim columns per warp (32 or 16)
+    uint8_t* p_row = p_s + half * 16384 + row * 128;          // this warp's 64-key block of P / dS
+    uint8_t* ds_row = ds_s + half * 16384 + row * 128;
+    uint8_t* my_dq = dq_s + cw * (32 * HH * 4);               // 32 rows x HH fp32
+    // dK/dV staging: 32 rows x HH bf16, in rows of this warp's own P / dS block
+    uint8_t* st_dv = p_s + half * 16384 + qd * 4096;
+    uint8_t* st_dk = ds_s + half * 16384 + qd * 4096;
     const float LOG2E = 1.4426950408889634f;
     uint32_t it = 0, tc = 0;
 
@@ -221,10 +227,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         const float2 sl2 = mk2(p.scale_log2), nlse2 = mk2(nlse), sc2 = mk2(p.scale), nds2 = mk2(-delta * p.scale);
 #pragma unroll 1
-        for (int c = 0; c < T / 32; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t sv[32], dv[32];
-          tmem_ld32(t_s + lane_addr + c * 32, sv);
-          tmem_ld32(t_dp + lane_addr + c * 32, dv);
+          tmem_ld32(t_s + lane_addr + half * 64 + c * 32, sv);
+          tmem_ld32(t_dp + lane_addr + half * 64 + c * 32, dv);
           tmem_wait_ld();
           uint32_t pk[16], dk[16];
 #pragma unroll
@@ -236,12 +242,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             pk[e >> 1] = pack_bf16x2(pp.x, pp.y);
             dk[e >> 1] = pack_bf16x2(dd.x, dd.y);
           }
-          const int blk = (c >> 1) * 16384;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const uint32_t off = ((static_cast<uint32_t>((c & 1) * 4 + g)) ^ row_sw) << 4;
-            *reinterpret_cast<uint4*>(p_row + blk + off) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-            *reinterpret_cast<uint4*>(ds_row + blk + off) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+            const uint32_t off = ((static_cast<uint32_t>(c * 4 + g)) ^ row_sw) << 4;
+            *reinterpret_cast<uint4*>(p_row + off) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            *reinterpret_cast<uint4*>(ds_row + off) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
           }
         }
         tc_fence_before();
@@ -249,26 +254,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         fence_proxy_async_smem();
         mbar_arrive(pds_full);
 
-        // dQ_i tile -> fp32 staging -> TMA reduce-add
+        // dQ_i tile (this warp's HH columns) -> fp32 staging -> TMA reduce-add
         mbar_wait(dq_full, tc & 1);
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < HD / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_dq + lane_addr + c * 32, v);
+        {
+          uint32_t v[HH];
+          if (HH == 32) tmem_ld32(t_dq + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          else tmem_ld16(t_dq + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
           tmem_wait_ld();
+          // rows of HH fp32 = 128 B (SWIZZLE_128B) or 64 B (SWIZZLE_64B)
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<uint4*>(my_dq + c * 4096 + lane * 128 + ((static_cast<uint32_t>(g) ^ lrow_sw) << 4)) =
-                make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          for (int g = 0; g < HH / 4; ++g) {
+            uint8_t* dst = (HH == 32) ? my_dq + lane * 128 + ((static_cast<uint32_t>(g) ^ lrow_sw) << 4)
+                                      : my_dq + lane * 64 + ((static_cast<uint32_t>(g) ^ ((lane >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          }
         }
         tc_fence_before();
         mbar_arrive(dq_empty);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && i * T + qd * 32 < p.Nq) {
-#pragma unroll
-          for (int c = 0; c < HD / 32; ++c) tma_reduce_add_4d(&tmdQacc, my_dq + c * 4096, c * 32, h, i * T + qd * 32, b);
+          tma_reduce_add_4d(&tmdQacc, my_dq, half * HH, h, i * T + qd * 32, b);
           tma_store_commit();
         }
       }
@@ -279,23 +286,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
         uint8_t* st = which == 0 ? st_dv : st_dk;
-        const uint32_t t_src = which == 0 ? t_dv : t_dk;
+        const uint32_t t_src = (which == 0 ? t_dv : t_dk) + half * HH;
+        uint32_t v[HH];
+        if (HH == 32) tmem_ld32(t_src + lane_addr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        else tmem_ld16(t_src + lane_addr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_wait_ld();
+        // rows of HH bf16 = 64 B (SWIZZLE_64B) or 32 B (SWIZZLE_32B)
 #pragma unroll
-        for (int c = 0; c < HD / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_src + lane_addr + c * 32, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t chunk = static_cast<uint32_t>(c * 4 + g);
-            uint8_t* dst = (RB == 128) ? st + lane * 128 + ((chunk ^ lrow_sw) << 4)
-                                       : st + lane * 64 + ((chunk ^ ((lane >> 1) & 3)) << 4);
-            *reinterpret_cast<uint4*>(dst) =
-                make_uint4(pack_bf16x2(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
-                           pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
-                           pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
-                           pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
-          }
+        for (int g = 0; g < HH / 8; ++g) {
+          uint8_t* dst = (HH == 32) ? st + lane * 64 + ((static_cast<uint32_t>(g) ^ ((lane >> 1) & 3)) << 4)
+                                    : st + lane * 32 + ((static_cast<uint32_t>(g) ^ ((lane >> 2) & 1)) << 4);
+          *reinterpret_cast<uint4*>(dst) =
+              make_uint4(pack_bf16x2(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                         pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                         pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                         pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
         }
       }
       tc_fence_before();
@@ -303,8 +308,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0 && k0 + qd * 32 < p.Nk) {
-        tma_store_4d(&tmdV, st_dv, 0, h, k0 + qd * 32, b);
-        tma_store_4d(&tmdK, st_dk, 0, h, k0 + qd * 32, b);
+        tma_store_4d(&tmdV, st_dv, half * HH, h, k0 + qd * 32, b);
+        tma_store_4d(&tmdK, st_dk, half * HH, h, k0 + qd * 32, b);
         tma_store_commit();
       }
     }
@@ -426,10 +431,11 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
   if ((rc = make_bnhd_tmap(&tK, k, B, H, Nk, hd, k_sb, k_sn, k_sh, 128, bf, 2, hd))) return rc;
   if ((rc = make_bnhd_tmap(&tV, v, B, H, Nk, hd, v_sb, v_sn, v_sh, 128, bf, 2, hd))) return rc;
   if ((rc = make_bnhd_tmap(&tdO, d_o, B, H, Nq, hd, o_sb, o_sn, o_sh, 128, bf, 2, hd))) return rc;
+  // output boxes are 32 rows x hd/2 columns (each compute warp owns half of the head dimension)
   if ((rc = make_bnhd_tmap(&tdQ, dq_acc, B, H, Nq, hd, static_cast<long long>(Nq) * H * hd, static_cast<long long>(H) * hd, hd,
-                           32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 32))) return rc;
-  if ((rc = make_bnhd_tmap(&tdK, dk, B, H, Nk, hd, dk_sb, dk_sn, dk_sh, 32, bf, 2, hd))) return rc;
-  if ((rc = make_bnhd_tmap(&tdV, dv, B, H, Nk, hd, dv_sb, dv_sn, dv_sh, 32, bf, 2, hd))) return rc;
+                           32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, hd / 2))) return rc;
+  if ((rc = make_bnhd_tmap(&tdK, dk, B, H, Nk, hd, dk_sb, dk_sn, dk_sh, 32, bf, 2, hd / 2))) return rc;
+  if ((rc = make_bnhd_tmap(&tdV, dv, B, H, Nk, hd, dv_sb, dv_sn, dv_sh, 32, bf, 2, hd / 2))) return rc;
 
   AttnBwdParams p;
   p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
@@ -447,7 +453,7 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
       if (e != cudaSuccess) { set_last_error("attention_bwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
       attr = true;
     }
-    attn_bwd_kernel<64><<<grid, 192, AttnBwdCfg<64>::SMEM_BYTES, st>>>(tQ, tK, tV, tdO, tdQ, tdK, tdV, p);
+    attn_bwd_kernel<64><<<grid, 320, AttnBwdCfg<64>::SMEM_BYTES, st>>>(tQ, tK, tV, tdO, tdQ, tdK, tdV, p);
   } else {
     static bool attr = false;
     if (!attr) {
@@ -455,7 +461,7 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
       if (e != cudaSuccess) { set_last_error("attention_bwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
       attr = true;
     }
-    attn_bwd_kernel<32><<<grid, 192, AttnBwdCfg<32>::SMEM_BYTES, st>>>(tQ, tK, tV, tdO, tdQ, tdK, tdV, p);
+    attn_bwd_kernel<32><<<grid, 320, AttnBwdCfg<32>::SMEM_BYTES, st>>>(tQ, tK, tV, tdO, tdQ, tdK, tdV, p);
   }
   if ((rc = check_launch("attn_bwd_kernel"))) return rc;
 

@@ -366,6 +366,7 @@ int make_bnhd_tmap(CUtensorMap* tm, const void* ptr, int B, int H, int N, int hd
   const int inner_bytes = box_cols * elem_bytes;
   CUtensorMapSwizzle swz = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                          : inner_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                         : inner_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
                                               : CU_TENSOR_MAP_SWIZZLE_NONE;
   return make_tmap(tm, ptr, dt, 4, dims, strides, box, swz);
 }

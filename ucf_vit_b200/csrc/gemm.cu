@@ -321,6 +321,300 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant: a cluster of two CTAs (one TPC) works on a 256 x BN tile with
+// tcgen05.mma.cta_group::2.  Each CTA stages its own 128 rows of A and HALF of the B tile, so the
+// shared-memory traffic per MMA flop is halved and a pipeline stage is 16 KB smaller.  Only the
+// leader CTA (cluster rank 0) issues MMAs; its commits are multicast to both CTAs' barriers; both
+// CTAs' TMA loads credit the leader's "full" barrier; each CTA's epilogue warps drain the 128
+// accumulator rows that live in their own TMEM.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
+struct Gemm2Cfg {
+  static constexpr int BM = 128, BK = 64;                    // per CTA; the pair covers 256 rows
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;          // this CTA's half of B
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr bool HAS_AUX = (EPI == EPI_BIAS_RESIDUAL || EPI == EPI_BIAS_GELU_AUX || EPI == EPI_DGELU);
+  static constexpr bool AUX_IN = (EPI == EPI_BIAS_RESIDUAL || EPI == EPI_DGELU);
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int CW = 32;
+  static constexpr int OUT_BUF = (EPI == EPI_F32_ADD) ? 4096 : 2048;
+  static constexpr int AUX_BUF = 2048;
+  static constexpr int OUT_NBUF = 2;
+  static constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_NBUF * OUT_BUF;
+  static constexpr int AUX_STAGE_BYTES = HAS_AUX ? EPI_WARPS * 2 * AUX_BUF : 0;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_STAGE_BYTES + AUX_STAGE_BYTES + BN * 4 +
+                                    (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
+  static_assert(BN == 256, "pair kernel is instantiated for BN = 256");
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * 8, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
+                  const GemmParams p) {
+  using Cfg = Gemm2Cfg<BN, STAGES, A_MN, B_MN, EPI>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, HN = BN / 2;
+  constexpr int A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* epi_out = smem + STAGES * STAGE_BYTES;
+  uint8_t* epi_aux = epi_out + Cfg::OUT_STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(epi_aux + Cfg::AUX_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + BN);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* aux_bar = tempty_bar + 2;   // [EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * Cfg::EPI_WARPS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (Cfg::HAS_AUX) tma_prefetch_desc(&tmAux);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);      // leader's producer arrives (+ 2 CTAs' transaction bytes)
+      mbar_init(&empty_bar[s], 1);     // multicast commit from the leader's MMA thread
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);                       // multicast commit
+      mbar_init(&tempty_bar[b], 2 * Cfg::EPI_WARPS);     // epilogue warps of BOTH CTAs (leader's copy is used)
+    }
+    for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();          // barriers of both CTAs initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.tiles_m * p.tiles_n * p.splits;       // tiles_m counts 256-row tiles here
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t kiter = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int n_blk = tile % p.tiles_n;
+        const int rest = tile / p.tiles_n;
+        const int m_blk = rest % p.tiles_m;
+        const int split = rest / p.tiles_m;
+        const int m0 = m_blk * 2 * BM + rank * BM;        // this CTA's 128 rows
+        const int n0 = n_blk * BN + rank * HN;            // this CTA's half of the B tile
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
+          const int s = kiter % STAGES;
+          const uint32_t ph = (kiter / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t full0 = mapa_u32(smem_u32(&full_bar[s]), 0);     // the leader's barrier
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+          uint8_t* a_dst = stage_base + s * STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_BYTES;
+          if (!A_MN) {
+            tma_load_2d_2sm(a_dst, &tmA, full0, kb * BK, m0);
+          } else {
+            tma_load_2d_2sm(a_dst, &tmA, full0, m0, kb * BK);
+            tma_load_2d_2sm(a_dst + 8192, &tmA, full0, m0 + 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(b_dst, &tmB, full0, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < HN / 64; ++j)
+              tma_load_2d_2sm(b_dst + j * 8192, &tmB, full0, n0 + j * 64, kb * BK);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, A_MN, B_MN);
+      uint32_t kiter = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+        const int rest = tile / p.tiles_n;
+        const int split = rest / p.tiles_m;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        const int buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
+          const int s = kiter % STAGES;
+          const uint32_t ph = (kiter / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(stage_base + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
+                                        : umma_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                        : umma_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[s], 3);     // both CTAs may refill this stage
+        }
+        umma_commit_2sm(&tfull_bar[buf], 3);     // accumulator complete in both CTAs' TMEM
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs)
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    const int half = ew >> 2;
+    const int etid = threadIdx.x - 64;
+    constexpr int CW = Cfg::CW;
+    constexpr int NCHUNK = BN / 2 / CW;
+    constexpr int OUT_BUF = Cfg::OUT_BUF, AUX_BUF = Cfg::AUX_BUF;
+    uint8_t* my_out = epi_out + ew * Cfg::OUT_NBUF * OUT_BUF;
+    uint8_t* my_aux = epi_aux + ew * 2 * AUX_BUF;
+    uint64_t* my_aux_bar = aux_bar + ew * 2;
+    const uint32_t sw64 = (lane >> 1) & 3, sw128 = lane & 7;
+    uint32_t cc = 0;
+    int it = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
+      const int n_blk = tile % p.tiles_n;
+      const int rest = tile / p.tiles_n;
+      const int m_blk = rest % p.tiles_m;
+      const int m0 = m_blk * 2 * BM + rank * BM, n0 = n_blk * BN;
+      const int buf = it & 1;
+      const int r0 = m0 + q * 32;
+      const int cbase = half * (BN / 2);
+
+      if (EPI != EPI_F32_ADD && EPI != EPI_DGELU) {
+        named_bar_sync(1, 32 * Cfg::EPI_WARPS);
+        for (int i = etid; i < BN; i += 32 * Cfg::EPI_WARPS) {
+          float b = 0.f;
+          if (p.bias != nullptr && n0 + i < p.N)
+            b = p.bias_is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n0 + i])
+                               : reinterpret_cast<const float*>(p.bias)[n0 + i];
+          bias_s[i] = b;
+        }
+        named_bar_sync(1, 32 * Cfg::EPI_WARPS);
+      }
+      const bool active = r0 < p.M && n0 + cbase < p.N;
+      if (Cfg::AUX_IN && lane == 0 && active) {
+        mbar_expect_tx(&my_aux_bar[cc & 1], AUX_BUF);
+        tma_load_2d(my_aux + (cc & 1) * AUX_BUF, &tmAux, &my_aux_bar[cc & 1], n0 + cbase, r0);
+      }
+      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + buf * BN + cbase + (static_cast<uint32_t>(q * 32) << 16);
+
+      if (active) {
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int col0 = n0 + cbase + c * CW;
+          if (col0 >= p.N) break;
+          const uint32_t b = cc & 1;
+          if (Cfg::AUX_IN && lane == 0 && c + 1 < NCHUNK && col0 + CW < p.N) {
+            mbar_expect_tx(&my_aux_bar[b ^ 1], AUX_BUF);
+            tma_load_2d(my_aux + (b ^ 1) * AUX_BUF, &tmAux, &my_aux_bar[b ^ 1], col0 + CW, r0);
+          }
+          uint32_t v[32];
+          tmem_ld32(t_row + c * CW, v);
+          tmem_wait_ld();
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          if (Cfg::AUX_IN) mbar_wait(&my_aux_bar[b], (cc >> 1) & 1);
+          if (EPI == EPI_F32_ADD) {
+            uint8_t* out_row = my_out + b * OUT_BUF + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(out_row + ((j ^ sw128) << 4)) =
+                  make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint8_t* out_row = my_out + b * OUT_BUF + lane * 64;
+            uint8_t* aux_row = my_aux + b * AUX_BUF + lane * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                f[e] = make_float2(__uint_as_float(v[8 * j + 2 * e]), __uint_as_float(v[8 * j + 2 * e + 1]));
+              if (EPI != EPI_DGELU) {
+                const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[cbase + c * CW + 8 * j]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[cbase + c * CW + 8 * j + 4]);
+                f[0] = __fadd2_rn(f[0], make_float2(b0.x, b0.y));
+                f[1] = __fadd2_rn(f[1], make_float2(b0.z, b0.w));
+                f[2] = __fadd2_rn(f[2], make_float2(b1.x, b1.y));
+                f[3] = __fadd2_rn(f[3], make_float2(b1.z, b1.w));
+              }
+              const uint32_t sw = (static_cast<uint32_t>(j) ^ sw64) << 4;
+              if (EPI == EPI_BIAS_RESIDUAL) {
+                const uint4 r = *reinterpret_cast<const uint4*>(aux_row + sw);
+                f[0] = __fadd2_rn(f[0], bf16x2_to_f32x2(r.x));
+                f[1] = __fadd2_rn(f[1], bf16x2_to_f32x2(r.y));
+                f[2] = __fadd2_rn(f[2], bf16x2_to_f32x2(r.z));
+                f[3] = __fadd2_rn(f[3], bf16x2_to_f32x2(r.w));
+              } else if (EPI == EPI_DGELU) {
+                const uint4 r = *reinterpret_cast<const uint4*>(aux_row + sw);
+                f[0] = __fmul2_rn(f[0], gelu_erf_grad2(bf16x2_to_f32x2(r.x)));
+                f[1] = __fmul2_rn(f[1], gelu_erf_grad2(bf16x2_to_f32x2(r.y)));
+                f[2] = __fmul2_rn(f[2], gelu_erf_grad2(bf16x2_to_f32x2(r.z)));
+                f[3] = __fmul2_rn(f[3], gelu_erf_grad2(bf16x2_to_f32x2(r.w)));
+              } else if (EPI == EPI_BIAS_GELU_AUX) {
+                uint4 zq = make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y),
+                                      pack_bf16x2(f[2].x, f[2].y), pack_bf16x2(f[3].x, f[3].y));
+                *reinterpret_cast<uint4*>(aux_row + sw) = zq;
+                f[0] = gelu_erf2(bf16x2_to_f32x2(zq.x));
+                f[1] = gelu_erf2(bf16x2_to_f32x2(zq.y));
+                f[2] = gelu_erf2(bf16x2_to_f32x2(zq.z));
+                f[3] = gelu_erf2(bf16x2_to_f32x2(zq.w));
+              }
+              *reinterpret_cast<uint4*>(out_row + sw) =
+                  make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y), pack_bf16x2(f[2].x, f[2].y),
+                             pack_bf16x2(f[3].x, f[3].y));
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (EPI == EPI_F32_ADD) {
+              tma_reduce_add_2d(&tmC, my_out + b * OUT_BUF, col0, r0);
+            } else {
+              tma_store_2d(&tmC, my_out + b * OUT_BUF, col0, r0);
+              if (EPI == EPI_BIAS_GELU_AUX) tma_store_2d(&tmAux, my_aux + b * AUX_BUF, col0, r0);
+            }
+            tma_store_commit();
+          }
+          ++cc;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      // the accumulator buffer is free once the epilogue warps of BOTH CTAs are done: arrive on the
+      // leader's barrier (the only one the MMA thread waits on)
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // nobody tears TMEM / smem down while the peer may still touch it
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
@@ -355,6 +649,27 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   return check_launch("gemm_bf16_kernel");
 }
 
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm2(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
+                        const CUtensorMap& tAux, const GemmParams& p, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN, STAGES, A_MN, B_MN, EPI>;
+  auto kern = gemm2_bf16_kernel<BN, STAGES, A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("gemm2: cudaFuncSetAttribute(%d B smem): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.splits;
+  int clusters = num_sms() / 2;
+  if (clusters > total) clusters = total;
+  kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tA, tB, tC, tAux, p);   // __cluster_dims__(2,1,1)
+  return check_launch("gemm2_bf16_kernel");
+}
+
 }  // namespace ucf
 
 using namespace ucf;
@@ -380,12 +695,14 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
   if (epilogue != EPI_F32_ADD) splits = 1;
   if (splits < 1) splits = 1;
 
-  int BN = tile_n;
+  // tile_n: 128 / 256 = single-CTA kernels; 512 = CTA-pair kernel (256 x 256 tile per 2-CTA cluster)
+  const bool pair = tile_n == 512;
+  int BN = pair ? 256 : tile_n;
   if (BN != 128 && BN != 256) BN = (N <= 128 || (N % 256 != 0 && N % 128 == 0 && N < 1024)) ? 128 : 256;
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
-  p.tiles_m = (M + 127) / 128;
+  p.tiles_m = pair ? (M + 255) / 256 : (M + 127) / 128;
   p.tiles_n = (N + BN - 1) / BN;
   p.kb_total = (K + 63) / 64;
   if (splits > p.kb_total) splits = p.kb_total;
@@ -405,7 +722,7 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
     else       { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = 64; }
     strides[0] = static_cast<uint64_t>(lda) * 2;
     if ((rc = make_tmap(&tA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = BN; }
+    if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = pair ? BN / 2 : BN; }
     else       { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = 64; }
     strides[0] = static_cast<uint64_t>(ldb) * 2;
     if ((rc = make_tmap(&tB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -424,6 +741,21 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
     }
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+#define UCF_GEMM2_CASE(stg, amn, bmn, epi)                                            \
+  if (pair && a_mn == amn && b_mn == bmn && epilogue == epi)                          \
+    return launch_gemm2<256, stg, amn, bmn, epi>(tA, tB, tC, tAux, p, st);
+  UCF_GEMM2_CASE(6, false, false, EPI_BIAS)
+  UCF_GEMM2_CASE(5, false, false, EPI_BIAS_RESIDUAL)
+  UCF_GEMM2_CASE(5, false, false, EPI_BIAS_GELU_AUX)
+  UCF_GEMM2_CASE(6, false, true, EPI_BIAS)
+  UCF_GEMM2_CASE(5, false, true, EPI_DGELU)
+  UCF_GEMM2_CASE(5, true, true, EPI_F32_ADD)
+#undef UCF_GEMM2_CASE
+  if (pair) {
+    set_last_error("gemm: no CTA-pair kernel for a_layout=%d b_layout=%d epilogue=%d", a_layout, b_layout, epilogue);
+    return UCF_ERR_UNSUPPORTED;
+  }
 
 #define UCF_GEMM_CASE(bn, stg, amn, bmn, epi)                                        \
   if (BN == bn && a_mn == amn && b_mn == bmn && epilogue == epi)                     \
