@@ -26,6 +26,7 @@ struct AttnBwdParams {
   float scale, scale_log2;
   const float* lse;     // [B,H,Nq]
   const float* delta;   // [B,H,Nq]
+  long long* timeline;  // optional [64] clock64 stamps of CTA 0 (profiling aid; NULL in production)
 };
 
 template <int HD>
@@ -33,10 +34,9 @@ struct AttnBwdCfg {
   static constexpr int T = 128;
   static constexpr int TILE_BYTES = T * HD * 2;       // one Q / K / V / dO tile
   static constexpr int PS_BYTES = T * T * 2;          // P or dS
-  static constexpr int DQ_STAGE = T * HD * 4;
-  static constexpr int NBAR = 16;
-  static constexpr int SMEM_BYTES = 1024 + 4 * TILE_BYTES /*K,V x2*/ + 4 * TILE_BYTES /*Q,dO x2*/ +
-                                    2 * PS_BYTES + DQ_STAGE + NBAR * 8 + 16;
+  static constexpr int NBAR = 20;
+  // K,V (one item) | Q x2 | dO x2 | P x2 | dS x2.  dQ / dK / dV staging reuses dead P / dS rows.
+  static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES + 4 * TILE_BYTES + 4 * PS_BYTES + NBAR * 8 + 16;
   static constexpr int ROW_BYTES = HD * 2;
   static constexpr int ATOM_BYTES = 8 * ROW_BYTES;
   static_assert(SMEM_BYTES <= 232448, "smem");
@@ -49,9 +49,12 @@ __device__ __forceinline__ uint64_t bwd_desc(uint32_t saddr, uint32_t lbo, uint3
   return d;
 }
 
-// Persistent: one CTA per SM loops over work items (batch, head, 128-key tile).  K/V are
-// double-buffered across items and Q/dO tiles stream through a 2-slot ring, so the producer is
-// always one item ahead and set-up (TMEM allocation, barrier init, first loads) is paid once.
+// Persistent: one CTA per SM loops over work items (batch, head, 128-key tile); Q/dO tiles stream
+// through a 2-slot ring that runs ahead across items.  Software pipeline inside an item (measured
+// with the clock64 timeline hook: S/dP MMAs 770 cycles, exp/dS math 1700, dV/dK/dQ MMAs 1650):
+// P/dS are double-buffered in shared memory and dQ in tensor memory, and the S/dP product of query
+// tile i+1 is issued BEFORE the dV/dK/dQ products of tile i, so the exponent/dS math of tile i+1
+// runs on the CUDA cores while the tensor core finishes tile i.
 template <int HD>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -60,27 +63,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmdV, const AttnBwdParams p) {
   using Cfg = AttnBwdCfg<HD>;
   constexpr int T = Cfg::T, TB = Cfg::TILE_BYTES, RB = Cfg::ROW_BYTES, AB = Cfg::ATOM_BYTES;
+  constexpr int PSB = Cfg::PS_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* kv_s = smem;             // [2 buffers][K, V]
-  uint8_t* q_s = kv_s + 4 * TB;     // [2]
+  uint8_t* kv_s = smem;             // [K, V]
+  uint8_t* q_s = kv_s + 2 * TB;     // [2]
   uint8_t* do_s = q_s + 2 * TB;     // [2]
-  uint8_t* p_s = do_s + 2 * TB;
-  uint8_t* ds_s = p_s + Cfg::PS_BYTES;
-  uint8_t* dq_s = ds_s + Cfg::PS_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dq_s + Cfg::DQ_STAGE);
-  uint64_t* kv_full = bars;          // [2]
-  uint64_t* kv_empty = bars + 2;     // [2]
-  uint64_t* qdo_full = bars + 4;     // [2]
-  uint64_t* qdo_empty = bars + 6;    // [2]
-  uint64_t* sdp_full = bars + 8;
-  uint64_t* sdp_empty = bars + 9;
-  uint64_t* pds_full = bars + 10;
-  uint64_t* dq_full = bars + 11;
-  uint64_t* dq_empty = bars + 12;
-  uint64_t* dkv_full = bars + 13;
-  uint64_t* dkv_empty = bars + 14;
+  uint8_t* p_s = do_s + 2 * TB;     // [2]
+  uint8_t* ds_s = p_s + 2 * PSB;    // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ds_s + 2 * PSB);
+  uint64_t* kv_full = bars;          // 1
+  uint64_t* kv_empty = bars + 1;     // 1
+  uint64_t* qdo_full = bars + 2;     // [2]
+  uint64_t* qdo_empty = bars + 4;    // [2]
+  uint64_t* sdp_full = bars + 6;
+  uint64_t* sdp_empty = bars + 7;
+  uint64_t* pds_full = bars + 8;     // [2]
+  uint64_t* dq_full = bars + 10;     // [2]
+  uint64_t* dq_empty = bars + 12;    // [2]
+  uint64_t* dkv_full = bars + 14;
+  uint64_t* dkv_empty = bars + 15;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,15 +92,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     tma_prefetch_desc(&tmdQacc); tma_prefetch_desc(&tmdK); tma_prefetch_desc(&tmdV);
+    mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
       mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
+      mbar_init(&pds_full[i], 256);
+      mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 256);
     }
     mbar_init(sdp_full, 1);
     mbar_init(sdp_empty, 256);
-    mbar_init(pds_full, 256);
-    mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 256);
     mbar_init(dkv_full, 1);
     mbar_init(dkv_empty, 256);
     fence_barrier_init();
@@ -108,7 +110,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dv = tmem_base + 256, t_dk = tmem_base + 320,
-                 t_dq = tmem_base + 384;
+                 t_dq = tmem_base + 384;   // two dQ buffers: +0, +64
 
   auto decode = [&](int item, int& b, int& h, int& k0) {
     const int jt = item % p.nkt;
@@ -124,11 +126,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         int b, h, k0;
         decode(item, b, h, k0);
-        const int kb = it & 1;
-        mbar_wait(&kv_empty[kb], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[kb], 2 * TB);
-        tma_load_4d(kv_s + (kb * 2 + 0) * TB, &tmK, &kv_full[kb], 0, h, k0, b);
-        tma_load_4d(kv_s + (kb * 2 + 1) * TB, &tmV, &kv_full[kb], 0, h, k0, b);
+        mbar_wait(kv_empty, (it & 1) ^ 1);
+        mbar_expect_tx(kv_full, 2 * TB);
+        tma_load_4d(kv_s, &tmK, kv_full, 0, h, k0, b);
+        tma_load_4d(kv_s + TB, &tmV, kv_full, 0, h, k0, b);
         for (int i = 0; i < nq; ++i, ++qr) {
           const int slot = qr & 1;
           mbar_wait(&qdo_empty[slot], ((qr >> 1) & 1) ^ 1);
@@ -143,30 +144,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_qk = umma_idesc_bf16(T, T, false, false);     // S, dP
       constexpr uint32_t idesc_tn = umma_idesc_bf16(T, HD, true, true);      // dV, dK
       constexpr uint32_t idesc_dq = umma_idesc_bf16(T, HD, false, true);     // dQ
-      const uint32_t p_addr = smem_u32(p_s), ds_addr = smem_u32(ds_s);
-      uint32_t it = 0, qr = 0, tc = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        const int kb = it & 1;
-        const uint32_t k_addr = smem_u32(kv_s + (kb * 2 + 0) * TB), v_addr = smem_u32(kv_s + (kb * 2 + 1) * TB);
-        mbar_wait(&kv_full[kb], (it >> 1) & 1);
-        for (int i = 0; i < nq; ++i, ++qr, ++tc) {
-          const int slot = qr & 1;
-          const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
-          mbar_wait(&qdo_full[slot], (qr >> 1) & 1);
-          mbar_wait(sdp_empty, (tc & 1) ^ 1);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16(t_s, bwd_desc<RB>(q_addr + k * 32, 16, AB), bwd_desc<RB>(k_addr + k * 32, 16, AB), idesc_qk, k > 0);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16(t_dp, bwd_desc<RB>(do_addr + k * 32, 16, AB), bwd_desc<RB>(v_addr + k * 32, 16, AB), idesc_qk, k > 0);
-          umma_commit(sdp_full);
+      const uint32_t k_addr = smem_u32(kv_s), v_addr = smem_u32(kv_s + TB);
+      uint32_t it = 0, tc = 0;      // tc: global query-tile counter (ring slot, P/dS buffer, dQ buffer = tc & 1)
 
-          mbar_wait(pds_full, tc & 1);
-          mbar_wait(dq_empty, (tc & 1) ^ 1);
+      auto issue_sdp = [&](uint32_t t) {        // S, dP of global tile t
+        const int slot = t & 1;
+        const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
+        mbar_wait(&qdo_full[slot], (t >> 1) & 1);
+        mbar_wait(sdp_empty, (t & 1) ^ 1);
+        tc_fence_after();
+        if (p.timeline && blockIdx.x == 0 && t < 4) p.timeline[t * 8 + 0] = clock64();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(t_s, bwd_desc<RB>(q_addr + k * 32, 16, AB), bwd_desc<RB>(k_addr + k * 32, 16, AB), idesc_qk, k > 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(t_dp, bwd_desc<RB>(do_addr + k * 32, 16, AB), bwd_desc<RB>(v_addr + k * 32, 16, AB), idesc_qk, k > 0);
+        umma_commit(sdp_full);
+      };
+
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        mbar_wait(kv_full, it & 1);
+        issue_sdp(tc);
+        for (int i = 0; i < nq; ++i, ++tc) {
+          const int slot = tc & 1, pb = tc & 1;
+          const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
+          const uint32_t p_addr = smem_u32(p_s + pb * PSB), ds_addr = smem_u32(ds_s + pb * PSB);
+          mbar_wait(&pds_full[pb], (tc >> 1) & 1);
+          if (i + 1 < nq) issue_sdp(tc + 1);            // next tile's S/dP goes first: its math overlaps the MMAs below
+          mbar_wait(&dq_empty[pb], ((tc >> 1) & 1) ^ 1);
           if (i == 0) mbar_wait(dkv_empty, (it & 1) ^ 1);   // previous item's dK/dV have left TMEM
           tc_fence_after();
+          if (p.timeline && blockIdx.x == 0 && tc < 4) p.timeline[tc * 8 + 1] = clock64();
           // dV += P^T dO_i ; dK += dS^T Q_i   (reduction over the 128 query rows, 16 per MMA)
 #pragma unroll
           for (int kk = 0; kk < T / 16; ++kk)
@@ -179,13 +188,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           // dQ_i = dS K_j   (reduction over the 128 keys)
 #pragma unroll
           for (int kk = 0; kk < T / 16; ++kk)
-            umma_bf16(t_dq, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+            umma_bf16(t_dq + pb * 64, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                       bwd_desc<RB>(k_addr + kk * 2 * AB, 0, AB), idesc_dq, kk > 0 ? 1u : 0u);
-          umma_commit(dq_full);
+          umma_commit(&dq_full[pb]);
           umma_commit(&qdo_empty[slot]);
         }
         umma_commit(dkv_full);
-        umma_commit(&kv_empty[kb]);
+        umma_commit(kv_empty);
       }
     }
   } else {
@@ -200,32 +209,61 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t row_sw = row & 7;
     const uint32_t lrow_sw = lane & 7;
     constexpr int HH = HD / 2;                                // head-dim columns per warp (32 or 16)
-    uint8_t* p_row = p_s + half * 16384 + row * 128;          // this warp's 64-key block of P / dS
-    uint8_t* ds_row = ds_s + half * 16384 + row * 128;
-    uint8_t* my_dq = dq_s + cw * (32 * HH * 4);               // 32 rows x HH fp32
-    // dK/dV staging: 32 rows x HH bf16, in rows of this warp's own P / dS block
-    uint8_t* st_dv = p_s + half * 16384 + qd * 4096;
-    uint8_t* st_dk = ds_s + half * 16384 + qd * 4096;
+    const uint32_t blk_off = half * 16384 + row * 128;        // this thread's row in its 64-key block of P / dS
+    const uint32_t stage_off = half * 16384 + qd * 4096;      // 4 KB of this warp's OWN rows, reused for staging
     const float LOG2E = 1.4426950408889634f;
     uint32_t it = 0, tc = 0;
+
+    // dQ of global tile t (its MMAs have completed): TMEM -> fp32 staging (dead P rows) -> TMA reduce-add
+    auto flush_dq = [&](uint32_t t, int b, int h, int qrow0) {
+      const uint32_t pb = t & 1;
+      mbar_wait(&dq_full[pb], (t >> 1) & 1);
+      tc_fence_after();
+      if (p.timeline && blockIdx.x == 0 && t < 4 && threadIdx.x == 64) p.timeline[t * 8 + 4] = clock64();
+      uint8_t* my_dq = p_s + pb * PSB + stage_off;
+      uint32_t v[HH];
+      if (HH == 32) tmem_ld32(t_dq + pb * 64 + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      else tmem_ld16(t_dq + pb * 64 + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+      tmem_wait_ld();
+#pragma unroll
+      for (int g = 0; g < HH / 4; ++g) {
+        uint8_t* dst = (HH == 32) ? my_dq + lane * 128 + ((static_cast<uint32_t>(g) ^ lrow_sw) << 4)
+                                  : my_dq + lane * 64 + ((static_cast<uint32_t>(g) ^ ((lane >> 1) & 3)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      }
+      tc_fence_before();
+      mbar_arrive(&dq_empty[pb]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && qrow0 + qd * 32 < p.Nq) {
+        tma_reduce_add_4d(&tmdQacc, my_dq, half * HH, h, qrow0 + qd * 32, b);
+        tma_store_commit();
+      }
+      if (p.timeline && blockIdx.x == 0 && t < 4 && threadIdx.x == 64) p.timeline[t * 8 + 5] = clock64();
+    };
 
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       int b, h, k0;
       decode(item, b, h, k0);
       const long long stat_base = (static_cast<long long>(b) * p.H + h) * p.Nq;
       for (int i = 0; i < nq; ++i, ++tc) {
+        const uint32_t pb = tc & 1;
         const int qrow = i * T + row;
-        float nlse = -INFINITY, delta = 0.f;   // rows past Nq: P = exp2(-inf) = 0
+        float lse_v = INFINITY, delta = 0.f;   // rows past Nq: P = exp2(-inf) = 0
         if (qrow < p.Nq) {
-          nlse = -p.lse[stat_base + qrow] * LOG2E;
+          lse_v = p.lse[stat_base + qrow];
           delta = p.delta[stat_base + qrow];
         }
-        // every earlier TMA store of this warp (dQ staging, dK/dV staging == P/dS rows) has been read
+        // every earlier TMA store of this warp has finished reading its staging rows (== P/dS rows)
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
         mbar_wait(sdp_full, tc & 1);
         tc_fence_after();
+        if (p.timeline && blockIdx.x == 0 && tc < 4 && threadIdx.x == 64) p.timeline[tc * 8 + 2] = clock64();
+        const float nlse = -lse_v * LOG2E;
         const float2 sl2 = mk2(p.scale_log2), nlse2 = mk2(nlse), sc2 = mk2(p.scale), nds2 = mk2(-delta * p.scale);
+        uint8_t* p_row = p_s + pb * PSB + blk_off;
+        uint8_t* ds_row = ds_s + pb * PSB + blk_off;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           uint32_t sv[32], dv[32];
@@ -252,37 +290,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_before();
         mbar_arrive(sdp_empty);
         fence_proxy_async_smem();
-        mbar_arrive(pds_full);
-
-        // dQ_i tile (this warp's HH columns) -> fp32 staging -> TMA reduce-add
-        mbar_wait(dq_full, tc & 1);
-        tc_fence_after();
-        {
-          uint32_t v[HH];
-          if (HH == 32) tmem_ld32(t_dq + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          else tmem_ld16(t_dq + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-          tmem_wait_ld();
-          // rows of HH fp32 = 128 B (SWIZZLE_128B) or 64 B (SWIZZLE_64B)
-#pragma unroll
-          for (int g = 0; g < HH / 4; ++g) {
-            uint8_t* dst = (HH == 32) ? my_dq + lane * 128 + ((static_cast<uint32_t>(g) ^ lrow_sw) << 4)
-                                      : my_dq + lane * 64 + ((static_cast<uint32_t>(g) ^ ((lane >> 1) & 3)) << 4);
-            *reinterpret_cast<uint4*>(dst) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(dq_empty);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0 && i * T + qd * 32 < p.Nq) {
-          tma_reduce_add_4d(&tmdQacc, my_dq, half * HH, h, i * T + qd * 32, b);
-          tma_store_commit();
-        }
+        mbar_arrive(&pds_full[pb]);
+        if (p.timeline && blockIdx.x == 0 && tc < 4 && threadIdx.x == 64) p.timeline[tc * 8 + 3] = clock64();
+        // the previous tile's dQ is drained one tile late, so it never delays this tile's math
+        if (i > 0) flush_dq(tc - 1, b, h, (i - 1) * T);
       }
+      flush_dq(tc - 1, b, h, (nq - 1) * T);
 
-      // ---- dK_j, dV_j: TMEM -> bf16 -> staging (this item's P / dS are dead) -> TMA store
+      // ---- dK_j, dV_j: TMEM -> bf16 -> staging (both dS buffers are dead) -> TMA store
       mbar_wait(dkv_full, it & 1);
       tc_fence_after();
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      uint8_t* st_dv = ds_s + stage_off;
+      uint8_t* st_dk = ds_s + PSB + stage_off;
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
         uint8_t* st = which == 0 ? st_dv : st_dk;
@@ -380,6 +401,10 @@ attn_dq_cast_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ d
 
 using namespace ucf;
 
+static long long* g_bwd_timeline = nullptr;
+/* profiling aid (not part of the public header): device buffer of 64 int64 receiving clock64 stamps */
+extern "C" void ucf_debug_set_attn_bwd_timeline(void* dev_ptr) { g_bwd_timeline = static_cast<long long*>(dev_ptr); }
+
 extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                                  const float* lse, void* dq, void* dk, void* dv, float* dq_acc, float* delta,
                                  int B, int H, int Nq, int Nk, int hd,
@@ -441,6 +466,7 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
   p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse; p.delta = delta;
+  p.timeline = g_bwd_timeline;
   p.nkt = (Nk + 127) / 128;
   const long long n_items = static_cast<long long>(B) * H * p.nkt;
   if (n_items > 0x7fffffffLL) { set_last_error("attention_bwd: too many work items"); return UCF_ERR_BAD_ARG; }

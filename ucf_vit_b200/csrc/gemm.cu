@@ -696,6 +696,12 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
   if (splits < 1) splits = 1;
 
   // tile_n: 128 / 256 = single-CTA kernels; 512 = CTA-pair kernel (256 x 256 tile per 2-CTA cluster)
+  // auto (tile_n == 0): tall problems with several 256-wide column tiles go to the CTA-pair kernel
+  // (measured +7..11 % on the ViT-B shapes); everything else to the single-CTA kernels.
+  const bool pair_supported =
+      (!a_mn && !b_mn && (epilogue == EPI_BIAS || epilogue == EPI_BIAS_RESIDUAL || epilogue == EPI_BIAS_GELU_AUX)) ||
+      (!a_mn && b_mn && (epilogue == EPI_BIAS || epilogue == EPI_DGELU)) || (a_mn && b_mn && epilogue == EPI_F32_ADD);
+  if (tile_n == 0 && pair_supported && M >= 1024 && N >= 512 && N <= 4096) tile_n = 512;
   const bool pair = tile_n == 512;
   int BN = pair ? 256 : tile_n;
   if (BN != 128 && BN != 256) BN = (N <= 128 || (N % 256 != 0 && N % 128 == 0 && N < 1024)) ? 128 : 256;
