@@ -73,8 +73,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* p_s = do_s + 2 * TB;     // [2]
   uint8_t* ds_s = p_s + 2 * PSB;    // [2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ds_s + 2 * PSB);
-  uint64_t* kv_full = bars;          // 1
-  uint64_t* kv_empty = bars + 1;     // 1
+  uint64_t* kv_full = bars;          // K and V of the item have landed
+  uint64_t* k_empty = bars + 1;      // K released right after the item's last dQ product
+  uint64_t* v_empty = bars + 16;     // V released right after the item's last dP product
   uint64_t* qdo_full = bars + 2;     // [2]
   uint64_t* qdo_empty = bars + 4;    // [2]
   uint64_t* sdp_full = bars + 6;
@@ -92,7 +93,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     tma_prefetch_desc(&tmdQacc); tma_prefetch_desc(&tmdK); tma_prefetch_desc(&tmdV);
-    mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+    mbar_init(kv_full, 1); mbar_init(k_empty, 1); mbar_init(v_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
       mbar_init(&pds_full[i], 256);
@@ -126,10 +127,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         int b, h, k0;
         decode(item, b, h, k0);
-        mbar_wait(kv_empty, (it & 1) ^ 1);
+        // V is dead after the item's last dP product, K after its last dQ product: both are
+        // released (and re-filled for the next item) while the remaining dK/dV MMAs still run
+        mbar_wait(v_empty, (it & 1) ^ 1);
         mbar_expect_tx(kv_full, 2 * TB);
-        tma_load_4d(kv_s, &tmK, kv_full, 0, h, k0, b);
         tma_load_4d(kv_s + TB, &tmV, kv_full, 0, h, k0, b);
+        mbar_wait(k_empty, (it & 1) ^ 1);
+        tma_load_4d(kv_s, &tmK, kv_full, 0, h, k0, b);
         for (int i = 0; i < nq; ++i, ++qr) {
           const int slot = qr & 1;
           mbar_wait(&qdo_empty[slot], ((qr >> 1) & 1) ^ 1);
@@ -147,7 +151,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t k_addr = smem_u32(kv_s), v_addr = smem_u32(kv_s + TB);
       uint32_t it = 0, tc = 0;      // tc: global query-tile counter (ring slot, P/dS buffer, dQ buffer = tc & 1)
 
-      auto issue_sdp = [&](uint32_t t) {        // S, dP of global tile t
+      auto issue_sdp = [&](uint32_t t, bool last_of_item) {        // S, dP of global tile t
         const int slot = t & 1;
         const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
         mbar_wait(&qdo_full[slot], (t >> 1) & 1);
@@ -161,21 +165,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16(t_dp, bwd_desc<RB>(do_addr + k * 32, 16, AB), bwd_desc<RB>(v_addr + k * 32, 16, AB), idesc_qk, k > 0);
         umma_commit(sdp_full);
+        if (last_of_item) umma_commit(v_empty);       // no later product of this item reads V
       };
 
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         mbar_wait(kv_full, it & 1);
-        issue_sdp(tc);
+        issue_sdp(tc, nq == 1);
         for (int i = 0; i < nq; ++i, ++tc) {
           const int slot = tc & 1, pb = tc & 1;
           const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
           const uint32_t p_addr = smem_u32(p_s + pb * PSB), ds_addr = smem_u32(ds_s + pb * PSB);
           mbar_wait(&pds_full[pb], (tc >> 1) & 1);
-          if (i + 1 < nq) issue_sdp(tc + 1);            // next tile's S/dP goes first: its math overlaps the MMAs below
+          if (i + 1 < nq) issue_sdp(tc + 1, i + 2 == nq);   // next tile's S/dP goes first: its math overlaps the MMAs below
           mbar_wait(&dq_empty[pb], ((tc >> 1) & 1) ^ 1);
           if (i == 0) mbar_wait(dkv_empty, (it & 1) ^ 1);   // previous item's dK/dV have left TMEM
           tc_fence_after();
           if (p.timeline && blockIdx.x == 0 && tc < 4) p.timeline[tc * 8 + 1] = clock64();
+          // dQ_i = dS K_j   (reduction over the 128 keys) -- first, so that K can be released early
+#pragma unroll
+          for (int kk = 0; kk < T / 16; ++kk)
+            umma_bf16(t_dq + pb * 64, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                      bwd_desc<RB>(k_addr + kk * 2 * AB, 0, AB), idesc_dq, kk > 0 ? 1u : 0u);
+          if (i + 1 == nq) umma_commit(k_empty);
           // dV += P^T dO_i ; dK += dS^T Q_i   (reduction over the 128 query rows, 16 per MMA)
 #pragma unroll
           for (int kk = 0; kk < T / 16; ++kk)
@@ -185,16 +196,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int kk = 0; kk < T / 16; ++kk)
             umma_bf16(t_dk, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(q_addr + kk * 2 * AB, 0, AB),
                       idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
-          // dQ_i = dS K_j   (reduction over the 128 keys)
-#pragma unroll
-          for (int kk = 0; kk < T / 16; ++kk)
-            umma_bf16(t_dq + pb * 64, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                      bwd_desc<RB>(k_addr + kk * 2 * AB, 0, AB), idesc_dq, kk > 0 ? 1u : 0u);
+          // dq_full doubles as "every product of tile i has retired": the dQ staging area is made of
+          // rows of P[pb], which the dV product above is still reading until then
           umma_commit(&dq_full[pb]);
           umma_commit(&qdo_empty[slot]);
         }
         umma_commit(dkv_full);
-        umma_commit(kv_empty);
       }
     }
   } else {

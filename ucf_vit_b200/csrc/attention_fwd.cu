@@ -26,6 +26,7 @@ struct AttnFwdParams {
   int items;          // B * H * nqp
   float scale_log2;   // scale * log2(e)
   float* lse;         // [B, H, Nq]
+  long long* timeline;   // optional clock64 stamps of CTA 0 (profiling aid; NULL in production)
 };
 
 template <int HD>
@@ -149,6 +150,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         auto issue_s = [&](int g, uint32_t k_addr) {
           mbar_wait(&s_empty[g], (tc[g] & 1) ^ 1);
           tc_fence_after();
+          if (p.timeline && blockIdx.x == 0 && tc[g] < 4) p.timeline[(g * 4 + tc[g]) * 8 + 0] = clock64();   // S issue
           const uint32_t d = tmem_base + g * 256;
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k)
@@ -159,6 +161,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         auto issue_pv = [&](int g, uint32_t v_addr) {
           mbar_wait(&p_full[g], tc[g] & 1);
           tc_fence_after();
+          if (p.timeline && blockIdx.x == 0 && tc[g] < 4) p.timeline[(g * 4 + tc[g]) * 8 + 1] = clock64();   // PV issue
           const uint32_t d = tmem_base + g * 256 + 128;
           const uint32_t pa = p_addr0 + g * Cfg::P_BYTES;
 #pragma unroll
@@ -230,6 +233,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int j = 0; j < nkv; ++j, ++tc) {
         mbar_wait(&s_full[g], tc & 1);
         tc_fence_after();
+        const bool stamp = p.timeline && blockIdx.x == 0 && tc < 4 && (threadIdx.x & 127) == 64;
+        if (stamp) p.timeline[(g * 4 + tc) * 8 + 2] = clock64();   // S visible
         const int kbase = j * BKV;
         const int nvalid = min(BKV, p.Nk - kbase);          // keys of this tile that exist
         const int nchunk = (nvalid + 31) >> 5;
@@ -250,6 +255,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               if (c * 32 + e < nvalid) m_tile = fmaxf(m_tile, __uint_as_float(v[e]));
           }
         }
+        if (stamp) p.timeline[(g * 4 + tc) * 8 + 3] = clock64();   // pass 1 done
         const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
         const float alpha = exp2f(m_run - m_new);            // first tile: exp2(-inf) = 0
         if (j > 0) {                                          // fold PV_{j-1}; also frees the P buffer
@@ -305,6 +311,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_arrive(&s_empty[g]);        // S_g may be overwritten by the next QK^T
         fence_proxy_async_smem();
         mbar_arrive(&p_full[g]);         // P_g(j) visible to the tensor core
+        if (stamp) p.timeline[(g * 4 + tc) * 8 + 4] = clock64();   // P written
         l_run = fmaf(l_run, alpha, l2.x + l2.y);
         m_run = m_new;
         alpha_prev = alpha;
@@ -394,6 +401,10 @@ static int launch_attn_fwd(const CUtensorMap& tQ, const CUtensorMap& tK, const C
 
 using namespace ucf;
 
+static long long* g_fwd_timeline = nullptr;
+/* profiling aid (not part of the public header): device buffer of 64 int64 receiving clock64 stamps */
+extern "C" void ucf_debug_set_attn_fwd_timeline(void* dev_ptr) { g_fwd_timeline = static_cast<long long*>(dev_ptr); }
+
 extern "C" int ucf_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
                                  int B, int H, int Nq, int Nk, int hd,
                                  long long q_sb, long long q_sn, long long q_sh,
@@ -429,6 +440,7 @@ extern "C" int ucf_attention_fwd(const void* q, const void* k, const void* v, vo
   p.items = static_cast<int>(items);
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
+  p.timeline = g_fwd_timeline;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return hd == 64 ? launch_attn_fwd<64>(tQ, tK, tV, tO, p, st) : launch_attn_fwd<32>(tQ, tK, tV, tO, p, st);
 }
