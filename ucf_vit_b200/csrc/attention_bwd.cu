@@ -34,9 +34,9 @@ struct AttnBwdCfg {
   static constexpr int T = 128;
   static constexpr int TILE_BYTES = T * HD * 2;       // one Q / K / V / dO tile
   static constexpr int PS_BYTES = T * T * 2;          // P or dS
-  static constexpr int NBAR = 20;
-  // K,V (one item) | Q x2 | dO x2 | P x2 | dS x2.  dQ / dK / dV staging reuses dead P / dS rows.
-  static constexpr int SMEM_BYTES = 1024 + 2 * TILE_BYTES + 4 * TILE_BYTES + 4 * PS_BYTES + NBAR * 8 + 16;
+  static constexpr int NBAR = 24;
+  // K,V x2 (per item) | Q x2 | dO x2 | P | dS x2.   dQ / dK / dV staging reuses dead dS rows.
+  static constexpr int SMEM_BYTES = 1024 + 4 * TILE_BYTES + 4 * TILE_BYTES + 3 * PS_BYTES + NBAR * 8 + 16;
   static constexpr int ROW_BYTES = HD * 2;
   static constexpr int ATOM_BYTES = 8 * ROW_BYTES;
   static_assert(SMEM_BYTES <= 232448, "smem");
@@ -49,12 +49,19 @@ __device__ __forceinline__ uint64_t bwd_desc(uint32_t saddr, uint32_t lbo, uint3
   return d;
 }
 
-// Persistent: one CTA per SM loops over work items (batch, head, 128-key tile); Q/dO tiles stream
-// through a 2-slot ring that runs ahead across items.  Software pipeline inside an item (measured
-// with the clock64 timeline hook: S/dP MMAs 770 cycles, exp/dS math 1700, dV/dK/dQ MMAs 1650):
-// P/dS are double-buffered in shared memory and dQ in tensor memory, and the S/dP product of query
-// tile i+1 is issued BEFORE the dV/dK/dQ products of tile i, so the exponent/dS math of tile i+1
-// runs on the CUDA cores while the tensor core finishes tile i.
+// Persistent: one CTA per SM walks ONE continuous stream of (item, query-tile) pairs, item =
+// (batch, head, 128-key tile).  The tensor core is the critical resource (all five products read
+// both operands from shared memory: ~224 KB of operand traffic per tile), so everything else is
+// arranged to keep it fed (cycle counts from the clock64 timeline hook at N = 197, hd = 64:
+// S/dP 770, exp/dS math 1700-1800, dV+dQ+dK 2200):
+//   * K/V are double-buffered per item and Q/dO stream through a 2-slot ring, so the producer
+//     runs a whole item ahead -- no load bubble at item boundaries;
+//   * per tile the issue order is S/dP(t+1), dV(t), dQ(t), dK(t): the next tile's S/dP goes first so
+//     that its exp/dS math runs on the CUDA cores under all three products of tile t; dS and the
+//     dQ accumulator are double-buffered, the single P buffer is written last (P waits in
+//     registers until dV(t) has retired);
+//   * the compute warps drain dQ(t-1) after the math of tile t, and an item's dK/dV after the
+//     math of the NEXT item's first tile, so draining never delays math.
 template <int HD>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -67,34 +74,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* kv_s = smem;             // [K, V]
-  uint8_t* q_s = kv_s + 2 * TB;     // [2]
+  uint8_t* kv_s = smem;             // [2 items][K, V]
+  uint8_t* q_s = kv_s + 4 * TB;     // [2]
   uint8_t* do_s = q_s + 2 * TB;     // [2]
-  uint8_t* p_s = do_s + 2 * TB;     // [2]
-  uint8_t* ds_s = p_s + 2 * PSB;    // [2]
+  uint8_t* p_s = do_s + 2 * TB;     // [1]
+  uint8_t* ds_s = p_s + PSB;        // [2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ds_s + 2 * PSB);
-  uint64_t* kv_full = bars;          // K and V of the item have landed
-  uint64_t* k_empty = bars + 1;      // K released right after the item's last dQ product
-  uint64_t* v_empty = bars + 16;     // V released right after the item's last dP product
-  uint64_t* qdo_full = bars + 2;     // [2]
-  uint64_t* qdo_empty = bars + 4;    // [2]
-  uint64_t* sdp_full = bars + 6;
-  uint64_t* sdp_empty = bars + 7;
-  uint64_t* pds_full = bars + 8;     // [2]
-  uint64_t* dq_full = bars + 10;     // [2]
-  uint64_t* dq_empty = bars + 12;    // [2]
-  uint64_t* dkv_full = bars + 14;
-  uint64_t* dkv_empty = bars + 15;
+  uint64_t* kv_full = bars;          // [2]
+  uint64_t* kv_empty = bars + 2;     // [2]
+  uint64_t* qdo_full = bars + 4;     // [2]
+  uint64_t* qdo_empty = bars + 6;    // [2]
+  uint64_t* sdp_full = bars + 8;
+  uint64_t* sdp_empty = bars + 9;
+  uint64_t* pds_full = bars + 10;    // [2]
+  uint64_t* dq_full = bars + 12;     // [2]  (also: every product of that tile has retired)
+  uint64_t* dq_empty = bars + 14;    // [2]
+  uint64_t* dkv_full = bars + 16;
+  uint64_t* dkv_empty = bars + 17;
+  uint64_t* p_free = bars + 18;      // dV(t) retired: P may be rewritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = (p.Nq + T - 1) / T;
+  const int my_items = (p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const uint32_t total_tiles = static_cast<uint32_t>(my_items) * nq;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     tma_prefetch_desc(&tmdQacc); tma_prefetch_desc(&tmdK); tma_prefetch_desc(&tmdV);
-    mbar_init(kv_full, 1); mbar_init(k_empty, 1); mbar_init(v_empty, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
       mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
       mbar_init(&pds_full[i], 256);
       mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 256);
@@ -103,6 +112,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(sdp_empty, 256);
     mbar_init(dkv_full, 1);
     mbar_init(dkv_empty, 256);
+    mbar_init(p_free, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -113,7 +123,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dv = tmem_base + 256, t_dk = tmem_base + 320,
                  t_dq = tmem_base + 384;   // two dQ buffers: +0, +64
 
-  auto decode = [&](int item, int& b, int& h, int& k0) {
+  // n-th item of this CTA -> (b, h, first key row)
+  auto decode = [&](uint32_t n, int& b, int& h, int& k0) {
+    const int item = static_cast<int>(blockIdx.x) + static_cast<int>(n) * static_cast<int>(gridDim.x);
     const int jt = item % p.nkt;
     const int bh = item / p.nkt;
     h = bh % p.H;
@@ -122,21 +134,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   };
 
   if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t it = 0, qr = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      uint32_t t = 0;
+      for (uint32_t n = 0; n < static_cast<uint32_t>(my_items); ++n) {
         int b, h, k0;
-        decode(item, b, h, k0);
-        // V is dead after the item's last dP product, K after its last dQ product: both are
-        // released (and re-filled for the next item) while the remaining dK/dV MMAs still run
-        mbar_wait(v_empty, (it & 1) ^ 1);
-        mbar_expect_tx(kv_full, 2 * TB);
-        tma_load_4d(kv_s + TB, &tmV, kv_full, 0, h, k0, b);
-        mbar_wait(k_empty, (it & 1) ^ 1);
-        tma_load_4d(kv_s, &tmK, kv_full, 0, h, k0, b);
-        for (int i = 0; i < nq; ++i, ++qr) {
-          const int slot = qr & 1;
-          mbar_wait(&qdo_empty[slot], ((qr >> 1) & 1) ^ 1);
+        decode(n, b, h, k0);
+        const int kb = n & 1;
+        mbar_wait(&kv_empty[kb], ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[kb], 2 * TB);
+        tma_load_4d(kv_s + (kb * 2 + 0) * TB, &tmK, &kv_full[kb], 0, h, k0, b);
+        tma_load_4d(kv_s + (kb * 2 + 1) * TB, &tmV, &kv_full[kb], 0, h, k0, b);
+        for (int i = 0; i < nq; ++i, ++t) {
+          const int slot = t & 1;
+          mbar_wait(&qdo_empty[slot], ((t >> 1) & 1) ^ 1);
           mbar_expect_tx(&qdo_full[slot], 2 * TB);
           tma_load_4d(q_s + slot * TB, &tmQ, &qdo_full[slot], 0, h, i * T, b);
           tma_load_4d(do_s + slot * TB, &tmdO, &qdo_full[slot], 0, h, i * T, b);
@@ -144,15 +155,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && total_tiles > 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(T, T, false, false);     // S, dP
       constexpr uint32_t idesc_tn = umma_idesc_bf16(T, HD, true, true);      // dV, dK
       constexpr uint32_t idesc_dq = umma_idesc_bf16(T, HD, false, true);     // dQ
-      const uint32_t k_addr = smem_u32(kv_s), v_addr = smem_u32(kv_s + TB);
-      uint32_t it = 0, tc = 0;      // tc: global query-tile counter (ring slot, P/dS buffer, dQ buffer = tc & 1)
+      const uint32_t p_addr = smem_u32(p_s);
 
-      auto issue_sdp = [&](uint32_t t, bool last_of_item) {        // S, dP of global tile t
+      auto issue_sdp = [&](uint32_t t) {        // S, dP of global tile t (item n = t / nq)
+        const uint32_t n = t / nq;
+        if (t % nq == 0) mbar_wait(&kv_full[n & 1], (n >> 1) & 1);
         const int slot = t & 1;
+        const uint32_t k_addr = smem_u32(kv_s + ((n & 1) * 2 + 0) * TB), v_addr = smem_u32(kv_s + ((n & 1) * 2 + 1) * TB);
         const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
         mbar_wait(&qdo_full[slot], (t >> 1) & 1);
         mbar_wait(sdp_empty, (t & 1) ^ 1);
@@ -165,43 +179,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16(t_dp, bwd_desc<RB>(do_addr + k * 32, 16, AB), bwd_desc<RB>(v_addr + k * 32, 16, AB), idesc_qk, k > 0);
         umma_commit(sdp_full);
-        if (last_of_item) umma_commit(v_empty);       // no later product of this item reads V
       };
 
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        mbar_wait(kv_full, it & 1);
-        issue_sdp(tc, nq == 1);
-        for (int i = 0; i < nq; ++i, ++tc) {
-          const int slot = tc & 1, pb = tc & 1;
-          const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
-          const uint32_t p_addr = smem_u32(p_s + pb * PSB), ds_addr = smem_u32(ds_s + pb * PSB);
-          mbar_wait(&pds_full[pb], (tc >> 1) & 1);
-          if (i + 1 < nq) issue_sdp(tc + 1, i + 2 == nq);   // next tile's S/dP goes first: its math overlaps the MMAs below
-          mbar_wait(&dq_empty[pb], ((tc >> 1) & 1) ^ 1);
-          if (i == 0) mbar_wait(dkv_empty, (it & 1) ^ 1);   // previous item's dK/dV have left TMEM
-          tc_fence_after();
-          if (p.timeline && blockIdx.x == 0 && tc < 4) p.timeline[tc * 8 + 1] = clock64();
-          // dQ_i = dS K_j   (reduction over the 128 keys) -- first, so that K can be released early
+      issue_sdp(0);
+      for (uint32_t t = 0; t < total_tiles; ++t) {
+        const uint32_t n = t / nq;
+        const int i = static_cast<int>(t - n * nq);
+        const int slot = t & 1, db = t & 1;
+        const uint32_t k_addr = smem_u32(kv_s + ((n & 1) * 2 + 0) * TB);
+        const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
+        const uint32_t ds_addr = smem_u32(ds_s + db * PSB);
+        mbar_wait(&pds_full[db], (t >> 1) & 1);                      // P(t), dS(t) are in shared memory
+        if (i == 0) mbar_wait(dkv_empty, (n & 1) ^ 1);               // previous item's dK/dV have left TMEM
+        tc_fence_after();
+        if (p.timeline && blockIdx.x == 0 && t < 4) p.timeline[t * 8 + 1] = clock64();
+        // next tile's S/dP first: its exp/dS math then overlaps all three products of tile t
+        if (t + 1 < total_tiles) issue_sdp(t + 1);
+        // dV += P^T dO_t   (reduction over the 128 query rows, 16 per MMA); releases the single P buffer
 #pragma unroll
-          for (int kk = 0; kk < T / 16; ++kk)
-            umma_bf16(t_dq + pb * 64, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                      bwd_desc<RB>(k_addr + kk * 2 * AB, 0, AB), idesc_dq, kk > 0 ? 1u : 0u);
-          if (i + 1 == nq) umma_commit(k_empty);
-          // dV += P^T dO_i ; dK += dS^T Q_i   (reduction over the 128 query rows, 16 per MMA)
+        for (int kk = 0; kk < T / 16; ++kk)
+          umma_bf16(t_dv, umma_smem_desc(p_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(do_addr + kk * 2 * AB, 0, AB),
+                    idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(p_free);
+        mbar_wait(&dq_empty[db], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        // dQ_t = dS K_j   (reduction over the 128 keys)
 #pragma unroll
-          for (int kk = 0; kk < T / 16; ++kk)
-            umma_bf16(t_dv, umma_smem_desc(p_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(do_addr + kk * 2 * AB, 0, AB),
-                      idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < T / 16; ++kk)
+          umma_bf16(t_dq + db * 64, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                    bwd_desc<RB>(k_addr + kk * 2 * AB, 0, AB), idesc_dq, kk > 0 ? 1u : 0u);
+        // dK += dS^T Q_t
 #pragma unroll
-          for (int kk = 0; kk < T / 16; ++kk)
-            umma_bf16(t_dk, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(q_addr + kk * 2 * AB, 0, AB),
-                      idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
-          // dq_full doubles as "every product of tile i has retired": the dQ staging area is made of
-          // rows of P[pb], which the dV product above is still reading until then
-          umma_commit(&dq_full[pb]);
-          umma_commit(&qdo_empty[slot]);
+        for (int kk = 0; kk < T / 16; ++kk)
+          umma_bf16(t_dk, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(q_addr + kk * 2 * AB, 0, AB),
+                    idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&dq_full[db]);          // every product of tile t has retired
+        umma_commit(&qdo_empty[slot]);
+        if (i + 1 == nq) {
+          umma_commit(dkv_full);
+          umma_commit(&kv_empty[n & 1]);
         }
-        umma_commit(dkv_full);
       }
     }
   } else {
@@ -217,20 +234,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lrow_sw = lane & 7;
     constexpr int HH = HD / 2;                                // head-dim columns per warp (32 or 16)
     const uint32_t blk_off = half * 16384 + row * 128;        // this thread's row in its 64-key block of P / dS
-    const uint32_t stage_off = half * 16384 + qd * 4096;      // 4 KB of this warp's OWN rows, reused for staging
+    const uint32_t stage_off = half * 16384 + qd * 4096;      // 4 KB of this warp's OWN dS rows, reused for staging
     const float LOG2E = 1.4426950408889634f;
-    uint32_t it = 0, tc = 0;
 
-    // dQ of global tile t (its MMAs have completed): TMEM -> fp32 staging (dead P rows) -> TMA reduce-add
+    // dQ of global tile t (all its products have retired): TMEM -> fp32 staging in the dead rows of
+    // dS[t&1] -> TMA reduce-add into dq_acc
     auto flush_dq = [&](uint32_t t, int b, int h, int qrow0) {
-      const uint32_t pb = t & 1;
-      mbar_wait(&dq_full[pb], (t >> 1) & 1);
+      const uint32_t db = t & 1;
+      mbar_wait(&dq_full[db], (t >> 1) & 1);
       tc_fence_after();
       if (p.timeline && blockIdx.x == 0 && t < 4 && threadIdx.x == 64) p.timeline[t * 8 + 4] = clock64();
-      uint8_t* my_dq = p_s + pb * PSB + stage_off;
+      uint8_t* my_dq = ds_s + db * PSB + stage_off;
       uint32_t v[HH];
-      if (HH == 32) tmem_ld32(t_dq + pb * 64 + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-      else tmem_ld16(t_dq + pb * 64 + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+      if (HH == 32) tmem_ld32(t_dq + db * 64 + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      else tmem_ld16(t_dq + db * 64 + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
       tmem_wait_ld();
 #pragma unroll
       for (int g = 0; g < HH / 4; ++g) {
@@ -239,7 +256,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         *reinterpret_cast<uint4*>(dst) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
       }
       tc_fence_before();
-      mbar_arrive(&dq_empty[pb]);
+      mbar_arrive(&dq_empty[db]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0 && qrow0 + qd * 32 < p.Nq) {
@@ -248,69 +265,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       if (p.timeline && blockIdx.x == 0 && t < 4 && threadIdx.x == 64) p.timeline[t * 8 + 5] = clock64();
     };
-
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      int b, h, k0;
-      decode(item, b, h, k0);
-      const long long stat_base = (static_cast<long long>(b) * p.H + h) * p.Nq;
-      for (int i = 0; i < nq; ++i, ++tc) {
-        const uint32_t pb = tc & 1;
-        const int qrow = i * T + row;
-        float lse_v = INFINITY, delta = 0.f;   // rows past Nq: P = exp2(-inf) = 0
-        if (qrow < p.Nq) {
-          lse_v = p.lse[stat_base + qrow];
-          delta = p.delta[stat_base + qrow];
-        }
-        // every earlier TMA store of this warp has finished reading its staging rows (== P/dS rows)
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-        mbar_wait(sdp_full, tc & 1);
-        tc_fence_after();
-        if (p.timeline && blockIdx.x == 0 && tc < 4 && threadIdx.x == 64) p.timeline[tc * 8 + 2] = clock64();
-        const float nlse = -lse_v * LOG2E;
-        const float2 sl2 = mk2(p.scale_log2), nlse2 = mk2(nlse), sc2 = mk2(p.scale), nds2 = mk2(-delta * p.scale);
-        uint8_t* p_row = p_s + pb * PSB + blk_off;
-        uint8_t* ds_row = ds_s + pb * PSB + blk_off;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t sv[32], dv[32];
-          tmem_ld32(t_s + lane_addr + half * 64 + c * 32, sv);
-          tmem_ld32(t_dp + lane_addr + half * 64 + c * 32, dv);
-          tmem_wait_ld();
-          uint32_t pk[16], dk[16];
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float2 t = __ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2, nlse2);
-            const float2 pp = make_float2(fast_ex2(t.x), fast_ex2(t.y));
-            // dS = scale * P * (dP - delta)
-            const float2 dd = __fmul2_rn(pp, __ffma2_rn(make_float2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), sc2, nds2));
-            pk[e >> 1] = pack_bf16x2(pp.x, pp.y);
-            dk[e >> 1] = pack_bf16x2(dd.x, dd.y);
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t off = ((static_cast<uint32_t>(c * 4 + g)) ^ row_sw) << 4;
-            *reinterpret_cast<uint4*>(p_row + off) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-            *reinterpret_cast<uint4*>(ds_row + off) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(sdp_empty);
-        fence_proxy_async_smem();
-        mbar_arrive(&pds_full[pb]);
-        if (p.timeline && blockIdx.x == 0 && tc < 4 && threadIdx.x == 64) p.timeline[tc * 8 + 3] = clock64();
-        // the previous tile's dQ is drained one tile late, so it never delays this tile's math
-        if (i > 0) flush_dq(tc - 1, b, h, (i - 1) * T);
-      }
-      flush_dq(tc - 1, b, h, (nq - 1) * T);
-
-      // ---- dK_j, dV_j: TMEM -> bf16 -> staging (both dS buffers are dead) -> TMA store
-      mbar_wait(dkv_full, it & 1);
+    // dK / dV of this CTA's n-th item (its last tile is `t_last`, whose dQ staging has been issued)
+    auto flush_dkv = [&](uint32_t n, uint32_t t_last, int b, int h, int k0) {
+      mbar_wait(dkv_full, n & 1);
       tc_fence_after();
-      if (lane == 0) tma_store_wait_read<0>();
+      if (lane == 0) tma_store_wait_read<0>();        // dQ(t_last) staging shares these rows
       __syncwarp();
-      uint8_t* st_dv = ds_s + stage_off;
-      uint8_t* st_dk = ds_s + PSB + stage_off;
+      uint8_t* st_dv = ds_s + (t_last & 1) * PSB + stage_off;
+      uint8_t* st_dk = st_dv + 2048;
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
         uint8_t* st = which == 0 ? st_dv : st_dk;
@@ -340,6 +302,84 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_store_4d(&tmdK, st_dk, half * HH, h, k0 + qd * 32, b);
         tma_store_commit();
       }
+    };
+
+    int pb_ = 0, ph_ = 0, pk0_ = 0;      // coordinates of the previous item (drained one tile late)
+    uint32_t t = 0;
+    for (uint32_t n = 0; n < static_cast<uint32_t>(my_items); ++n) {
+      int b, h, k0;
+      decode(n, b, h, k0);
+      const long long stat_base = (static_cast<long long>(b) * p.H + h) * p.Nq;
+      for (int i = 0; i < nq; ++i, ++t) {
+        const uint32_t db = t & 1;
+        const int qrow = i * T + row;
+        float lse_v = INFINITY, delta = 0.f;   // rows past Nq: P = exp2(-inf) = 0
+        if (qrow < p.Nq) {
+          lse_v = p.lse[stat_base + qrow];
+          delta = p.delta[stat_base + qrow];
+        }
+        // every earlier TMA store of this warp has finished reading its staging rows (dS rows)
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        mbar_wait(sdp_full, t & 1);
+        tc_fence_after();
+        if (p.timeline && blockIdx.x == 0 && t < 4 && threadIdx.x == 64) p.timeline[t * 8 + 2] = clock64();
+        const float nlse = -lse_v * LOG2E;
+        const float2 sl2 = mk2(p.scale_log2), nlse2 = mk2(nlse), sc2 = mk2(p.scale), nds2 = mk2(-delta * p.scale);
+        uint8_t* p_row = p_s + blk_off;
+        uint8_t* ds_row = ds_s + db * PSB + blk_off;
+        uint32_t pk[2][16];       // P stays in registers until dV(t-1) has released the single P buffer
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t sv[32], dv[32];
+          tmem_ld32(t_s + lane_addr + half * 64 + c * 32, sv);
+          tmem_ld32(t_dp + lane_addr + half * 64 + c * 32, dv);
+          tmem_wait_ld();
+          uint32_t dk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float2 tt = __ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2, nlse2);
+            const float2 pp = make_float2(fast_ex2(tt.x), fast_ex2(tt.y));
+            // dS = scale * P * (dP - delta)
+            const float2 dd = __fmul2_rn(pp, __ffma2_rn(make_float2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), sc2, nds2));
+            pk[c][e >> 1] = pack_bf16x2(pp.x, pp.y);
+            dk[e >> 1] = pack_bf16x2(dd.x, dd.y);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t off = ((static_cast<uint32_t>(c * 4 + g)) ^ row_sw) << 4;
+            *reinterpret_cast<uint4*>(ds_row + off) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(sdp_empty);                          // S / dP may be overwritten
+        if (t > 0) mbar_wait(p_free, (t - 1) & 1);       // dV(t-1) has finished reading P
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t off = ((static_cast<uint32_t>(c * 4 + g)) ^ row_sw) << 4;
+            *reinterpret_cast<uint4*>(p_row + off) = make_uint4(pk[c][4 * g], pk[c][4 * g + 1], pk[c][4 * g + 2], pk[c][4 * g + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&pds_full[db]);
+        if (p.timeline && blockIdx.x == 0 && t < 4 && threadIdx.x == 64) p.timeline[t * 8 + 3] = clock64();
+        // drain what the tensor core finished while this tile's math ran
+        if (t > 0) {
+          if (i > 0) {
+            flush_dq(t - 1, b, h, (i - 1) * T);
+          } else {                                   // previous tile closed the previous item
+            flush_dq(t - 1, pb_, ph_, (nq - 1) * T);
+            flush_dkv(n - 1, t - 1, pb_, ph_, pk0_);
+          }
+        }
+      }
+      pb_ = b; ph_ = h; pk0_ = k0;
+    }
+    if (total_tiles > 0) {
+      flush_dq(total_tiles - 1, pb_, ph_, (nq - 1) * T);
+      flush_dkv(static_cast<uint32_t>(my_items) - 1, total_tiles - 1, pb_, ph_, pk0_);
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
