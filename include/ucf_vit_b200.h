@@ -56,12 +56,15 @@ unsigned long long ucf_launch_count(void);
  * a_layout/b_layout: K_MAJOR  = operand stored [rows, K] with K contiguous (pitch ld, elements)
  *                    MN_MAJOR = operand stored [K, rows] with rows contiguous (pitch ld)
  * bias: length N, dtype bias_dtype, may be NULL.  splits: split-K factor (UCF_EPI_F32_ADD only).
+ * bias_grad: wgrad form only (A MN-major + UCF_EPI_F32_ADD, i.e. C = dW += dY^T X): if non-NULL, fp32
+ * [M] += row sums of A = column sums of dY -- the bias gradient, taken from the dY tiles already staged
+ * in shared memory (replaces a separate reduction pass over dY).  NULL otherwise.
  * tile_n: 0 = auto, 128 / 256 = single-CTA kernels, 512 = CTA-pair kernel (tcgen05 cta_group::2,
  * 256 x 256 tile per 2-CTA cluster).  Pointers and pitches*elemsize must be 16-byte aligned. */
 int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* bias, void* aux,
                   int M, int N, int K, long long lda, long long ldb, long long ldc, long long ldaux,
                   int a_layout, int b_layout, int epilogue, int bias_dtype, int splits, int tile_n,
-                  void* stream);
+                  void* bias_grad, void* stream);
 
 /* ---- LayerNorm (replaces nn.LayerNorm at arch.py:170,266; building_blocks.py:212,226) ------
  * x: [rows, D] (x_dtype), gamma/beta: [D] (param_dtype, may be NULL = 1/0), y: [rows, D] bf16,

@@ -36,7 +36,7 @@ def test_abi_version_and_error_string():
 def test_bad_arguments_are_rejected_without_a_device():
     lib = _lib.lib()
     # M = 0 is rejected before any CUDA call is made
-    rc = lib.ucf_gemm_bf16(0, 0, 0, 0, 0, 0, 8, 8, 8, 8, 8, 0, 0, 0, 0, 0, 1, 0, None)
+    rc = lib.ucf_gemm_bf16(0, 0, 0, 0, 0, 0, 8, 8, 8, 8, 8, 0, 0, 0, 0, 0, 1, 0, None, None)
     assert rc == -1 and b"empty problem" in lib.ucf_last_error()
     rc = lib.ucf_attention_fwd(1, 1, 1, 1, 1, 1, 1, 4, 4, 36, *([8] * 12), 1.0, None)
     assert rc == -4 and b"head_dim 36" in lib.ucf_last_error()

@@ -45,8 +45,11 @@ def test_gemm_family(M, N, K, tn):
     wref = dy.float().t() @ a.float()
     for splits in (1, 4):
         dw = torch.ones(N, K, device=dev)
-        ops.gemm(dy, a, M=N, N=K, K=M, a_mn=True, b_mn=True, epilogue=L.EPI_F32_ADD, out=dw, splits=splits, tile_n=tn)
+        dbias = torch.full((N,), 2.0, device=dev)        # fused bias gradient: += colsum(dy)
+        ops.gemm(dy, a, M=N, N=K, K=M, a_mn=True, b_mn=True, epilogue=L.EPI_F32_ADD, out=dw, splits=splits, tile_n=tn,
+                 bias_grad=dbias)
         _ok(dw, wref + 1.0, 2e-3)
+        _ok(dbias, dy.float().sum(0) + 2.0, 2e-3)
 
 
 def test_gemm_linearity_at_benchmark_size():

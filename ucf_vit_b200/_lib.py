@@ -21,7 +21,7 @@ _SIGNATURES = {
     "ucf_last_error": (c_char_p, []),
     "ucf_launch_count": (c_ulonglong, []),
     "ucf_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                              _LL, _LL, _LL, _LL, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                              _LL, _LL, _LL, _LL, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ucf_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, _LL, c_int,
                                   c_float, c_int, c_int, c_void_p]),
     "ucf_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

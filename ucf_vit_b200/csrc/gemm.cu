@@ -26,9 +26,73 @@ struct GemmParams {
   int kb_total, kb_per_split;
   const void* bias;   // length N or null
   int bias_is_bf16;
+  float* bias_grad;   // wgrad only (A MN-major, fp32 reduce-add): [M] += row sums of A, i.e. the bias gradient
 };
 
 enum { EPI_BIAS = 0, EPI_BIAS_RESIDUAL = 1, EPI_BIAS_GELU_AUX = 2, EPI_DGELU = 3, EPI_F32_ADD = 4 };
+
+// Bias-gradient warps of the wgrad kernels.  In wgrad, A = dY^T (MN-major: 64 token rows x 128
+// channels per stage, two 64-channel boxes of 128-byte swizzled rows), so the bias gradient
+// db[c] = sum_tokens dY[token, c] is the row sum of A -- the data is already in shared memory.
+// Two extra warps re-read each stage of the n_blk == 0 tiles AFTER the MMAs that consumed it have
+// retired (they wait on the same `empty` barrier as the producer) and hand the stage back through
+// `bias_done`; the producer waits for both.  Replaces a separate pass over dY (colsum kernel).
+template <int STAGES, int STAGE_BYTES>
+__device__ __forceinline__ void bias_grad_warp_loop(const GemmParams& p, uint8_t* stage_base, uint64_t* empty_bar,
+                                                    uint64_t* bias_done, int bw, int lane, int first_tile,
+                                                    int tile_stride, int total_tiles, int m_rows_per_tile,
+                                                    int m_sub_off) {
+  uint32_t kiter = 0;
+  const int c = lane & 15;                       // 16-byte chunk (8 channels) of the 128-channel row
+  const int box = c >> 3, cin = c & 7;
+  const int rsel = lane >> 4;                    // this lane reads rows of one parity
+  for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+    const int n_blk = tile % p.tiles_n;
+    const int rest = tile / p.tiles_n;
+    const int m_blk = rest % p.tiles_m;
+    const int split = rest / p.tiles_m;
+    const int kb0 = split * p.kb_per_split;
+    const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+    const bool work = n_blk == 0 && p.bias_grad != nullptr;
+    float2 acc[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] = make_float2(0.f, 0.f);
+    for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
+      const int s = kiter % STAGES;
+      const uint32_t ph = (kiter / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph);              // the MMAs that read this fill of stage s have retired
+      if (work) {
+        const uint8_t* a = stage_base + s * STAGE_BYTES + box * 8192;
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j) {
+          const int r = bw * 32 + 2 * j + rsel;  // token row inside the stage (rows past K are zero-filled)
+          const uint4 v = *reinterpret_cast<const uint4*>(a + r * 128 + ((cin ^ (r & 7)) << 4));
+          acc[0] = __fadd2_rn(acc[0], bf16x2_to_f32x2(v.x));
+          acc[1] = __fadd2_rn(acc[1], bf16x2_to_f32x2(v.y));
+          acc[2] = __fadd2_rn(acc[2], bf16x2_to_f32x2(v.z));
+          acc[3] = __fadd2_rn(acc[3], bf16x2_to_f32x2(v.w));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bias_done[s]);
+    }
+    if (work) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[e].x += __shfl_xor_sync(0xffffffffu, acc[e].x, 16);
+        acc[e].y += __shfl_xor_sync(0xffffffffu, acc[e].y, 16);
+      }
+      if (lane < 16) {
+        const int ch = m_blk * m_rows_per_tile + m_sub_off + c * 8;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (ch + 2 * e < p.M) atomicAdd(&p.bias_grad[ch + 2 * e], acc[e].x);
+          if (ch + 2 * e + 1 < p.M) atomicAdd(&p.bias_grad[ch + 2 * e + 1], acc[e].y);
+        }
+      }
+    }
+  }
+}
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
 struct GemmCfg {
@@ -47,16 +111,17 @@ struct GemmCfg {
   static constexpr int OUT_NBUF = (EPI == EPI_F32_ADD) ? 1 : 2;   // wgrad: light epilogue, spend smem on stages
   static constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_NBUF * OUT_BUF;
   static constexpr int AUX_STAGE_BYTES = HAS_AUX ? EPI_WARPS * 2 * AUX_BUF : 0;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr bool BIASW = A_MN && EPI == EPI_F32_ADD;   // wgrad: two extra bias-gradient warps
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + (BIASW ? 64 : 0);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_STAGE_BYTES + AUX_STAGE_BYTES +
-                                    BN * 4 + (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
+                                    BN * 4 + (3 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
   static_assert(2 * BN <= 512, "two accumulators must fit in TMEM");
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(64 + 32 * 8, 1)
+__global__ void __launch_bounds__(GemmCfg<BN, STAGES, A_MN, B_MN, EPI>::THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
                  const GemmParams p) {
@@ -75,7 +140,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* aux_bar = tempty_bar + 2;   // [EPI_WARPS][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * Cfg::EPI_WARPS);
+  uint64_t* bias_done = aux_bar + 2 * Cfg::EPI_WARPS;   // [STAGES] (wgrad bias-gradient warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_done + STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,6 +160,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tempty_bar[b], Cfg::EPI_WARPS);
     }
     for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < STAGES; ++i) mbar_init(&bias_done[i], 2);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -120,6 +187,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = kiter % STAGES;
           const uint32_t ph = (kiter / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if (Cfg::BIASW) mbar_wait(&bias_done[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           uint8_t* a_dst = stage_base + s * STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_BYTES;
@@ -174,6 +242,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         umma_commit(&tfull_bar[buf]);   // accumulator complete
       }
     }
+  } else if (Cfg::BIASW && warp >= 2 + Cfg::EPI_WARPS) {
+    // ------------------------------------------------------------------ bias-gradient warps (wgrad)
+    bias_grad_warp_loop<STAGES, STAGE_BYTES>(p, stage_base, empty_bar, bias_done, warp - 2 - Cfg::EPI_WARPS, lane,
+                                             blockIdx.x, gridDim.x, total_tiles, BM, 0);
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;             // TMEM lane quarter this warp may touch
@@ -343,16 +415,17 @@ struct Gemm2Cfg {
   static constexpr int OUT_NBUF = 2;
   static constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_NBUF * OUT_BUF;
   static constexpr int AUX_STAGE_BYTES = HAS_AUX ? EPI_WARPS * 2 * AUX_BUF : 0;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr bool BIASW = A_MN && EPI == EPI_F32_ADD;   // wgrad: two extra bias-gradient warps
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + (BIASW ? 64 : 0);
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_STAGE_BYTES + AUX_STAGE_BYTES + BN * 4 +
-                                    (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
+                                    (3 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
   static_assert(BN == 256, "pair kernel is instantiated for BN = 256");
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * 8, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<BN, STAGES, A_MN, B_MN, EPI>::THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
                   const GemmParams p) {
@@ -371,7 +444,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* aux_bar = tempty_bar + 2;   // [EPI_WARPS][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * Cfg::EPI_WARPS);
+  uint64_t* bias_done = aux_bar + 2 * Cfg::EPI_WARPS;   // [STAGES] (wgrad bias-gradient warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_done + STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -392,6 +466,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tempty_bar[b], 2 * Cfg::EPI_WARPS);     // epilogue warps of BOTH CTAs (leader's copy is used)
     }
     for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < STAGES; ++i) mbar_init(&bias_done[i], 2);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
@@ -420,6 +495,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int s = kiter % STAGES;
           const uint32_t ph = (kiter / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if (Cfg::BIASW) mbar_wait(&bias_done[s], ph ^ 1);
           const uint32_t full0 = mapa_u32(smem_u32(&full_bar[s]), 0);     // the leader's barrier
           if (leader) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
           uint8_t* a_dst = stage_base + s * STAGE_BYTES;
@@ -475,6 +551,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         umma_commit_2sm(&tfull_bar[buf], 3);     // accumulator complete in both CTAs' TMEM
       }
     }
+  } else if (Cfg::BIASW && warp >= 2 + Cfg::EPI_WARPS) {
+    // ------------------------------------------------------------------ bias-gradient warps (wgrad, both CTAs)
+    bias_grad_warp_loop<STAGES, STAGE_BYTES>(p, stage_base, empty_bar, bias_done, warp - 2 - Cfg::EPI_WARPS, lane,
+                                             cluster_id, num_clusters, total_tiles, 2 * BM, static_cast<int>(rank) * BM);
   } else {
     // ------------------------------------------------------------------ epilogue warps (both CTAs)
     const int q = warp & 3;
@@ -677,7 +757,7 @@ using namespace ucf;
 extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* bias, void* aux,
                              int M, int N, int K, long long lda, long long ldb, long long ldc,
                              long long ldaux, int a_layout, int b_layout, int epilogue,
-                             int bias_dtype, int splits, int tile_n, void* stream) {
+                             int bias_dtype, int splits, int tile_n, void* bias_grad, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) { set_last_error("gemm: empty problem M=%d N=%d K=%d", M, N, K); return UCF_ERR_BAD_ARG; }
   if (!A || !B || !C) { set_last_error("gemm: null operand"); return UCF_ERR_BAD_ARG; }
   if (epilogue < 0 || epilogue > 4) { set_last_error("gemm: bad epilogue %d", epilogue); return UCF_ERR_BAD_ARG; }
@@ -716,6 +796,11 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.bias = bias;
   p.bias_is_bf16 = bias_dtype == UCF_DTYPE_BF16;
+  p.bias_grad = static_cast<float*>(bias_grad);
+  if (bias_grad && !(a_mn && epilogue == EPI_F32_ADD)) {
+    set_last_error("gemm: bias_grad is only produced by the wgrad form (A MN-major, UCF_EPI_F32_ADD)");
+    return UCF_ERR_BAD_ARG;
+  }
 
   CUtensorMap tA, tB, tC, tAux;
   memset(&tAux, 0, sizeof(tAux));

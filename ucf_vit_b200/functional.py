@@ -37,15 +37,23 @@ def bf16_param(p: torch.Tensor) -> torch.Tensor:
     return q
 
 
-def _wgrad(dy2, x2, n_out, k_in, like: torch.Tensor):
-    """dW[n_out,k_in] = dy2^T x2 (fp32, split-K TMA reduce-add) returned in `like`'s dtype."""
+def _wgrad(dy2, x2, n_out, k_in, like: torch.Tensor, bias_like=None):
+    """dW[n_out,k_in] = dy2^T x2 (fp32, split-K TMA reduce-add) in `like`'s dtype, and -- fused in the
+    same kernel from the dY tiles it stages anyway -- the bias gradient db[n_out] = colsum(dy2).
+    Returns (dW, db); db is None when `bias_like` is None."""
     M = dy2.shape[0]
     dw = torch.zeros((n_out, k_in), dtype=torch.float32, device=dy2.device)
+    db = torch.zeros((n_out,), dtype=torch.float32, device=dy2.device) if bias_like is not None else None
     tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
     kb = (M + 63) // 64
     splits = max(1, min(kb // 8 if kb >= 16 else 1, (2 * 148 + tiles - 1) // tiles, 16))
-    ops.gemm(dy2, x2, M=n_out, N=k_in, K=M, a_mn=True, b_mn=True, epilogue=L.EPI_F32_ADD, out=dw, splits=splits)
-    return dw if like.dtype == torch.float32 else dw.to(like.dtype)
+    ops.gemm(dy2, x2, M=n_out, N=k_in, K=M, a_mn=True, b_mn=True, epilogue=L.EPI_F32_ADD, out=dw, splits=splits,
+             bias_grad=db)
+    if like.dtype != torch.float32:
+        dw = dw.to(like.dtype)
+    if db is not None and bias_like.dtype != torch.float32:
+        db = db.to(bias_like.dtype)
+    return dw, db
 
 
 def _bgrad(dy2, like):
@@ -157,8 +165,8 @@ class _LinearFn(torch.autograd.Function):
             if ctx.x_dtype != BF16:
                 dx = dx.to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(dy2, x2, N, K, weight)
-        if bias is not None and ctx.needs_input_grad[2]:
+            dw, db = _wgrad(dy2, x2, N, K, weight, bias if (bias is not None and ctx.needs_input_grad[2]) else None)
+        elif bias is not None and ctx.needs_input_grad[2]:
             db = _bgrad(dy2, bias)
         dres = dy if ctx.has_res else None
         return dx, dw, db, dres
@@ -199,11 +207,9 @@ class _MlpFn(torch.autograd.Function):
         Nout = w2.shape[0]
         dy2 = _as_bf16_2d(dy)
         M = dy2.shape[0]
-        dw2 = _wgrad(dy2, u, Nout, Hd, w2)
-        db2 = _bgrad(dy2, b2)
+        dw2, db2 = _wgrad(dy2, u, Nout, Hd, w2, b2)
         dz = ops.gemm(dy2, bf16_param(w2), M=M, N=Hd, K=Nout, b_mn=True, aux=z, epilogue=L.EPI_DGELU)
-        dw1 = _wgrad(dz, x2, Hd, K, w1)
-        db1 = _bgrad(dz, b1)
+        dw1, db1 = _wgrad(dz, x2, Hd, K, w1, b1)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(dz, bf16_param(w1), M=M, N=K, K=Hd, b_mn=True).view(ctx.shp)
@@ -320,11 +326,9 @@ class _BlockFn(torch.autograd.Function):
             return g if (g is None or like.dtype == f32) else g.to(like.dtype)
 
         # ---- MLP
-        d_fc2_w = _wgrad(dy2, u, D, Hd, fc2_w)
-        d_fc2_b = _bgrad(dy2, fc2_b)
+        d_fc2_w, d_fc2_b = _wgrad(dy2, u, D, Hd, fc2_w, fc2_b)
         dz = ops.gemm(dy2, bf16_param(fc2_w), M=M, N=Hd, K=D, b_mn=True, aux=z, epilogue=L.EPI_DGELU)
-        d_fc1_w = _wgrad(dz, h2, Hd, D, fc1_w)
-        d_fc1_b = _bgrad(dz, fc1_b)
+        d_fc1_w, d_fc1_b = _wgrad(dz, h2, Hd, D, fc1_w, fc1_b)
         dh2 = ops.gemm(dz, bf16_param(fc1_w), M=M, N=D, K=Hd, b_mn=True)
         del dz
         d_n2w = torch.zeros(D, dtype=f32, device=dev)
@@ -332,8 +336,7 @@ class _BlockFn(torch.autograd.Function):
         dx1 = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dy2, dgamma=d_n2w, dbeta=d_n2b)
         del dh2
         # ---- attention
-        d_proj_w = _wgrad(dx1, o.view(M, D), D, D, proj_w)
-        d_proj_b = _bgrad(dx1, proj_b)
+        d_proj_w, d_proj_b = _wgrad(dx1, o.view(M, D), D, D, proj_w, proj_b)
         d_o = ops.gemm(dx1, bf16_param(proj_w), M=M, N=D, K=D, b_mn=True)
         dqkv = torch.empty_like(qkv)
         qkv5 = qkv.view(B, N, 3, H, hd)
@@ -341,8 +344,7 @@ class _BlockFn(torch.autograd.Function):
         ops.attention_bwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], o, d_o.view(B, N, H, hd), lse, hd ** -0.5,
                           dq=dqkv5[:, :, 0], dk=dqkv5[:, :, 1], dv=dqkv5[:, :, 2])
         del d_o
-        d_qkv_w = _wgrad(dqkv, h1, 3 * D, D, qkv_w)
-        d_qkv_b = _bgrad(dqkv, qkv_b)
+        d_qkv_w, d_qkv_b = _wgrad(dqkv, h1, 3 * D, D, qkv_w, qkv_b)
         dh1 = ops.gemm(dqkv, bf16_param(qkv_w), M=M, N=D, K=3 * D, b_mn=True)
         del dqkv
         d_n1w = torch.zeros(D, dtype=f32, device=dev)

@@ -28,7 +28,7 @@ def _dt(t):
 
 
 def gemm(a, b, *, M, N, K, a_mn=False, b_mn=False, epilogue=L.EPI_BIAS, bias=None, aux=None, out=None,
-         splits=1, tile_n=0):
+         splits=1, tile_n=0, bias_grad=None):
     """C[M,N] = epi(A * B^T).  `a` is stored [M,K] (a_mn=False) or [K,M] (a_mn=True); same for b with N.
     Only the pitch of dim 0 is free; dim 1 must be contiguous."""
     _require_cuda(a, b, bias, aux, out)
@@ -45,10 +45,13 @@ def gemm(a, b, *, M, N, K, a_mn=False, b_mn=False, epilogue=L.EPI_BIAS, bias=Non
         aux = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
     if aux is not None:
         assert aux.dtype == torch.bfloat16 and tuple(aux.shape) == (M, N) and aux.stride(1) == 1
+    if bias_grad is not None:
+        assert bias_grad.dtype == torch.float32 and bias_grad.numel() == M and bias_grad.is_contiguous()
     rc = L.lib().ucf_gemm_bf16(
         a.data_ptr(), b.data_ptr(), out.data_ptr(), _ptr(bias), _ptr(aux), M, N, K,
         a.stride(0), b.stride(0), out.stride(0), aux.stride(0) if aux is not None else 0,
-        int(a_mn), int(b_mn), epilogue, _dt(bias) if bias is not None else 0, splits, tile_n, _stream())
+        int(a_mn), int(b_mn), epilogue, _dt(bias) if bias is not None else 0, splits, tile_n, _ptr(bias_grad),
+        _stream())
     L.check(rc, "gemm_bf16")
     return (out, aux) if epilogue == L.EPI_BIAS_GELU_AUX else out
 
