@@ -90,7 +90,8 @@ int ucf_attention_fwd(const void* q, const void* k, const void* v, void* o, floa
                       long long v_sb, long long v_sn, long long v_sh,
                       long long o_sb, long long o_sn, long long o_sh,
                       float scale, void* stream);
-/* dq_acc: fp32 workspace [B,Nq,H,hd] (zero-filled by this call), delta: fp32 [B,H,Nq] workspace.
+/* dq_acc: fp32 workspace [B,Nq,H,hd] (zero-filled by this call; unused and may be NULL when Nq <= 256,
+ * where dQ accumulates in tensor memory), delta: fp32 [B,H,Nq] workspace.
  * dq/dk/dv: bf16, addressed like q/k/v (may alias a packed dqkv buffer). */
 int ucf_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                       const float* lse, void* dq, void* dk, void* dv, float* dq_acc, float* delta,

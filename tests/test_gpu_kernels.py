@@ -126,6 +126,25 @@ def test_attention_cross_lengths():
     _ok(lse, lref, 1e-3)
 
 
+@pytest.mark.parametrize("B,Nq,Nk,H,hd", [(2, 70, 300, 2, 64), (2, 300, 70, 2, 64), (3, 256, 257, 2, 32), (40, 197, 197, 4, 64),
+                                          (20, 130, 520, 8, 64)])
+def test_attention_bwd_cross_lengths_and_many_items(B, Nq, Nk, H, hd):
+    """Backward with Nq != Nk on both schedules (Nq <= 256: dQ accumulated in tensor memory over all key
+    tiles; longer: fp32 reduce-add), and with more work items than SMs so every CTA walks several."""
+    torch.manual_seed(Nq * 1000 + Nk)
+    scale = hd ** -0.5
+    q, k, v = [bf(torch.randn(B, n, H, hd, device=dev)) for n in (Nq, Nk, Nk)]
+    o, lse = ops.attention_fwd(q, k, v, scale)
+    qf, kf, vf = [t.float().detach().requires_grad_(True) for t in (q, k, v)]
+    oref, _ = _ref_attn(qf, kf, vf, scale)
+    do = bf(torch.randn(B, Nq, H, hd, device=dev) * 0.5)
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, do, lse, scale)
+    oref.backward(do.float())
+    _ok(dq, qf.grad, 2e-2)
+    _ok(dk, kf.grad, 2e-2)
+    _ok(dv, vf.grad, 2e-2)
+
+
 def test_attention_rows_sum_to_one_at_long_sequence():
     """N = 4096 (SAP config): with V = 1 every output must be exactly ~1 (softmax rows sum to 1)."""
     B, N, H, hd = 1, 4096, 2, 64

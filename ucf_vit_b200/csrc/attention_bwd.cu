@@ -22,11 +22,11 @@ int make_bnhd_tmap(CUtensorMap* tm, const void* ptr, int B, int H, int N, int hd
 struct AttnBwdParams {
   int B, H, Nq, Nk;
   int nkt;              // key tiles per (b, h)
-  int items;            // B * H * nkt
+  int items;            // LONG: B * H * nkt work items (b, h, key tile); SHORT: B * H work items (b, h)
   float scale, scale_log2;
   const float* lse;     // [B,H,Nq]
   const float* delta;   // [B,H,Nq]
-  long long* timeline;  // optional [64] clock64 stamps of CTA 0 (profiling aid; NULL in production)
+  long long* timeline;  // optional [256] clock64 stamps of CTA 0 (profiling aid; NULL in production)
 };
 
 template <int HD>
@@ -41,6 +41,12 @@ struct AttnBwdCfg {
   static constexpr int ATOM_BYTES = 8 * ROW_BYTES;
   static_assert(SMEM_BYTES <= 232448, "smem");
 };
+
+// profiling aid: clock64 stamps of CTA 0's first 8 tiles, 32 slots per tile (NULL in production)
+#define UCF_TL(t_, k_)                                                                   \
+  do {                                                                                   \
+    if (p.timeline && blockIdx.x == 0 && (t_) < 8) p.timeline[(t_) * 32 + (k_)] = clock64(); \
+  } while (0)
 
 template <int ROW_BYTES>
 __device__ __forceinline__ uint64_t bwd_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -62,7 +68,14 @@ __device__ __forceinline__ uint64_t bwd_desc(uint32_t saddr, uint32_t lbo, uint3
 //     registers until dV(t) has retired);
 //   * the compute warps drain dQ(t-1) after the math of tile t, and an item's dK/dV after the
 //     math of the NEXT item's first tile, so draining never delays math.
-template <int HD>
+//
+// Two schedules share the code.  LONG (any Nq): a work item is (b, h, key tile); Q/dO tiles stream through
+// the ring once per key tile and every tile's dQ leaves through a fp32 TMA reduce-add into dq_acc (summed
+// over key tiles by the L2), converted to bf16 by a post-pass.  SHORT (Nq <= 256, i.e. at most two query
+// tiles -- ViT-B/16 at 224 px has 197 tokens): a work item is (b, h) and the CTA walks ALL its key tiles, so
+// the two Q/dO tiles are loaded once and stay resident, and dQ_i accumulates over the key tiles in its own
+// TMEM buffer and is written once, as bf16 -- no fp32 workspace, no zero fill, no reduce traffic, no cast.
+template <int HD, bool SHORT>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -96,7 +109,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = (p.Nq + T - 1) / T;
-  const int my_items = (p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int nkt = p.nkt;
+  // sub-item = (b, h, key tile): nq tiles each.  LONG: one per work item; SHORT: nkt consecutive per work item.
+  const int my_items = ((p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)) *
+                       (SHORT ? nkt : 1);
   const uint32_t total_tiles = static_cast<uint32_t>(my_items) * nq;
 
   if (warp == 0 && lane == 0) {
@@ -123,14 +139,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dv = tmem_base + 256, t_dk = tmem_base + 320,
                  t_dq = tmem_base + 384;   // two dQ buffers: +0, +64
 
-  // n-th item of this CTA -> (b, h, first key row)
-  auto decode = [&](uint32_t n, int& b, int& h, int& k0) {
-    const int item = static_cast<int>(blockIdx.x) + static_cast<int>(n) * static_cast<int>(gridDim.x);
-    const int jt = item % p.nkt;
-    const int bh = item / p.nkt;
+  // n-th sub-item of this CTA -> (b, h, key tile index)
+  auto decode = [&](uint32_t n, int& b, int& h, int& jt) {
+    int bh;
+    if (SHORT) {
+      jt = static_cast<int>(n) % nkt;
+      bh = static_cast<int>(blockIdx.x) + (static_cast<int>(n) / nkt) * static_cast<int>(gridDim.x);
+    } else {
+      const int item = static_cast<int>(blockIdx.x) + static_cast<int>(n) * static_cast<int>(gridDim.x);
+      jt = item % nkt;
+      bh = item / nkt;
+    }
     h = bh % p.H;
     b = bh / p.H;
-    k0 = jt * T;
+  };
+  // Q/dO ring slot and dQ TMEM buffer of tile t = (sub-item n, query tile i) are picked by a counter u
+  // of query-tile INSTANCES: LONG u = t (fresh Q/dO and dQ every tile); SHORT u counts (work item, i)
+  // pairs, so the tiles of all key tiles of one work item share the slot.
+  auto qinst = [&](uint32_t t, uint32_t n, int i) -> uint32_t {
+    return SHORT ? (n / static_cast<uint32_t>(nkt)) * nq + i : t;
   };
 
   if (warp == 0) {
@@ -138,16 +165,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (lane == 0) {
       uint32_t t = 0;
       for (uint32_t n = 0; n < static_cast<uint32_t>(my_items); ++n) {
-        int b, h, k0;
-        decode(n, b, h, k0);
+        int b, h, jt;
+        decode(n, b, h, jt);
         const int kb = n & 1;
         mbar_wait(&kv_empty[kb], ((n >> 1) & 1) ^ 1);
         mbar_expect_tx(&kv_full[kb], 2 * TB);
-        tma_load_4d(kv_s + (kb * 2 + 0) * TB, &tmK, &kv_full[kb], 0, h, k0, b);
-        tma_load_4d(kv_s + (kb * 2 + 1) * TB, &tmV, &kv_full[kb], 0, h, k0, b);
+        tma_load_4d(kv_s + (kb * 2 + 0) * TB, &tmK, &kv_full[kb], 0, h, jt * T, b);
+        tma_load_4d(kv_s + (kb * 2 + 1) * TB, &tmV, &kv_full[kb], 0, h, jt * T, b);
         for (int i = 0; i < nq; ++i, ++t) {
-          const int slot = t & 1;
-          mbar_wait(&qdo_empty[slot], ((t >> 1) & 1) ^ 1);
+          if (SHORT && jt > 0) continue;            // resident since the work item's first key tile
+          const uint32_t u = qinst(t, n, i);
+          const int slot = u & 1;
+          mbar_wait(&qdo_empty[slot], ((u >> 1) & 1) ^ 1);
           mbar_expect_tx(&qdo_full[slot], 2 * TB);
           tma_load_4d(q_s + slot * TB, &tmQ, &qdo_full[slot], 0, h, i * T, b);
           tma_load_4d(do_s + slot * TB, &tmdO, &qdo_full[slot], 0, h, i * T, b);
@@ -164,14 +193,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
       auto issue_sdp = [&](uint32_t t) {        // S, dP of global tile t (item n = t / nq)
         const uint32_t n = t / nq;
+        UCF_TL(t, 7);
         if (t % nq == 0) mbar_wait(&kv_full[n & 1], (n >> 1) & 1);
-        const int slot = t & 1;
+        UCF_TL(t, 8);
+        const uint32_t u = qinst(t, n, static_cast<int>(t % nq));
+        const int slot = u & 1;
         const uint32_t k_addr = smem_u32(kv_s + ((n & 1) * 2 + 0) * TB), v_addr = smem_u32(kv_s + ((n & 1) * 2 + 1) * TB);
         const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
-        mbar_wait(&qdo_full[slot], (t >> 1) & 1);
+        mbar_wait(&qdo_full[slot], (u >> 1) & 1);     // SHORT, later key tiles: phase already complete
+        UCF_TL(t, 9);
         mbar_wait(sdp_empty, (t & 1) ^ 1);
         tc_fence_after();
-        if (p.timeline && blockIdx.x == 0 && t < 4) p.timeline[t * 8 + 0] = clock64();
+        UCF_TL(t, 0);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16(t_s, bwd_desc<RB>(q_addr + k * 32, 16, AB), bwd_desc<RB>(k_addr + k * 32, 16, AB), idesc_qk, k > 0);
@@ -185,14 +218,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (uint32_t t = 0; t < total_tiles; ++t) {
         const uint32_t n = t / nq;
         const int i = static_cast<int>(t - n * nq);
-        const int slot = t & 1, db = t & 1;
+        const uint32_t u = qinst(t, n, i);
+        const int slot = u & 1, db = t & 1;
+        const int jt = SHORT ? static_cast<int>(n) % nkt : 0;
+        const bool first_kt = !SHORT || jt == 0, last_kt = !SHORT || jt == nkt - 1;
         const uint32_t k_addr = smem_u32(kv_s + ((n & 1) * 2 + 0) * TB);
         const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
         const uint32_t ds_addr = smem_u32(ds_s + db * PSB);
         mbar_wait(&pds_full[db], (t >> 1) & 1);                      // P(t), dS(t) are in shared memory
         if (i == 0) mbar_wait(dkv_empty, (n & 1) ^ 1);               // previous item's dK/dV have left TMEM
         tc_fence_after();
-        if (p.timeline && blockIdx.x == 0 && t < 4) p.timeline[t * 8 + 1] = clock64();
+        UCF_TL(t, 1);
         // next tile's S/dP first: its exp/dS math then overlaps all three products of tile t
         if (t + 1 < total_tiles) issue_sdp(t + 1);
         // dV += P^T dO_t   (reduction over the 128 query rows, 16 per MMA); releases the single P buffer
@@ -201,24 +237,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_bf16(t_dv, umma_smem_desc(p_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(do_addr + kk * 2 * AB, 0, AB),
                     idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
         umma_commit(p_free);
-        mbar_wait(&dq_empty[db], ((t >> 1) & 1) ^ 1);
-        tc_fence_after();
-        // dQ_t = dS K_j   (reduction over the 128 keys)
+        if (first_kt) {
+          mbar_wait(&dq_empty[slot], ((u >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        UCF_TL(t, 11);
+        // dQ_t (+)= dS K_j   (reduction over the 128 keys; SHORT: accumulated over the key tiles)
 #pragma unroll
         for (int kk = 0; kk < T / 16; ++kk)
-          umma_bf16(t_dq + db * 64, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                    bwd_desc<RB>(k_addr + kk * 2 * AB, 0, AB), idesc_dq, kk > 0 ? 1u : 0u);
+          umma_bf16(t_dq + slot * 64, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                    bwd_desc<RB>(k_addr + kk * 2 * AB, 0, AB), idesc_dq, (!first_kt || kk > 0) ? 1u : 0u);
         // dK += dS^T Q_t
 #pragma unroll
         for (int kk = 0; kk < T / 16; ++kk)
           umma_bf16(t_dk, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(q_addr + kk * 2 * AB, 0, AB),
                     idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&dq_full[db]);          // every product of tile t has retired
-        umma_commit(&qdo_empty[slot]);
+        if (last_kt) umma_commit(&qdo_empty[slot]);
         if (i + 1 == nq) {
           umma_commit(dkv_full);
           umma_commit(&kv_empty[n & 1]);
         }
+        UCF_TL(t, 12);
       }
     }
   } else {
@@ -239,31 +279,48 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     // dQ of global tile t (all its products have retired): TMEM -> fp32 staging in the dead rows of
     // dS[t&1] -> TMA reduce-add into dq_acc
-    auto flush_dq = [&](uint32_t t, int b, int h, int qrow0) {
-      const uint32_t db = t & 1;
+    // `drain` is false for the SHORT schedule's tiles before the last key tile: the wait still happens
+    // (it is what frees dS[t&1] for tile t+2), dQ stays in TMEM.
+    auto flush_dq = [&](uint32_t t, uint32_t u, bool drain, int b, int h, int qrow0) {
+      const uint32_t db = t & 1, slot = u & 1;
       mbar_wait(&dq_full[db], (t >> 1) & 1);
+      if (!drain) return;
       tc_fence_after();
-      if (p.timeline && blockIdx.x == 0 && t < 4 && threadIdx.x == 64) p.timeline[t * 8 + 4] = clock64();
+      if (threadIdx.x == 64) UCF_TL(t, 4);
       uint8_t* my_dq = ds_s + db * PSB + stage_off;
       uint32_t v[HH];
-      if (HH == 32) tmem_ld32(t_dq + db * 64 + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-      else tmem_ld16(t_dq + db * 64 + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+      if (HH == 32) tmem_ld32(t_dq + slot * 64 + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      else tmem_ld16(t_dq + slot * 64 + lane_addr + half * HH, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
       tmem_wait_ld();
+      if (SHORT) {       // final values: bf16 rows of HH elements (64 B SWIZZLE_64B / 32 B SWIZZLE_32B)
 #pragma unroll
-      for (int g = 0; g < HH / 4; ++g) {
-        uint8_t* dst = (HH == 32) ? my_dq + lane * 128 + ((static_cast<uint32_t>(g) ^ lrow_sw) << 4)
-                                  : my_dq + lane * 64 + ((static_cast<uint32_t>(g) ^ ((lane >> 1) & 3)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        for (int g = 0; g < HH / 8; ++g) {
+          uint8_t* dst = (HH == 32) ? my_dq + lane * 64 + ((static_cast<uint32_t>(g) ^ ((lane >> 1) & 3)) << 4)
+                                    : my_dq + lane * 32 + ((static_cast<uint32_t>(g) ^ ((lane >> 2) & 1)) << 4);
+          *reinterpret_cast<uint4*>(dst) =
+              make_uint4(pack_bf16x2(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1])),
+                         pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                         pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                         pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+        }
+      } else {           // partial sums: fp32 rows of HH elements (128 B SWIZZLE_128B / 64 B SWIZZLE_64B)
+#pragma unroll
+        for (int g = 0; g < HH / 4; ++g) {
+          uint8_t* dst = (HH == 32) ? my_dq + lane * 128 + ((static_cast<uint32_t>(g) ^ lrow_sw) << 4)
+                                    : my_dq + lane * 64 + ((static_cast<uint32_t>(g) ^ ((lane >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
       }
       tc_fence_before();
-      mbar_arrive(&dq_empty[db]);
+      mbar_arrive(&dq_empty[slot]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0 && qrow0 + qd * 32 < p.Nq) {
-        tma_reduce_add_4d(&tmdQacc, my_dq, half * HH, h, qrow0 + qd * 32, b);
+        if (SHORT) tma_store_4d(&tmdQacc, my_dq, half * HH, h, qrow0 + qd * 32, b);
+        else tma_reduce_add_4d(&tmdQacc, my_dq, half * HH, h, qrow0 + qd * 32, b);
         tma_store_commit();
       }
-      if (p.timeline && blockIdx.x == 0 && t < 4 && threadIdx.x == 64) p.timeline[t * 8 + 5] = clock64();
+      if (threadIdx.x == 64) UCF_TL(t, 5);
     };
     // dK / dV of this CTA's n-th item (its last tile is `t_last`, whose dQ staging has been issued)
     auto flush_dkv = [&](uint32_t n, uint32_t t_last, int b, int h, int k0) {
@@ -304,11 +361,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     };
 
-    int pb_ = 0, ph_ = 0, pk0_ = 0;      // coordinates of the previous item (drained one tile late)
+    int pb_ = 0, ph_ = 0, pk0_ = 0;      // coordinates of the previous sub-item (drained one tile late)
+    bool plast_ = true;                  // ... and whether it was its work item's last key tile
     uint32_t t = 0;
     for (uint32_t n = 0; n < static_cast<uint32_t>(my_items); ++n) {
-      int b, h, k0;
-      decode(n, b, h, k0);
+      int b, h, jt;
+      decode(n, b, h, jt);
+      const int k0 = jt * T;
+      const bool last_kt = !SHORT || jt == nkt - 1;
       const long long stat_base = (static_cast<long long>(b) * p.H + h) * p.Nq;
       for (int i = 0; i < nq; ++i, ++t) {
         const uint32_t db = t & 1;
@@ -323,7 +383,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         mbar_wait(sdp_full, t & 1);
         tc_fence_after();
-        if (p.timeline && blockIdx.x == 0 && t < 4 && threadIdx.x == 64) p.timeline[t * 8 + 2] = clock64();
+        if (threadIdx.x == 64) UCF_TL(t, 2);
+        if (lane == 0) UCF_TL(t, 24 + cw);
         const float nlse = -lse_v * LOG2E;
         const float2 sl2 = mk2(p.scale_log2), nlse2 = mk2(nlse), sc2 = mk2(p.scale), nds2 = mk2(-delta * p.scale);
         uint8_t* p_row = p_s + blk_off;
@@ -353,7 +414,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         tc_fence_before();
         mbar_arrive(sdp_empty);                          // S / dP may be overwritten
+        if (lane == 0 && cw == 0) UCF_TL(t, 13);
         if (t > 0) mbar_wait(p_free, (t - 1) & 1);       // dV(t-1) has finished reading P
+        if (lane == 0 && cw == 0) UCF_TL(t, 14);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
 #pragma unroll
@@ -364,22 +427,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         fence_proxy_async_smem();
         mbar_arrive(&pds_full[db]);
-        if (p.timeline && blockIdx.x == 0 && t < 4 && threadIdx.x == 64) p.timeline[t * 8 + 3] = clock64();
+        if (threadIdx.x == 64) UCF_TL(t, 3);
+        if (lane == 0) UCF_TL(t, 16 + cw);
         // drain what the tensor core finished while this tile's math ran
         if (t > 0) {
           if (i > 0) {
-            flush_dq(t - 1, b, h, (i - 1) * T);
-          } else {                                   // previous tile closed the previous item
-            flush_dq(t - 1, pb_, ph_, (nq - 1) * T);
+            flush_dq(t - 1, qinst(t - 1, n, i - 1), last_kt, b, h, (i - 1) * T);
+          } else {                                   // previous tile closed the previous sub-item
+            flush_dq(t - 1, qinst(t - 1, n - 1, nq - 1), plast_, pb_, ph_, (nq - 1) * T);
             flush_dkv(n - 1, t - 1, pb_, ph_, pk0_);
           }
         }
       }
-      pb_ = b; ph_ = h; pk0_ = k0;
+      pb_ = b; ph_ = h; pk0_ = k0; plast_ = last_kt;
     }
     if (total_tiles > 0) {
-      flush_dq(total_tiles - 1, pb_, ph_, (nq - 1) * T);
-      flush_dkv(static_cast<uint32_t>(my_items) - 1, total_tiles - 1, pb_, ph_, pk0_);
+      const uint32_t nl = static_cast<uint32_t>(my_items) - 1;
+      flush_dq(total_tiles - 1, qinst(total_tiles - 1, nl, nq - 1), true, pb_, ph_, (nq - 1) * T);
+      flush_dkv(nl, total_tiles - 1, pb_, ph_, pk0_);
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
@@ -465,7 +530,8 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
                                  float scale, void* stream) {
   if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) { set_last_error("attention_bwd: empty problem"); return UCF_ERR_BAD_ARG; }
   if (hd != 64 && hd != 32) { set_last_error("attention_bwd: head_dim %d not supported (32 or 64)", hd); return UCF_ERR_UNSUPPORTED; }
-  if (!q || !k || !v || !o || !d_o || !lse || !dq || !dk || !dv || !dq_acc || !delta) {
+  const bool short_q = Nq <= 256;      // dQ accumulates in tensor memory: dq_acc is not touched (may be NULL)
+  if (!q || !k || !v || !o || !d_o || !lse || !dq || !dk || !dv || (!dq_acc && !short_q) || !delta) {
     set_last_error("attention_bwd: null pointer"); return UCF_ERR_BAD_ARG;
   }
   const long long all_strides[] = {q_sb, q_sn, q_sh, k_sb, k_sn, k_sh, v_sb, v_sn, v_sh, o_sb, o_sn, o_sh,
@@ -473,8 +539,11 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
   for (long long s : all_strides)
     if (s % 8) { set_last_error("attention_bwd: strides must be multiples of 8 elements"); return UCF_ERR_BAD_ARG; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(dq_acc, 0, sizeof(float) * static_cast<size_t>(B) * Nq * H * hd, st);
-  if (e != cudaSuccess) { set_last_error("attention_bwd: memset: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  cudaError_t e = cudaSuccess;
+  if (!short_q) {
+    e = cudaMemsetAsync(dq_acc, 0, sizeof(float) * static_cast<size_t>(B) * Nq * H * hd, st);
+    if (e != cudaSuccess) { set_last_error("attention_bwd: memset: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  }
 
   // d_o is addressed with o's strides (both are (B,N,H*hd) activations produced by this library)
   const long long items = static_cast<long long>(B) * Nq * H;
@@ -504,8 +573,12 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
   if ((rc = make_bnhd_tmap(&tV, v, B, H, Nk, hd, v_sb, v_sn, v_sh, 128, bf, 2, hd))) return rc;
   if ((rc = make_bnhd_tmap(&tdO, d_o, B, H, Nq, hd, o_sb, o_sn, o_sh, 128, bf, 2, hd))) return rc;
   // output boxes are 32 rows x hd/2 columns (each compute warp owns half of the head dimension)
-  if ((rc = make_bnhd_tmap(&tdQ, dq_acc, B, H, Nq, hd, static_cast<long long>(Nq) * H * hd, static_cast<long long>(H) * hd, hd,
-                           32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, hd / 2))) return rc;
+  if (short_q) {
+    if ((rc = make_bnhd_tmap(&tdQ, dq, B, H, Nq, hd, dq_sb, dq_sn, dq_sh, 32, bf, 2, hd / 2))) return rc;
+  } else {
+    if ((rc = make_bnhd_tmap(&tdQ, dq_acc, B, H, Nq, hd, static_cast<long long>(Nq) * H * hd, static_cast<long long>(H) * hd, hd,
+                             32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, hd / 2))) return rc;
+  }
   if ((rc = make_bnhd_tmap(&tdK, dk, B, H, Nk, hd, dk_sb, dk_sn, dk_sh, 32, bf, 2, hd / 2))) return rc;
   if ((rc = make_bnhd_tmap(&tdV, dv, B, H, Nk, hd, dv_sb, dv_sn, dv_sh, 32, bf, 2, hd / 2))) return rc;
 
@@ -515,30 +588,29 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
   p.lse = lse; p.delta = delta;
   p.timeline = g_bwd_timeline;
   p.nkt = (Nk + 127) / 128;
-  const long long n_items = static_cast<long long>(B) * H * p.nkt;
+  const long long n_items = static_cast<long long>(B) * H * (short_q ? 1 : p.nkt);
   if (n_items > 0x7fffffffLL) { set_last_error("attention_bwd: too many work items"); return UCF_ERR_BAD_ARG; }
   p.items = static_cast<int>(n_items);
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  if (hd == 64) {
-    static bool attr = false;
-    if (!attr) {
-      e = cudaFuncSetAttribute(attn_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwdCfg<64>::SMEM_BYTES);
-      if (e != cudaSuccess) { set_last_error("attention_bwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-      attr = true;
-    }
-    attn_bwd_kernel<64><<<grid, 320, AttnBwdCfg<64>::SMEM_BYTES, st>>>(tQ, tK, tV, tdO, tdQ, tdK, tdV, p);
-  } else {
-    static bool attr = false;
-    if (!attr) {
-      e = cudaFuncSetAttribute(attn_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwdCfg<32>::SMEM_BYTES);
-      if (e != cudaSuccess) { set_last_error("attention_bwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-      attr = true;
-    }
-    attn_bwd_kernel<32><<<grid, 320, AttnBwdCfg<32>::SMEM_BYTES, st>>>(tQ, tK, tV, tdO, tdQ, tdK, tdV, p);
+#define UCF_ATTN_BWD_LAUNCH(HD_, SHORT_)                                                                        \
+  {                                                                                                             \
+    static bool attr = false;                                                                                   \
+    if (!attr) {                                                                                                \
+      e = cudaFuncSetAttribute(attn_bwd_kernel<HD_, SHORT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                               AttnBwdCfg<HD_>::SMEM_BYTES);                                                    \
+      if (e != cudaSuccess) { set_last_error("attention_bwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; } \
+      attr = true;                                                                                              \
+    }                                                                                                           \
+    attn_bwd_kernel<HD_, SHORT_><<<grid, 320, AttnBwdCfg<HD_>::SMEM_BYTES, st>>>(tQ, tK, tV, tdO, tdQ, tdK, tdV, p); \
   }
+  if (hd == 64 && short_q) UCF_ATTN_BWD_LAUNCH(64, true)
+  else if (hd == 64) UCF_ATTN_BWD_LAUNCH(64, false)
+  else if (short_q) UCF_ATTN_BWD_LAUNCH(32, true)
+  else UCF_ATTN_BWD_LAUNCH(32, false)
+#undef UCF_ATTN_BWD_LAUNCH
   if ((rc = check_launch("attn_bwd_kernel"))) return rc;
 
-  {
+  if (!short_q) {
     const long long total = static_cast<long long>(B) * Nq * H * (hd / 8);
     long long blocks = (total + 255) / 256;
     const long long cap = static_cast<long long>(num_sms()) * 16;

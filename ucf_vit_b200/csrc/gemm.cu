@@ -781,7 +781,7 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
   const bool pair_supported =
       (!a_mn && !b_mn && (epilogue == EPI_BIAS || epilogue == EPI_BIAS_RESIDUAL || epilogue == EPI_BIAS_GELU_AUX)) ||
       (!a_mn && b_mn && (epilogue == EPI_BIAS || epilogue == EPI_DGELU)) || (a_mn && b_mn && epilogue == EPI_F32_ADD);
-  if (tile_n == 0 && pair_supported && M >= 1024 && N >= 512 && N <= 4096) tile_n = 512;
+  if (tile_n == 0 && pair_supported && M >= 512 && N >= 512 && N <= 4096) tile_n = 512;
   const bool pair = tile_n == 512;
   int BN = pair ? 256 : tile_n;
   if (BN != 128 && BN != 256) BN = (N <= 128 || (N % 256 != 0 && N % 128 == 0 && N < 1024)) ? 128 : 256;

@@ -6,6 +6,8 @@ tensor-memory accumulators through the TMA reduce-add epilogue).
 Reference semantics: /root/reference/src/UCF_VIT/simple/building_blocks.py
   Mlp.forward :122-129, Attention.forward :157-192, Block.forward :236-239.
 """
+import math
+
 import torch
 
 from . import _lib as L
@@ -37,13 +39,28 @@ def bf16_param(p: torch.Tensor) -> torch.Tensor:
     return q
 
 
-def _wgrad(dy2, x2, n_out, k_in, like: torch.Tensor, bias_like=None):
+def _zeros_f32(dev, *shapes):
+    """One zero-filled fp32 allocation carved into 256-byte aligned views (one fill launch instead of
+    one per gradient; the reduce-add epilogues accumulate into them).  A shape of None yields None."""
+    sizes = [0 if s is None else -(-math.prod(s) // 64) * 64 for s in shapes]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+    out, off = [], 0
+    for s, n in zip(shapes, sizes):
+        out.append(None if s is None else flat[off:off + math.prod(s)].view(s))
+        off += n
+    return out
+
+
+def _wgrad(dy2, x2, n_out, k_in, like: torch.Tensor, bias_like=None, out=None, bias_out=None):
     """dW[n_out,k_in] = dy2^T x2 (fp32, split-K TMA reduce-add) in `like`'s dtype, and -- fused in the
     same kernel from the dY tiles it stages anyway -- the bias gradient db[n_out] = colsum(dy2).
+    `out` / `bias_out` are zeroed fp32 buffers to accumulate into (allocated here when None).
     Returns (dW, db); db is None when `bias_like` is None."""
     M = dy2.shape[0]
-    dw = torch.zeros((n_out, k_in), dtype=torch.float32, device=dy2.device)
-    db = torch.zeros((n_out,), dtype=torch.float32, device=dy2.device) if bias_like is not None else None
+    dw = out if out is not None else torch.zeros((n_out, k_in), dtype=torch.float32, device=dy2.device)
+    db = None
+    if bias_like is not None:
+        db = bias_out if bias_out is not None else torch.zeros((n_out,), dtype=torch.float32, device=dy2.device)
     tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
     kb = (M + 63) // 64
     splits = max(1, min(kb // 8 if kb >= 16 else 1, (2 * 148 + tiles - 1) // tiles, 16))
@@ -325,18 +342,22 @@ class _BlockFn(torch.autograd.Function):
         def cast_like(g, like):
             return g if (g is None or like.dtype == f32) else g.to(like.dtype)
 
+        def opt(b, shape):
+            return shape if b is not None else None
+
+        (g_fc2_w, g_fc2_b, g_fc1_w, g_fc1_b, d_n2w, d_n2b, g_proj_w, g_proj_b, g_qkv_w, g_qkv_b, d_n1w,
+         d_n1b) = _zeros_f32(dev, (D, Hd), opt(fc2_b, (D,)), (Hd, D), opt(fc1_b, (Hd,)), (D,), opt(n2b, (D,)),
+                             (D, D), opt(proj_b, (D,)), (3 * D, D), opt(qkv_b, (3 * D,)), (D,), opt(n1b, (D,)))
         # ---- MLP
-        d_fc2_w, d_fc2_b = _wgrad(dy2, u, D, Hd, fc2_w, fc2_b)
+        d_fc2_w, d_fc2_b = _wgrad(dy2, u, D, Hd, fc2_w, fc2_b, g_fc2_w, g_fc2_b)
         dz = ops.gemm(dy2, bf16_param(fc2_w), M=M, N=Hd, K=D, b_mn=True, aux=z, epilogue=L.EPI_DGELU)
-        d_fc1_w, d_fc1_b = _wgrad(dz, h2, Hd, D, fc1_w, fc1_b)
+        d_fc1_w, d_fc1_b = _wgrad(dz, h2, Hd, D, fc1_w, fc1_b, g_fc1_w, g_fc1_b)
         dh2 = ops.gemm(dz, bf16_param(fc1_w), M=M, N=D, K=Hd, b_mn=True)
         del dz
-        d_n2w = torch.zeros(D, dtype=f32, device=dev)
-        d_n2b = torch.zeros(D, dtype=f32, device=dev) if n2b is not None else None
         dx1 = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dy2, dgamma=d_n2w, dbeta=d_n2b)
         del dh2
         # ---- attention
-        d_proj_w, d_proj_b = _wgrad(dx1, o.view(M, D), D, D, proj_w, proj_b)
+        d_proj_w, d_proj_b = _wgrad(dx1, o.view(M, D), D, D, proj_w, proj_b, g_proj_w, g_proj_b)
         d_o = ops.gemm(dx1, bf16_param(proj_w), M=M, N=D, K=D, b_mn=True)
         dqkv = torch.empty_like(qkv)
         qkv5 = qkv.view(B, N, 3, H, hd)
@@ -344,11 +365,9 @@ class _BlockFn(torch.autograd.Function):
         ops.attention_bwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], o, d_o.view(B, N, H, hd), lse, hd ** -0.5,
                           dq=dqkv5[:, :, 0], dk=dqkv5[:, :, 1], dv=dqkv5[:, :, 2])
         del d_o
-        d_qkv_w, d_qkv_b = _wgrad(dqkv, h1, 3 * D, D, qkv_w, qkv_b)
+        d_qkv_w, d_qkv_b = _wgrad(dqkv, h1, 3 * D, D, qkv_w, qkv_b, g_qkv_w, g_qkv_b)
         dh1 = ops.gemm(dqkv, bf16_param(qkv_w), M=M, N=D, K=3 * D, b_mn=True)
         del dqkv
-        d_n1w = torch.zeros(D, dtype=f32, device=dev)
-        d_n1b = torch.zeros(D, dtype=f32, device=dev) if n1b is not None else None
         dx = ops.layernorm_bwd(dh1, x2, n1w, mean1, rstd1, dres=dx1, dgamma=d_n1w, dbeta=d_n1b)
         return (dx.view(B, N, D), cast_like(d_n1w, n1w), cast_like(d_n1b, n1b) if n1b is not None else None,
                 d_qkv_w, d_qkv_b, d_proj_w, d_proj_b,

@@ -174,10 +174,12 @@ def attention_bwd(q, k, v, o, d_o, lse, scale, dq=None, dk=None, dv=None):
         dk = torch.empty((B, Nk, H, hd), dtype=torch.bfloat16, device=q.device)
     if dv is None:
         dv = torch.empty((B, Nk, H, hd), dtype=torch.bfloat16, device=q.device)
-    dq_acc = torch.empty((B, Nq, H, hd), dtype=torch.float32, device=q.device)
+    # Nq <= 256: dQ is accumulated in tensor memory, no fp32 workspace
+    dq_acc = torch.empty((B, Nq, H, hd), dtype=torch.float32, device=q.device) if Nq > 256 else None
     delta = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
     rc = L.lib().ucf_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),
-                                   lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dq_acc.data_ptr(),
+                                   lse.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                   dq_acc.data_ptr() if dq_acc is not None else None,
                                    delta.data_ptr(), B, H, Nq, Nk, hd, *_bnhd(q), *_bnhd(k), *_bnhd(v), *_bnhd(o),
                                    *_bnhd(dq), *_bnhd(dk), *_bnhd(dv), float(scale), _stream())
     L.check(rc, "attention_bwd")
