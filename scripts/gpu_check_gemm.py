@@ -114,6 +114,43 @@ def run_misc():
     report("patchify 3d", ops.patchify(vol, p), ref.to(torch.bfloat16), 0)
 
 
+def _time(f, iters=20):
+    for _ in range(3):
+        f()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        f()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_epilogues():
+    """The ViT-B/16 block's epilogue-carrying GEMMs (auto tile selection), batch 256 x 197 tokens."""
+    print("---- epilogue GEMMs (CUDA events, 20 iters)")
+    M, D, Hd = 50432, 768, 3072
+    x = bf(torch.randn(M, D, device=dev)); w1 = bf(torch.randn(Hd, D, device=dev) * 0.03); b1 = torch.randn(Hd, device=dev)
+    h = bf(torch.randn(M, Hd, device=dev)); w2 = bf(torch.randn(D, Hd, device=dev) * 0.03); b2 = torch.randn(D, device=dev)
+    dy = bf(torch.randn(M, D, device=dev)); dz = bf(torch.randn(M, Hd, device=dev))
+    res = bf(torch.randn(M, D, device=dev))
+    dw1 = torch.zeros(Hd, D, device=dev); db1 = torch.zeros(Hd, device=dev)
+    dw2 = torch.zeros(D, Hd, device=dev); db2 = torch.zeros(D, device=dev)
+    cases = [
+        ("fc1 plain bias      ", 2 * M * Hd * D, lambda: ops.gemm(x, w1, M=M, N=Hd, K=D, bias=b1)),
+        ("fc1 bias+GELU(+aux) ", 2 * M * Hd * D, lambda: ops.gemm(x, w1, M=M, N=Hd, K=D, bias=b1, epilogue=L.EPI_BIAS_GELU_AUX)),
+        ("fc2 bias+residual   ", 2 * M * Hd * D, lambda: ops.gemm(h, w2, M=M, N=D, K=Hd, bias=b2, aux=res, epilogue=L.EPI_BIAS_RESIDUAL)),
+        ("fc2 dgrad plain     ", 2 * M * Hd * D, lambda: ops.gemm(dy, w2, M=M, N=Hd, K=D, b_mn=True)),
+        ("fc2 dgrad * GELU'   ", 2 * M * Hd * D, lambda: ops.gemm(dy, w2, M=M, N=Hd, K=D, b_mn=True, aux=h, epilogue=L.EPI_DGELU)),
+        ("fc1 wgrad           ", 2 * M * Hd * D, lambda: ops.gemm(dz, x, M=Hd, N=D, K=M, a_mn=True, b_mn=True, epilogue=L.EPI_F32_ADD, out=dw1, splits=8)),
+        ("fc1 wgrad + bias grad", 2 * M * Hd * D, lambda: ops.gemm(dz, x, M=Hd, N=D, K=M, a_mn=True, b_mn=True, epilogue=L.EPI_F32_ADD, out=dw1, splits=8, bias_grad=db1)),
+        ("fc2 wgrad + bias grad", 2 * M * Hd * D, lambda: ops.gemm(dy, h, M=D, N=Hd, K=M, a_mn=True, b_mn=True, epilogue=L.EPI_F32_ADD, out=dw2, splits=8, bias_grad=db2)),
+    ]
+    for name, fl, f in cases:
+        ms = _time(f)
+        print(f"{name}: {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TFLOP/s", flush=True)
+
+
 def bench_gemm():
     print("---- GEMM throughput (CUDA events, 20 iters, inputs > L2 where stated)")
     for (M, N, K, kind) in [(50432, 2304, 768, "fwd"), (50432, 768, 768, "fwd"), (50432, 3072, 768, "fwd"),
@@ -161,5 +198,6 @@ if __name__ == "__main__":
     if "ln" in which: run_ln_cases()
     if "gemm" in which: run_gemm_cases()
     if "bench" in which and fails == 0: bench_gemm()
+    if "epi" in which and fails == 0: bench_epilogues()
     print("FAILS", fails)
     sys.exit(1 if fails else 0)

@@ -1,0 +1,42 @@
+"""Run ONE hot kernel a few times so that ncu can capture it in isolation.
+python scripts/gpu_one_kernel.py {fc1_gelu|fc2_dgelu|fc1_plain|attn_fwd|attn_bwd|ln_fwd|ln_bwd|wgrad}"""
+import sys
+import torch
+sys.path.insert(0, ".")
+from ucf_vit_b200 import ops, _lib as L
+
+which = sys.argv[1] if len(sys.argv) > 1 else "fc1_gelu"
+dev = "cuda"
+M, D, Hd = 50432, 768, 3072
+bf = lambda t: t.to(torch.bfloat16)
+if which in ("fc1_gelu", "fc1_plain"):
+    x = bf(torch.randn(M, D, device=dev)); w = bf(torch.randn(Hd, D, device=dev) * 0.03); b = torch.randn(Hd, device=dev)
+    f = (lambda: ops.gemm(x, w, M=M, N=Hd, K=D, bias=b, epilogue=L.EPI_BIAS_GELU_AUX)) if which == "fc1_gelu" else \
+        (lambda: ops.gemm(x, w, M=M, N=Hd, K=D, bias=b))
+elif which == "fc2_dgelu":
+    dy = bf(torch.randn(M, D, device=dev)); w = bf(torch.randn(D, Hd, device=dev) * 0.03); z = bf(torch.randn(M, Hd, device=dev))
+    f = lambda: ops.gemm(dy, w, M=M, N=Hd, K=D, b_mn=True, aux=z, epilogue=L.EPI_DGELU)
+elif which == "wgrad":
+    dz = bf(torch.randn(M, Hd, device=dev)); x = bf(torch.randn(M, D, device=dev))
+    dw = torch.zeros(Hd, D, device=dev); db = torch.zeros(Hd, device=dev)
+    f = lambda: ops.gemm(dz, x, M=Hd, N=D, K=M, a_mn=True, b_mn=True, epilogue=L.EPI_F32_ADD, out=dw, splits=8, bias_grad=db)
+elif which in ("attn_fwd", "attn_bwd"):
+    B, N, H, hd = 256, 197, 12, 64
+    qkv = bf(torch.randn(B, N, 3, H, hd, device=dev))
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    o, lse = ops.attention_fwd(q, k, v, hd ** -0.5)
+    do = torch.randn_like(o); dqkv = torch.empty_like(qkv)
+    f = (lambda: ops.attention_fwd(q, k, v, hd ** -0.5)) if which == "attn_fwd" else \
+        (lambda: ops.attention_bwd(q, k, v, o, do, lse, hd ** -0.5, dq=dqkv[:, :, 0], dk=dqkv[:, :, 1], dv=dqkv[:, :, 2]))
+elif which in ("ln_fwd", "ln_bwd"):
+    x = bf(torch.randn(M, D, device=dev)); g = torch.randn(D, device=dev); b = torch.randn(D, device=dev)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-6)
+    dy = bf(torch.randn(M, D, device=dev)); dg = torch.zeros(D, device=dev); dbb = torch.zeros(D, device=dev)
+    f = (lambda: ops.layernorm_fwd(x, g, b, 1e-6)) if which == "ln_fwd" else \
+        (lambda: ops.layernorm_bwd(dy, x, g, mean, rstd, dres=dy, dgamma=dg, dbeta=dbb))
+else:
+    raise SystemExit("unknown kernel " + which)
+for _ in range(4):
+    f()
+torch.cuda.synchronize()
+print("ok", which)

@@ -86,7 +86,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int PSB = Cfg::PS_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic)
   uint8_t* kv_s = smem;             // [2 items][K, V]
   uint8_t* q_s = kv_s + 4 * TB;     // [2]
   uint8_t* do_s = q_s + 2 * TB;     // [2]
@@ -225,12 +225,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t k_addr = smem_u32(kv_s + ((n & 1) * 2 + 0) * TB);
         const uint32_t q_addr = smem_u32(q_s + slot * TB), do_addr = smem_u32(do_s + slot * TB);
         const uint32_t ds_addr = smem_u32(ds_s + db * PSB);
+        // next tile's S/dP first -- as soon as the compute warps have read S/dP(t) out of tensor memory,
+        // i.e. before P(t)/dS(t) are even written: its exp/dS math then overlaps all three products of tile t
+        if (t + 1 < total_tiles) issue_sdp(t + 1);
         mbar_wait(&pds_full[db], (t >> 1) & 1);                      // P(t), dS(t) are in shared memory
         if (i == 0) mbar_wait(dkv_empty, (n & 1) ^ 1);               // previous item's dK/dV have left TMEM
         tc_fence_after();
         UCF_TL(t, 1);
-        // next tile's S/dP first: its exp/dS math then overlaps all three products of tile t
-        if (t + 1 < total_tiles) issue_sdp(t + 1);
         // dV += P^T dO_t   (reduction over the 128 query rows, 16 per MMA); releases the single P buffer
 #pragma unroll
         for (int kk = 0; kk < T / 16; ++kk)

@@ -64,7 +64,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr int RB = Cfg::ROW_BYTES, AB = Cfg::ATOM_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic)
   uint8_t* q_s = smem;                                  // [2 buffers][2 tiles]
   uint8_t* kv_s = q_s + 4 * Cfg::Q_BYTES;               // [RING]
   uint8_t* p_s = kv_s + RING * Cfg::KV_BYTES;           // [2 warpgroups]

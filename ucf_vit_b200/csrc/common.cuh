@@ -292,6 +292,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Remote arrive without the release fence (MEMBAR.ALL + ERRBAR, ~20 % of an epilogue warp's time when
+// paid once per tile).  Only for signals that publish no ordinary memory writes: "my tcgen05.ld of this
+// accumulator buffer have completed" (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load issued by either CTA of a pair; the transaction bytes are credited to the barrier at
 // `bar_cluster_addr` (a shared::cluster address, normally in the leader CTA).
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
@@ -432,6 +438,54 @@ __device__ __forceinline__ float2 gelu_erf_grad2(float2 z) {
   gelu_terms2(z, q, e);
   const float2 cdf = make_float2(z.x >= 0.f ? 1.0f - q.x : q.x, z.y >= 0.f ? 1.0f - q.y : q.y);
   return __ffma2_rn(__fmul2_rn(z, mk2(0.39894228040143267794f)), e, cdf);
+}
+// ---- MUFU-free forms for the GEMM epilogues (the A&S form above costs two MUFU ops per element and
+// made the fc1 / fc2-dgrad epilogues MUFU-bound: 16 MUFU lanes per SM against 128 FMA lanes).
+// With zc = clamp(z, -5, 5) and u = zc^2 * (2/25) - 1 in [-1, 1]:
+//   Phi(z) - 1/2            = zc * P12(u)     |error| <= 4e-7   (near-minimax fit, fp32 Horner)
+//   Phi(z) + z phi(z) - 1/2 = zc * D13(u)     |error| <= 6e-6
+// (beyond |z| = 5, Phi is within 3e-7 of 0 / 1 and z phi(z) below 8e-6).
+__device__ __forceinline__ float2 gelu_poly_u2(float2 z, float2& zc) {
+  zc = make_float2(fminf(fmaxf(z.x, -5.0f), 5.0f), fminf(fmaxf(z.y, -5.0f), 5.0f));
+  return __ffma2_rn(__fmul2_rn(zc, zc), mk2(0.08f), mk2(-1.0f));
+}
+__device__ __forceinline__ float2 gelu_poly2(float2 z) {       // z * Phi(z)
+  float2 zc;
+  const float2 u = gelu_poly_u2(z, zc);
+  float2 p = mk2(7.353763888e-04f);
+  p = __ffma2_rn(p, u, mk2(-1.676730979e-03f));
+  p = __ffma2_rn(p, u, mk2(1.374596151e-03f));
+  p = __ffma2_rn(p, u, mk2(-2.526916729e-03f));
+  p = __ffma2_rn(p, u, mk2(6.766527505e-03f));
+  p = __ffma2_rn(p, u, mk2(-1.130712491e-02f));
+  p = __ffma2_rn(p, u, mk2(1.623608981e-02f));
+  p = __ffma2_rn(p, u, mk2(-2.321312828e-02f));
+  p = __ffma2_rn(p, u, mk2(3.147675865e-02f));
+  p = __ffma2_rn(p, u, mk2(-4.045128240e-02f));
+  p = __ffma2_rn(p, u, mk2(5.151792974e-02f));
+  p = __ffma2_rn(p, u, mk2(-7.029590887e-02f));
+  p = __ffma2_rn(p, u, mk2(1.413638185e-01f));
+  const float2 t = __fmul2_rn(zc, p);                            // Phi - 1/2
+  return __ffma2_rn(z, t, __fmul2_rn(z, mk2(0.5f)));
+}
+__device__ __forceinline__ float2 gelu_grad_poly2(float2 z) {  // Phi(z) + z phi(z)
+  float2 zc;
+  const float2 u = gelu_poly_u2(z, zc);
+  float2 p = mk2(-5.735615125e-03f);
+  p = __ffma2_rn(p, u, mk2(1.261547586e-02f));
+  p = __ffma2_rn(p, u, mk2(-7.203916122e-03f));
+  p = __ffma2_rn(p, u, mk2(1.123988696e-02f));
+  p = __ffma2_rn(p, u, mk2(-3.821696020e-02f));
+  p = __ffma2_rn(p, u, mk2(5.801962140e-02f));
+  p = __ffma2_rn(p, u, mk2(-6.598634567e-02f));
+  p = __ffma2_rn(p, u, mk2(7.754241580e-02f));
+  p = __ffma2_rn(p, u, mk2(-8.495648970e-02f));
+  p = __ffma2_rn(p, u, mk2(8.085778139e-02f));
+  p = __ffma2_rn(p, u, mk2(-7.173111262e-02f));
+  p = __ffma2_rn(p, u, mk2(6.653327323e-02f));
+  p = __ffma2_rn(p, u, mk2(-7.511106477e-02f));
+  p = __ffma2_rn(p, u, mk2(1.421342312e-01f));
+  return __ffma2_rn(zc, p, mk2(0.5f));
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -130,7 +130,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic)
   uint8_t* stage_base = smem;
   uint8_t* epi_out = smem + STAGES * STAGE_BYTES;
   uint8_t* epi_aux = epi_out + Cfg::OUT_STAGE_BYTES;
@@ -345,20 +345,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 f[3] = __fadd2_rn(f[3], bf16x2_to_f32x2(r.w));
               } else if (EPI == EPI_DGELU) {
                 const uint4 r = *reinterpret_cast<const uint4*>(aux_row + sw);
-                f[0] = __fmul2_rn(f[0], gelu_erf_grad2(bf16x2_to_f32x2(r.x)));
-                f[1] = __fmul2_rn(f[1], gelu_erf_grad2(bf16x2_to_f32x2(r.y)));
-                f[2] = __fmul2_rn(f[2], gelu_erf_grad2(bf16x2_to_f32x2(r.z)));
-                f[3] = __fmul2_rn(f[3], gelu_erf_grad2(bf16x2_to_f32x2(r.w)));
+                f[0] = __fmul2_rn(f[0], gelu_grad_poly2(bf16x2_to_f32x2(r.x)));
+                f[1] = __fmul2_rn(f[1], gelu_grad_poly2(bf16x2_to_f32x2(r.y)));
+                f[2] = __fmul2_rn(f[2], gelu_grad_poly2(bf16x2_to_f32x2(r.z)));
+                f[3] = __fmul2_rn(f[3], gelu_grad_poly2(bf16x2_to_f32x2(r.w)));
               } else if (EPI == EPI_BIAS_GELU_AUX) {
                 // pre-activation is rounded to bf16 first so that backward (which re-reads the
                 // stored bf16 z) differentiates exactly the function forward evaluated.
                 uint4 zq = make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y),
                                       pack_bf16x2(f[2].x, f[2].y), pack_bf16x2(f[3].x, f[3].y));
                 *reinterpret_cast<uint4*>(aux_row + sw) = zq;
-                f[0] = gelu_erf2(bf16x2_to_f32x2(zq.x));
-                f[1] = gelu_erf2(bf16x2_to_f32x2(zq.y));
-                f[2] = gelu_erf2(bf16x2_to_f32x2(zq.z));
-                f[3] = gelu_erf2(bf16x2_to_f32x2(zq.w));
+                f[0] = gelu_poly2(bf16x2_to_f32x2(zq.x));
+                f[1] = gelu_poly2(bf16x2_to_f32x2(zq.y));
+                f[2] = gelu_poly2(bf16x2_to_f32x2(zq.z));
+                f[3] = gelu_poly2(bf16x2_to_f32x2(zq.w));
               }
               *reinterpret_cast<uint4*>(out_row + sw) =
                   make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y), pack_bf16x2(f[2].x, f[2].y),
@@ -434,7 +434,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr int A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (STS/LDS, not generic)
   uint8_t* stage_base = smem;
   uint8_t* epi_out = smem + STAGES * STAGE_BYTES;
   uint8_t* epi_aux = epi_out + Cfg::OUT_STAGE_BYTES;
@@ -647,18 +647,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 f[3] = __fadd2_rn(f[3], bf16x2_to_f32x2(r.w));
               } else if (EPI == EPI_DGELU) {
                 const uint4 r = *reinterpret_cast<const uint4*>(aux_row + sw);
-                f[0] = __fmul2_rn(f[0], gelu_erf_grad2(bf16x2_to_f32x2(r.x)));
-                f[1] = __fmul2_rn(f[1], gelu_erf_grad2(bf16x2_to_f32x2(r.y)));
-                f[2] = __fmul2_rn(f[2], gelu_erf_grad2(bf16x2_to_f32x2(r.z)));
-                f[3] = __fmul2_rn(f[3], gelu_erf_grad2(bf16x2_to_f32x2(r.w)));
+                f[0] = __fmul2_rn(f[0], gelu_grad_poly2(bf16x2_to_f32x2(r.x)));
+                f[1] = __fmul2_rn(f[1], gelu_grad_poly2(bf16x2_to_f32x2(r.y)));
+                f[2] = __fmul2_rn(f[2], gelu_grad_poly2(bf16x2_to_f32x2(r.z)));
+                f[3] = __fmul2_rn(f[3], gelu_grad_poly2(bf16x2_to_f32x2(r.w)));
               } else if (EPI == EPI_BIAS_GELU_AUX) {
                 uint4 zq = make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y),
                                       pack_bf16x2(f[2].x, f[2].y), pack_bf16x2(f[3].x, f[3].y));
                 *reinterpret_cast<uint4*>(aux_row + sw) = zq;
-                f[0] = gelu_erf2(bf16x2_to_f32x2(zq.x));
-                f[1] = gelu_erf2(bf16x2_to_f32x2(zq.y));
-                f[2] = gelu_erf2(bf16x2_to_f32x2(zq.z));
-                f[3] = gelu_erf2(bf16x2_to_f32x2(zq.w));
+                f[0] = gelu_poly2(bf16x2_to_f32x2(zq.x));
+                f[1] = gelu_poly2(bf16x2_to_f32x2(zq.y));
+                f[2] = gelu_poly2(bf16x2_to_f32x2(zq.z));
+                f[3] = gelu_poly2(bf16x2_to_f32x2(zq.w));
               }
               *reinterpret_cast<uint4*>(out_row + sw) =
                   make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y), pack_bf16x2(f[2].x, f[2].y),
@@ -683,7 +683,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       __syncwarp();
       // the accumulator buffer is free once the epilogue warps of BOTH CTAs are done: arrive on the
       // leader's barrier (the only one the MMA thread waits on)
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tempty_bar[buf]);
+        else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[buf]), 0));
+      }
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
