@@ -151,6 +151,23 @@ def bench_epilogues():
         print(f"{name}: {ms*1e3:8.1f} us  {fl/ms/1e9:8.1f} TFLOP/s", flush=True)
 
 
+def bench_power_scaling():
+    """Same kernel on fewer SM pairs: time x clusters stays constant when the SMs are the limit and drops
+    when the whole-chip power budget is (fewer active SMs -> each runs faster)."""
+    print("---- time x clusters for the pair kernels (constant => per-SM bound; falling => chip power/bandwidth bound)")
+    lib = L.lib()
+    M, D, Hd = 50432, 768, 3072
+    x = bf(torch.randn(M, D, device=dev)); w1 = bf(torch.randn(Hd, D, device=dev) * 0.03); b1 = torch.randn(Hd, device=dev)
+    cases = [("fc1 plain", lambda: ops.gemm(x, w1, M=M, N=Hd, K=D, bias=b1)),
+             ("fc1 gelu ", lambda: ops.gemm(x, w1, M=M, N=Hd, K=D, bias=b1, epilogue=L.EPI_BIAS_GELU_AUX))]
+    for name, f in cases:
+        for ncl in (74, 56, 37, 18, 8):
+            lib.ucf_debug_set_gemm_max_clusters(ncl)
+            ms = _time(f, iters=10)
+            print(f"{name} clusters={ncl:3d}: {ms*1e3:8.1f} us   time x clusters = {ms*1e3*ncl:9.0f} us", flush=True)
+    lib.ucf_debug_set_gemm_max_clusters(0)
+
+
 def bench_gemm():
     print("---- GEMM throughput (CUDA events, 20 iters, inputs > L2 where stated)")
     for (M, N, K, kind) in [(50432, 2304, 768, "fwd"), (50432, 768, 768, "fwd"), (50432, 3072, 768, "fwd"),
@@ -199,5 +216,6 @@ if __name__ == "__main__":
     if "gemm" in which: run_gemm_cases()
     if "bench" in which and fails == 0: bench_gemm()
     if "epi" in which and fails == 0: bench_epilogues()
+    if "power" in which: bench_power_scaling()
     print("FAILS", fails)
     sys.exit(1 if fails else 0)

@@ -408,13 +408,20 @@ struct Gemm2Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr bool HAS_AUX = (EPI == EPI_BIAS_RESIDUAL || EPI == EPI_BIAS_GELU_AUX || EPI == EPI_DGELU);
   static constexpr bool AUX_IN = (EPI == EPI_BIAS_RESIDUAL || EPI == EPI_DGELU);
-  static constexpr int EPI_WARPS = 8;
+  // The GELU / GELU' epilogues carry ~20 issue slots per element pair plus a second tensor: with two
+  // warps per scheduler the epilogue of tile i did not fit under the MMAs of tile i+1 (measured 234 us
+  // against 178 us for the plain kernel, issue slots 40 % busy -- latency-, not throughput-bound).
+  // They run 16 epilogue warps (four per TMEM lane quarter, 64 columns each) with single staging
+  // buffers; the light epilogues keep 8 warps (128 columns each) with double buffers.
+  static constexpr bool HEAVY = (EPI == EPI_BIAS_GELU_AUX || EPI == EPI_DGELU);
+  static constexpr int EPI_WARPS = HEAVY ? 16 : 8;
   static constexpr int CW = 32;
   static constexpr int OUT_BUF = (EPI == EPI_F32_ADD) ? 4096 : 2048;
   static constexpr int AUX_BUF = 2048;
-  static constexpr int OUT_NBUF = 2;
+  static constexpr int OUT_NBUF = HEAVY ? 1 : 2;
+  static constexpr int AUX_NBUF = (HEAVY && !AUX_IN) ? 1 : 2;   // aux as an input is prefetched one chunk ahead
   static constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_NBUF * OUT_BUF;
-  static constexpr int AUX_STAGE_BYTES = HAS_AUX ? EPI_WARPS * 2 * AUX_BUF : 0;
+  static constexpr int AUX_STAGE_BYTES = HAS_AUX ? EPI_WARPS * AUX_NBUF * AUX_BUF : 0;
   static constexpr bool BIASW = A_MN && EPI == EPI_F32_ADD;   // wgrad: two extra bias-gradient warps
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + (BIASW ? 64 : 0);
   static constexpr int TMEM_COLS = 512;
@@ -447,7 +454,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* bias_done = aux_bar + 2 * Cfg::EPI_WARPS;   // [STAGES] (wgrad bias-gradient warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_done + STAGES);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler: uniform branches / registers
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -518,8 +525,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    // The whole warp walks the loop converged; one elected lane issues (see elect_one()).
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, A_MN, B_MN);
+      constexpr uint32_t A_KSTEP = A_MN ? (2048 >> 4) : (32 >> 4), B_KSTEP = B_MN ? (2048 >> 4) : (32 >> 4);
       uint32_t kiter = 0;
       int it = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++it) {
@@ -538,17 +547,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           const uint32_t a_addr = smem_u32(stage_base + s * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
+          const uint64_t adesc = A_MN ? umma_smem_desc(a_addr, 8192, 1024) : umma_smem_desc(a_addr, 16, 1024);
+          const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr, 8192, 1024) : umma_smem_desc(b_addr, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
-                                        : umma_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
-                                        : umma_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_2sm(d_tmem, adesc + k * A_KSTEP, bdesc + k * B_KSTEP, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[s], 3);     // both CTAs may refill this stage
           }
-          umma_commit_2sm(&empty_bar[s], 3);     // both CTAs may refill this stage
+          __syncwarp();
         }
-        umma_commit_2sm(&tfull_bar[buf], 3);     // accumulator complete in both CTAs' TMEM
+        if (elect_one()) umma_commit_2sm(&tfull_bar[buf], 3);     // accumulator complete in both CTAs' TMEM
+        __syncwarp();
       }
     }
   } else if (Cfg::BIASW && warp >= 2 + Cfg::EPI_WARPS) {
@@ -559,13 +569,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------------ epilogue warps (both CTAs)
     const int q = warp & 3;
     const int ew = warp - 2;
-    const int half = ew >> 2;
+    constexpr int G = Cfg::EPI_WARPS / 4;        // column groups: each warp owns BN / G columns of its 32 rows
+    const int grp = ew >> 2;
     const int etid = threadIdx.x - 64;
     constexpr int CW = Cfg::CW;
-    constexpr int NCHUNK = BN / 2 / CW;
+    constexpr int NCHUNK = BN / G / CW;
     constexpr int OUT_BUF = Cfg::OUT_BUF, AUX_BUF = Cfg::AUX_BUF;
-    uint8_t* my_out = epi_out + ew * Cfg::OUT_NBUF * OUT_BUF;
-    uint8_t* my_aux = epi_aux + ew * 2 * AUX_BUF;
+    constexpr int ONB = Cfg::OUT_NBUF, ANB = Cfg::AUX_NBUF;
+    uint8_t* my_out = epi_out + ew * ONB * OUT_BUF;
+    uint8_t* my_aux = epi_aux + ew * ANB * AUX_BUF;
     uint64_t* my_aux_bar = aux_bar + ew * 2;
     const uint32_t sw64 = (lane >> 1) & 3, sw128 = lane & 7;
     uint32_t cc = 0;
@@ -577,7 +589,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m0 = m_blk * 2 * BM + rank * BM, n0 = n_blk * BN;
       const int buf = it & 1;
       const int r0 = m0 + q * 32;
-      const int cbase = half * (BN / 2);
+      const int cbase = grp * (BN / G);
 
       if (EPI != EPI_F32_ADD && EPI != EPI_DGELU) {
         named_bar_sync(1, 32 * Cfg::EPI_WARPS);
@@ -605,6 +617,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int col0 = n0 + cbase + c * CW;
           if (col0 >= p.N) break;
           const uint32_t b = cc & 1;
+          const uint32_t ob = (ONB == 2) ? b : 0u, ab = (ANB == 2) ? b : 0u;
           if (Cfg::AUX_IN && lane == 0 && c + 1 < NCHUNK && col0 + CW < p.N) {
             mbar_expect_tx(&my_aux_bar[b ^ 1], AUX_BUF);
             tma_load_2d(my_aux + (b ^ 1) * AUX_BUF, &tmAux, &my_aux_bar[b ^ 1], col0 + CW, r0);
@@ -612,18 +625,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint32_t v[32];
           tmem_ld32(t_row + c * CW, v);
           tmem_wait_ld();
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
           if (Cfg::AUX_IN) mbar_wait(&my_aux_bar[b], (cc >> 1) & 1);
           if (EPI == EPI_F32_ADD) {
-            uint8_t* out_row = my_out + b * OUT_BUF + lane * 128;
+            if (lane == 0) tma_store_wait_read<ONB - 1>();
+            __syncwarp();
+            uint8_t* out_row = my_out + ob * OUT_BUF + lane * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<uint4*>(out_row + ((j ^ sw128) << 4)) =
                   make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            uint8_t* out_row = my_out + b * OUT_BUF + lane * 64;
-            uint8_t* aux_row = my_aux + b * AUX_BUF + lane * 64;
+            uint8_t* out_row = my_out + ob * OUT_BUF + lane * 64;
+            uint8_t* aux_row = my_aux + ab * AUX_BUF + lane * 64;
+            // results are formed in registers first, so that waiting for the staging buffer's previous TMA
+            // store (single-buffered in the heavy epilogues) overlaps the math
+            uint4 o_pk[4], z_pk[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float2 f[4];
@@ -652,27 +668,34 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 f[2] = __fmul2_rn(f[2], gelu_grad_poly2(bf16x2_to_f32x2(r.z)));
                 f[3] = __fmul2_rn(f[3], gelu_grad_poly2(bf16x2_to_f32x2(r.w)));
               } else if (EPI == EPI_BIAS_GELU_AUX) {
-                uint4 zq = make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y),
-                                      pack_bf16x2(f[2].x, f[2].y), pack_bf16x2(f[3].x, f[3].y));
-                *reinterpret_cast<uint4*>(aux_row + sw) = zq;
+                const uint4 zq = make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y),
+                                            pack_bf16x2(f[2].x, f[2].y), pack_bf16x2(f[3].x, f[3].y));
+                z_pk[j] = zq;
                 f[0] = gelu_poly2(bf16x2_to_f32x2(zq.x));
                 f[1] = gelu_poly2(bf16x2_to_f32x2(zq.y));
                 f[2] = gelu_poly2(bf16x2_to_f32x2(zq.z));
                 f[3] = gelu_poly2(bf16x2_to_f32x2(zq.w));
               }
-              *reinterpret_cast<uint4*>(out_row + sw) =
-                  make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y), pack_bf16x2(f[2].x, f[2].y),
-                             pack_bf16x2(f[3].x, f[3].y));
+              o_pk[j] = make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y), pack_bf16x2(f[2].x, f[2].y),
+                                   pack_bf16x2(f[3].x, f[3].y));
+            }
+            if (lane == 0) tma_store_wait_read<ONB - 1>();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t sw = (static_cast<uint32_t>(j) ^ sw64) << 4;
+              *reinterpret_cast<uint4*>(out_row + sw) = o_pk[j];
+              if (EPI == EPI_BIAS_GELU_AUX) *reinterpret_cast<uint4*>(aux_row + sw) = z_pk[j];
             }
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             if (EPI == EPI_F32_ADD) {
-              tma_reduce_add_2d(&tmC, my_out + b * OUT_BUF, col0, r0);
+              tma_reduce_add_2d(&tmC, my_out + ob * OUT_BUF, col0, r0);
             } else {
-              tma_store_2d(&tmC, my_out + b * OUT_BUF, col0, r0);
-              if (EPI == EPI_BIAS_GELU_AUX) tma_store_2d(&tmAux, my_aux + b * AUX_BUF, col0, r0);
+              tma_store_2d(&tmC, my_out + ob * OUT_BUF, col0, r0);
+              if (EPI == EPI_BIAS_GELU_AUX) tma_store_2d(&tmAux, my_aux + ab * AUX_BUF, col0, r0);
             }
             tma_store_commit();
           }
@@ -732,6 +755,8 @@ static int launch_gemm(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   return check_launch("gemm_bf16_kernel");
 }
 
+static int g_debug_max_clusters = 0;   // profiling aid (ucf_debug_set_gemm_max_clusters): run on fewer SM pairs
+
 template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm2(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC,
                         const CUtensorMap& tAux, const GemmParams& p, cudaStream_t st) {
@@ -748,6 +773,7 @@ static int launch_gemm2(const CUtensorMap& tA, const CUtensorMap& tB, const CUte
   }
   const int total = p.tiles_m * p.tiles_n * p.splits;
   int clusters = num_sms() / 2;
+  if (g_debug_max_clusters > 0 && clusters > g_debug_max_clusters) clusters = g_debug_max_clusters;
   if (clusters > total) clusters = total;
   kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tA, tB, tC, tAux, p);   // __cluster_dims__(2,1,1)
   return check_launch("gemm2_bf16_kernel");
@@ -756,6 +782,9 @@ static int launch_gemm2(const CUtensorMap& tA, const CUtensorMap& tB, const CUte
 }  // namespace ucf
 
 using namespace ucf;
+
+/* profiling aid (not part of the public header): limit the CTA-pair kernels to n clusters (0 = all SMs) */
+extern "C" void ucf_debug_set_gemm_max_clusters(int n) { ucf::g_debug_max_clusters = n; }
 
 extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* bias, void* aux,
                              int M, int N, int K, long long lda, long long ldb, long long ldc,
@@ -843,7 +872,7 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
   UCF_GEMM2_CASE(5, false, false, EPI_BIAS_RESIDUAL)
   UCF_GEMM2_CASE(5, false, false, EPI_BIAS_GELU_AUX)
   UCF_GEMM2_CASE(6, false, true, EPI_BIAS)
-  UCF_GEMM2_CASE(5, false, true, EPI_DGELU)
+  UCF_GEMM2_CASE(4, false, true, EPI_DGELU)
   UCF_GEMM2_CASE(5, true, true, EPI_F32_ADD)
 #undef UCF_GEMM2_CASE
   if (pair) {
