@@ -107,7 +107,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_free = bars + 18;      // dV(t) retired: P may be rewritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: warp-uniform for the compiler, so the producer / MMA warps run converged and
+  // keep TMA / UMMA descriptors in uniform registers (no per-instruction ELECT / R2UR waterfall)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int nq = (p.Nq + T - 1) / T;
   const int nkt = p.nkt;
   // sub-item = (b, h, key tile): nq tiles each.  LONG: one per work item; SHORT: nkt consecutive per work item.
@@ -161,31 +163,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (converged warp, elected lane issues)
+    {
       uint32_t t = 0;
       for (uint32_t n = 0; n < static_cast<uint32_t>(my_items); ++n) {
         int b, h, jt;
         decode(n, b, h, jt);
         const int kb = n & 1;
         mbar_wait(&kv_empty[kb], ((n >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[kb], 2 * TB);
-        tma_load_4d(kv_s + (kb * 2 + 0) * TB, &tmK, &kv_full[kb], 0, h, jt * T, b);
-        tma_load_4d(kv_s + (kb * 2 + 1) * TB, &tmV, &kv_full[kb], 0, h, jt * T, b);
+        if (elect_one()) {
+          mbar_expect_tx(&kv_full[kb], 2 * TB);
+          tma_load_4d(kv_s + (kb * 2 + 0) * TB, &tmK, &kv_full[kb], 0, h, jt * T, b);
+          tma_load_4d(kv_s + (kb * 2 + 1) * TB, &tmV, &kv_full[kb], 0, h, jt * T, b);
+        }
+        __syncwarp();
         for (int i = 0; i < nq; ++i, ++t) {
           if (SHORT && jt > 0) continue;            // resident since the work item's first key tile
           const uint32_t u = qinst(t, n, i);
           const int slot = u & 1;
           mbar_wait(&qdo_empty[slot], ((u >> 1) & 1) ^ 1);
-          mbar_expect_tx(&qdo_full[slot], 2 * TB);
-          tma_load_4d(q_s + slot * TB, &tmQ, &qdo_full[slot], 0, h, i * T, b);
-          tma_load_4d(do_s + slot * TB, &tmdO, &qdo_full[slot], 0, h, i * T, b);
+          if (elect_one()) {
+            mbar_expect_tx(&qdo_full[slot], 2 * TB);
+            tma_load_4d(q_s + slot * TB, &tmQ, &qdo_full[slot], 0, h, i * T, b);
+            tma_load_4d(do_s + slot * TB, &tmdO, &qdo_full[slot], 0, h, i * T, b);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && total_tiles > 0) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane issues)
+    if (total_tiles > 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(T, T, false, false);     // S, dP
       constexpr uint32_t idesc_tn = umma_idesc_bf16(T, HD, true, true);      // dV, dK
       constexpr uint32_t idesc_dq = umma_idesc_bf16(T, HD, false, true);     // dQ
@@ -205,13 +213,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(sdp_empty, (t & 1) ^ 1);
         tc_fence_after();
         UCF_TL(t, 0);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(t_s, bwd_desc<RB>(q_addr + k * 32, 16, AB), bwd_desc<RB>(k_addr + k * 32, 16, AB), idesc_qk, k > 0);
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16(t_s, bwd_desc<RB>(q_addr + k * 32, 16, AB), bwd_desc<RB>(k_addr + k * 32, 16, AB), idesc_qk, k > 0);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(t_dp, bwd_desc<RB>(do_addr + k * 32, 16, AB), bwd_desc<RB>(v_addr + k * 32, 16, AB), idesc_qk, k > 0);
-        umma_commit(sdp_full);
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16(t_dp, bwd_desc<RB>(do_addr + k * 32, 16, AB), bwd_desc<RB>(v_addr + k * 32, 16, AB), idesc_qk, k > 0);
+          umma_commit(sdp_full);
+        }
+        __syncwarp();
       };
 
       issue_sdp(0);
@@ -233,32 +244,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         UCF_TL(t, 1);
         // dV += P^T dO_t   (reduction over the 128 query rows, 16 per MMA); releases the single P buffer
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < T / 16; ++kk)
-          umma_bf16(t_dv, umma_smem_desc(p_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(do_addr + kk * 2 * AB, 0, AB),
-                    idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(p_free);
+          for (int kk = 0; kk < T / 16; ++kk)
+            umma_bf16(t_dv, umma_smem_desc(p_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(do_addr + kk * 2 * AB, 0, AB),
+                      idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(p_free);
+        }
+        __syncwarp();
         if (first_kt) {
           mbar_wait(&dq_empty[slot], ((u >> 1) & 1) ^ 1);
           tc_fence_after();
         }
         UCF_TL(t, 11);
         // dQ_t (+)= dS K_j   (reduction over the 128 keys; SHORT: accumulated over the key tiles)
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < T / 16; ++kk)
-          umma_bf16(t_dq + slot * 64, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                    bwd_desc<RB>(k_addr + kk * 2 * AB, 0, AB), idesc_dq, (!first_kt || kk > 0) ? 1u : 0u);
-        // dK += dS^T Q_t
+          for (int kk = 0; kk < T / 16; ++kk)
+            umma_bf16(t_dq + slot * 64, umma_smem_desc(ds_addr + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                      bwd_desc<RB>(k_addr + kk * 2 * AB, 0, AB), idesc_dq, (!first_kt || kk > 0) ? 1u : 0u);
+          // dK += dS^T Q_t
 #pragma unroll
-        for (int kk = 0; kk < T / 16; ++kk)
-          umma_bf16(t_dk, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(q_addr + kk * 2 * AB, 0, AB),
-                    idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&dq_full[db]);          // every product of tile t has retired
-        if (last_kt) umma_commit(&qdo_empty[slot]);
-        if (i + 1 == nq) {
-          umma_commit(dkv_full);
-          umma_commit(&kv_empty[n & 1]);
+          for (int kk = 0; kk < T / 16; ++kk)
+            umma_bf16(t_dk, umma_smem_desc(ds_addr + kk * 2048, 16384, 1024), bwd_desc<RB>(q_addr + kk * 2 * AB, 0, AB),
+                      idesc_tn, (i > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&dq_full[db]);          // every product of tile t has retired
+          if (last_kt) umma_commit(&qdo_empty[slot]);
+          if (i + 1 == nq) {
+            umma_commit(dkv_full);
+            umma_commit(&kv_empty[n & 1]);
+          }
         }
+        __syncwarp();
         UCF_TL(t, 12);
       }
     }

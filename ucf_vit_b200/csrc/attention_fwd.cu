@@ -79,7 +79,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* pv_full = s_full + 6;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: warp-uniform for the compiler, so the producer / MMA warps run converged and
+  // keep TMA / UMMA descriptors in uniform registers (no per-instruction ELECT / R2UR waterfall)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const int nkv = (p.Nk + BKV - 1) / BKV;
 
   if (warp == 0 && lane == 0) {
@@ -110,30 +112,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (converged warp, elected lane issues)
+    {
       uint32_t it = 0, r = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         int b, h, q0;
         decode(item, b, h, q0);
         const int qb = it & 1;
         mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&q_full[qb], 2 * Cfg::Q_BYTES);
-        tma_load_4d(q_s + (qb * 2 + 0) * Cfg::Q_BYTES, &tmQ, &q_full[qb], 0, h, q0, b);
-        tma_load_4d(q_s + (qb * 2 + 1) * Cfg::Q_BYTES, &tmQ, &q_full[qb], 0, h, q0 + BQ, b);
+        if (elect_one()) {
+          mbar_expect_tx(&q_full[qb], 2 * Cfg::Q_BYTES);
+          tma_load_4d(q_s + (qb * 2 + 0) * Cfg::Q_BYTES, &tmQ, &q_full[qb], 0, h, q0, b);
+          tma_load_4d(q_s + (qb * 2 + 1) * Cfg::Q_BYTES, &tmQ, &q_full[qb], 0, h, q0 + BQ, b);
+        }
+        __syncwarp();
         for (int j = 0; j < nkv; ++j) {
           for (int t = 0; t < 2; ++t, ++r) {
             const int slot = r % RING;
             mbar_wait(&kv_empty[slot], ((r / RING) & 1) ^ 1);
-            mbar_expect_tx(&kv_full[slot], Cfg::KV_BYTES);
-            tma_load_4d(kv_s + slot * Cfg::KV_BYTES, t == 0 ? &tmK : &tmV, &kv_full[slot], 0, h, j * BKV, b);
+            if (elect_one()) {
+              mbar_expect_tx(&kv_full[slot], Cfg::KV_BYTES);
+              tma_load_4d(kv_s + slot * Cfg::KV_BYTES, t == 0 ? &tmK : &tmV, &kv_full[slot], 0, h, j * BKV, b);
+            }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane issues)
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, false, false);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, false, true);
       const uint32_t p_addr0 = smem_u32(p_s);
@@ -152,11 +160,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc_fence_after();
           if (p.timeline && blockIdx.x == 0 && tc[g] < 4) p.timeline[(g * 4 + tc[g]) * 8 + 0] = clock64();   // S issue
           const uint32_t d = tmem_base + g * 256;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16(d, attn_desc<RB>(q_addr + g * Cfg::Q_BYTES + k * 32, 16, AB), attn_desc<RB>(k_addr + k * 32, 16, AB),
-                      idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(&s_full[g]);
+            for (int k = 0; k < HD / 16; ++k)
+              umma_bf16(d, attn_desc<RB>(q_addr + g * Cfg::Q_BYTES + k * 32, 16, AB), attn_desc<RB>(k_addr + k * 32, 16, AB),
+                        idesc_s, k > 0 ? 1u : 0u);
+            umma_commit(&s_full[g]);
+          }
+          __syncwarp();
         };
         auto issue_pv = [&](int g, uint32_t v_addr) {
           mbar_wait(&p_full[g], tc[g] & 1);
@@ -164,11 +175,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (p.timeline && blockIdx.x == 0 && tc[g] < 4) p.timeline[(g * 4 + tc[g]) * 8 + 1] = clock64();   // PV issue
           const uint32_t d = tmem_base + g * 256 + 128;
           const uint32_t pa = p_addr0 + g * Cfg::P_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < BKV / 16; ++kk)
-            umma_bf16(d, umma_smem_desc(pa + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                      attn_desc<RB>(v_addr + kk * 2 * AB, 0, AB), idesc_pv, kk > 0 ? 1u : 0u);
-          umma_commit(&pv_full[g]);
+            for (int kk = 0; kk < BKV / 16; ++kk)
+              umma_bf16(d, umma_smem_desc(pa + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                        attn_desc<RB>(v_addr + kk * 2 * AB, 0, AB), idesc_pv, kk > 0 ? 1u : 0u);
+            umma_commit(&pv_full[g]);
+          }
+          __syncwarp();
           ++tc[g];
         };
 
@@ -178,7 +192,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mbar_wait(&kv_full[sk], (r / RING) & 1);
           const uint32_t k_addr = smem_u32(kv_s + sk * Cfg::KV_BYTES);
           for (int g = 0; g < ng; ++g) issue_s(g, k_addr);
-          umma_commit(&kv_empty[sk]);
+          if (elect_one()) umma_commit(&kv_empty[sk]);
+          __syncwarp();
           ++r;
         }
         for (int j = 0; j < nkv; ++j) {
@@ -199,10 +214,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             issue_pv(g, v_addr);                 // waits for P_g(j)
             if (more) issue_s(g, k_addr);        // S_g(j+1): overlaps the other warpgroup's softmax
           }
-          umma_commit(&kv_empty[sv]);
-          if (more) umma_commit(&kv_empty[sk]);
+          if (elect_one()) {
+            umma_commit(&kv_empty[sv]);
+            if (more) umma_commit(&kv_empty[sk]);
+          }
+          __syncwarp();
         }
-        umma_commit(&q_empty[qb]);               // every S product of this item has been issued
+        if (elect_one()) umma_commit(&q_empty[qb]);               // every S product of this item has been issued
+        __syncwarp();
       }
     }
   } else {

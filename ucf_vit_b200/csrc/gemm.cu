@@ -143,7 +143,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* bias_done = aux_bar + 2 * Cfg::EPI_WARPS;   // [STAGES] (wgrad bias-gradient warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_done + STAGES);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler: uniform branches / registers
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -173,7 +173,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {   // converged warp; one elected lane issues the TMA loads (descriptors stay in uniform registers)
       uint32_t kiter = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_blk = tile % p.tiles_n;
@@ -188,28 +188,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t ph = (kiter / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (Cfg::BIASW) mbar_wait(&bias_done[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-          uint8_t* a_dst = stage_base + s * STAGE_BYTES;
-          uint8_t* b_dst = a_dst + A_BYTES;
-          if (!A_MN) {
-            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
-          } else {
-            tma_load_2d(a_dst, &tmA, &full_bar[s], m0, kb * BK);
-            tma_load_2d(a_dst + 8192, &tmA, &full_bar[s], m0 + 64, kb * BK);
-          }
-          if (!B_MN) {
-            tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
-          } else {
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            uint8_t* a_dst = stage_base + s * STAGE_BYTES;
+            uint8_t* b_dst = a_dst + A_BYTES;
+            if (!A_MN) {
+              tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+            } else {
+              tma_load_2d(a_dst, &tmA, &full_bar[s], m0, kb * BK);
+              tma_load_2d(a_dst + 8192, &tmA, &full_bar[s], m0 + 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * BK);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(b_dst + j * 8192, &tmB, &full_bar[s], n0 + j * 64, kb * BK);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane issues)
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       uint32_t kiter = 0;
       int it = 0;
@@ -229,17 +232,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t a_addr = smem_u32(stage_base + s * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
-                                        : umma_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
-                                        : umma_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + k * 2048, 8192, 1024)
+                                          : umma_smem_desc(a_addr + k * 32, 16, 1024);
+              const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + k * 2048, 8192, 1024)
+                                          : umma_smem_desc(b_addr + k * 32, 16, 1024);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[s]);   // smem slot reusable once these MMAs retire
           }
-          umma_commit(&empty_bar[s]);   // smem slot reusable once these MMAs retire
+          __syncwarp();
         }
-        umma_commit(&tfull_bar[buf]);   // accumulator complete
+        if (elect_one()) umma_commit(&tfull_bar[buf]);   // accumulator complete
+        __syncwarp();
       }
     }
   } else if (Cfg::BIASW && warp >= 2 + Cfg::EPI_WARPS) {
@@ -486,8 +493,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs; converged warp)
+    {
       uint32_t kiter = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int n_blk = tile % p.tiles_n;
@@ -503,23 +510,26 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t ph = (kiter / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (Cfg::BIASW) mbar_wait(&bias_done[s], ph ^ 1);
-          const uint32_t full0 = mapa_u32(smem_u32(&full_bar[s]), 0);     // the leader's barrier
-          if (leader) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
-          uint8_t* a_dst = stage_base + s * STAGE_BYTES;
-          uint8_t* b_dst = a_dst + A_BYTES;
-          if (!A_MN) {
-            tma_load_2d_2sm(a_dst, &tmA, full0, kb * BK, m0);
-          } else {
-            tma_load_2d_2sm(a_dst, &tmA, full0, m0, kb * BK);
-            tma_load_2d_2sm(a_dst + 8192, &tmA, full0, m0 + 64, kb * BK);
-          }
-          if (!B_MN) {
-            tma_load_2d_2sm(b_dst, &tmB, full0, kb * BK, n0);
-          } else {
+          if (elect_one()) {
+            const uint32_t full0 = mapa_u32(smem_u32(&full_bar[s]), 0);     // the leader's barrier
+            if (leader) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+            uint8_t* a_dst = stage_base + s * STAGE_BYTES;
+            uint8_t* b_dst = a_dst + A_BYTES;
+            if (!A_MN) {
+              tma_load_2d_2sm(a_dst, &tmA, full0, kb * BK, m0);
+            } else {
+              tma_load_2d_2sm(a_dst, &tmA, full0, m0, kb * BK);
+              tma_load_2d_2sm(a_dst + 8192, &tmA, full0, m0 + 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d_2sm(b_dst, &tmB, full0, kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < HN / 64; ++j)
-              tma_load_2d_2sm(b_dst + j * 8192, &tmB, full0, n0 + j * 64, kb * BK);
+              for (int j = 0; j < HN / 64; ++j)
+                tma_load_2d_2sm(b_dst + j * 8192, &tmB, full0, n0 + j * 64, kb * BK);
+            }
           }
+          __syncwarp();
         }
       }
     }
