@@ -24,6 +24,7 @@ import json
 import os
 import statistics
 import subprocess
+import threading
 import sys
 import time
 
@@ -116,47 +117,101 @@ def run_reference_arm(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, board power and throttle reasons sampled DURING the timed region.
+
+    Primary source: NVML in a background thread of this process (pynvml; ~5 ms period -- the main thread
+    sits in cudaStreamSynchronize with the GIL released).  Fallback: an `nvidia-smi -lms` child.  The sampler
+    is started before warm-up; `mark()` / `stop()` bracket the timed region and only samples taken between
+    them are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.path = index, None, f"/tmp/ucf_clocks_{os.getpid()}.csv"
+        self.samples, self.t_mark, self.thread, self.stop_flag, self.nvml = [], None, None, None, None
+
+    def _nvml_loop(self):
+        nv, h = self.nvml, self.handle
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
+                                               getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
+                                               getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4))}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                mask = get_reasons(h)
+                self.samples.append((time.time(), float(sm), pw, [k for k, b in bits.items() if mask & b]))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.nvml, self.stop_flag = nv, threading.Event()
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+        try:
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu=timestamp,{self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
 
+    def mark(self):
+        self.t_mark = time.time()
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        self.f.close()
+        t_end = time.time()
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
+        t0 = self.t_mark or 0.0
         sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in open(self.path):
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            for ts, c, w, rs in self.samples:
+                if t0 <= ts <= t_end:
+                    sm.append(c); pw.append(w); reasons.update(rs)
+            mx = [self.max_sm]
+            out["source"] = "nvml"
+        elif self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        try:
-            os.remove(self.path)
-        except OSError:
-            pass
+                self.proc.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+            self.f.close()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            import datetime
+            for ln in open(self.path):
+                parts = [q.strip() for q in ln.split(",")]
+                if len(parts) < 8:
+                    continue
+                try:
+                    ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if not (t0 - 0.05 <= ts <= t_end + 0.05):
+                        continue
+                    sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            try:
+                os.remove(self.path)
+            except OSError:
+                pass
+            out["source"] = "nvidia-smi"
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
                        power_w_max=max(pw))
@@ -241,15 +296,16 @@ def run_gpu_arm(args):
         timer.install()
 
     # ---------------- resident-input arm
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step(x_dev, y_dev)
     fence()
-    sampler = ClockSampler(local)
-    sampler.start()
     n0 = _lib.launch_count()
     timer.enabled = rank == 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
+    sampler.mark()
     e0.record()
     for _ in range(args.steps):
         loss = step(x_dev, y_dev)

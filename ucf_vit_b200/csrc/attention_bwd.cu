@@ -225,6 +225,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
       };
 
+      // are the operands of tile t's S/dP in shared memory yet?  (non-blocking; lane 0 decides for the warp)
+      auto sdp_inputs_ready = [&](uint32_t t) -> bool {
+        const uint32_t n = t / nq;
+        const uint32_t u = qinst(t, n, static_cast<int>(t % nq));
+        bool ok = mbar_try_wait(&qdo_full[u & 1], (u >> 1) & 1);
+        if (ok && t % nq == 0) ok = mbar_try_wait(&kv_full[n & 1], (n >> 1) & 1);
+        return __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+      };
+
       issue_sdp(0);
       for (uint32_t t = 0; t < total_tiles; ++t) {
         const uint32_t n = t / nq;
@@ -238,7 +247,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t ds_addr = smem_u32(ds_s + db * PSB);
         // next tile's S/dP first -- as soon as the compute warps have read S/dP(t) out of tensor memory,
         // i.e. before P(t)/dS(t) are even written: its exp/dS math then overlaps all three products of tile t
-        if (t + 1 < total_tiles) issue_sdp(t + 1);
+        // (at a work-item boundary the next Q/dO may still be in flight: then tile t's products go first
+        // instead of stalling the in-order issue behind the load)
+        const bool sdp_first = t + 1 < total_tiles && sdp_inputs_ready(t + 1);
+        if (sdp_first) issue_sdp(t + 1);
         mbar_wait(&pds_full[db], (t >> 1) & 1);                      // P(t), dS(t) are in shared memory
         if (i == 0) mbar_wait(dkv_empty, (n & 1) ^ 1);               // previous item's dK/dV have left TMEM
         tc_fence_after();
@@ -276,6 +288,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         __syncwarp();
+        if (t + 1 < total_tiles && !sdp_first) issue_sdp(t + 1);
         UCF_TL(t, 12);
       }
     }
