@@ -27,6 +27,7 @@ struct AttnFwdParams {
   float scale_log2;   // scale * log2(e)
   float* lse;         // [B, H, Nq]
   long long* timeline;   // optional clock64 stamps of CTA 0 (profiling aid; NULL in production)
+  int stagger_cycles;    // short-key kernel: start offset of warpgroup 1
 };
 
 template <int HD>
@@ -382,6 +383,352 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// profiling aid of the short-key kernel: clock64 stamps of CTA 0's first 4 items, 16 slots per (item, warpgroup)
+#define UCF_FTL(k_, g_, idx_)                                                                          \
+  do {                                                                                                 \
+    if (p.timeline && blockIdx.x == 0 && (k_) < 4) p.timeline[((k_) * 2 + (g_)) * 16 + (idx_)] = clock64(); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Short-key schedule (Nk <= 256: at most two key tiles -- ViT-B/16 at 224 px has 197 tokens).
+// With every score of a row available at once the softmax is exact in one sweep: S0 = Q K0^T and
+// S1 = Q K1^T go to tensor memory up front (2 x 128 columns per warpgroup), the row maximum is taken
+// over both, P0 / P1 are exponentiated against the FINAL maximum and O = P0 V0 + P1 V1 accumulates in
+// tensor memory (aliasing S0's columns) -- no running maximum, no rescaling, no O accumulator in
+// registers.  Each warpgroup has its OWN MMA-issuing warp (warps 1 and 10) walking an independent
+// command stream (S -> PV0 -> PV1 per item) with blocking waits, so the warpgroups are free to run out
+// of phase and share the MUFU pipe instead of colliding on it.  The tail key tile is trimmed to
+// a multiple of 16 keys in both the S1 and the PV1 products.
+// Same shared-memory layout, barriers and producer as the general kernel (the 4-slot ring holds exactly
+// one item's K0, V0, K1, V1); kv_empty / q_empty count two arrivals (one commit per stream).
+template <int HD>
+__global__ void __launch_bounds__(352, 1)
+attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                      const AttnFwdParams p) {
+  using Cfg = AttnFwdCfg<HD>;
+  constexpr int BQ = Cfg::BQ, BKV = Cfg::BKV, RING = Cfg::RING;
+  constexpr int RB = Cfg::ROW_BYTES, AB = Cfg::ATOM_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* q_s = smem;                                  // [2 buffers][2 tiles]
+  uint8_t* kv_s = q_s + 4 * Cfg::Q_BYTES;               // [RING]
+  uint8_t* p_s = kv_s + RING * Cfg::KV_BYTES;           // [2 warpgroups]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * Cfg::P_BYTES);
+  uint64_t* q_full = bars;                 // [2]
+  uint64_t* q_empty = bars + 2;            // [2]
+  uint64_t* kv_full = bars + 4;            // [RING]
+  uint64_t* kv_empty = bars + 4 + RING;    // [RING]
+  uint64_t* s_full = bars + 4 + 2 * RING;  // [2]
+  uint64_t* s_empty = s_full + 2;          // [2]
+  uint64_t* p_full = s_full + 4;           // [2]
+  uint64_t* pv_full = s_full + 6;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int nkv = (p.Nk + BKV - 1) / BKV;               // 1 or 2
+  const int nvalid1 = p.Nk - BKV;                       // valid keys of the tail tile (nkv == 2)
+  const int n1 = (nvalid1 + 15) & ~15;                  // ... rounded up to an MMA K / N step
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 2); }
+    for (int i = 0; i < RING; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&s_empty[g], 128);
+      mbar_init(&p_full[g], 128);
+      mbar_init(&pv_full[g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int item, int& b, int& h, int& q0) {
+    const int qp = item % p.nqp;
+    const int bh = item / p.nqp;
+    h = bh % p.H;
+    b = bh / p.H;
+    q0 = qp * 2 * BQ;
+  };
+  const int my_items = (p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (converged warp)
+    uint32_t r = 0;
+    for (int k = 0; k < my_items; ++k) {
+      int b, h, q0;
+      decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), b, h, q0);
+      const int qb = k & 1;
+      mbar_wait(&q_empty[qb], ((k >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&q_full[qb], 2 * Cfg::Q_BYTES);
+        tma_load_4d(q_s + (qb * 2 + 0) * Cfg::Q_BYTES, &tmQ, &q_full[qb], 0, h, q0, b);
+        tma_load_4d(q_s + (qb * 2 + 1) * Cfg::Q_BYTES, &tmQ, &q_full[qb], 0, h, q0 + BQ, b);
+      }
+      __syncwarp();
+      // K tiles first (both S products are issued up front), then the V tiles
+      for (int t = 0; t < 2 * nkv; ++t, ++r) {
+        const int slot = r % RING;
+        const int j = (nkv == 2) ? (t & 1) : 0;          // order: K0, K1, V0, V1
+        const bool is_v = (nkv == 2) ? (t >= 2) : (t == 1);
+        mbar_wait(&kv_empty[slot], ((r / RING) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&kv_full[slot], Cfg::KV_BYTES);
+          tma_load_4d(kv_s + slot * Cfg::KV_BYTES, is_v ? &tmV : &tmK, &kv_full[slot], 0, h, j * BKV, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1 || warp == 10) {
+    // ------------------------------------------------------------------ MMA issuers: one warp per warpgroup stream
+    // (S -> PV0 -> PV1 per item, blocking waits; the two streams never wait for each other)
+    const int g = warp == 1 ? 0 : 1;
+    constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, false, false);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, false, true);
+    const uint32_t idesc_s1 = umma_idesc_bf16(BQ, n1 > 0 ? n1 : 16, false, false);
+    const uint32_t pa = smem_u32(p_s) + g * Cfg::P_BYTES;
+    const uint32_t d_s = tmem_base + g * 256;
+    uint32_t nvalid_items = 0;     // s_empty parity
+    uint32_t pc = 0;               // p_full parity
+    for (int k = 0; k < my_items; ++k) {
+      int b, h, q0;
+      decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), b, h, q0);
+      const bool valid = q0 + g * BQ < p.Nq;
+      const int qb = k & 1;
+      const uint32_t r0 = static_cast<uint32_t>(k) * 2 * nkv;          // ring position of this item's first tile
+      const uint32_t rk0 = r0, rk1 = r0 + 1, rv0 = r0 + nkv, rv1 = r0 + 3;   // producer order K0, K1, V0, V1 (or K0, V0)
+      mbar_wait(&q_full[qb], (k >> 1) & 1);
+      mbar_wait(&kv_full[rk0 % RING], (rk0 / RING) & 1);
+      if (nkv == 2) mbar_wait(&kv_full[rk1 % RING], (rk1 / RING) & 1);
+      if (valid) mbar_wait(&s_empty[g], (nvalid_items & 1) ^ 1);
+      tc_fence_after();
+      UCF_FTL(k, g, 8);
+      if (elect_one()) {
+        if (valid) {
+          const uint32_t q_addr = smem_u32(q_s + (qb * 2 + g) * Cfg::Q_BYTES);
+          const uint32_t k0_addr = smem_u32(kv_s + (rk0 % RING) * Cfg::KV_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < HD / 16; ++kk)
+            umma_bf16(d_s, attn_desc<RB>(q_addr + kk * 32, 16, AB), attn_desc<RB>(k0_addr + kk * 32, 16, AB), idesc_s,
+                      kk > 0 ? 1u : 0u);
+          if (nkv == 2) {
+            const uint32_t k1_addr = smem_u32(kv_s + (rk1 % RING) * Cfg::KV_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; ++kk)
+              umma_bf16(d_s + 128, attn_desc<RB>(q_addr + kk * 32, 16, AB), attn_desc<RB>(k1_addr + kk * 32, 16, AB),
+                        idesc_s1, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[g]);
+        }
+        umma_commit(&kv_empty[rk0 % RING]);
+        if (nkv == 2) umma_commit(&kv_empty[rk1 % RING]);
+        umma_commit(&q_empty[qb]);
+      }
+      __syncwarp();
+      if (valid) ++nvalid_items;
+      for (int j = 0; j < nkv; ++j) {
+        const uint32_t rv = j == 0 ? rv0 : rv1;
+        // (an idle warpgroup's stream still waits for the tile before releasing it: its release must not
+        // run a whole item ahead of the other stream's)
+        mbar_wait(&kv_full[rv % RING], (rv / RING) & 1);
+        if (valid) {
+          mbar_wait(&p_full[g], pc & 1);
+          ++pc;
+          tc_fence_after();
+          UCF_FTL(k, g, j == 0 ? 9 : 10);
+        }
+        if (elect_one()) {
+          if (valid) {
+            const uint32_t v_addr = smem_u32(kv_s + (rv % RING) * Cfg::KV_BYTES);
+            const int ksteps = j == 0 ? BKV / 16 : n1 / 16;
+            for (int kk = 0; kk < ksteps; ++kk)
+              umma_bf16(d_s, umma_smem_desc(pa + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                        attn_desc<RB>(v_addr + kk * 2 * AB, 0, AB), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(&pv_full[g]);
+          }
+          umma_commit(&kv_empty[rv % RING]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int g = (warp - 2) >> 2;
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t tmem_s = tmem_base + g * 256;          // S0 at +0, S1 at +128, O aliases S0
+    const uint32_t row_sw = row & 7, lrow_sw = lane & 7;
+    uint8_t* p_row = p_s + g * Cfg::P_BYTES + row * 128;
+    uint8_t* o_stage = p_s + g * Cfg::P_BYTES + qd * 4096;
+    uint32_t tcnt = 0;       // valid items processed (s_full parity)
+    uint32_t pcnt = 0;       // P tiles published (pv_full parity)
+    const int nchunk1 = nkv == 2 ? (nvalid1 + 31) >> 5 : 0;
+    const float2 sc2 = mk2(p.scale_log2);
+
+    for (int k = 0; k < my_items; ++k) {
+      int b, h, q0;
+      decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), b, h, q0);
+      const int qt0 = q0 + g * BQ;
+      if (qt0 >= p.Nq) continue;
+      const bool st = (threadIdx.x & 127) == 64;
+      if (st) UCF_FTL(k, g, 7);
+      mbar_wait(&s_full[g], tcnt & 1);
+      tc_fence_after();
+      // Warpgroup 1 holds its first tile back by half an item: the two warpgroups then alternate on the
+      // MUFU pipe (one runs its exponentials while the other waits for S / takes the row maximum / writes
+      // O) instead of halving each other's rate; nothing couples the two streams, so the offset persists.
+      if (g == 1 && tcnt == 0 && my_items > 1) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.stagger_cycles) { }
+      }
+      if (st) UCF_FTL(k, g, 0);
+      // ---- pass 1: row maximum over every valid key
+      float m_row = -INFINITY;
+      const int nv0 = min(BKV, p.Nk);
+      auto max_chunk = [&](const uint32_t (&v)[32], int nv) {
+        if (nv >= 32) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2)
+            m_row = fmaxf(m_row, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (e < nv) m_row = fmaxf(m_row, __uint_as_float(v[e]));
+        }
+      };
+      // two tensor-memory loads in flight per wait
+#pragma unroll 1
+      for (int c = 0; c < 4 + nchunk1; c += 2) {
+        const int nva = c < 4 ? nv0 - c * 32 : nvalid1 - (c - 4) * 32;            // valid columns left in chunk c
+        const int nvb = c + 1 < 4 ? nv0 - (c + 1) * 32 : (c + 1 < 4 + nchunk1 ? nvalid1 - (c + 1 - 4) * 32 : 0);
+        uint32_t va[32], vb[32];
+        if (nva > 0) tmem_ld32(tmem_s + lane_addr + c * 32, va);
+        if (nvb > 0) tmem_ld32(tmem_s + lane_addr + (c + 1) * 32, vb);
+        tmem_wait_ld();
+        if (nva > 0) max_chunk(va, nva);
+        if (nvb > 0) max_chunk(vb, nvb);
+      }
+      if (st) UCF_FTL(k, g, 1);
+      const float m2 = m_row * p.scale_log2;
+      const float2 nm2 = mk2(-m2);
+      float2 l2 = make_float2(0.f, 0.f);
+      // one 32-column chunk of probabilities -> 16 packed bf16 pairs (masked past `nv` valid columns)
+      auto exp_chunk = [&](int c, int nv, uint32_t (&pk)[16]) {
+        uint32_t v[32];
+        tmem_ld32(tmem_s + lane_addr + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), sc2, nm2);
+          float2 pp = make_float2(fast_ex2(t.x), fast_ex2(t.y));
+          if (nv < 32) {
+            if (e >= nv) pp.x = 0.f;
+            if (e + 1 >= nv) pp.y = 0.f;
+          }
+          l2 = __fadd2_rn(l2, pp);
+          pk[e >> 1] = pack_bf16x2(pp.x, pp.y);
+        }
+      };
+      auto store_chunk = [&](int c, const uint32_t (&pk)[16]) {      // chunk c (0..3) of the P tile
+        uint8_t* blk = p_row + (c >> 1) * 16384;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q4);
+          *reinterpret_cast<uint4*>(blk + ((chunk ^ row_sw) << 4)) =
+              make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+        }
+      };
+      // ---- pass 2a: P0   (the previous item's O tile must have left the staging area == P buffer)
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+        const int nv = nv0 - c * 32;
+        if (nv > 0) exp_chunk(c, nv, pk);
+        else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pk[e] = 0u;
+        }
+        store_chunk(c, pk);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&p_full[g]);           // P0 visible; S0's columns may now receive O = P0 V0
+      if (st) UCF_FTL(k, g, 2);
+      // ---- pass 2b: P1 is formed in registers while PV0 still reads the P buffer
+      if (nkv == 2) {
+        uint32_t pk1[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int nv = nvalid1 - c * 32;
+          if (c < nchunk1) exp_chunk(4 + c, nv, pk1[c]);
+        }
+        if (st) UCF_FTL(k, g, 11);
+        mbar_wait(&pv_full[g], pcnt & 1);       // PV0 retired: the P buffer is free
+        ++pcnt;
+        if (st) UCF_FTL(k, g, 3);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < nchunk1) store_chunk(c, pk1[c]);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[g]);         // P1 visible
+        if (st) UCF_FTL(k, g, 4);
+      }
+      // ---- epilogue: O / l
+      mbar_wait(&pv_full[g], pcnt & 1);
+      ++pcnt;
+      tc_fence_after();
+      if (st) UCF_FTL(k, g, 5);
+      const float l_row = l2.x + l2.y;
+      const float inv_l = 1.0f / l_row;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_s + lane_addr + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q4 * 8 + e]) * inv_l;
+          const uint32_t chunk = static_cast<uint32_t>(c * 4 + q4);
+          uint8_t* dst = (RB == 128) ? o_stage + lane * 128 + ((chunk ^ lrow_sw) << 4)
+                                     : o_stage + lane * 64 + ((chunk ^ ((lane >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                      pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[g]);          // S0 / S1 / O of this warpgroup are free for the next item
+      if (qt0 + row < p.Nq)
+        p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qt0 + row] = (m2 + log2f(l_row)) * 0.69314718055994531f;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && qt0 + qd * 32 < p.Nq) {
+        tma_store_4d(&tmO, o_stage, 0, h, qt0 + qd * 32, b);
+        tma_store_commit();
+      }
+      if (st) UCF_FTL(k, g, 6);
+      ++tcnt;
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
 int make_bnhd_tmap(CUtensorMap* tm, const void* ptr, int B, int H, int N, int hd, long long sb, long long sn,
                    long long sh, int box_rows, CUtensorMapDataType dt, int elem_bytes, int box_cols) {
   uint64_t dims[4] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(H), static_cast<uint64_t>(N),
@@ -401,6 +748,9 @@ static bool strides_ok(long long sb, long long sn, long long sh) {
   return sb % 8 == 0 && sn % 8 == 0 && sh % 8 == 0;
 }
 
+static int g_fwd_stagger = -1;     // < 0: derived from the problem size
+static bool g_force_general_fwd = false;   // profiling aid: ucf_debug_force_general_attn_fwd
+
 template <int HD>
 static int launch_attn_fwd(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const CUtensorMap& tO,
                            const AttnFwdParams& p, cudaStream_t st) {
@@ -412,6 +762,16 @@ static int launch_attn_fwd(const CUtensorMap& tQ, const CUtensorMap& tK, const C
     attr = true;
   }
   const int grid = p.items < num_sms() ? p.items : num_sms();
+  if (p.Nk <= 2 * Cfg::BKV && !g_force_general_fwd) {
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_short_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+      if (e != cudaSuccess) { set_last_error("attention_fwd: smem attr: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+      attr2 = true;
+    }
+    attn_fwd_short_kernel<HD><<<grid, Cfg::THREADS + 32, Cfg::SMEM_BYTES, st>>>(tQ, tK, tV, tO, p);
+    return check_launch("attn_fwd_short_kernel");
+  }
   attn_fwd_kernel<HD><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tQ, tK, tV, tO, p);
   return check_launch("attn_fwd_kernel");
 }
@@ -423,6 +783,9 @@ using namespace ucf;
 static long long* g_fwd_timeline = nullptr;
 /* profiling aid (not part of the public header): device buffer of 64 int64 receiving clock64 stamps */
 extern "C" void ucf_debug_set_attn_fwd_timeline(void* dev_ptr) { g_fwd_timeline = static_cast<long long*>(dev_ptr); }
+/* profiling aid: 1 = always run the general (online-softmax) kernel, also for Nk <= 256 */
+extern "C" void ucf_debug_force_general_attn_fwd(int on) { ucf::g_force_general_fwd = on != 0; }
+extern "C" void ucf_debug_set_attn_fwd_stagger(int cycles) { ucf::g_fwd_stagger = cycles; }
 
 extern "C" int ucf_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
                                  int B, int H, int Nq, int Nk, int hd,
@@ -460,6 +823,12 @@ extern "C" int ucf_attention_fwd(const void* q, const void* k, const void* v, vo
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse;
   p.timeline = g_fwd_timeline;
+  // half of an item's period; the kernel is bound by tensor-memory reads (64 B/clk/SM: S twice + O once per
+  // warpgroup and item), ~9 cycles per 32-bit column of a 128-row tile and warpgroup pair
+  {
+    const int c0 = ((Nk < 128 ? Nk : 128) + 31) / 32 * 32, c1 = Nk > 128 ? (Nk - 128 + 31) / 32 * 32 : 0;
+    p.stagger_cycles = g_fwd_stagger >= 0 ? g_fwd_stagger : 9 * (2 * (c0 + c1) + hd);
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   return hd == 64 ? launch_attn_fwd<64>(tQ, tK, tV, tO, p, st) : launch_attn_fwd<32>(tQ, tK, tV, tO, p, st);
 }

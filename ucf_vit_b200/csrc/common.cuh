@@ -81,6 +81,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a hardware-defined time when the phase is not
+// complete -- wrong for a warp that polls several barriers in turn).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Spin with a watchdog: a protocol bug traps (reported as a launch failure) instead of hanging
 // the GPU box.  ~4 s at 2 GHz.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -673,17 +673,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 f[3] = __fadd2_rn(f[3], bf16x2_to_f32x2(r.w));
               } else if (EPI == EPI_DGELU) {
                 const uint4 r = *reinterpret_cast<const uint4*>(aux_row + sw);
-                f[0] = __fmul2_rn(f[0], gelu_grad_poly2(bf16x2_to_f32x2(r.x)));
+                // half of the elements on the MUFU form (2 MUFU + 8 FMA-pipe ops), half on the polynomial
+                // (17 FMA-pipe ops): the two pipes work side by side
+                f[0] = __fmul2_rn(f[0], gelu_erf_grad2(bf16x2_to_f32x2(r.x)));
                 f[1] = __fmul2_rn(f[1], gelu_grad_poly2(bf16x2_to_f32x2(r.y)));
-                f[2] = __fmul2_rn(f[2], gelu_grad_poly2(bf16x2_to_f32x2(r.z)));
+                f[2] = __fmul2_rn(f[2], gelu_erf_grad2(bf16x2_to_f32x2(r.z)));
                 f[3] = __fmul2_rn(f[3], gelu_grad_poly2(bf16x2_to_f32x2(r.w)));
               } else if (EPI == EPI_BIAS_GELU_AUX) {
                 const uint4 zq = make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y),
                                             pack_bf16x2(f[2].x, f[2].y), pack_bf16x2(f[3].x, f[3].y));
                 z_pk[j] = zq;
-                f[0] = gelu_poly2(bf16x2_to_f32x2(zq.x));
+                f[0] = gelu_erf2(bf16x2_to_f32x2(zq.x));      // MUFU form / polynomial alternate (see GELU' above)
                 f[1] = gelu_poly2(bf16x2_to_f32x2(zq.y));
-                f[2] = gelu_poly2(bf16x2_to_f32x2(zq.z));
+                f[2] = gelu_erf2(bf16x2_to_f32x2(zq.z));
                 f[3] = gelu_poly2(bf16x2_to_f32x2(zq.w));
               }
               o_pk[j] = make_uint4(pack_bf16x2(f[0].x, f[0].y), pack_bf16x2(f[1].x, f[1].y), pack_bf16x2(f[2].x, f[2].y),
