@@ -34,7 +34,7 @@ __device__ __forceinline__ uint4 pack4(const float2 (&f)[4]) {
 
 // NCH = number of 256-element chunks a warp covers per row (D <= 256*NCH)
 template <int NCH, bool X_BF16, bool P_BF16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NCH <= 3 ? 2 : 1))
 layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma, const void* __restrict__ beta,
                      void* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                      long long rows, int D, float eps) {
@@ -44,6 +44,32 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
   const float inv_d = 1.0f / static_cast<float>(D);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
 
+  // gamma / beta of this lane's columns live in registers for the whole (persistent) kernel when the row
+  // is short enough: re-loading them per row put a long-scoreboard stall in front of every write pass
+  constexpr bool HOIST = NCH <= 3;
+  float2 gr[HOIST ? NCH : 1][4], br[HOIST ? NCH : 1][4];
+  if (HOIST) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = c * 256 + lane * 8;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { gr[c][e] = f2(1.f, 1.f); br[c][e] = f2(0.f, 0.f); }
+      if (col < D) {
+        if (gamma) load4x2<P_BF16>(gamma, col, gr[c]);
+        if (beta) load4x2<P_BF16>(beta, col, br[c]);
+      }
+    }
+  }
+  // bf16 rows are software-prefetched one row ahead (raw 16-byte vectors): a warp otherwise has no load in
+  // flight while it reduces and writes, and 24 resident warps x 1.5 KB is short of the bytes-in-flight that
+  // HBM3e latency x bandwidth asks for
+  uint4 nxt[NCH];
+  if (X_BF16 && warp_global < rows) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+      if (c * 256 + lane * 8 < D)
+        nxt[c] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + warp_global * D + lane * 8 + c * 256));
+  }
   for (long long row = warp_global; row < rows; row += nwarps) {
     const long long base = row * D + lane * 8;
     float2 v[NCH][4];
@@ -51,13 +77,20 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       if (c * 256 + lane * 8 < D) {
-        load4x2<X_BF16>(x, base + c * 256, v[c]);
+        if (X_BF16) unpack4(nxt[c], v[c]);
+        else load4x2<X_BF16>(x, base + c * 256, v[c]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) s = __fadd2_rn(s, v[c][e]);
       } else {
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[c][e] = f2(0.f, 0.f);
       }
+    }
+    if (X_BF16 && row + nwarps < rows) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if (c * 256 + lane * 8 < D)
+          nxt[c] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + (row + nwarps) * D + lane * 8 + c * 256));
     }
     const float mu = warp_sum(s.x + s.y) * inv_d;
     const float2 nmu = f2(-mu, -mu);
@@ -83,12 +116,15 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
       const int col = c * 256 + lane * 8;
       if (col < D) {
         float2 g[4], b[4], o[4];
-        if (gamma) load4x2<P_BF16>(gamma, col, g);
-        if (beta) load4x2<P_BF16>(beta, col, b);
+        if (!HOIST) {
+          if (gamma) load4x2<P_BF16>(gamma, col, g);
+          if (beta) load4x2<P_BF16>(beta, col, b);
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float2 t = __fmul2_rn(v[c][e], rs2);
-          if (gamma) t = beta ? __ffma2_rn(t, g[e], b[e]) : __fmul2_rn(t, g[e]);
+          if (HOIST) t = __ffma2_rn(t, gr[c][e], br[c][e]);           // (gamma = 1 / beta = 0 when absent)
+          else if (gamma) t = beta ? __ffma2_rn(t, g[e], b[e]) : __fmul2_rn(t, g[e]);
           else if (beta) t = __fadd2_rn(t, b[e]);
           o[e] = t;
         }
@@ -112,7 +148,13 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const void* __restrict__ dres, void* __restrict__ dx, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, long long rows, int D) {
-  extern __shared__ float red[];   // [2][D]
+  extern __shared__ float red[];   // [2][D] dgamma / dbeta partials, then [D] gamma as fp32
+  float* gam_s = red + 2 * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x)
+    gam_s[i] = gamma ? (P_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(gamma)[i])
+                               : reinterpret_cast<const float*>(gamma)[i])
+                     : 1.0f;
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -128,13 +170,12 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
 #pragma unroll
     for (int e = 0; e < 4; ++e) { dg[c][e] = f2(0.f, 0.f); db[c][e] = f2(0.f, 0.f); }
   }
-  // gamma is re-read per row (L1-resident) instead of pinning 8*NCH registers
+  // gamma is re-read per row from shared memory (two LDS.128) instead of pinning 8*NCH registers; the
+  // global (L1-hit) loads used before stalled both passes on the long scoreboard
   auto load_gamma = [&](int col, float2 (&gv)[4]) {
-    if (gamma) load4x2<P_BF16>(gamma, col, gv);
-    else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) gv[e] = f2(1.f, 1.f);
-    }
+    const float4 a = *reinterpret_cast<const float4*>(gam_s + col);
+    const float4 b = *reinterpret_cast<const float4*>(gam_s + col + 4);
+    gv[0] = f2(a.x, a.y); gv[1] = f2(a.z, a.w); gv[2] = f2(b.x, b.y); gv[3] = f2(b.z, b.w);
   };
 
   for (long long row = warp_global; row < rows; row += nwarps) {
@@ -232,7 +273,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
 static int ln_grid(long long rows) {
   const long long warps_per_block = 8;
   long long blocks = (rows + warps_per_block - 1) / warps_per_block;
-  const long long cap = static_cast<long long>(num_sms()) * 8;   // 8 CTAs of 256 threads per SM
+  const long long cap = static_cast<long long>(num_sms()) * 2;   // persistent: the 2 resident CTAs per SM, no tail wave
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return static_cast<int>(blocks);
@@ -285,7 +326,7 @@ extern "C" int ucf_layernorm_bwd(const void* dy, const void* x, const void* gamm
   const long long cap = static_cast<long long>(ucf::num_sms()) * (D <= 768 ? 2 : 1);   // resident CTAs per SM, persistent
   if (blocks > cap) blocks = cap;
   const int grid = static_cast<int>(blocks < 1 ? 1 : blocks);
-  const size_t smem = 2 * static_cast<size_t>(D) * sizeof(float);
+  const size_t smem = 3 * static_cast<size_t>(D) * sizeof(float);
   const bool pb = param_dtype == UCF_DTYPE_BF16;
 #define LAUNCH(NCH)                                                                                      \
   if (NCH <= 8) {                                                                                        \
