@@ -8,27 +8,34 @@ using namespace ucf;
 
 constexpr int STAGES = 6, BOX_BYTES = 16384;
 
-__global__ void __launch_bounds__(64) k(const __grid_constant__ CUtensorMap tm, int iters, int rows, long long* cyc) {
+template <int NPROD>   // 1: one thread issues both boxes of a stage; 2: two warps issue one box each
+__global__ void __launch_bounds__(96) k(const __grid_constant__ CUtensorMap tm, int iters, int rows, long long* cyc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * 2 * BOX_BYTES);
   uint64_t* empty = full + STAGES;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NPROD); mbar_init(&empty[s], 1); }
     fence_barrier_init();
   }
   __syncthreads();
   const long long t0 = clock64();
   const int row_blocks = rows / 128;
-  if (threadIdx.x == 0) {             // producer: two 16 KB boxes per stage (like A + B of one k-block)
+  if (threadIdx.x == 0 || (NPROD == 2 && threadIdx.x == 64)) {   // producer(s): two 16 KB boxes per stage (like A + B of one k-block)
+    const int me = threadIdx.x == 0 ? 0 : 1;
     for (int it = 0; it < iters; ++it) {
       const int s = it % STAGES;
       mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-      mbar_expect_tx(&full[s], 2 * BOX_BYTES);
       const int kb = it % 12;
       const int rb = (blockIdx.x * 7 + it / 12) % row_blocks;
-      tma_load_2d(smem + (s * 2 + 0) * BOX_BYTES, &tm, &full[s], kb * 64, rb * 128);
-      tma_load_2d(smem + (s * 2 + 1) * BOX_BYTES, &tm, &full[s], kb * 64, ((rb + 3) % row_blocks) * 128);
+      if (NPROD == 1) {
+        mbar_expect_tx(&full[s], 2 * BOX_BYTES);
+        tma_load_2d(smem + (s * 2 + 0) * BOX_BYTES, &tm, &full[s], kb * 64, rb * 128);
+        tma_load_2d(smem + (s * 2 + 1) * BOX_BYTES, &tm, &full[s], kb * 64, ((rb + 3) % row_blocks) * 128);
+      } else {
+        mbar_expect_tx(&full[s], BOX_BYTES);
+        tma_load_2d(smem + (s * 2 + me) * BOX_BYTES, &tm, &full[s], kb * 64, ((rb + 3 * me) % row_blocks) * 128);
+      }
     }
   } else if (threadIdx.x == 32) {     // consumer: releases the stage as soon as it has landed
     for (int it = 0; it < iters; ++it) {
@@ -47,14 +54,20 @@ int main() {
   cudaMemset(d, 0, size_t(rows) * cols * 2);
   long long* cyc; cudaMalloc(&cyc, 148 * 8);
   const int smem = STAGES * 2 * BOX_BYTES + 1024 + 256;
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   CUtensorMap tm;
   uint64_t dims[2] = {uint64_t(cols), uint64_t(rows)}, strides[1] = {uint64_t(cols) * 2};
   uint32_t box[2] = {64, 128};
   if (make_tmap(&tm, d, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) { printf("tmap fail\n"); return 1; }
-  for (int grid : {148, 74, 16, 4}) {
+  cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int nprod : {1, 2})
+  for (int grid : {148, 16}) {
     const int iters = 2048;
-    for (int rep = 0; rep < 3; ++rep) { k<<<grid, 64, smem>>>(tm, iters, rows, cyc); cudaDeviceSynchronize(); }
+    for (int rep = 0; rep < 3; ++rep) {
+      if (nprod == 1) k<1><<<grid, 96, smem>>>(tm, iters, rows, cyc); else k<2><<<grid, 96, smem>>>(tm, iters, rows, cyc);
+      cudaDeviceSynchronize();
+    }
+    printf("%d producer thread(s): ", nprod);
     long long h[148]; cudaMemcpy(h, cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
     long long mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
     const double bytes = double(iters) * 2 * BOX_BYTES;

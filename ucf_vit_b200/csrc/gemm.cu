@@ -430,7 +430,11 @@ struct Gemm2Cfg {
   static constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_NBUF * OUT_BUF;
   static constexpr int AUX_STAGE_BYTES = HAS_AUX ? EPI_WARPS * AUX_NBUF * AUX_BUF : 0;
   static constexpr bool BIASW = A_MN && EPI == EPI_F32_ADD;   // wgrad: two extra bias-gradient warps
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS + (BIASW ? 64 : 0);
+  // warps: 0 = TMA producer (A operand), 1 = MMA issuer, 2.. = epilogue, then the two bias-gradient warps
+  // (wgrad), last = second TMA producer (B operand).  One issuing thread tops out at 55 B/clk of TMA loads,
+  // two reach 70 (scripts/micro/tma_load_rate.cu) -- and a 256x256 pair tile needs 64 B/clk per CTA.
+  static constexpr int PRODUCER2_WARP = 2 + EPI_WARPS + (BIASW ? 2 : 0);
+  static constexpr int THREADS = 32 * (PRODUCER2_WARP + 1);
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_STAGE_BYTES + AUX_STAGE_BYTES + BN * 4 +
                                     (3 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
@@ -472,7 +476,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmC);
     if (Cfg::HAS_AUX) tma_prefetch_desc(&tmAux);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);      // leader's producer arrives (+ 2 CTAs' transaction bytes)
+      mbar_init(&full_bar[s], 2);      // the leader's two producers arrive (+ 2 CTAs' transaction bytes)
       mbar_init(&empty_bar[s], 1);     // multicast commit from the leader's MMA thread
     }
     for (int b = 0; b < 2; ++b) {
@@ -492,8 +496,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int total_tiles = p.tiles_m * p.tiles_n * p.splits;       // tiles_m counts 256-row tiles here
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs; converged warp)
+  if (warp == 0 || warp == Cfg::PRODUCER2_WARP) {
+    // ------------------------------------------------------------------ TMA producers (both CTAs; converged warps):
+    // warp 0 loads the A operand of every stage, the last warp the B operand
+    const bool load_a = warp == 0;
     {
       uint32_t kiter = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
@@ -512,21 +518,25 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (Cfg::BIASW) mbar_wait(&bias_done[s], ph ^ 1);
           if (elect_one()) {
             const uint32_t full0 = mapa_u32(smem_u32(&full_bar[s]), 0);     // the leader's barrier
-            if (leader) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
             uint8_t* a_dst = stage_base + s * STAGE_BYTES;
             uint8_t* b_dst = a_dst + A_BYTES;
-            if (!A_MN) {
-              tma_load_2d_2sm(a_dst, &tmA, full0, kb * BK, m0);
+            if (load_a) {
+              if (leader) mbar_expect_tx(&full_bar[s], 2 * A_BYTES);        // both CTAs' A tiles
+              if (!A_MN) {
+                tma_load_2d_2sm(a_dst, &tmA, full0, kb * BK, m0);
+              } else {
+                tma_load_2d_2sm(a_dst, &tmA, full0, m0, kb * BK);
+                tma_load_2d_2sm(a_dst + 8192, &tmA, full0, m0 + 64, kb * BK);
+              }
             } else {
-              tma_load_2d_2sm(a_dst, &tmA, full0, m0, kb * BK);
-              tma_load_2d_2sm(a_dst + 8192, &tmA, full0, m0 + 64, kb * BK);
-            }
-            if (!B_MN) {
-              tma_load_2d_2sm(b_dst, &tmB, full0, kb * BK, n0);
-            } else {
+              if (leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::B_BYTES);   // both CTAs' halves of B
+              if (!B_MN) {
+                tma_load_2d_2sm(b_dst, &tmB, full0, kb * BK, n0);
+              } else {
 #pragma unroll
-              for (int j = 0; j < HN / 64; ++j)
-                tma_load_2d_2sm(b_dst + j * 8192, &tmB, full0, n0 + j * 64, kb * BK);
+                for (int j = 0; j < HN / 64; ++j)
+                  tma_load_2d_2sm(b_dst + j * 8192, &tmB, full0, n0 + j * 64, kb * BK);
+              }
             }
           }
           __syncwarp();
@@ -571,7 +581,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
       }
     }
-  } else if (Cfg::BIASW && warp >= 2 + Cfg::EPI_WARPS) {
+  } else if (Cfg::BIASW && warp >= 2 + Cfg::EPI_WARPS && warp < Cfg::PRODUCER2_WARP) {
     // ------------------------------------------------------------------ bias-gradient warps (wgrad, both CTAs)
     bias_grad_warp_loop<STAGES, STAGE_BYTES>(p, stage_base, empty_bar, bias_done, warp - 2 - Cfg::EPI_WARPS, lane,
                                              cluster_id, num_clusters, total_tiles, 2 * BM, static_cast<int>(rank) * BM);
