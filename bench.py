@@ -301,6 +301,11 @@ def run_gpu_arm(args):
     for _ in range(args.warmup):
         step(x_dev, y_dev)
     fence()
+    # host cost of enqueueing ONE (untimed) step into an empty launch queue: is the step launch-bound?
+    t_host0 = time.perf_counter()
+    step(x_dev, y_dev)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
+    fence()
     n0 = _lib.launch_count()
     timer.enabled = rank == 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -394,6 +399,7 @@ def run_gpu_arm(args):
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8) * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all layouts/epilogues)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "launches_timed": gemm_n,

@@ -163,3 +163,46 @@ def test_block_general_path_equals_fused_path():
     x = torch.randn(2, 50, D, device="cuda")
     ya, yb = a(x), b(x)
     assert _rel_l2(yb.float(), ya.float()) <= 1e-2
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_weights_used_by_kernels_follow_the_optimizer(fused):
+    """Training for several steps must track an fp32 oracle trained with the same optimizer.
+
+    Regression test: torch's fused CUDA AdamW updates parameters WITHOUT bumping their version counters, so a
+    bf16 compute copy cached on `_version` went stale after the first step (the kernels kept multiplying by
+    the initial weights while only un-cached parameters learned)."""
+    from functools import partial
+    from oracle import fixtures as fx
+    from oracle import vit_ref as R
+    from ucf_vit_b200.simple.building_blocks import Block
+    D, H, B, N, steps, lr = 128, 2, 4, 50, 6, 3e-2
+    blk = Block(dim=D, num_heads=H, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    sd = fx.det_state_dict({k: tuple(v.shape) for k, v in blk.state_dict().items()}, 21)
+    blk.load_state_dict(sd)
+    x = fx.det_tensor((B, N, D), 93)
+    tgt = fx.det_tensor((B, N, D), 94)
+    # oracle: same optimizer on CPU fp32 tensors
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt_o = torch.optim.AdamW(list(sdo.values()), lr=lr, betas=(0.9, 0.95), weight_decay=0.0)
+    for _ in range(steps):
+        opt_o.zero_grad(set_to_none=True)
+        ((R.block(x, sdo, "", H) - tgt) ** 2).mean().backward()
+        opt_o.step()
+    y_o = R.block(x, sdo, "", H).detach()
+    y_init = R.block(x, {k: v for k, v in sd.items()}, "", H).detach()
+    # product
+    blk = blk.cuda()
+    opt = torch.optim.AdamW(blk.parameters(), lr=lr, betas=(0.9, 0.95), weight_decay=0.0, fused=fused)
+    xc, tc = x.cuda(), tgt.cuda()
+    for _ in range(steps):
+        opt.zero_grad(set_to_none=True)
+        ((blk(xc).float() - tc) ** 2).mean().backward()
+        opt.step()
+    y_p = blk(xc).float().cpu()
+    moved = _rel_l2(y_o, y_init)
+    assert moved > 0.05, "test is vacuous: the oracle barely moved"
+    assert _rel_l2(y_p, y_o) <= 0.25 * moved, (_rel_l2(y_p, y_o), moved)
+    # and every fp32 master moved (Adam's sign-like steps make per-element comparison with the oracle too noisy)
+    for k, p in blk.named_parameters():
+        assert _rel_l2(p.detach().float().cpu(), sd[k]) > 1e-3, k

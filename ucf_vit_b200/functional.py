@@ -17,26 +17,22 @@ BF16 = torch.bfloat16
 
 
 # ---------------------------------------------------------------------------------------------
-# parameter staging: fp32 master -> bf16 compute copy, cached until the parameter is modified
+# parameter staging: fp32 master -> bf16 compute copy
 # ---------------------------------------------------------------------------------------------
 def bf16_param(p: torch.Tensor) -> torch.Tensor:
-    """bf16, contiguous, detached compute copy of a parameter (no copy if it already is bf16)."""
-    if p.dtype == BF16:
-        q = p.detach()
+    """bf16, contiguous, detached compute copy of a parameter (no copy if it already is bf16).
+
+    Made afresh on every forward call and handed to that call's backward through `ctx` -- never cached
+    across calls.  A cache keyed on the tensor's version counter is NOT safe: torch's fused (CUDA) AdamW /
+    SGD update parameters without bumping `_version` (and so does any `p.data` mutation), so a cached copy
+    silently goes stale after the first optimizer step.  Cost of doing it right: one pass over the weights
+    per forward (0.5 GB for ViT-B, ~0.2 ms)."""
+    q = p.detach()
+    if q.dtype == BF16:
         return q if q.is_contiguous() else q.contiguous()
-    cached = getattr(p, "_ucf_bf16", None)
-    ver = p._version
-    if cached is not None and cached[0] == ver and cached[1] == p.data_ptr():
-        return cached[2]
-    src = p.detach()
-    if not src.is_contiguous():
-        src = src.contiguous()
-    q = ops.cast_to_bf16(src)
-    try:
-        p._ucf_bf16 = (ver, p.data_ptr(), q)
-    except Exception:  # noqa: BLE001 - tensors that refuse attributes simply are not cached
-        pass
-    return q
+    if not q.is_contiguous():
+        q = q.contiguous()
+    return ops.cast_to_bf16(q) if q.dtype == torch.float32 else q.to(BF16)
 
 
 def _zeros_f32(dev, *shapes):
@@ -165,6 +161,7 @@ class _LinearFn(torch.autograd.Function):
         else:
             y = ops.gemm(x2, w, M=M, N=N, K=K, bias=bias)
         ctx.save_for_backward(x2, weight, bias)
+        ctx.w16 = w                      # this call's bf16 weight copy, reused by its backward
         ctx.has_res = residual is not None
         ctx.x_dtype = x.dtype
         ctx.shp = shp
@@ -178,7 +175,7 @@ class _LinearFn(torch.autograd.Function):
         M = dy2.shape[0]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.gemm(dy2, bf16_param(weight), M=M, N=K, K=N, b_mn=True).view(ctx.shp)
+            dx = ops.gemm(dy2, ctx.w16, M=M, N=K, K=N, b_mn=True).view(ctx.shp)
             if ctx.x_dtype != BF16:
                 dx = dx.to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
@@ -205,13 +202,15 @@ class _MlpFn(torch.autograd.Function):
         Nout = w2.shape[0]
         x2 = _as_bf16_2d(x)
         M = x2.shape[0]
-        u, z = ops.gemm(x2, bf16_param(w1), M=M, N=Hd, K=K, bias=b1, epilogue=L.EPI_BIAS_GELU_AUX)
+        w1h, w2h = bf16_param(w1), bf16_param(w2)
+        u, z = ops.gemm(x2, w1h, M=M, N=Hd, K=K, bias=b1, epilogue=L.EPI_BIAS_GELU_AUX)
         if residual is not None:
-            y = ops.gemm(u, bf16_param(w2), M=M, N=Nout, K=Hd, bias=b2, aux=_as_bf16_2d(residual),
+            y = ops.gemm(u, w2h, M=M, N=Nout, K=Hd, bias=b2, aux=_as_bf16_2d(residual),
                          epilogue=L.EPI_BIAS_RESIDUAL)
         else:
-            y = ops.gemm(u, bf16_param(w2), M=M, N=Nout, K=Hd, bias=b2)
+            y = ops.gemm(u, w2h, M=M, N=Nout, K=Hd, bias=b2)
         ctx.save_for_backward(x2, z, u, w1, b1, w2, b2)
+        ctx.w16 = (w1h, w2h)
         ctx.has_res = residual is not None
         ctx.shp = shp
         ctx.x_dtype = x.dtype
@@ -225,11 +224,12 @@ class _MlpFn(torch.autograd.Function):
         dy2 = _as_bf16_2d(dy)
         M = dy2.shape[0]
         dw2, db2 = _wgrad(dy2, u, Nout, Hd, w2, b2)
-        dz = ops.gemm(dy2, bf16_param(w2), M=M, N=Hd, K=Nout, b_mn=True, aux=z, epilogue=L.EPI_DGELU)
+        w1h, w2h = ctx.w16
+        dz = ops.gemm(dy2, w2h, M=M, N=Hd, K=Nout, b_mn=True, aux=z, epilogue=L.EPI_DGELU)
         dw1, db1 = _wgrad(dz, x2, Hd, K, w1, b1)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = ops.gemm(dz, bf16_param(w1), M=M, N=K, K=Hd, b_mn=True).view(ctx.shp)
+            dx = ops.gemm(dz, w1h, M=M, N=K, K=Hd, b_mn=True).view(ctx.shp)
             if ctx.x_dtype != BF16:
                 dx = dx.to(ctx.x_dtype)
         return dx, dw1, db1, dw2, db2, (dy if ctx.has_res else None)
@@ -311,15 +311,17 @@ class _BlockFn(torch.autograd.Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         h1, mean1, rstd1 = ops.layernorm_fwd(x2, n1w, n1b, eps1)
-        qkv = ops.gemm(h1, bf16_param(qkv_w), M=M, N=3 * D, K=D, bias=qkv_b)
+        wq, wp, w1h, w2h = bf16_param(qkv_w), bf16_param(proj_w), bf16_param(fc1_w), bf16_param(fc2_w)
+        qkv = ops.gemm(h1, wq, M=M, N=3 * D, K=D, bias=qkv_b)
         qkv5 = qkv.view(B, N, 3, H, hd)
         o, lse = ops.attention_fwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], hd ** -0.5)
         o2 = o.view(M, D)
-        x1 = ops.gemm(o2, bf16_param(proj_w), M=M, N=D, K=D, bias=proj_b, aux=x2, epilogue=L.EPI_BIAS_RESIDUAL)
+        x1 = ops.gemm(o2, wp, M=M, N=D, K=D, bias=proj_b, aux=x2, epilogue=L.EPI_BIAS_RESIDUAL)
         h2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b, eps2)
         Hd = fc1_w.shape[0]
-        u, z = ops.gemm(h2, bf16_param(fc1_w), M=M, N=Hd, K=D, bias=fc1_b, epilogue=L.EPI_BIAS_GELU_AUX)
-        y = ops.gemm(u, bf16_param(fc2_w), M=M, N=D, K=Hd, bias=fc2_b, aux=x1, epilogue=L.EPI_BIAS_RESIDUAL)
+        u, z = ops.gemm(h2, w1h, M=M, N=Hd, K=D, bias=fc1_b, epilogue=L.EPI_BIAS_GELU_AUX)
+        y = ops.gemm(u, w2h, M=M, N=D, K=Hd, bias=fc2_b, aux=x1, epilogue=L.EPI_BIAS_RESIDUAL)
+        ctx.w16 = (wq, wp, w1h, w2h)     # this call's bf16 weight copies, reused by its backward
         ctx.save_for_backward(x2, mean1, rstd1, h1, qkv, o, lse, x1, mean2, rstd2, h2, z, u,
                               n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
         ctx.dims = (B, N, D, H, hd, Hd)
@@ -350,15 +352,16 @@ class _BlockFn(torch.autograd.Function):
                              (D, D), opt(proj_b, (D,)), (3 * D, D), opt(qkv_b, (3 * D,)), (D,), opt(n1b, (D,)))
         # ---- MLP
         d_fc2_w, d_fc2_b = _wgrad(dy2, u, D, Hd, fc2_w, fc2_b, g_fc2_w, g_fc2_b)
-        dz = ops.gemm(dy2, bf16_param(fc2_w), M=M, N=Hd, K=D, b_mn=True, aux=z, epilogue=L.EPI_DGELU)
+        wq, wp, w1h, w2h = ctx.w16
+        dz = ops.gemm(dy2, w2h, M=M, N=Hd, K=D, b_mn=True, aux=z, epilogue=L.EPI_DGELU)
         d_fc1_w, d_fc1_b = _wgrad(dz, h2, Hd, D, fc1_w, fc1_b, g_fc1_w, g_fc1_b)
-        dh2 = ops.gemm(dz, bf16_param(fc1_w), M=M, N=D, K=Hd, b_mn=True)
+        dh2 = ops.gemm(dz, w1h, M=M, N=D, K=Hd, b_mn=True)
         del dz
         dx1 = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dy2, dgamma=d_n2w, dbeta=d_n2b)
         del dh2
         # ---- attention
         d_proj_w, d_proj_b = _wgrad(dx1, o.view(M, D), D, D, proj_w, proj_b, g_proj_w, g_proj_b)
-        d_o = ops.gemm(dx1, bf16_param(proj_w), M=M, N=D, K=D, b_mn=True)
+        d_o = ops.gemm(dx1, wp, M=M, N=D, K=D, b_mn=True)
         dqkv = torch.empty_like(qkv)
         qkv5 = qkv.view(B, N, 3, H, hd)
         dqkv5 = dqkv.view(B, N, 3, H, hd)
@@ -366,7 +369,7 @@ class _BlockFn(torch.autograd.Function):
                           dq=dqkv5[:, :, 0], dk=dqkv5[:, :, 1], dv=dqkv5[:, :, 2])
         del d_o
         d_qkv_w, d_qkv_b = _wgrad(dqkv, h1, 3 * D, D, qkv_w, qkv_b, g_qkv_w, g_qkv_b)
-        dh1 = ops.gemm(dqkv, bf16_param(qkv_w), M=M, N=D, K=3 * D, b_mn=True)
+        dh1 = ops.gemm(dqkv, wq, M=M, N=D, K=3 * D, b_mn=True)
         del dqkv
         dx = ops.layernorm_bwd(dh1, x2, n1w, mean1, rstd1, dres=dx1, dgamma=d_n1w, dbeta=d_n1b)
         return (dx.view(B, N, D), cast_like(d_n1w, n1w), cast_like(d_n1b, n1b) if n1b is not None else None,
