@@ -206,3 +206,43 @@ def test_weights_used_by_kernels_follow_the_optimizer(fused):
     # and every fp32 master moved (Adam's sign-like steps make per-element comparison with the oracle too noisy)
     for k, p in blk.named_parameters():
         assert _rel_l2(p.detach().float().cpu(), sd[k]) > 1e-3, k
+
+
+@pytest.mark.parametrize("name", ["vit_cls_hd64", "mae_hd64_dec32"])
+def test_model_trains_like_the_oracle_under_fused_adamw(name):
+    """Five optimizer steps (torch AdamW, fused=True) on a whole model: the loss trajectory must follow the fp32
+    oracle trained with the same optimizer -- every weight the kernels read has to follow its fp32 master."""
+    cfg, shapes, arrays, sd = C.load(name)
+    inp = C.inputs(cfg, arrays)
+    steps, lr = 5, 2e-3
+    if cfg["kind"] == "mae":
+        torch.manual_seed(0)
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt_o = torch.optim.AdamW([v for v in sdo.values()], lr=lr, betas=(0.9, 0.95), weight_decay=0.0)
+    losses_o = []
+    for _ in range(steps):
+        if cfg["kind"] == "mae":
+            torch.manual_seed(0)                     # same random mask every step, both sides
+        opt_o.zero_grad(set_to_none=True)
+        _, loss = C.run_oracle(cfg, sdo, inp)
+        loss.backward()
+        opt_o.step()
+        losses_o.append(loss.item())
+    model = C.build_product(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train(cfg.get("train", True))
+    opt = torch.optim.AdamW(model.parameters(), lr=lr, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
+    dinp = _to_dev(inp)
+    losses_p = []
+    for _ in range(steps):
+        if cfg["kind"] == "mae":
+            torch.manual_seed(0)
+        opt.zero_grad(set_to_none=True)
+        _, loss = C.run_product(cfg, model, dinp)
+        loss.backward()
+        opt.step()
+        losses_p.append(loss.item())
+    drop = losses_o[0] - losses_o[-1]
+    assert drop > 0.02 * abs(losses_o[0]), ("test is vacuous: the oracle's loss did not move", losses_o)
+    for lo, lp in zip(losses_o, losses_p):
+        assert abs(lp - lo) <= 0.25 * drop + 2e-2 * abs(lo), (losses_o, losses_p)
