@@ -37,7 +37,7 @@ enum { EPI_BIAS = 0, EPI_BIAS_RESIDUAL = 1, EPI_BIAS_GELU_AUX = 2, EPI_DGELU = 3
 // Two extra warps re-read each stage of the n_blk == 0 tiles AFTER the MMAs that consumed it have
 // retired (they wait on the same `empty` barrier as the producer) and hand the stage back through
 // `bias_done`; the producer waits for both.  Replaces a separate pass over dY (colsum kernel).
-template <int STAGES, int STAGE_BYTES>
+template <int STAGES, int STAGE_BYTES, int NBW>
 __device__ __forceinline__ void bias_grad_warp_loop(const GemmParams& p, uint8_t* stage_base, uint64_t* empty_bar,
                                                     uint64_t* bias_done, int bw, int lane, int first_tile,
                                                     int tile_stride, int total_tiles, int m_rows_per_tile,
@@ -64,8 +64,8 @@ __device__ __forceinline__ void bias_grad_warp_loop(const GemmParams& p, uint8_t
       if (work) {
         const uint8_t* a = stage_base + s * STAGE_BYTES + box * 8192;
 #pragma unroll 4
-        for (int j = 0; j < 16; ++j) {
-          const int r = bw * 32 + 2 * j + rsel;  // token row inside the stage (rows past K are zero-filled)
+        for (int j = 0; j < 32 / NBW; ++j) {
+          const int r = bw * (64 / NBW) + 2 * j + rsel;  // token row inside the stage (rows past K are zero-filled)
           const uint4 v = *reinterpret_cast<const uint4*>(a + r * 128 + ((cin ^ (r & 7)) << 4));
           acc[0] = __fadd2_rn(acc[0], bf16x2_to_f32x2(v.x));
           acc[1] = __fadd2_rn(acc[1], bf16x2_to_f32x2(v.y));
@@ -251,7 +251,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (Cfg::BIASW && warp >= 2 + Cfg::EPI_WARPS) {
     // ------------------------------------------------------------------ bias-gradient warps (wgrad)
-    bias_grad_warp_loop<STAGES, STAGE_BYTES>(p, stage_base, empty_bar, bias_done, warp - 2 - Cfg::EPI_WARPS, lane,
+    bias_grad_warp_loop<STAGES, STAGE_BYTES, 2>(p, stage_base, empty_bar, bias_done, warp - 2 - Cfg::EPI_WARPS, lane,
                                              blockIdx.x, gridDim.x, total_tiles, BM, 0);
   } else {
     // ------------------------------------------------------------------ epilogue warps
@@ -433,7 +433,8 @@ struct Gemm2Cfg {
   // warps: 0 = TMA producer (A operand), 1 = MMA issuer, 2.. = epilogue, then the two bias-gradient warps
   // (wgrad), last = second TMA producer (B operand).  One issuing thread tops out at 55 B/clk of TMA loads,
   // two reach 70 (scripts/micro/tma_load_rate.cu) -- and a 256x256 pair tile needs 64 B/clk per CTA.
-  static constexpr int PRODUCER2_WARP = 2 + EPI_WARPS + (BIASW ? 2 : 0);
+  static constexpr int BIAS_WARPS = 4;     // with two, re-reading a stage after its MMAs took ~350 cycles and delayed its refill
+  static constexpr int PRODUCER2_WARP = 2 + EPI_WARPS + (BIASW ? BIAS_WARPS : 0);
   static constexpr int THREADS = 32 * (PRODUCER2_WARP + 1);
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_STAGE_BYTES + AUX_STAGE_BYTES + BN * 4 +
@@ -484,7 +485,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tempty_bar[b], 2 * Cfg::EPI_WARPS);     // epilogue warps of BOTH CTAs (leader's copy is used)
     }
     for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(&aux_bar[i], 1);
-    for (int i = 0; i < STAGES; ++i) mbar_init(&bias_done[i], 2);
+    for (int i = 0; i < STAGES; ++i) mbar_init(&bias_done[i], Cfg::BIAS_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
@@ -583,7 +584,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (Cfg::BIASW && warp >= 2 + Cfg::EPI_WARPS && warp < Cfg::PRODUCER2_WARP) {
     // ------------------------------------------------------------------ bias-gradient warps (wgrad, both CTAs)
-    bias_grad_warp_loop<STAGES, STAGE_BYTES>(p, stage_base, empty_bar, bias_done, warp - 2 - Cfg::EPI_WARPS, lane,
+    bias_grad_warp_loop<STAGES, STAGE_BYTES, Cfg::BIAS_WARPS>(p, stage_base, empty_bar, bias_done, warp - 2 - Cfg::EPI_WARPS, lane,
                                              cluster_id, num_clusters, total_tiles, 2 * BM, static_cast<int>(rank) * BM);
   } else {
     // ------------------------------------------------------------------ epilogue warps (both CTAs)
