@@ -425,7 +425,7 @@ struct Gemm2Cfg {
   static constexpr int CW = 32;
   static constexpr int OUT_BUF = (EPI == EPI_F32_ADD) ? 4096 : 2048;
   static constexpr int AUX_BUF = 2048;
-  static constexpr int OUT_NBUF = HEAVY ? 1 : 2;
+  static constexpr int OUT_NBUF = (HEAVY || EPI == EPI_F32_ADD) ? 1 : 2;   // wgrad: one epilogue per ~100 k-blocks, spend smem on stages
   static constexpr int AUX_NBUF = (HEAVY && !AUX_IN) ? 1 : 2;   // aux as an input is prefetched one chunk ahead
   static constexpr int OUT_STAGE_BYTES = EPI_WARPS * OUT_NBUF * OUT_BUF;
   static constexpr int AUX_STAGE_BYTES = HAS_AUX ? EPI_WARPS * AUX_NBUF * AUX_BUF : 0;
@@ -896,7 +896,7 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
   UCF_GEMM2_CASE(5, false, false, EPI_BIAS_GELU_AUX)
   UCF_GEMM2_CASE(6, false, true, EPI_BIAS)
   UCF_GEMM2_CASE(4, false, true, EPI_DGELU)
-  UCF_GEMM2_CASE(5, true, true, EPI_F32_ADD)
+  UCF_GEMM2_CASE(6, true, true, EPI_F32_ADD)
 #undef UCF_GEMM2_CASE
   if (pair) {
     set_last_error("gemm: no CTA-pair kernel for a_layout=%d b_layout=%d epilogue=%d", a_layout, b_layout, epilogue);

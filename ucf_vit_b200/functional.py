@@ -47,6 +47,46 @@ def _zeros_f32(dev, *shapes):
     return out
 
 
+_SM_COUNT = {}
+
+
+def _wgrad_splits(n_out, k_in, M, dev):
+    """Split-K factor of the weight-gradient GEMM dW[n_out, k_in] = dY^T X over M tokens.
+
+    The persistent kernels hand tile x split work units to SMs (CTA-pair kernel: 256x256 tiles over
+    SMs/2 clusters) in rounds, so the factor is picked to fill whole rounds: 36 tiles x 5 splits on 74
+    clusters is 2.43 rounds = 81 % busy, 36 x 4 is 1.95 rounds = 97 %."""
+    kb = (M + 63) // 64
+    if kb < 16:
+        return 1
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    sms = _SM_COUNT.get(idx)
+    if sms is None:
+        sms = _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    pair = n_out >= 512 and 512 <= k_in <= 4096          # mirrors the auto tile selection in ucf_gemm_bf16
+    if pair:
+        tiles, workers = ((n_out + 255) // 256) * ((k_in + 255) // 256), max(1, sms // 2)
+    else:
+        tiles, workers = ((n_out + 127) // 128) * ((k_in + 255) // 256), sms
+    best, best_eff = 1, 0.0
+    cands = []
+    for s_ in range(1, 17):
+        if kb // s_ < 8:
+            break
+        per = -(-kb // s_)
+        units = tiles * (-(-kb // per))                   # the launcher drops empty splits the same way
+        eff = units / (-(-units // workers) * workers)
+        cands.append((s_, units, eff))
+        best_eff = max(best_eff, eff)
+    for s_, units, eff in cands:                          # fewest splits within 0.5 % of the best fill, two rounds if possible
+        if eff >= best_eff - 0.005 and units >= 2 * workers:
+            return s_
+    for s_, units, eff in cands:
+        if eff >= best_eff - 0.005:
+            return s_
+    return best
+
+
 def _wgrad(dy2, x2, n_out, k_in, like: torch.Tensor, bias_like=None, out=None, bias_out=None):
     """dW[n_out,k_in] = dy2^T x2 (fp32, split-K TMA reduce-add) in `like`'s dtype, and -- fused in the
     same kernel from the dY tiles it stages anyway -- the bias gradient db[n_out] = colsum(dy2).
@@ -57,9 +97,7 @@ def _wgrad(dy2, x2, n_out, k_in, like: torch.Tensor, bias_like=None, out=None, b
     db = None
     if bias_like is not None:
         db = bias_out if bias_out is not None else torch.zeros((n_out,), dtype=torch.float32, device=dy2.device)
-    tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
-    kb = (M + 63) // 64
-    splits = max(1, min(kb // 8 if kb >= 16 else 1, (2 * 148 + tiles - 1) // tiles, 16))
+    splits = _wgrad_splits(n_out, k_in, M, dy2.device)
     ops.gemm(dy2, x2, M=n_out, N=k_in, K=M, a_mn=True, b_mn=True, epilogue=L.EPI_F32_ADD, out=dw, splits=splits,
              bias_grad=db)
     if like.dtype != torch.float32:
