@@ -147,6 +147,10 @@ int ucf_sap_scatter(const float* seq, int ndim, int n0, int n1, int n2, int C, c
 /* ---- bandwidth-bound helpers ------------------------------------------------------------- */
 /* dst_bf16[i] = (bf16) src_f32[i] */
 int ucf_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+/* Up to 8 such casts in ONE launch (the per-step bf16 copies of a Block's four weight matrices): srcs / dsts /
+ * counts are HOST arrays of n device pointers / element counts; every pointer 16-byte aligned. */
+int ucf_cast_f32_to_bf16_multi(int n, const float* const* srcs, void* const* dsts, const long long* counts,
+                               void* stream);
 /* dst_f32[i] (+)= (float) src_bf16[i] */
 int ucf_cast_bf16_to_f32(const void* src, float* dst, long long n, int accumulate, void* stream);
 /* out[n] (+)= sum_m x[m, n]   x bf16 [M, N] pitch ld; out fp32 [N]  (bias gradients) */

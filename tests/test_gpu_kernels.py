@@ -173,6 +173,17 @@ def test_var_attention(rows, Na, V, H, hd, shared):
     _ok(dq_acc, qf.grad, 2e-2)
 
 
+def test_cast_multi_matches_single_casts():
+    """One launch casting several fp32 tensors must equal the per-tensor casts (ragged sizes, 1..8 tensors)."""
+    torch.manual_seed(3)
+    for shapes in ([(2304, 768), (768, 768), (3072, 768), (768, 3072)], [(17,)], [(64, 3), (5, 5, 5), (1,), (1024,), (9, 8), (8,), (3, 3), (40,)]):
+        xs = [torch.randn(*sh, device=dev) for sh in shapes]
+        outs = ops.cast_to_bf16_multi(xs)
+        for x, o in zip(xs, outs):
+            assert o.shape == x.shape and o.dtype == torch.bfloat16
+            assert torch.equal(o, x.to(torch.bfloat16))
+
+
 def test_elementwise_helpers():
     x = torch.randn(1000000, device=dev)
     assert torch.equal(ops.cast_to_bf16(x), x.to(torch.bfloat16))

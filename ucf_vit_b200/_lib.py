@@ -38,6 +38,7 @@ _SIGNATURES = {
     "ucf_sap_scatter": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                 c_void_p]),
     "ucf_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, _LL, c_void_p]),
+    "ucf_cast_f32_to_bf16_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ucf_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, _LL, c_int, c_void_p]),
     "ucf_colsum_bf16": (c_int, [c_void_p, c_void_p, _LL, c_int, _LL, c_int, c_void_p]),
     "ucf_assemble_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, _LL, c_int,

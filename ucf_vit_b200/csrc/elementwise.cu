@@ -20,6 +20,29 @@ cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict
   }
 }
 
+struct CastMultiArgs {
+  const float* src[8];
+  __nv_bfloat16* dst[8];
+  long long n[8];
+};
+// blockIdx.y selects the tensor; same body as the single-tensor kernel
+__global__ void __launch_bounds__(256) cast_f32_to_bf16_multi_kernel(const CastMultiArgs a) {
+  const float* __restrict__ src = a.src[blockIdx.y];
+  __nv_bfloat16* __restrict__ dst = a.dst[blockIdx.y];
+  const long long n = a.n[blockIdx.y];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(src + i));
+      const float4 y = __ldg(reinterpret_cast<const float4*>(src + i + 4));
+      *reinterpret_cast<uint4*>(dst + i) =
+          make_uint4(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w), pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+    }
+  }
+}
+
 template <bool ACC>
 __global__ void __launch_bounds__(256)
 cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
@@ -198,6 +221,30 @@ extern "C" int ucf_cast_f32_to_bf16(const float* src, void* dst, long long n, vo
   cast_f32_to_bf16_kernel<<<ew_grid((n + 7) / 8, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   return check_launch("cast_f32_to_bf16_kernel");
+}
+
+extern "C" int ucf_cast_f32_to_bf16_multi(int n, const float* const* srcs, void* const* dsts, const long long* counts,
+                                          void* stream) {
+  if (n <= 0) return UCF_OK;
+  if (n > 8 || !srcs || !dsts || !counts) { set_last_error("cast_f32_to_bf16_multi: 1..8 tensors, non-null arrays"); return UCF_ERR_BAD_ARG; }
+  CastMultiArgs a;
+  long long nmax = 0;
+  for (int i = 0; i < 8; ++i) {
+    const int j = i < n ? i : 0;
+    a.src[i] = srcs[j]; a.dst[i] = static_cast<__nv_bfloat16*>(dsts[j]); a.n[i] = i < n ? counts[j] : 0;
+    if (i < n) {
+      if (!srcs[i] || !dsts[i] || (reinterpret_cast<uintptr_t>(srcs[i]) & 15) || (reinterpret_cast<uintptr_t>(dsts[i]) & 15)) {
+        set_last_error("cast_f32_to_bf16_multi: pointer %d null or not 16-byte aligned", i); return UCF_ERR_BAD_ARG;
+      }
+      if (counts[i] > nmax) nmax = counts[i];
+    }
+  }
+  if (nmax <= 0) return UCF_OK;
+  int gx = ew_grid((nmax + 7) / 8, 256);
+  const int cap = (num_sms() * 16 + n - 1) / n;          // ~16 CTAs per SM over all tensors
+  if (gx > cap) gx = cap;
+  cast_f32_to_bf16_multi_kernel<<<dim3(gx, n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("cast_f32_to_bf16_multi_kernel");
 }
 
 extern "C" int ucf_cast_bf16_to_f32(const void* src, float* dst, long long n, int accumulate, void* stream) {

@@ -35,6 +35,13 @@ def bf16_param(p: torch.Tensor) -> torch.Tensor:
     return ops.cast_to_bf16(q) if q.dtype == torch.float32 else q.to(BF16)
 
 
+def bf16_params(*ps):
+    """bf16_param for several parameters; fp32 contiguous ones share one cast launch."""
+    if all(p.dtype == torch.float32 and p.is_contiguous() for p in ps) and 1 < len(ps) <= 8:
+        return ops.cast_to_bf16_multi([p.detach() for p in ps])
+    return [bf16_param(p) for p in ps]
+
+
 def _zeros_f32(dev, *shapes):
     """One zero-filled fp32 allocation carved into 256-byte aligned views (one fill launch instead of
     one per gradient; the reduce-add epilogues accumulate into them).  A shape of None yields None."""
@@ -349,7 +356,7 @@ class _BlockFn(torch.autograd.Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         h1, mean1, rstd1 = ops.layernorm_fwd(x2, n1w, n1b, eps1)
-        wq, wp, w1h, w2h = bf16_param(qkv_w), bf16_param(proj_w), bf16_param(fc1_w), bf16_param(fc2_w)
+        wq, wp, w1h, w2h = bf16_params(qkv_w, proj_w, fc1_w, fc2_w)
         qkv = ops.gemm(h1, wq, M=M, N=3 * D, K=D, bias=qkv_b)
         qkv5 = qkv.view(B, N, 3, H, hd)
         o, lse = ops.attention_fwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], hd ** -0.5)

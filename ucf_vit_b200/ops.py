@@ -101,6 +101,25 @@ def cast_to_bf16(x, out=None):
     return out
 
 
+def cast_to_bf16_multi(xs):
+    """bf16 copies of up to 8 contiguous fp32 tensors in one launch (views of one allocation)."""
+    import ctypes
+    _require_cuda(*xs)
+    n = len(xs)
+    assert 1 <= n <= 8 and all(x.dtype == torch.float32 and x.is_contiguous() for x in xs)
+    sizes = [-(-x.numel() // 64) * 64 for x in xs]
+    flat = torch.empty(sum(sizes), dtype=torch.bfloat16, device=xs[0].device)
+    outs, off = [], 0
+    for x, sz in zip(xs, sizes):
+        outs.append(flat[off:off + x.numel()].view(x.shape))
+        off += sz
+    srcs = (ctypes.c_void_p * n)(*[x.data_ptr() for x in xs])
+    dsts = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+    cnts = (ctypes.c_longlong * n)(*[x.numel() for x in xs])
+    L.check(L.lib().ucf_cast_f32_to_bf16_multi(n, srcs, dsts, cnts, _stream()), "cast_f32_to_bf16_multi")
+    return outs
+
+
 def cast_to_f32(x, out=None, accumulate=False):
     _require_cuda(x)
     assert x.dtype == torch.bfloat16 and x.is_contiguous()
