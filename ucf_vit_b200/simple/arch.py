@@ -349,7 +349,12 @@ class VIT(nn.Module):
 
     def forward_head(self, x: torch.Tensor) -> torch.Tensor:
         x = self.head_drop(self.pool(x))
-        return _torch_head(self.head, x)
+        h = self.head
+        # a plain Linear head whose pitches satisfy TMA alignment reuses the block GEMM ("the
+        # Linears can reuse the a5/a7 GEMM kernel for free"); anything else stays in PyTorch
+        if isinstance(h, nn.Linear) and x.is_cuda and h.in_features % 8 == 0 and h.out_features % 8 == 0:
+            return UF.linear(x, h.weight, h.bias)
+        return _torch_head(h, x)
 
     def forward(self, x: torch.Tensor, variables, seq_ps=None) -> torch.Tensor:
         return self.forward_head(self.forward_features(x, variables, seq_ps))
