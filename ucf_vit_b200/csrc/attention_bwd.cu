@@ -123,13 +123,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
       mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1);
-      mbar_init(&pds_full[i], 256);
-      mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 256);
+      mbar_init(&pds_full[i], 8);
+      mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 8);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_empty, 256);
+    mbar_init(sdp_empty, 8);
     mbar_init(dkv_full, 1);
-    mbar_init(dkv_empty, 256);
+    mbar_init(dkv_empty, 8);
     mbar_init(p_free, 1);
     fence_barrier_init();
   }
@@ -343,7 +343,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       tc_fence_before();
-      mbar_arrive(&dq_empty[slot]);
+      mbar_arrive_warp(&dq_empty[slot]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0 && qrow0 + qd * 32 < p.Nq) {
@@ -382,7 +382,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       tc_fence_before();
-      mbar_arrive(dkv_empty);
+      mbar_arrive_warp(dkv_empty);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0 && k0 + qd * 32 < p.Nk) {
@@ -444,7 +444,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         tc_fence_before();
-        mbar_arrive(sdp_empty);                          // S / dP may be overwritten
+        mbar_arrive_warp(sdp_empty);                          // S / dP may be overwritten
         if (lane == 0 && cw == 0) UCF_TL(t, 13);
         if (t > 0) mbar_wait(p_free, (t - 1) & 1);       // dV(t-1) has finished reading P
         if (lane == 0 && cw == 0) UCF_TL(t, 14);
@@ -457,7 +457,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(&pds_full[db]);
+        mbar_arrive_warp(&pds_full[db]);
         if (threadIdx.x == 64) UCF_TL(t, 3);
         if (lane == 0) UCF_TL(t, 16 + cw);
         // drain what the tensor core finished while this tile's math ran

@@ -91,8 +91,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < RING; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&s_empty[g], 128);
-      mbar_init(&p_full[g], 128);
+      mbar_init(&s_empty[g], 4);
+      mbar_init(&p_full[g], 4);
       mbar_init(&pv_full[g], 1);
     }
     fence_barrier_init();
@@ -328,9 +328,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         tc_fence_before();
-        mbar_arrive(&s_empty[g]);        // S_g may be overwritten by the next QK^T
+        mbar_arrive_warp(&s_empty[g]);        // S_g may be overwritten by the next QK^T
         fence_proxy_async_smem();
-        mbar_arrive(&p_full[g]);         // P_g(j) visible to the tensor core
+        mbar_arrive_warp(&p_full[g]);         // P_g(j) visible to the tensor core
         if (stamp) p.timeline[(g * 4 + tc) * 8 + 4] = clock64();   // P written
         l_run = fmaf(l_run, alpha, l2.x + l2.y);
         m_run = m_new;
@@ -437,8 +437,8 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int i = 0; i < RING; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&s_empty[g], 128);
-      mbar_init(&p_full[g], 128);
+      mbar_init(&s_empty[g], 4);
+      mbar_init(&p_full[g], 4);
       mbar_init(&pv_full[g], 1);
     }
     fence_barrier_init();
@@ -661,7 +661,7 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(&p_full[g]);           // P0 visible; S0's columns may now receive O = P0 V0
+      mbar_arrive_warp(&p_full[g]);           // P0 visible; S0's columns may now receive O = P0 V0
       if (st) UCF_FTL(k, g, 2);
       // ---- pass 2b: P1 is formed in registers while PV0 still reads the P buffer
       if (nkv == 2) {
@@ -680,7 +680,7 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if (c < nchunk1) store_chunk(c, pk1[c]);
         tc_fence_before();
         fence_proxy_async_smem();
-        mbar_arrive(&p_full[g]);         // P1 visible
+        mbar_arrive_warp(&p_full[g]);         // P1 visible
         if (st) UCF_FTL(k, g, 4);
       }
       // ---- epilogue: O / l
@@ -708,7 +708,7 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       }
       tc_fence_before();
-      mbar_arrive(&s_empty[g]);          // S0 / S1 / O of this warpgroup are free for the next item
+      mbar_arrive_warp(&s_empty[g]);          // S0 / S1 / O of this warpgroup are free for the next item
       if (qt0 + row < p.Nq)
         p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qt0 + row] = (m2 + log2f(l_row)) * 0.69314718055994531f;
       fence_proxy_async_smem();

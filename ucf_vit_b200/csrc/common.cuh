@@ -103,6 +103,13 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// One arrival per WARP: every lane has finished what the barrier publishes (callers issue their own
+// tcgen05 / proxy fences first), the warp converges, lane 0 arrives.  A barrier counting all 128 / 256 threads
+// serialises that many shared-memory atomics on one word -- hundreds of cycles on every hand-off.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 // Spin with a watchdog: a protocol bug traps (reported as a launch failure) instead of hanging
 // the GPU box.  ~4 s at 2 GHz.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
