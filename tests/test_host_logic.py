@@ -91,3 +91,32 @@ def test_product_never_imports_oracle():
     for f in root.rglob("*.py"):
         txt = f.read_text()
         assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_wgrad_split_factor_fills_whole_rounds():
+    """Host-side choice of the weight-gradient split-K factor (functional._wgrad_splits): at the benchmark shapes the
+    tile x split work units must fill the persistent schedule's rounds (74 CTA pairs on a 148-SM part) to >= 95 %,
+    keep >= 8 k-blocks per split and stay within the 16-way limit of the reduce-add epilogue."""
+    import torch
+    from ucf_vit_b200 import functional as F
+
+    class Dev:
+        index = 0
+    F._SM_COUNT[0] = 148
+    try:
+        M = 256 * 197
+        kb = (M + 63) // 64
+        for n_out, k_in in ((3072, 768), (768, 3072), (2304, 768), (768, 768)):
+            s = F._wgrad_splits(n_out, k_in, M, Dev)
+            assert 1 <= s <= 16 and kb // s >= 8
+            tiles = ((n_out + 255) // 256) * ((k_in + 255) // 256)
+            per = -(-kb // s)
+            units = tiles * (-(-kb // per))
+            fill = units / (-(-units // 74) * 74)
+            assert fill >= 0.95, (n_out, k_in, s, fill)
+        assert F._wgrad_splits(768, 768, 512, Dev) == 1          # fewer than 16 k-blocks: no split
+        # small (single-CTA kernel) shapes still get a legal factor
+        s = F._wgrad_splits(192, 192, M, Dev)
+        assert 1 <= s <= 16 and kb // s >= 8
+    finally:
+        F._SM_COUNT.pop(0, None)
