@@ -268,7 +268,7 @@ def run_gpu_arm(args):
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                         bucket_cap_mb=64)
-    opt = configure_optimizer(model, 1e-4, 0.9, 0.95, 1e-5, fused=True)
+    opt = configure_optimizer(model, 1e-4, 0.9, 0.95, 1e-5, fused="ucf" if args.optimizer == "ucf" else True)
     variables = ["r", "g", "b"]
     B = PER_GPU_BATCH
     g = torch.Generator().manual_seed(1234 + rank)
@@ -389,7 +389,8 @@ def run_gpu_arm(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": imgs, "parallelism": f"dp{world}",
                    "l2_policy": "per-step inputs (154 MB) and activations (>10 GB) exceed the 126 MB L2",
-                   "optimizer": "AdamW fused, fp32 master weights", "loss_final": final_loss},
+                   "optimizer": ("AdamW, ucf_adamw_multi kernel" if args.optimizer == "ucf" else "AdamW, torch fused kernel") +
+                                ", fp32 master weights", "loss_final": final_loss},
         "model_tflops": value * f_img / 1e12,
         "attn_mlp_tflops": value * f_blocks / 1e12,
         "attn_mlp_frac_of_peak": value * f_blocks / 1e12 / (peak * world),
@@ -424,6 +425,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="torch", choices=["torch", "ucf"],
+                    help="AdamW update: torch's fused CUDA kernel or this package's ucf_adamw_multi")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -170,6 +170,41 @@ int ucf_patchify(const void* x, void* out, int B, int C, int G0, int G1, int G2,
 int ucf_assemble_tokens(const void* tok, const void* prefix, const void* pos, void* out, int B, int L,
                         int P, int D, long long pos_bstride, int pos_off, int param_dtype, void* stream);
 
+/* ---- either side of the path in a training step ---------------- */
+/* Reconstruction loss against the patchified image WITHOUT materialising the patchified target:
+ * replaces `target = patchify(data, p, twoD); loss = masked_mse(output, target, mask)` or
+ * `nn.MSELoss()(output, target)` (training_scripts/train_masked_fsdp.py:48-62, utils/misc.py:14-33,
+ * utils/metrics.py:11-17), and with (G0, G1, G2, p0, p1, p2) = (L, 1, 1, 1, P, 1) the adaptive variant
+ * `target = rearrange(seq, 'b c s p -> b s (p c)')` (train_masked_fsdp.py:40-43).
+ *   pred  [B, L, p0*p1*p2*C]  f32|bf16, L = G0*G1*G2, channel fastest inside a patch
+ *   img   [B, C, G0*p0, G1*p1, G2*p2]  f32|bf16 contiguous (2-D images: G2 = p2 = 1)
+ *   mask  f32 [B*L] weights (1 = token counts) or NULL for the plain mean over every element
+ *   workspace  UCF_PATCH_MSE_MAX_BLOCKS doubles of scratch
+ *   out   f32 [2]: out[0] = loss, out[1] = 1 / denominator (input of the backward call)
+ * The per-CTA partial sums are combined in a fixed order in double: the loss is reproducible. */
+#define UCF_PATCH_MSE_MAX_BLOCKS 4096
+int ucf_patch_mse_fwd(const void* pred, int pred_dtype, const void* img, int img_dtype, const float* mask,
+                      int B, int C, int G0, int G1, int G2, int p0, int p1, int p2, double* workspace,
+                      float* out, void* stream);
+/* dpred = grad_out * d loss / d pred  (same dtype and shape as pred); fwd_out is `out` of the forward
+ * call, grad_out a DEVICE f32 scalar (autograd's incoming gradient).  The image gets no gradient. */
+int ucf_patch_mse_bwd(const void* pred, int pred_dtype, const void* img, int img_dtype, const float* mask,
+                      const float* fwd_out, const float* grad_out, int B, int C, int G0, int G1, int G2,
+                      int p0, int p1, int p2, void* dpred, void* stream);
+
+/* One AdamW step (decoupled weight decay, no amsgrad) over n fp32 tensors that share the same
+ * hyper-parameters and step count: the arithmetic of torch.optim.AdamW as configured by
+ * utils/misc.py:58-84 (`configure_optimizer`: two groups, weight_decay 0 for var/pos embeddings) and
+ * stepped at training_scripts/train_class_simple.py:355.
+ *   p *= 1 - lr*wd;  m += (1-b1)(g-m);  v = b2 v + (1-b2) g^2;
+ *   p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps)
+ * params / grads / exp_avg / exp_avg_sq / counts are HOST arrays of n device pointers / element
+ * counts; `step` is the 1-based count AFTER this update.  16-byte aligned tensors take the float4 path,
+ * others a scalar one.  Hyper-parameters are doubles and rounded to fp32 once on the host. */
+int ucf_adamw_multi(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                    float* const* exp_avg_sq, const long long* counts, double lr, double beta1, double beta2,
+                    double eps, double weight_decay, long long step, int maximize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

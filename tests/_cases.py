@@ -11,7 +11,7 @@ from oracle import vit_ref as R
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MODEL_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                     if not p.endswith("host_logic.npz") and not os.path.basename(p).startswith("sap_tree"))
+                     if not os.path.basename(p).startswith(("host_", "sap_tree")))
 VARS3 = ["r", "g", "b"]
 
 

@@ -5,7 +5,7 @@ non-zero code, a RuntimeError is raised.  PyTorch is used only for device memory
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_ulonglong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libucfvit_b200.so")
@@ -14,6 +14,7 @@ _lib = None
 UCF_DTYPE_F32, UCF_DTYPE_BF16, UCF_DTYPE_U8, UCF_DTYPE_F64 = 0, 1, 2, 3
 UCF_LAYOUT_K_MAJOR, UCF_LAYOUT_MN_MAJOR = 0, 1
 EPI_BIAS, EPI_BIAS_RESIDUAL, EPI_BIAS_GELU_AUX, EPI_DGELU, EPI_F32_ADD = 0, 1, 2, 3, 4
+PATCH_MSE_MAX_BLOCKS = 4096
 
 _LL = c_longlong
 _SIGNATURES = {
@@ -43,6 +44,10 @@ _SIGNATURES = {
     "ucf_colsum_bf16": (c_int, [c_void_p, c_void_p, _LL, c_int, _LL, c_int, c_void_p]),
     "ucf_assemble_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, _LL, c_int,
                                     c_int, c_void_p]),
+    "ucf_patch_mse_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p] + [c_int] * 8 + [c_void_p] * 3),
+    "ucf_patch_mse_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 8 +
+                          [c_void_p] * 2),
+    "ucf_adamw_multi": (c_int, [c_int] + [c_void_p] * 5 + [c_double] * 5 + [_LL, c_int, c_void_p]),
     "ucf_patchify": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_void_p]),
 }

@@ -1,5 +1,7 @@
 """Thin tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers,
 launch on torch's current stream.  No autograd here (see `functional.py`)."""
+import ctypes
+
 import torch
 
 from . import _lib as L
@@ -103,7 +105,6 @@ def cast_to_bf16(x, out=None):
 
 def cast_to_bf16_multi(xs):
     """bf16 copies of up to 8 contiguous fp32 tensors in one launch (views of one allocation)."""
-    import ctypes
     _require_cuda(*xs)
     n = len(xs)
     assert 1 <= n <= 8 and all(x.dtype == torch.float32 and x.is_contiguous() for x in xs)
@@ -315,3 +316,63 @@ def assemble_tokens(tok, prefix, pos, pos_has_prefix):
     L.check(L.lib().ucf_assemble_tokens(tok.data_ptr(), _ptr(prefix), _ptr(pos), out.data_ptr(), B, L_, P, D, bstride,
                                         0 if pos_has_prefix else P, pd, _stream()), "assemble_tokens")
     return out
+
+
+def _patch_geometry(pred, img, grid, patch):
+    """Validate pred [B, L, P*C] against img [B, C, G0*p0, G1*p1, G2*p2]; returns the int arguments."""
+    G0, G1, G2 = grid
+    p0, p1, p2 = patch
+    B, C = img.shape[0], img.shape[1]
+    if img.numel() != B * C * G0 * p0 * G1 * p1 * G2 * p2:
+        raise ValueError(f"image {tuple(img.shape)} is not [B, C] x grid {grid} x patch {patch}")
+    if tuple(pred.shape) != (B, G0 * G1 * G2, p0 * p1 * p2 * C):
+        raise ValueError(f"pred {tuple(pred.shape)} does not match {(B, G0 * G1 * G2, p0 * p1 * p2 * C)}")
+    return B, C, G0, G1, G2, p0, p1, p2
+
+
+def patch_mse_fwd(pred, img, grid, patch, mask=None):
+    """Loss of `pred` against the patchified `img` (never materialised).  Returns a fp32 [2] tensor:
+    [loss, 1 / denominator]; the second entry is what `patch_mse_bwd` needs."""
+    _require_cuda(pred, img, mask)
+    assert pred.is_contiguous() and img.is_contiguous()
+    dims = _patch_geometry(pred, img, grid, patch)
+    if mask is not None:
+        assert mask.dtype == torch.float32 and mask.is_contiguous() and mask.numel() == pred.shape[0] * pred.shape[1]
+    ws = torch.empty(L.PATCH_MSE_MAX_BLOCKS, dtype=torch.float64, device=pred.device)
+    out = torch.empty(2, dtype=torch.float32, device=pred.device)
+    L.check(L.lib().ucf_patch_mse_fwd(pred.data_ptr(), _dt(pred), img.data_ptr(), _dt(img), _ptr(mask), *dims,
+                                      ws.data_ptr(), out.data_ptr(), _stream()), "patch_mse_fwd")
+    return out
+
+
+def patch_mse_bwd(pred, img, grid, patch, mask, fwd_out, grad_out):
+    """d loss / d pred scaled by the device scalar `grad_out`; same dtype / shape as pred."""
+    _require_cuda(pred, img, mask, fwd_out, grad_out)
+    dims = _patch_geometry(pred, img, grid, patch)
+    assert fwd_out.dtype == torch.float32 and fwd_out.numel() == 2 and fwd_out.is_contiguous()
+    assert grad_out.dtype == torch.float32 and grad_out.numel() == 1
+    dpred = torch.empty_like(pred)
+    L.check(L.lib().ucf_patch_mse_bwd(pred.data_ptr(), _dt(pred), img.data_ptr(), _dt(img), _ptr(mask),
+                                      fwd_out.data_ptr(), grad_out.data_ptr(), *dims, dpred.data_ptr(), _stream()),
+            "patch_mse_bwd")
+    return dpred
+
+
+def adamw_multi(params, grads, exp_avgs, exp_avg_sqs, *, lr, beta1, beta2, eps, weight_decay, step, maximize=False):
+    """One in-place AdamW update of the fp32 tensors `params` (+ both moments) that share a step count."""
+    n = len(params)
+    if n == 0:
+        return
+    assert len(grads) == n and len(exp_avgs) == n and len(exp_avg_sqs) == n
+    for ts in (params, grads, exp_avgs, exp_avg_sqs):
+        _require_cuda(*ts)
+        for t in ts:
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise TypeError("adamw_multi: every tensor must be a contiguous fp32 CUDA tensor")
+    for p, g, m, v in zip(params, grads, exp_avgs, exp_avg_sqs):
+        if not (p.numel() == g.numel() == m.numel() == v.numel()):
+            raise ValueError("adamw_multi: parameter, gradient and moments differ in size")
+    tbl = [(ctypes.c_void_p * n)(*[t.data_ptr() for t in ts]) for ts in (params, grads, exp_avgs, exp_avg_sqs)]
+    cnts = (ctypes.c_longlong * n)(*[p.numel() for p in params])
+    L.check(L.lib().ucf_adamw_multi(n, *tbl, cnts, float(lr), float(beta1), float(beta2), float(eps),
+                                    float(weight_decay), int(step), int(bool(maximize)), _stream()), "adamw_multi")

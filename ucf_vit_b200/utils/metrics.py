@@ -1,13 +1,71 @@
 """Losses next to the hot path (/root/reference/src/UCF_VIT/utils/metrics.py:11-17,95-121).
-Tiny element-wise reductions; they stay in PyTorch."""
+
+`masked_mse` / `DiceBLoss` keep the reference's signatures (pre-patchified target, PyTorch ops).
+`patch_mse` and `adaptive_patch_mse` are the fused CUDA form of the MAE drivers' loss lines
+(`target = patchify(data, p, twoD); loss = masked_mse(output, target, mask)` or `nn.MSELoss()`,
+training_scripts/train_masked_fsdp.py:40-62): the target is indexed out of the image inside the
+kernel, so neither the patchified copy nor the squared-difference temporaries are written
+(SURVEY.md §8f rank 2).  CUDA only -- they raise on CPU tensors."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from .. import ops
 
 
 def masked_mse(pred, y, mask):
     per_token = ((pred - y) ** 2).mean(dim=-1)
     return (per_token * mask).sum() / mask.sum()
+
+
+class _PatchMseFn(torch.autograd.Function):
+    """loss(pred; img, mask) through ucf_patch_mse_fwd / _bwd.  Only `pred` is differentiable."""
+
+    @staticmethod
+    def forward(ctx, pred, img, mask, grid, patch):
+        out = ops.patch_mse_fwd(pred, img, grid, patch, mask)
+        ctx.save_for_backward(pred, img, mask, out)
+        ctx.geometry = (grid, patch)
+        return out[0].clone() if pred.dtype == torch.float32 else out[0].to(pred.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        pred, img, mask, out = ctx.saved_tensors
+        grid, patch = ctx.geometry
+        g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        return ops.patch_mse_bwd(pred, img, grid, patch, mask, out, g), None, None, None, None
+
+
+def _fused_patch_loss(pred, img, mask, grid, patch):
+    if img.requires_grad:
+        raise NotImplementedError("patch_mse: the image / target is a constant of the loss (no gradient is produced)")
+    if not pred.is_cuda:
+        raise RuntimeError("patch_mse runs on CUDA tensors only (sm_100a); use masked_mse(pred, patchify(...), mask) "
+                           "from this module for a PyTorch evaluation")
+    if mask is not None:
+        mask = mask.detach().to(torch.float32).contiguous()
+    return _PatchMseFn.apply(pred.contiguous(), img.detach().contiguous(), mask, grid, patch)
+
+
+def patch_mse(pred, data, patch_size, twoD, mask=None):
+    """`masked_mse(pred, patchify(data, patch_size, twoD), mask)` when `mask` is given ([B, L], 1 = token
+    counts), else `nn.MSELoss()(pred, patchify(data, patch_size, twoD))`.
+    pred [B, L, p^d * C] (f32 | bf16), data [B, C, X, Y(, Z)] (f32 | bf16)."""
+    p = int(patch_size)
+    sp = tuple(data.shape[2:])
+    if len(sp) != (2 if twoD else 3) or any(s % p for s in sp):
+        raise ValueError(f"patch_mse: data {tuple(data.shape)} is not a {'2' if twoD else '3'}-D image divisible by {p}")
+    grid = tuple(s // p for s in sp) + ((1,) if twoD else ())
+    patch = (p, p, 1) if twoD else (p, p, p)
+    return _fused_patch_loss(pred, data, mask, grid, patch)
+
+
+def adaptive_patch_mse(pred, seq, mask=None):
+    """`nn.MSELoss()(pred, rearrange(seq, 'b c s p -> b s (p c)'))` of the adaptive-patching MAE driver
+    (train_masked_fsdp.py:40-43): seq [B, C, L, P] holds the gathered patches, pred is [B, L, P * C]."""
+    if seq.dim() != 4:
+        raise ValueError(f"adaptive_patch_mse: seq must be [B, C, L, P], got {tuple(seq.shape)}")
+    return _fused_patch_loss(pred, seq, mask, (seq.shape[2], 1, 1), (1, seq.shape[3], 1))
 
 
 class DiceBLoss(nn.Module):

@@ -32,7 +32,10 @@ def unpatchify(patchified_pixel_values, data, patch_size, twoD):
 
 
 def configure_optimizer(model, lr, beta_1, beta_2, weight_decay, fused=None):
-    """AdamW with two groups: weight decay everywhere except var/pos/time embeddings."""
+    """AdamW with two groups: weight decay everywhere except var/pos/time embeddings.
+
+    `fused`: None = stock torch.optim.AdamW defaults (what the reference builds), True / False = torch's own
+    `fused` flag, "ucf" = this package's `FusedAdamW` (same state layout, multi-tensor CUDA update)."""
     decay, no_decay = [], []
     for name, prm in model.named_parameters():
         (no_decay if ("var_embed" in name or "pos_embed" in name or "time_pos_embed" in name) else decay).append(prm)
@@ -40,6 +43,9 @@ def configure_optimizer(model, lr, beta_1, beta_2, weight_decay, fused=None):
         {"params": decay, "lr": lr, "betas": (beta_1, beta_2), "weight_decay": weight_decay},
         {"params": no_decay, "lr": lr, "betas": (beta_1, beta_2), "weight_decay": 0},
     ]
+    if fused == "ucf":
+        from .optim import FusedAdamW
+        return FusedAdamW(groups)
     kw = {} if fused is None else {"fused": fused}
     return torch.optim.AdamW(groups, **kw)
 
