@@ -174,13 +174,16 @@ int ucf_assemble_tokens(const void* tok, const void* prefix, const void* pos, vo
 /* Reconstruction loss against the patchified image WITHOUT materialising the patchified target:
  * replaces `target = patchify(data, p, twoD); loss = masked_mse(output, target, mask)` or
  * `nn.MSELoss()(output, target)` (training_scripts/train_masked_fsdp.py:48-62, utils/misc.py:14-33,
- * utils/metrics.py:11-17), and with (G0, G1, G2, p0, p1, p2) = (L, 1, 1, 1, P, 1) the adaptive variant
+ * utils/metrics.py:11-17), and with (G0, G1, G2, p0, p1, p2) = (1, L, 1, 1, 1, P) the adaptive variant
  * `target = rearrange(seq, 'b c s p -> b s (p c)')` (train_masked_fsdp.py:40-43).
  *   pred  [B, L, p0*p1*p2*C]  f32|bf16, L = G0*G1*G2, channel fastest inside a patch
  *   img   [B, C, G0*p0, G1*p1, G2*p2]  f32|bf16 contiguous (2-D images: G2 = p2 = 1)
  *   mask  f32 [B*L] weights (1 = token counts) or NULL for the plain mean over every element
- *   workspace  UCF_PATCH_MSE_MAX_BLOCKS doubles of scratch
+ *   workspace  2 * UCF_PATCH_MSE_MAX_BLOCKS doubles of scratch (per-CTA partial sums of the loss and of the mask)
  *   out   f32 [2]: out[0] = loss, out[1] = 1 / denominator (input of the backward call)
+ * Put the image's contiguous axis last in the geometry (2-D images as G = (1, Gy, Gx), p = (1, p, p); the
+ * adaptive layout as G = (1, L, 1), p = (1, 1, P)): with p2 % 4 == 0, C <= 4 and 16-byte (f32) / 8-byte (bf16)
+ * aligned tensors the kernels move four pixels per load; any other geometry takes a scalar path.
  * The per-CTA partial sums are combined in a fixed order in double: the loss is reproducible. */
 #define UCF_PATCH_MSE_MAX_BLOCKS 4096
 int ucf_patch_mse_fwd(const void* pred, int pred_dtype, const void* img, int img_dtype, const float* mask,

@@ -21,6 +21,7 @@ def timeit(fn, iters=20, warm=5):
     tot = 0.0
     for _ in range(iters):
         flush.zero_()                                   # evict L2 between iterations
+        torch.cuda._sleep(4_000_000)                    # ~2 ms of device idle: the host runs ahead, so launch cost is hidden
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()

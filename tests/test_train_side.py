@@ -257,7 +257,10 @@ def test_adaptive_patch_mse_matches_the_reference_vectors():
     (2, 5, (40, 24), 8, torch.float32, torch.bfloat16),      # bf16 image (FSDP mixed precision feeds bf16 data)
     (1, 2, (32, 16, 32), 16, torch.float32, torch.float32),  # 3-D, 4096-pixel patches (16 pixels per thread)
     (2, 1, (12, 20, 12), 4, torch.bfloat16, torch.bfloat16),
-    (1, 1, (20, 20), 20, torch.float32, torch.float32),      # 400 pixels: ragged second sweep of the CTA
+    (1, 1, (20, 20), 20, torch.float32, torch.float32),      # 400 pixels = 100 quads per token
+    (2, 2, (18, 30), 6, torch.float32, torch.float32),       # p % 4 != 0: scalar path, 36 pixels per token
+    (1, 3, (12, 12, 18), 6, torch.bfloat16, torch.float32),  # scalar path in 3-D (216 pixels)
+    (2, 4, (64, 32), 32, torch.bfloat16, torch.bfloat16),    # 1024 pixels, four channels
 ])
 def test_patch_mse_against_the_oracle(B, C, sp, p, dt_pred, dt_img):
     torch.manual_seed(B * 100 + C)
@@ -278,6 +281,26 @@ def test_patch_mse_against_the_oracle(B, C, sp, p, dt_pred, dt_img):
         _close(pr.grad.float().cpu().numpy(), 3.0 * go, tol)
         if mk is not None and (mk == 0).any():         # visible tokens get exact zeros
             assert pr.grad[mk.cuda() == 0].abs().max().item() == 0.0
+
+
+@gpu
+def test_patch_mse_unaligned_tensors_take_the_scalar_path():
+    """A prediction that starts 4 bytes past a 16-byte boundary cannot use vector loads: same numbers."""
+    torch.manual_seed(21)
+    data = torch.randn(2, 3, 32, 32, device="cuda")
+    store = torch.randn(2 * 4 * 768 + 1, device="cuda")
+    pred = store[1:].view(2, 4, 768)
+    assert pred.data_ptr() % 16 == 4
+    mask = torch.tensor([[1, 0, 1, 1], [0, 1, 1, 0]], device="cuda", dtype=torch.float32)
+    pa, pb = pred.clone().requires_grad_(True), pred.detach().requires_grad_(True)
+    la, lb = metrics.patch_mse(pa, data, 16, True, mask), metrics.patch_mse(pb, data, 16, True, mask)
+    la.backward()
+    lb.backward()
+    assert abs(la.item() - lb.item()) <= 1e-6 * abs(la.item())
+    _close(pb.grad.cpu().numpy(), pa.grad.cpu().numpy(), 1e-6)
+    lo, go = T.mse_loss_and_grad(pred.cpu().numpy(), T.patchify_np(data.cpu().numpy(), 16, True), mask.cpu().numpy())
+    assert abs(la.item() - lo) <= 2e-6 * abs(lo)
+    _close(pa.grad.cpu().numpy(), go, 2e-6)
 
 
 @gpu

@@ -12,7 +12,8 @@ namespace ucf {
 // ------------------------------------------------------------------------------------------------
 // multi-tensor AdamW
 // ------------------------------------------------------------------------------------------------
-constexpr int kAdamTensors = 24;   // 24 * 40 B of kernel arguments
+constexpr int kAdamTensors = 24;     // per launch: 24 * 40 B of pointers and counts + 25 chunk offsets
+constexpr int kAdamChunk = 4096;     // elements one CTA updates: 256 threads x 4 float4
 
 struct AdamWArgs {
   float* p[kAdamTensors];
@@ -20,6 +21,7 @@ struct AdamWArgs {
   float* m[kAdamTensors];
   float* v[kAdamTensors];
   long long n[kAdamTensors];
+  int first_chunk[kAdamTensors + 1];   // CTA b works on tensor t with first_chunk[t] <= b < first_chunk[t + 1]
 };
 
 struct AdamWScalars {
@@ -41,40 +43,58 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
   p -= s.step_size * (m / denom);
 }
 
+// One CTA per 4096-element chunk of one tensor, so tensors of any mix of sizes load the machine evenly.
+// VEC: all four streams of every tensor are 16-byte aligned -> float4, four independent chunks of loads in
+// flight per thread; otherwise a scalar walk over the same chunk.
 template <bool VEC>
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamWArgs a, const AdamWScalars s) {
-  float* __restrict__ p = a.p[blockIdx.y];
-  const float* __restrict__ g = a.g[blockIdx.y];
-  float* __restrict__ m = a.m[blockIdx.y];
-  float* __restrict__ v = a.v[blockIdx.y];
-  const long long n = a.n[blockIdx.y];
-  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  int t = 0;
+#pragma unroll
+  for (int i = 1; i < kAdamTensors; ++i) t += (static_cast<int>(blockIdx.x) >= a.first_chunk[i]) ? 1 : 0;
+  const long long base = static_cast<long long>(static_cast<int>(blockIdx.x) - a.first_chunk[t]) * kAdamChunk;
+  const long long left = a.n[t] - base;
+  const int cnt = left < kAdamChunk ? static_cast<int>(left) : kAdamChunk;
+  float* __restrict__ p = a.p[t] + base;
+  const float* __restrict__ g = a.g[t] + base;
+  float* __restrict__ m = a.m[t] + base;
+  float* __restrict__ v = a.v[t] + base;
   if (VEC) {
-    const long long nv = n >> 2;
-    for (long long i = tid; i < nv; i += nthreads) {
-      float4 pp = reinterpret_cast<float4*>(p)[i];
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
-      float4 mm = reinterpret_cast<float4*>(m)[i];
-      float4 vv = reinterpret_cast<float4*>(v)[i];
-      adamw_one(pp.x, gg.x, mm.x, vv.x, s);
-      adamw_one(pp.y, gg.y, mm.y, vv.y, s);
-      adamw_one(pp.z, gg.z, mm.z, vv.z, s);
-      adamw_one(pp.w, gg.w, mm.w, vv.w, s);
-      reinterpret_cast<float4*>(p)[i] = pp;
-      reinterpret_cast<float4*>(m)[i] = mm;
-      reinterpret_cast<float4*>(v)[i] = vv;
+    float4 pp[4], gg[4], mm[4], vv[4];
+    const int nv = cnt >> 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      if (i < nv) {
+        pp[j] = reinterpret_cast<const float4*>(p)[i];
+        gg[j] = __ldg(reinterpret_cast<const float4*>(g) + i);
+        mm[j] = reinterpret_cast<const float4*>(m)[i];
+        vv[j] = reinterpret_cast<const float4*>(v)[i];
+      }
     }
-    for (long long i = (nv << 2) + tid; i < n; i += nthreads) {   // < 4 trailing elements
-      float pp = p[i], mm = m[i], vv = v[i];
-      adamw_one(pp, g[i], mm, vv, s);
-      p[i] = pp; m[i] = mm; v[i] = vv;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      if (i < nv) {
+        adamw_one(pp[j].x, gg[j].x, mm[j].x, vv[j].x, s);
+        adamw_one(pp[j].y, gg[j].y, mm[j].y, vv[j].y, s);
+        adamw_one(pp[j].z, gg[j].z, mm[j].z, vv[j].z, s);
+        adamw_one(pp[j].w, gg[j].w, mm[j].w, vv[j].w, s);
+        reinterpret_cast<float4*>(p)[i] = pp[j];
+        reinterpret_cast<float4*>(m)[i] = mm[j];
+        reinterpret_cast<float4*>(v)[i] = vv[j];
+      }
+    }
+    const int i = (nv << 2) + threadIdx.x;             // < 4 trailing elements of the tensor's last chunk
+    if (i < cnt) {
+      float q = p[i], mq = m[i], vq = v[i];
+      adamw_one(q, g[i], mq, vq, s);
+      p[i] = q; m[i] = mq; v[i] = vq;
     }
   } else {
-    for (long long i = tid; i < n; i += nthreads) {
-      float pp = p[i], mm = m[i], vv = v[i];
-      adamw_one(pp, g[i], mm, vv, s);
-      p[i] = pp; m[i] = mm; v[i] = vv;
+    for (int i = threadIdx.x; i < cnt; i += 256) {
+      float q = p[i], mq = m[i], vq = v[i];
+      adamw_one(q, g[i], mq, vq, s);
+      p[i] = q; m[i] = mq; v[i] = vq;
     }
   }
 }
@@ -84,8 +104,11 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamWArgs a, con
 //
 // pred [B, L, P*C] (P = p0*p1*p2 pixels of a patch, channel fastest) is compared with
 // img [B, C, G0*p0, G1*p1, G2*p2], token l = (g0*G1 + g1)*G2 + g2, pixel q = (q0*p1 + q1)*p2 + q2.
-// One CTA walks whole tokens; a thread owns one pixel (all C channels) at a time, so image reads
-// are contiguous runs of p2 (or p1 when p2 == 1) elements and pred reads cover the token row densely.
+// Fast path ("quad"): p2 % 4 == 0 and C <= 4.  A work item is four consecutive pixels along the image's
+// fastest axis: C 16-byte image loads (one per channel plane) against the 4*C contiguous pred values they
+// pair with, all issued before the first subtraction.  Items are dealt to CTAs as contiguous ranges of the
+// flattened (token, quad) index, so small patches (64 quads at p = 16) fill every lane.
+// Generic path: one pixel per thread, scalar loads, any geometry.
 // ------------------------------------------------------------------------------------------------
 struct PatchGeom {
   int B, C, L;
@@ -93,13 +116,138 @@ struct PatchGeom {
   int p0, p1, p2;
   int sx, sy;            // image strides (elements) of axis 0 / axis 1 inside one channel plane; axis 2 is 1
   long long plane;       // X*Y*Z
+  long long items;       // quad path: B*L*(P/4)
+  int per_cta;           // quad path: items per CTA
 };
 
 __device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+// four consecutive elements as floats (16-byte / 8-byte aligned)
+__device__ __forceinline__ void ld4(const float* p, float* o) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void ld4(const __nv_bfloat16* p, float* o) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+__device__ __forceinline__ void st4(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, const float* v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
 
+// sum of two per-thread doubles over the CTA, in a fixed order (bit-reproducible); valid on thread 0
+__device__ __forceinline__ void block_sum2(double& a, double& b) {
+  __shared__ double red[2][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = 0.0; b = 0.0;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; }
+  }
+}
+
+// every CTA adds its strided share of the mask to the second half of the workspace
+__device__ __forceinline__ double mask_share(const float* __restrict__ mask, int BL) {
+  double ms = 0.0;
+  if (mask)
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < BL; i += gridDim.x * 256) ms += static_cast<double>(__ldg(mask + i));
+  return ms;
+}
+
+// (token, quad) of a CTA-local item index; offsets of the quad in pred and in channel plane 0 of the image
+struct QuadItem {
+  int token;
+  long long pred_off, img_off;
+  __device__ __forceinline__ QuadItem(const PatchGeom& gm, unsigned token0, unsigned r, unsigned Qn, int C) {
+    const unsigned tk = r / Qn, quad = r - tk * Qn;
+    token = static_cast<int>(token0 + tk);
+    const unsigned b = static_cast<unsigned>(token) / static_cast<unsigned>(gm.L);
+    const unsigned l = static_cast<unsigned>(token) - b * gm.L;
+    const unsigned g2 = l % gm.G2, lr = l / gm.G2, g1 = lr % gm.G1, g0 = lr / gm.G1;
+    const unsigned q = quad * 4u;
+    const unsigned q2 = q % gm.p2, qr = q / gm.p2, q1 = qr % gm.p1, q0 = qr / gm.p1;
+    pred_off = (static_cast<long long>(token) * Qn + quad) * (4 * C);
+    img_off = static_cast<long long>(b) * C * gm.plane + static_cast<long long>(g0 * gm.p0 + q0) * gm.sx +
+              static_cast<long long>(g1 * gm.p1 + q1) * gm.sy + (g2 * gm.p2 + q2);
+  }
+};
+
+template <typename TP, typename TI, int C>
+__global__ void __launch_bounds__(256)
+patch_mse_fwd_quad_kernel(const TP* __restrict__ pred, const TI* __restrict__ img, const float* __restrict__ mask,
+                          const PatchGeom gm, double* __restrict__ partials) {
+  const unsigned Qn = static_cast<unsigned>(gm.p0 * gm.p1 * gm.p2) >> 2;
+  const long long start = static_cast<long long>(blockIdx.x) * gm.per_cta;
+  const long long stop = start + gm.per_cta < gm.items ? start + gm.per_cta : gm.items;
+  const unsigned token0 = static_cast<unsigned>(start / Qn), rem0 = static_cast<unsigned>(start - 1LL * token0 * Qn);
+  const int n_here = stop > start ? static_cast<int>(stop - start) : 0;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n_here; i += 256) {
+    const QuadItem it(gm, token0, rem0 + i, Qn, C);
+    const float w = mask ? __ldg(mask + it.token) : 1.f;
+    if (w == 0.f) continue;
+    float iv[C][4], pv[4 * C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) ld4(img + it.img_off + c * gm.plane, iv[c]);
+#pragma unroll
+    for (int j = 0; j < C; ++j) ld4(pred + it.pred_off + 4 * j, pv + 4 * j);
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4 * C; ++e) {
+      const float d = pv[e] - iv[e % C][e / C];
+      s = fmaf(d, d, s);
+    }
+    acc = fmaf(w, s, acc);
+  }
+  double d = static_cast<double>(acc), ms = mask_share(mask, gm.B * gm.L);
+  block_sum2(d, ms);
+  if (threadIdx.x == 0) { partials[blockIdx.x] = d; partials[UCF_PATCH_MSE_MAX_BLOCKS + blockIdx.x] = ms; }
+}
+
+template <typename TP, typename TI, int C>
+__global__ void __launch_bounds__(256)
+patch_mse_bwd_quad_kernel(const TP* __restrict__ pred, const TI* __restrict__ img, const float* __restrict__ mask,
+                          const float* __restrict__ fwd_out, const float* __restrict__ grad_out, const PatchGeom gm,
+                          TP* __restrict__ dpred) {
+  const unsigned Qn = static_cast<unsigned>(gm.p0 * gm.p1 * gm.p2) >> 2;
+  const long long start = static_cast<long long>(blockIdx.x) * gm.per_cta;
+  const long long stop = start + gm.per_cta < gm.items ? start + gm.per_cta : gm.items;
+  const unsigned token0 = static_cast<unsigned>(start / Qn), rem0 = static_cast<unsigned>(start - 1LL * token0 * Qn);
+  const int n_here = stop > start ? static_cast<int>(stop - start) : 0;
+  const float coef0 = 2.f * __ldg(fwd_out + 1) * __ldg(grad_out);
+  for (int i = threadIdx.x; i < n_here; i += 256) {
+    const QuadItem it(gm, token0, rem0 + i, Qn, C);
+    const float w = mask ? __ldg(mask + it.token) : 1.f;
+    float pv[4 * C];
+    if (w == 0.f) {
+#pragma unroll
+      for (int e = 0; e < 4 * C; ++e) pv[e] = 0.f;
+    } else {
+      float iv[C][4];
+#pragma unroll
+      for (int c = 0; c < C; ++c) ld4(img + it.img_off + c * gm.plane, iv[c]);
+#pragma unroll
+      for (int j = 0; j < C; ++j) ld4(pred + it.pred_off + 4 * j, pv + 4 * j);
+      const float coef = coef0 * w;
+#pragma unroll
+      for (int e = 0; e < 4 * C; ++e) pv[e] = coef * (pv[e] - iv[e % C][e / C]);
+    }
+#pragma unroll
+    for (int j = 0; j < C; ++j) st4(dpred + it.pred_off + 4 * j, pv + 4 * j);
+  }
+}
+
+// ---- generic path -----------------------------------------------------------------------------
 // Pixel q = (q0*p1 + q1)*p2 + q2 of a patch as mixed-radix digits.  A thread visits q = tid, tid + 256, ...:
 // the digits advance by the digits of 256 with carries, so the loops below contain no division.
 struct PixelWalk {
@@ -165,41 +313,9 @@ patch_mse_fwd_kernel(const TP* __restrict__ pred, const TI* __restrict__ img, co
     }
     acc = fmaf(w, tok, acc);
   }
-  // block reduction in double: the order is fixed, so the loss is bit-reproducible run to run
-  __shared__ double red[8];
-  double d = static_cast<double>(acc);
-  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int i = 0; i < 8; ++i) s += red[i];
-    partials[blockIdx.x] = s;
-  }
-}
-
-// out[0] = loss, out[1] = 1 / denominator (kept for the backward pass)
-__global__ void __launch_bounds__(256)
-patch_mse_finish_kernel(const double* __restrict__ partials, int n_partials, const float* __restrict__ mask,
-                        int BL, double elems_per_token, float* __restrict__ out) {
-  __shared__ double red[8];
-  __shared__ double red_m[8];
-  double s = 0.0, ms = 0.0;
-  for (int i = threadIdx.x; i < n_partials; i += blockDim.x) s += partials[i];
-  if (mask) for (int i = threadIdx.x; i < BL; i += blockDim.x) ms += static_cast<double>(mask[i]);
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    ms += __shfl_xor_sync(0xffffffffu, ms, o);
-  }
-  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s; red_m[threadIdx.x >> 5] = ms; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0, tm = 0.0;
-    for (int i = 0; i < 8; ++i) { t += red[i]; tm += red_m[i]; }
-    const double denom = (mask ? tm : static_cast<double>(BL)) * elems_per_token;
-    out[0] = static_cast<float>(t / denom);     // 0/0 -> NaN like the reference when the mask is all zero
-    out[1] = static_cast<float>(1.0 / denom);
-  }
+  double d = static_cast<double>(acc), ms = mask_share(mask, gm.B * gm.L);
+  block_sum2(d, ms);
+  if (threadIdx.x == 0) { partials[blockIdx.x] = d; partials[UCF_PATCH_MSE_MAX_BLOCKS + blockIdx.x] = ms; }
 }
 
 template <typename TP, typename TI>
@@ -229,6 +345,24 @@ patch_mse_bwd_kernel(const TP* __restrict__ pred, const TI* __restrict__ img, co
   }
 }
 
+// workspace = [MAX per-CTA sums of w * (pred - target)^2 | MAX per-CTA shares of sum(mask)]
+// out[0] = loss, out[1] = 1 / denominator (kept for the backward pass)
+__global__ void __launch_bounds__(256)
+patch_mse_finish_kernel(const double* __restrict__ partials, int n_partials, int has_mask, int BL,
+                        double elems_per_token, float* __restrict__ out) {
+  double s = 0.0, ms = 0.0;
+  for (int i = threadIdx.x; i < n_partials; i += 256) {
+    s += partials[i];
+    ms += partials[UCF_PATCH_MSE_MAX_BLOCKS + i];
+  }
+  block_sum2(s, ms);
+  if (threadIdx.x == 0) {
+    const double denom = (has_mask ? ms : static_cast<double>(BL)) * elems_per_token;
+    out[0] = static_cast<float>(s / denom);     // 0/0 -> NaN like the reference when the mask is all zero
+    out[1] = static_cast<float>(1.0 / denom);
+  }
+}
+
 static int patch_geom(const char* who, int B, int C, int G0, int G1, int G2, int p0, int p1, int p2, PatchGeom* gm) {
   if (B <= 0 || C <= 0 || G0 <= 0 || G1 <= 0 || G2 <= 0 || p0 <= 0 || p1 <= 0 || p2 <= 0) {
     set_last_error("%s: every dimension must be positive", who); return UCF_ERR_BAD_ARG;
@@ -246,13 +380,32 @@ static int patch_geom(const char* who, int B, int C, int G0, int G1, int G2, int
   gm->sy = static_cast<int>(sy);
   gm->sx = static_cast<int>(sx);
   gm->plane = sx * G0 * p0;
+  gm->items = 0; gm->per_cta = 0;
   return UCF_OK;
 }
 
-static int patch_mse_grid(int BL) {
-  int g = num_sms() * 16;
-  if (g > UCF_PATCH_MSE_MAX_BLOCKS) g = UCF_PATCH_MSE_MAX_BLOCKS;
-  return BL < g ? BL : g;
+static int patch_mse_max_grid() {
+  const int g = num_sms() * 16;
+  return g < UCF_PATCH_MSE_MAX_BLOCKS ? g : UCF_PATCH_MSE_MAX_BLOCKS;
+}
+
+// Quad path when the fastest patch axis is a multiple of four pixels, C <= 4 and both tensors are aligned for
+// 4-element vector access; fills gm->items / per_cta and returns the grid, else returns 0 (generic path).
+static int patch_mse_quad_grid(PatchGeom* gm, const void* pred, int pred_dtype, const void* img, int img_dtype,
+                               const void* dpred) {
+  if (gm->C > 4 || gm->p2 % 4) return 0;
+  const uintptr_t pa = pred_dtype == UCF_DTYPE_F32 ? 15 : 7, ia = img_dtype == UCF_DTYPE_F32 ? 15 : 7;
+  if ((reinterpret_cast<uintptr_t>(pred) & pa) || (reinterpret_cast<uintptr_t>(dpred) & pa) ||
+      (reinterpret_cast<uintptr_t>(img) & ia)) return 0;
+  const long long Qn = 1LL * gm->p0 * gm->p1 * gm->p2 / 4;
+  gm->items = 1LL * gm->B * gm->L * Qn;
+  long long grid = (gm->items + 255) / 256;
+  if (grid > patch_mse_max_grid()) grid = patch_mse_max_grid();
+  long long per = (gm->items + grid - 1) / grid;
+  per = (per + 255) / 256 * 256;
+  if (per + Qn > 0x7fffffffLL) return 0;
+  gm->per_cta = static_cast<int>(per);
+  return static_cast<int>((gm->items + per - 1) / per);
 }
 
 }  // namespace ucf
@@ -283,12 +436,13 @@ extern "C" int ucf_adamw_multi(int n, float* const* params, const float* const* 
   for (int base = 0; base < n; base += kAdamTensors) {
     const int cnt = n - base < kAdamTensors ? n - base : kAdamTensors;
     AdamWArgs a;
-    long long nmax = 0;
+    long long chunks = 0;
     bool vec = true;
     for (int i = 0; i < kAdamTensors; ++i) {
       const int j = base + (i < cnt ? i : 0);
       a.p[i] = params[j]; a.g[i] = grads[j]; a.m[i] = exp_avg[j]; a.v[i] = exp_avg_sq[j];
       a.n[i] = i < cnt ? counts[j] : 0;
+      a.first_chunk[i] = static_cast<int>(chunks);
       if (i < cnt) {
         if (counts[j] < 0 || (counts[j] > 0 && (!params[j] || !grads[j] || !exp_avg[j] || !exp_avg_sq[j]))) {
           set_last_error("adamw_multi: tensor %d has a null pointer or a negative count", j); return UCF_ERR_BAD_ARG;
@@ -296,31 +450,20 @@ extern "C" int ucf_adamw_multi(int n, float* const* params, const float* const* 
         const uintptr_t bits = reinterpret_cast<uintptr_t>(params[j]) | reinterpret_cast<uintptr_t>(grads[j]) |
                                reinterpret_cast<uintptr_t>(exp_avg[j]) | reinterpret_cast<uintptr_t>(exp_avg_sq[j]);
         if (bits & 3) { set_last_error("adamw_multi: tensor %d is not 4-byte aligned", j); return UCF_ERR_BAD_ARG; }
-        if (bits & 15) vec = false;
-        if (counts[j] > nmax) nmax = counts[j];
+        if (counts[j] > 0 && (bits & 15)) vec = false;
+        chunks += (counts[j] + kAdamChunk - 1) / kAdamChunk;
+        if (chunks > 0x7fffffffLL) { set_last_error("adamw_multi: more than 2^31 chunks in one launch"); return UCF_ERR_BAD_ARG; }
       }
     }
-    if (nmax == 0) continue;
-    long long gx = (nmax / (vec ? 4 : 1) + 255) / 256;
-    const long long cap = (static_cast<long long>(num_sms()) * 16 + cnt - 1) / cnt;
-    if (gx > cap) gx = cap;
-    if (gx < 1) gx = 1;
-    const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(cnt));
-    if (vec) adamw_multi_kernel<true><<<grid, 256, 0, st>>>(a, s);
-    else adamw_multi_kernel<false><<<grid, 256, 0, st>>>(a, s);
+    a.first_chunk[kAdamTensors] = static_cast<int>(chunks);
+    if (chunks == 0) continue;
+    if (vec) adamw_multi_kernel<true><<<static_cast<unsigned>(chunks), 256, 0, st>>>(a, s);
+    else adamw_multi_kernel<false><<<static_cast<unsigned>(chunks), 256, 0, st>>>(a, s);
     const int rc = check_launch("adamw_multi_kernel");
     if (rc != UCF_OK) return rc;
   }
   return UCF_OK;
 }
-
-#define UCF_PATCH_MSE_DISPATCH(KERNEL, ...)                                                                  \
-  do {                                                                                                       \
-    if (pred_dtype == UCF_DTYPE_F32 && img_dtype == UCF_DTYPE_F32) KERNEL(float, float, __VA_ARGS__);        \
-    else if (pred_dtype == UCF_DTYPE_F32 && img_dtype == UCF_DTYPE_BF16) KERNEL(float, __nv_bfloat16, __VA_ARGS__); \
-    else if (pred_dtype == UCF_DTYPE_BF16 && img_dtype == UCF_DTYPE_F32) KERNEL(__nv_bfloat16, float, __VA_ARGS__); \
-    else KERNEL(__nv_bfloat16, __nv_bfloat16, __VA_ARGS__);                                                  \
-  } while (0)
 
 static int patch_mse_dtypes(const char* who, int pred_dtype, int img_dtype) {
   const bool okp = pred_dtype == UCF_DTYPE_F32 || pred_dtype == UCF_DTYPE_BF16;
@@ -328,6 +471,53 @@ static int patch_mse_dtypes(const char* who, int pred_dtype, int img_dtype) {
   if (!okp || !oki) { set_last_error("%s: pred and image must be f32 or bf16", who); return UCF_ERR_BAD_ARG; }
   return UCF_OK;
 }
+
+namespace {
+
+struct FwdLaunch {
+  const void* pred; const void* img; const float* mask; PatchGeom gm; double* ws; int grid; cudaStream_t st;
+  template <typename TP, typename TI, int C> void run() const {
+    if (C == 0)
+      patch_mse_fwd_kernel<TP, TI><<<grid, 256, 0, st>>>(static_cast<const TP*>(pred), static_cast<const TI*>(img), mask, gm, ws);
+    else
+      patch_mse_fwd_quad_kernel<TP, TI, (C == 0 ? 1 : C)><<<grid, 256, 0, st>>>(static_cast<const TP*>(pred),
+                                                                              static_cast<const TI*>(img), mask, gm, ws);
+  }
+};
+
+struct BwdLaunch {
+  const void* pred; const void* img; const float* mask; const float* fwd_out; const float* grad_out; PatchGeom gm;
+  void* dpred; int grid; cudaStream_t st;
+  template <typename TP, typename TI, int C> void run() const {
+    if (C == 0)
+      patch_mse_bwd_kernel<TP, TI><<<grid, 256, 0, st>>>(static_cast<const TP*>(pred), static_cast<const TI*>(img), mask,
+                                                         fwd_out, grad_out, gm, static_cast<TP*>(dpred));
+    else
+      patch_mse_bwd_quad_kernel<TP, TI, (C == 0 ? 1 : C)><<<grid, 256, 0, st>>>(
+          static_cast<const TP*>(pred), static_cast<const TI*>(img), mask, fwd_out, grad_out, gm, static_cast<TP*>(dpred));
+  }
+};
+
+// C = 0 selects the generic kernels
+template <typename Launch, typename TP, typename TI> void by_channels(const Launch& l, int c) {
+  switch (c) {
+    case 1: l.template run<TP, TI, 1>(); break;
+    case 2: l.template run<TP, TI, 2>(); break;
+    case 3: l.template run<TP, TI, 3>(); break;
+    case 4: l.template run<TP, TI, 4>(); break;
+    default: l.template run<TP, TI, 0>(); break;
+  }
+}
+
+template <typename Launch> void by_dtypes(const Launch& l, int pred_dtype, int img_dtype, int c) {
+  const bool pf = pred_dtype == UCF_DTYPE_F32, imf = img_dtype == UCF_DTYPE_F32;
+  if (pf && imf) by_channels<Launch, float, float>(l, c);
+  else if (pf) by_channels<Launch, float, __nv_bfloat16>(l, c);
+  else if (imf) by_channels<Launch, __nv_bfloat16, float>(l, c);
+  else by_channels<Launch, __nv_bfloat16, __nv_bfloat16>(l, c);
+}
+
+}  // namespace
 
 extern "C" int ucf_patch_mse_fwd(const void* pred, int pred_dtype, const void* img, int img_dtype, const float* mask,
                                  int B, int C, int G0, int G1, int G2, int p0, int p1, int p2, double* workspace,
@@ -339,15 +529,13 @@ extern "C" int ucf_patch_mse_fwd(const void* pred, int pred_dtype, const void* i
   if (!pred || !img || !workspace || !out) { set_last_error("patch_mse_fwd: null pointer"); return UCF_ERR_BAD_ARG; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int BL = gm.B * gm.L;
-  const int grid = patch_mse_grid(BL);
-#define UCF_FWD(TP, TI, dummy)                                                                         \
-  patch_mse_fwd_kernel<TP, TI><<<grid, 256, 0, st>>>(static_cast<const TP*>(pred), static_cast<const TI*>(img), \
-                                                     mask, gm, workspace)
-  UCF_PATCH_MSE_DISPATCH(UCF_FWD, 0);
-#undef UCF_FWD
-  rc = check_launch("patch_mse_fwd_kernel");
+  int grid = patch_mse_quad_grid(&gm, pred, pred_dtype, img, img_dtype, nullptr);
+  const bool quad = grid > 0;
+  if (!quad) grid = BL < patch_mse_max_grid() ? BL : patch_mse_max_grid();
+  by_dtypes(FwdLaunch{pred, img, mask, gm, workspace, grid, st}, pred_dtype, img_dtype, quad ? C : 0);
+  rc = check_launch(quad ? "patch_mse_fwd_quad_kernel" : "patch_mse_fwd_kernel");
   if (rc != UCF_OK) return rc;
-  patch_mse_finish_kernel<<<1, 256, 0, st>>>(workspace, grid, mask, BL, static_cast<double>(p0) * p1 * p2 * C, out);
+  patch_mse_finish_kernel<<<1, 256, 0, st>>>(workspace, grid, mask != nullptr, BL, static_cast<double>(p0) * p1 * p2 * C, out);
   return check_launch("patch_mse_finish_kernel");
 }
 
@@ -362,11 +550,10 @@ extern "C" int ucf_patch_mse_bwd(const void* pred, int pred_dtype, const void* i
     set_last_error("patch_mse_bwd: null pointer"); return UCF_ERR_BAD_ARG;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = patch_mse_grid(gm.B * gm.L);
-#define UCF_BWD(TP, TI, dummy)                                                                         \
-  patch_mse_bwd_kernel<TP, TI><<<grid, 256, 0, st>>>(static_cast<const TP*>(pred), static_cast<const TI*>(img), \
-                                                     mask, fwd_out, grad_out, gm, static_cast<TP*>(dpred))
-  UCF_PATCH_MSE_DISPATCH(UCF_BWD, 0);
-#undef UCF_BWD
-  return check_launch("patch_mse_bwd_kernel");
+  const int BL = gm.B * gm.L;
+  int grid = patch_mse_quad_grid(&gm, pred, pred_dtype, img, img_dtype, dpred);
+  const bool quad = grid > 0;
+  if (!quad) grid = BL < patch_mse_max_grid() ? BL : patch_mse_max_grid();
+  by_dtypes(BwdLaunch{pred, img, mask, fwd_out, grad_out, gm, dpred, grid, st}, pred_dtype, img_dtype, quad ? C : 0);
+  return check_launch(quad ? "patch_mse_bwd_quad_kernel" : "patch_mse_bwd_kernel");
 }

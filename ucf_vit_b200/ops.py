@@ -338,7 +338,7 @@ def patch_mse_fwd(pred, img, grid, patch, mask=None):
     dims = _patch_geometry(pred, img, grid, patch)
     if mask is not None:
         assert mask.dtype == torch.float32 and mask.is_contiguous() and mask.numel() == pred.shape[0] * pred.shape[1]
-    ws = torch.empty(L.PATCH_MSE_MAX_BLOCKS, dtype=torch.float64, device=pred.device)
+    ws = torch.empty(2 * L.PATCH_MSE_MAX_BLOCKS, dtype=torch.float64, device=pred.device)
     out = torch.empty(2, dtype=torch.float32, device=pred.device)
     L.check(L.lib().ucf_patch_mse_fwd(pred.data_ptr(), _dt(pred), img.data_ptr(), _dt(img), _ptr(mask), *dims,
                                       ws.data_ptr(), out.data_ptr(), _stream()), "patch_mse_fwd")

@@ -55,8 +55,9 @@ def patch_mse(pred, data, patch_size, twoD, mask=None):
     sp = tuple(data.shape[2:])
     if len(sp) != (2 if twoD else 3) or any(s % p for s in sp):
         raise ValueError(f"patch_mse: data {tuple(data.shape)} is not a {'2' if twoD else '3'}-D image divisible by {p}")
-    grid = tuple(s // p for s in sp) + ((1,) if twoD else ())
-    patch = (p, p, 1) if twoD else (p, p, p)
+    # the image's contiguous axis goes last in the geometry (vector path of the kernels)
+    grid = ((1,) if twoD else ()) + tuple(s // p for s in sp)
+    patch = (1, p, p) if twoD else (p, p, p)
     return _fused_patch_loss(pred, data, mask, grid, patch)
 
 
@@ -65,7 +66,7 @@ def adaptive_patch_mse(pred, seq, mask=None):
     (train_masked_fsdp.py:40-43): seq [B, C, L, P] holds the gathered patches, pred is [B, L, P * C]."""
     if seq.dim() != 4:
         raise ValueError(f"adaptive_patch_mse: seq must be [B, C, L, P], got {tuple(seq.shape)}")
-    return _fused_patch_loss(pred, seq, mask, (seq.shape[2], 1, 1), (1, seq.shape[3], 1))
+    return _fused_patch_loss(pred, seq, mask, (1, seq.shape[2], 1), (1, 1, seq.shape[3]))
 
 
 class DiceBLoss(nn.Module):
