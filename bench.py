@@ -425,7 +425,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--optimizer", default="torch", choices=["torch", "ucf"],
+    ap.add_argument("--optimizer", default="ucf", choices=["torch", "ucf"],
                     help="AdamW update: torch's fused CUDA kernel or this package's ucf_adamw_multi")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
