@@ -170,6 +170,28 @@ int ucf_patchify(const void* x, void* out, int B, int C, int G0, int G1, int G2,
 int ucf_assemble_tokens(const void* tok, const void* prefix, const void* pos, void* out, int B, int L,
                         int P, int D, long long pos_bstride, int pos_off, int param_dtype, void* stream);
 
+/* ---- MAE token masking (replaces MAE.random_masking / MAE.mask_head, simple/arch.py:663-702) ---------
+ * Shuffle / restore permutations and the mask from the per-token noise in ONE launch (replaces two
+ * torch.argsort calls, ones + slice-assign + gather): ids_restore[b, j] = rank of noise[b, j] in ascending order
+ * (ties: lower index first), ids_shuffle = its inverse permutation, mask[b, j] = 1 if rank >= len_keep (token
+ * removed) else 0.  noise / mask f32 [B, L], ids int64 [B, L]; L <= 12288. */
+int ucf_mask_plan(const float* noise, int B, int L, int len_keep, long long* ids_shuffle,
+                  long long* ids_restore, float* mask, void* stream);
+/* out[b, i, :] = (0 <= idx[b, i] < Ls ? src[b, idx[b, i], :] : fill[:]) + pos[b * pos_bstride + i * D + :]
+ * - kept-token gather of random_masking (arch.py:674-675): idx = ids_shuffle[:, :len_keep] (pass the row
+ *   pitch-free copy), fill = pos = NULL;
+ * - mask_head's cat(x, mask_token.repeat) + gather(ids_restore) + decoder_pos_embed add (arch.py:687-698) as one
+ *   pass: src = decoder_embed(x) [B, Ls, D], idx = ids_restore [B, Lo], fill = mask_token [D], pos = embedding.
+ * src / out bf16; idx int64 [B, Lo]; fill, pos of param_dtype (f32 | bf16), either may be NULL (fill NULL = zeros);
+ * pos_bstride = 0 for a table shared by the batch, Lo*D for per-sample embeddings.  D % 8 == 0. */
+int ucf_gather_tokens(const void* src, const long long* idx, const void* fill, const void* pos, void* out,
+                      int B, int Ls, int Lo, int D, long long pos_bstride, int param_dtype, void* stream);
+/* Gradient of ucf_gather_tokens: dsrc[b, idx[b, i], :] = dout[b, i, :] for rows taken from src (idx entries of a
+ * sample must be distinct); zero_first != 0 zero-fills dsrc [B, Ls, D] first (rows no index names get no
+ * gradient); dfill f32 [D] += sum of the dout rows that were filled.  dsrc or dfill may be NULL. */
+int ucf_scatter_tokens(const void* dout, const long long* idx, void* dsrc, float* dfill, int B, int Ls, int Lo,
+                       int D, int zero_first, void* stream);
+
 /* ---- either side of the path in a training step ---------------- */
 /* Reconstruction loss against the patchified image WITHOUT materialising the patchified target:
  * replaces `target = patchify(data, p, twoD); loss = masked_mse(output, target, mask)` or

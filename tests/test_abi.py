@@ -40,3 +40,15 @@ def test_bad_arguments_are_rejected_without_a_device():
     assert rc == -1 and b"empty problem" in lib.ucf_last_error()
     rc = lib.ucf_attention_fwd(1, 1, 1, 1, 1, 1, 1, 4, 4, 36, *([8] * 12), 1.0, None)
     assert rc == -4 and b"head_dim 36" in lib.ucf_last_error()
+
+
+def test_masking_entry_points_reject_bad_arguments_without_a_device():
+    lib = _lib.lib()
+    assert lib.ucf_mask_plan(1, 2, 8, 9, 1, 1, 1, None) == -1 and b"len_keep" in lib.ucf_last_error()
+    assert lib.ucf_mask_plan(1, 2, 20000, 5, 1, 1, 1, None) == -4 and b"12288" in lib.ucf_last_error()
+    assert lib.ucf_mask_plan(None, 0, 8, 2, None, None, None, None) == 0          # empty batch: nothing to do
+    assert lib.ucf_gather_tokens(16, 16, None, None, 16, 1, 4, 4, 12, 0, 0, None) == -1
+    assert b"multiple of 8" in lib.ucf_last_error()
+    assert lib.ucf_gather_tokens(16, 16, None, None, 24, 1, 4, 4, 16, 0, 0, None) == -1
+    assert b"16-byte aligned" in lib.ucf_last_error()
+    assert lib.ucf_scatter_tokens(16, 16, 16, None, 1, 4, 4, 12, 0, None) == -1

@@ -261,3 +261,64 @@ def test_errors_are_loud():
         ops.attention_fwd(q, q, q, 1.0)
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.layernorm_fwd(torch.randn(4, 64), None, None, 1e-5)
+
+
+@pytest.mark.parametrize("B,Lt,keep", [(4, 196, 49), (3, 64, 16), (2, 1000, 250), (1, 4096, 1024), (5, 7, 0), (2, 9, 9),
+                                       (256, 196, 49)])
+def test_mask_plan_matches_argsort(B, Lt, keep):
+    """MAE.random_masking's index work (arch.py:663-681): bit-exact against two stable argsorts, with and
+    without ties in the noise."""
+    torch.manual_seed(B + Lt)
+    for noise in (torch.rand(B, Lt, device=dev), torch.randint(0, 5, (B, Lt), device=dev).float()):
+        sh, rs, mk = ops.mask_plan(noise, keep)
+        ref_sh = torch.argsort(noise, dim=1, stable=True)
+        ref_rs = torch.argsort(ref_sh, dim=1)
+        ref_mk = torch.ones(B, Lt, device=dev)
+        ref_mk[:, :keep] = 0
+        ref_mk = torch.gather(ref_mk, 1, ref_rs)
+        assert torch.equal(sh, ref_sh) and torch.equal(rs, ref_rs) and torch.equal(mk, ref_mk)
+
+
+@pytest.mark.parametrize("B,Ls,Lo,D,per_sample_pos", [(3, 20, 50, 64, False), (2, 49, 196, 512, True), (4, 1, 9, 8, False)])
+def test_gather_tokens_restores_the_sequence_like_mask_head(B, Ls, Lo, D, per_sample_pos):
+    """cat(x, mask_token.repeat) -> gather(ids_restore) -> + pos (arch.py:687-698) and its gradients."""
+    from ucf_vit_b200 import functional as UF
+    torch.manual_seed(Ls + Lo)
+    src = bf(torch.randn(B, Ls, D, device=dev)).requires_grad_(True)
+    idx = torch.stack([torch.randperm(Lo, device=dev) for _ in range(B)])
+    fill = torch.randn(1, 1, D, device=dev, requires_grad=True)
+    pos = torch.randn(B if per_sample_pos else 1, Lo, D, device=dev, requires_grad=True)
+    out = UF.gather_tokens(src, idx, fill=fill, pos=pos, complete=True)
+    s32, f32_, p32 = (t.detach().float().requires_grad_(True) for t in (src, fill, pos))
+    full = torch.cat([s32, f32_.expand(B, Lo - Ls, D)], dim=1)
+    ref = torch.gather(full, 1, idx.unsqueeze(-1).expand(-1, -1, D)) + p32
+    _ok(out, ref, 1e-2)
+    g = bf(torch.randn(B, Lo, D, device=dev))
+    out.backward(g)
+    ref.backward(g.float())
+    assert torch.equal(src.grad.float(), s32.grad)                     # pure row moves
+    _ok(fill.grad, f32_.grad, 1e-2 if B * (Lo - Ls) > 100 else 2e-3)    # fp32 sum of bf16 rows, different order
+    _ok(pos.grad, p32.grad, 2e-3)
+    # without pos / fill the rows are copied bit for bit, and out-of-range indices give zero rows
+    out2 = ops.gather_tokens(src.detach(), idx)
+    ref2 = torch.gather(torch.cat([src.detach(), torch.zeros(B, Lo - Ls, D, device=dev, dtype=torch.bfloat16)], 1), 1,
+                        idx.unsqueeze(-1).expand(-1, -1, D))
+    assert torch.equal(out2, ref2)
+
+
+def test_gather_tokens_keeps_tokens_like_random_masking():
+    from ucf_vit_b200 import functional as UF
+    torch.manual_seed(9)
+    B, Lt, D, keep = 6, 196, 192, 49
+    seq = bf(torch.randn(B, Lt, D, device=dev)).requires_grad_(True)
+    sh, rs, mk = ops.mask_plan(torch.rand(B, Lt, device=dev), keep)
+    ids_keep = sh[:, :keep].contiguous()
+    kept = UF.gather_tokens(seq, ids_keep)
+    s32 = seq.detach().float().requires_grad_(True)
+    ref = torch.gather(s32, 1, ids_keep.unsqueeze(-1).expand(-1, -1, D))
+    assert torch.equal(kept.float(), ref)
+    g = bf(torch.randn(B, keep, D, device=dev))
+    kept.backward(g)
+    ref.backward(g.float())
+    assert torch.equal(seq.grad.float(), s32.grad)                     # removed tokens get exact zeros
+    assert (seq.grad.float().abs().sum(-1) == 0).sum().item() == B * (Lt - keep)

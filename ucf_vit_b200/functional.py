@@ -522,6 +522,53 @@ class _AssembleFn(torch.autograd.Function):
         return d_tok, d_prefix, d_pos, None
 
 
+class _GatherTokensFn(torch.autograd.Function):
+    """out[b, i] = (idx[b, i] < Ls ? src[b, idx[b, i]] : fill) + pos  (ucf_gather_tokens / ucf_scatter_tokens).
+    `complete`: every row of src is named exactly once by idx (idx is a permutation padded with fill rows), so
+    the backward scatter needs no zero-fill."""
+
+    @staticmethod
+    def forward(ctx, src, idx, fill, pos, complete):
+        src_c = src if src.is_contiguous() else src.contiguous()
+        idx_c = idx if idx.is_contiguous() else idx.contiguous()
+        pdt = None
+        for t in (fill, pos):
+            if t is not None:
+                pdt = t.dtype if pdt is None else pdt
+        fl = None if fill is None else fill.reshape(-1).to(pdt).contiguous()
+        ps = None if pos is None else pos.to(pdt).contiguous()
+        ctx.save_for_backward(idx_c)
+        ctx.meta = (src.shape[1], None if fill is None else (fill.shape, fill.dtype),
+                    None if pos is None else (pos.shape, pos.dtype), bool(complete))
+        return ops.gather_tokens(src_c, idx_c, fl, ps)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        Ls, fmeta, pmeta, complete = ctx.meta
+        g = g if g.is_contiguous() else g.contiguous()
+        need_src = ctx.needs_input_grad[0]
+        need_fill = fmeta is not None and ctx.needs_input_grad[2]
+        d_src = d_fill = d_pos = None
+        if need_src or need_fill:
+            d_src, df = ops.scatter_tokens(g, idx, Ls, need_src=need_src, need_fill=need_fill, zero_first=not complete)
+            if need_fill:
+                d_fill = df.reshape(fmeta[0]).to(fmeta[1])
+        if pmeta is not None and ctx.needs_input_grad[3]:
+            shp, dt = pmeta
+            if len(shp) == 3 and shp[0] == g.shape[0] and shp[0] != 1:
+                d_pos = g.to(dt)                                       # per-sample embedding
+            else:
+                d_pos = g.sum(0, dtype=torch.float32).reshape(shp).to(dt)
+        return d_src, None, d_fill, d_pos, None
+
+
+def gather_tokens(src, idx, fill=None, pos=None, complete=False):
+    """Row gather with an optional fill row for out-of-range indices and an optional embedding add:
+    MAE.random_masking's kept-token gather and MAE.mask_head's cat + gather + pos-embed add (arch.py:674-698)."""
+    return _GatherTokensFn.apply(src, idx, fill, pos, complete)
+
+
 def assemble_tokens(tok, prefix=None, pos=None, pos_has_prefix=True):
     """concat(prefix tokens, tok) + pos  ->  bf16 [B, P+L, D]  (VIT._pos_embed, arch.py:367-393)."""
     return _AssembleFn.apply(tok, prefix, pos, pos_has_prefix)

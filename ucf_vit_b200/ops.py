@@ -376,3 +376,51 @@ def adamw_multi(params, grads, exp_avgs, exp_avg_sqs, *, lr, beta1, beta2, eps, 
     cnts = (ctypes.c_longlong * n)(*[p.numel() for p in params])
     L.check(L.lib().ucf_adamw_multi(n, *tbl, cnts, float(lr), float(beta1), float(beta2), float(eps),
                                     float(weight_decay), int(step), int(bool(maximize)), _stream()), "adamw_multi")
+
+
+def mask_plan(noise, len_keep):
+    """(ids_shuffle, ids_restore, mask) of MAE.random_masking from the per-token noise [B, L] (fp32)."""
+    _require_cuda(noise)
+    assert noise.dim() == 2 and noise.dtype == torch.float32 and noise.is_contiguous()
+    B, Lt = noise.shape
+    ids_shuffle = torch.empty((B, Lt), dtype=torch.int64, device=noise.device)
+    ids_restore = torch.empty_like(ids_shuffle)
+    mask = torch.empty((B, Lt), dtype=torch.float32, device=noise.device)
+    L.check(L.lib().ucf_mask_plan(noise.data_ptr(), B, Lt, int(len_keep), ids_shuffle.data_ptr(), ids_restore.data_ptr(),
+                                  mask.data_ptr(), _stream()), "mask_plan")
+    return ids_shuffle, ids_restore, mask
+
+
+def gather_tokens(src, idx, fill=None, pos=None):
+    """out[b, i] = (idx[b, i] < Ls ? src[b, idx[b, i]] : fill) + pos[b or 0, i];  src bf16 [B, Ls, D], idx int64 [B, Lo]."""
+    _require_cuda(src, idx, fill, pos)
+    assert src.dtype == torch.bfloat16 and src.dim() == 3 and src.is_contiguous()
+    assert idx.dtype == torch.int64 and idx.dim() == 2 and idx.is_contiguous() and idx.shape[0] == src.shape[0]
+    B, Ls, D = src.shape
+    Lo = idx.shape[1]
+    pdt, bstride = 0, 0
+    if fill is not None:
+        assert fill.numel() == D and fill.is_contiguous()
+        pdt = _dt(fill)
+    if pos is not None:
+        assert pos.is_contiguous() and pos.shape[-2:] == (Lo, D) and pos.numel() in (Lo * D, B * Lo * D)
+        assert fill is None or pos.dtype == fill.dtype
+        pdt = _dt(pos)
+        bstride = Lo * D if (pos.numel() == B * Lo * D and B > 1) else 0
+    out = torch.empty((B, Lo, D), dtype=torch.bfloat16, device=src.device)
+    L.check(L.lib().ucf_gather_tokens(src.data_ptr(), idx.data_ptr(), _ptr(fill), _ptr(pos), out.data_ptr(), B, Ls, Lo, D,
+                                      bstride, pdt, _stream()), "gather_tokens")
+    return out
+
+
+def scatter_tokens(dout, idx, Ls, *, need_src=True, need_fill=False, zero_first=True):
+    """Gradient of gather_tokens: (dsrc bf16 [B, Ls, D] | None, dfill fp32 [D] | None)."""
+    _require_cuda(dout, idx)
+    assert dout.dtype == torch.bfloat16 and dout.dim() == 3 and dout.is_contiguous()
+    assert idx.dtype == torch.int64 and idx.is_contiguous() and tuple(idx.shape) == tuple(dout.shape[:2])
+    B, Lo, D = dout.shape
+    dsrc = torch.empty((B, Ls, D), dtype=torch.bfloat16, device=dout.device) if need_src else None
+    dfill = torch.zeros(D, dtype=torch.float32, device=dout.device) if need_fill else None
+    L.check(L.lib().ucf_scatter_tokens(dout.data_ptr(), idx.data_ptr(), _ptr(dsrc), _ptr(dfill), B, Ls, Lo, D,
+                                       int(zero_first), _stream()), "scatter_tokens")
+    return dsrc, dfill

@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as UF
+from .. import ops
 from ..utils.fused_attn import FusedAttn
 from ..utils.layers import named_apply, trunc_normal_
 from ..utils.pos_embed import (SinusoidalEmbeddings, get_1d_sincos_pos_embed_from_grid,
@@ -425,7 +426,8 @@ class _DecoderMixin:
             self.decoder_adaptive_pos_dep_emb = _pos_dep_mlp(3 if self.twoD else 4, dd)
 
     def _decode(self, x, pos):
-        x = x + pos.to(x.dtype)
+        if pos is not None:
+            x = UF.assemble_tokens(x, None, pos, True)
         x = self.decoder_blocks(x)
         x = UF.layer_norm(x, self.decoder_norm.weight, self.decoder_norm.bias, self.decoder_norm.eps)
         return UF.linear(x, self.decoder_pred.weight, self.decoder_pred.bias)
@@ -448,32 +450,29 @@ class MAE(_DecoderMixin, VIT):
 
     def random_masking(self, sequence, noise=None):
         """Keep the int(L*(1-r)) lowest-noise tokens per sample.  Returns (kept, mask, ids_restore);
-        mask is 1 for removed tokens, in original order."""
-        if self.aggregated_variables > 1:
-            batch_size, _, seq_length, dim = sequence.shape
-        else:
-            batch_size, seq_length, dim = sequence.shape
+        mask is 1 for removed tokens, in original order.  One kernel ranks the noise (both permutations and the
+        mask), one gathers the kept rows."""
+        if sequence.dim() != 3:
+            raise ValueError(f"random_masking expects [B, L, D] tokens, got {tuple(sequence.shape)}")
+        batch_size, seq_length, dim = sequence.shape
         len_keep = int(seq_length * (1 - self.mask_ratio))
         if noise is None:
             noise = torch.rand(batch_size, seq_length, device=sequence.device)
-        ids_shuffle = torch.argsort(noise, dim=1)
-        ids_restore = torch.argsort(ids_shuffle, dim=1)
-        kept = torch.gather(sequence, 1, ids_shuffle[:, :len_keep].unsqueeze(-1).expand(-1, -1, dim))
-        mask = torch.ones([batch_size, seq_length], device=sequence.device)
-        mask[:, :len_keep] = 0
-        return kept, torch.gather(mask, 1, ids_restore), ids_restore
+        ids_shuffle, ids_restore, mask = ops.mask_plan(noise.to(torch.float32).contiguous(), len_keep)
+        kept = UF.gather_tokens(sequence, ids_shuffle[:, :len_keep].contiguous())
+        return kept, mask, ids_restore
 
     def mask_head(self, x: torch.Tensor, ids_restore, seq_ps):
         if not self.linear_decoder:
             x = UF.linear(x, self.decoder_embed.weight, self.decoder_embed.bias)
-        n_mask = ids_restore.shape[1] - x.shape[1]
-        full = torch.cat([x, self.mask_token.to(x.dtype).expand(x.shape[0], n_mask, -1)], dim=1)
-        full = torch.gather(full, 1, ids_restore.unsqueeze(-1).expand(-1, -1, x.shape[2]))
+        # cat(x, mask tokens) -> gather(ids_restore) (-> + decoder position embedding): one pass
         if self.linear_decoder:
+            full = UF.gather_tokens(x, ids_restore, fill=self.mask_token, complete=True)
             return UF.linear(full, self.decoder_pred.weight, self.decoder_pred.bias)
         pos = (_torch_head(self.decoder_adaptive_pos_dep_emb, seq_ps) if self.use_adaptive_pos_emb
                else self.decoder_pos_embed)
-        return self._decode(full, pos)
+        full = UF.gather_tokens(x, ids_restore, fill=self.mask_token, pos=pos, complete=True)
+        return self._decode(full, None)
 
     def forward_features(self, x: torch.Tensor, variables, seq_ps, noise=None):
         # NB: like the reference (:735-736) every adaptive input is a pre-gathered sequence here
