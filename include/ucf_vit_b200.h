@@ -170,6 +170,14 @@ int ucf_patchify(const void* x, void* out, int B, int C, int G0, int G1, int G2,
 int ucf_assemble_tokens(const void* tok, const void* prefix, const void* pos, void* out, int B, int L,
                         int P, int D, long long pos_bstride, int pos_off, int param_dtype, void* stream);
 
+/* Broadcast add of an embedding to bf16 tokens in one pass: out[i0, i1, i2, :] = x[i0, i1, i2, :] +
+ * e[i0*s0 + i1*s1 + i2*s2 + :] with stride 0 along broadcast axes.  Replaces the variable-embedding add
+ * `x + var_embed.unsqueeze(2)` on [B, V, L, D] tokens (simple/arch.py:456-462: s = (0, D, 0)) and DiffusionVIT's
+ * time-embedding add `x + temb[:, None, :]` (arch.py:1263-1265: n = (B, 1, N), s = (D, 0, 0)).  x / out bf16
+ * [n0, n1, n2, D] contiguous (out may alias x); e of param_dtype (f32 | bf16); D and strides multiples of 8. */
+int ucf_add_bcast(const void* x, const void* e, void* out, long long n0, int n1, int n2, int D, long long s0,
+                  long long s1, long long s2, int param_dtype, void* stream);
+
 /* ---- MAE token masking (replaces MAE.random_masking / MAE.mask_head, simple/arch.py:663-702) ---------
  * Shuffle / restore permutations and the mask from the per-token noise in ONE launch (replaces two
  * torch.argsort calls, ones + slice-assign + gather): ids_restore[b, j] = rank of noise[b, j] in ascending order

@@ -52,3 +52,11 @@ def test_masking_entry_points_reject_bad_arguments_without_a_device():
     assert lib.ucf_gather_tokens(16, 16, None, None, 24, 1, 4, 4, 16, 0, 0, None) == -1
     assert b"16-byte aligned" in lib.ucf_last_error()
     assert lib.ucf_scatter_tokens(16, 16, 16, None, 1, 4, 4, 12, 0, None) == -1
+
+
+def test_add_bcast_rejects_bad_arguments_without_a_device():
+    lib = _lib.lib()
+    assert lib.ucf_add_bcast(16, 16, 16, 2, 3, 4, 12, 0, 0, 0, 0, None) == -1 and b"multiples of 8" in lib.ucf_last_error()
+    assert lib.ucf_add_bcast(16, 16, 16, 2, 3, 4, 16, 4, 0, 0, 0, None) == -1
+    assert lib.ucf_add_bcast(16, 8, 16, 2, 3, 4, 16, 0, 0, 0, 0, None) == -1 and b"16-byte aligned" in lib.ucf_last_error()
+    assert lib.ucf_add_bcast(None, None, None, 0, 3, 4, 16, 0, 0, 0, 0, None) == 0

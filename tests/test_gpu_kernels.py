@@ -322,3 +322,25 @@ def test_gather_tokens_keeps_tokens_like_random_masking():
     ref.backward(g.float())
     assert torch.equal(seq.grad.float(), s32.grad)                     # removed tokens get exact zeros
     assert (seq.grad.float().abs().sum(-1) == 0).sum().item() == B * (Lt - keep)
+
+
+@pytest.mark.parametrize("xs,es,edt", [((3, 4, 10, 64), (1, 4, 1, 64), torch.float32),     # variable embedding
+                                       ((5, 197, 128), (5, 1, 128), torch.float32),         # time embedding
+                                       ((2, 50, 64), (1, 1, 64), torch.bfloat16),
+                                       ((2, 3, 7, 8), (2, 3, 7, 8), torch.float32),         # no broadcast at all
+                                       ((6, 16), (16,), torch.float32)])
+def test_add_bcast_fwd_bwd(xs, es, edt):
+    from ucf_vit_b200 import functional as UF
+    torch.manual_seed(sum(xs))
+    x = bf(torch.randn(*xs, device=dev)).requires_grad_(True)
+    e = torch.randn(*es, device=dev).to(edt).requires_grad_(True)
+    out = UF.add_bcast(x, e)
+    x32, e32 = x.detach().float().requires_grad_(True), e.detach().float().requires_grad_(True)
+    ref = x32 + e32
+    _ok(out, ref, 1e-2)
+    g = bf(torch.randn(*xs, device=dev))
+    out.backward(g)
+    ref.backward(g.float())
+    assert torch.equal(x.grad.float(), x32.grad)
+    assert e.grad.dtype == edt and e.grad.shape == e.shape
+    _ok(e.grad, e32.grad, 1e-2 if edt == torch.bfloat16 else 2e-3)

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "ucf_colsum_bf16": (c_int, [c_void_p, c_void_p, _LL, c_int, _LL, c_int, c_void_p]),
     "ucf_assemble_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, _LL, c_int,
                                     c_int, c_void_p]),
+    "ucf_add_bcast": (c_int, [c_void_p, c_void_p, c_void_p, _LL, c_int, c_int, c_int, _LL, _LL, _LL, c_int, c_void_p]),
     "ucf_mask_plan": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ucf_gather_tokens": (c_int, [c_void_p] * 5 + [c_int] * 4 + [_LL, c_int, c_void_p]),
     "ucf_scatter_tokens": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),

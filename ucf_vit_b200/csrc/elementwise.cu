@@ -202,6 +202,38 @@ assemble_tokens_kernel(const __nv_bfloat16* __restrict__ tok, const void* __rest
   }
 }
 
+// out[i0, i1, i2, :] = x[i0, i1, i2, :] + e[i0*s0 + i1*s1 + i2*s2 + :]   (stride 0 = broadcast along that axis)
+template <bool PRM_BF16>
+__global__ void __launch_bounds__(256)
+add_bcast_kernel(const __nv_bfloat16* __restrict__ x, const void* __restrict__ e, __nv_bfloat16* __restrict__ out,
+                 int n1, int n2, int D, long long s0, long long s1, long long s2, long long nvec) {
+  const int dv = D >> 3;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < nvec; t += stride) {
+    const long long r = t / dv;
+    const int d = static_cast<int>(t - r * dv) << 3;
+    const long long q = r / n2;
+    const int i2 = static_cast<int>(r - q * n2);
+    const long long i0 = q / n1;
+    const int i1 = static_cast<int>(q - i0 * n1);
+    const long long eo = i0 * s0 + i1 * s1 + i2 * s2 + d;
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + r * D + d));
+    float2 a = unpack_bf16x2(xv.x), b = unpack_bf16x2(xv.y), c = unpack_bf16x2(xv.z), f = unpack_bf16x2(xv.w);
+    float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, f.x, f.y};
+    if (PRM_BF16) {
+      const uint4 ev = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e) + eo));
+      a = unpack_bf16x2(ev.x); b = unpack_bf16x2(ev.y); c = unpack_bf16x2(ev.z); f = unpack_bf16x2(ev.w);
+      v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += f.x; v[7] += f.y;
+    } else {
+      const float4 e0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e) + eo));
+      const float4 e1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e) + eo + 4));
+      v[0] += e0.x; v[1] += e0.y; v[2] += e0.z; v[3] += e0.w; v[4] += e1.x; v[5] += e1.y; v[6] += e1.z; v[7] += e1.w;
+    }
+    *reinterpret_cast<uint4*>(out + r * D + d) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
 static int ew_grid(long long work_items, int per_block) {
   long long blocks = (work_items + per_block - 1) / per_block;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -316,4 +348,29 @@ extern "C" int ucf_assemble_tokens(const void* tok, const void* prefix, const vo
     assemble_tokens_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(tok), prefix, pos,
                                                         reinterpret_cast<__nv_bfloat16*>(out), B, L, P, D, pos_bstride, pos_off);
   return check_launch("assemble_tokens_kernel");
+}
+
+extern "C" int ucf_add_bcast(const void* x, const void* e, void* out, long long n0, int n1, int n2, int D, long long s0,
+                             long long s1, long long s2, int param_dtype, void* stream) {
+  if (n0 < 0 || n1 <= 0 || n2 <= 0 || D <= 0) { set_last_error("add_bcast: bad shape"); return UCF_ERR_BAD_ARG; }
+  if (D % 8 || s0 % 8 || s1 % 8 || s2 % 8 || s0 < 0 || s1 < 0 || s2 < 0) {
+    set_last_error("add_bcast: D and the strides of e must be non-negative multiples of 8 elements"); return UCF_ERR_BAD_ARG;
+  }
+  if (param_dtype != UCF_DTYPE_F32 && param_dtype != UCF_DTYPE_BF16) {
+    set_last_error("add_bcast: e must be f32 or bf16"); return UCF_ERR_BAD_ARG;
+  }
+  const long long nvec = n0 * n1 * n2 * (D / 8);
+  if (nvec == 0) return UCF_OK;
+  if (!x || !e || !out || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+    set_last_error("add_bcast: pointers must be non-null and 16-byte aligned"); return UCF_ERR_BAD_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ew_grid(nvec, 256);
+  if (param_dtype == UCF_DTYPE_BF16)
+    add_bcast_kernel<true><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), e, static_cast<__nv_bfloat16*>(out),
+                                                 n1, n2, D, s0, s1, s2, nvec);
+  else
+    add_bcast_kernel<false><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), e, static_cast<__nv_bfloat16*>(out),
+                                                  n1, n2, D, s0, s1, s2, nvec);
+  return check_launch("add_bcast_kernel");
 }

@@ -522,6 +522,29 @@ class _AssembleFn(torch.autograd.Function):
         return d_tok, d_prefix, d_pos, None
 
 
+class _AddBcastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, e):
+        ctx.meta = (tuple(x.shape), tuple(e.shape), e.dtype)
+        return ops.add_bcast(x if x.is_contiguous() else x.contiguous(), e if e.is_contiguous() else e.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        xs, es, edt = ctx.meta
+        d_e = None
+        if ctx.needs_input_grad[1]:
+            pad = (1,) * (len(xs) - len(es)) + es
+            dims = [i for i in range(len(xs)) if pad[i] == 1 and xs[i] != 1]
+            d_e = (g.sum(dim=dims, keepdim=True, dtype=torch.float32) if dims else g.float()).reshape(es).to(edt)
+        return (g if ctx.needs_input_grad[0] else None), d_e
+
+
+def add_bcast(x, e):
+    """bf16 tokens + a broadcast embedding (variable embedding over [B, V, L, D], time embedding over [B, N, D])
+    in one pass (ucf_add_bcast); e keeps its own dtype (fp32 parameters are not cast first)."""
+    return _AddBcastFn.apply(x, e)
+
+
 class _GatherTokensFn(torch.autograd.Function):
     """out[b, i] = (idx[b, i] < Ls ? src[b, idx[b, i]] : fill) + pos  (ucf_gather_tokens / ucf_scatter_tokens).
     `complete`: every row of src is named exactly once by idx (idx is a permutation padded with fill rows), so

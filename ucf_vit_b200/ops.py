@@ -424,3 +424,19 @@ def scatter_tokens(dout, idx, Ls, *, need_src=True, need_fill=False, zero_first=
     L.check(L.lib().ucf_scatter_tokens(dout.data_ptr(), idx.data_ptr(), _ptr(dsrc), _ptr(dfill), B, Ls, Lo, D,
                                        int(zero_first), _stream()), "scatter_tokens")
     return dsrc, dfill
+
+
+def add_bcast(x, e):
+    """x bf16 [..., D] (<= 4 dims) + e (f32 | bf16, broadcastable to x, same last dim) -> bf16, one pass."""
+    _require_cuda(x, e)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and 1 <= x.dim() <= 4
+    assert e.is_contiguous() and e.shape[-1] == x.shape[-1] and e.dim() <= x.dim()
+    D = x.shape[-1]
+    shape = [1] * (4 - x.dim()) + list(x.shape)
+    ev = e.reshape([1] * (4 - e.dim()) + list(e.shape))
+    st = ev.expand(shape).stride()
+    assert st[3] == 1 or D == 1
+    out = torch.empty_like(x)
+    L.check(L.lib().ucf_add_bcast(x.data_ptr(), e.data_ptr(), out.data_ptr(), shape[0], shape[1], shape[2], D,
+                                  st[0], st[1], st[2], _dt(e), _stream()), "add_bcast")
+    return out

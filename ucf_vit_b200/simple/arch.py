@@ -303,7 +303,7 @@ class VIT(nn.Module):
         if self.single_channel:
             inp = torch.squeeze(x) if self.adaptive_patching else x
             tok = self._embed_one(self.token_embeds[var_ids[0]], inp)
-            return tok + var_embed.unsqueeze(2).squeeze(1).to(tok.dtype)
+            return UF.add_bcast(tok, var_embed.unsqueeze(2).squeeze(1))
         V = len(var_ids)
         shared = all(self.token_embeds[i] is self.token_embeds[0] for i in var_ids)
         if shared and not self.adaptive_patching:
@@ -317,7 +317,7 @@ class VIT(nn.Module):
                 toks.append(self._embed_one(self.token_embeds[var_ids[i]],
                                             torch.squeeze(xi) if self.adaptive_patching else xi))
             tok = torch.stack(toks, dim=1)
-        tok = tok + var_embed.unsqueeze(2).to(tok.dtype)
+        tok = UF.add_bcast(tok, var_embed.unsqueeze(2))
         return self.aggregate_variables(tok)
 
     def _pos_embed(self, x: torch.Tensor, seq_ps) -> torch.Tensor:
@@ -621,7 +621,7 @@ class DiffusionVIT(_DecoderMixin, VIT):
         x = self._pos_embed(x, None)
         temb = self.temporalEmbeddings(x, t)
         temb = _torch_head(self.timeEmbeddingMap, temb)[:, None, :]
-        x = x + temb.to(x.dtype)
+        x = UF.add_bcast(x, temb)
         x = self.blocks(x)
         return self._final_norm(x)
 
