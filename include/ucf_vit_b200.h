@@ -225,6 +225,20 @@ int ucf_patch_mse_bwd(const void* pred, int pred_dtype, const void* img, int img
                       const float* fwd_out, const float* grad_out, int B, int C, int G0, int G1, int G2,
                       int p0, int p1, int p2, void* dpred, void* stream);
 
+/* Dice + binary-cross-entropy loss of the SAP driver: replaces DiceBLoss.forward (utils/metrics.py:95-121, called at
+ * training_scripts/train_sap_simple.py:44-45).  pred = sigmoid(logits)[:, 1:] (act != 0; act == 0 takes logits as
+ * probabilities), true = targets[:, 1:]:
+ *   loss = weight * mean(BCE(pred, true)) + (1 - weight) * (1 - (2 sum(pred true) + smooth) / (sum pred + sum true + smooth))
+ * with torch's BCE conventions (logarithms clamped at -100; gradient denominator max(p(1-p), 1e-12)).
+ * logits / targets [B, C, HW] f32|bf16 contiguous, C >= 2; workspace 4 * UCF_PATCH_MSE_MAX_BLOCKS doubles;
+ * out f32 [4] = loss, 2I + smooth, denominator, 1/n (inputs of the backward call).  One read of both tensors. */
+int ucf_dice_bce_fwd(const void* logits, int logits_dtype, const void* targets, int targets_dtype, int B, int C,
+                     long long HW, float weight, float smooth, int act, double* workspace, float* out, void* stream);
+/* dlogits [B, C, HW] (dtype of logits; channel 0 = 0) = grad_out * d loss / d logits; grad_out a DEVICE f32 scalar. */
+int ucf_dice_bce_bwd(const void* logits, int logits_dtype, const void* targets, int targets_dtype,
+                     const float* fwd_out, const float* grad_out, int B, int C, long long HW, float weight, int act,
+                     void* dlogits, void* stream);
+
 /* One AdamW step (decoupled weight decay, no amsgrad) over n fp32 tensors that share the same
  * hyper-parameters and step count: the arithmetic of torch.optim.AdamW as configured by
  * utils/misc.py:58-84 (`configure_optimizer`: two groups, weight_decay 0 for var/pos embeddings) and

@@ -24,6 +24,7 @@ from oracle import fixtures as fx  # noqa: E402
 from oracle import train_side_ref as T  # noqa: E402
 
 from UCF_VIT.utils import misc as ref_misc  # noqa: E402
+from UCF_VIT.utils.metrics import DiceBLoss as RefDiceBLoss  # noqa: E402
 from UCF_VIT.utils.metrics import masked_mse as ref_masked_mse  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "host_train_side.npz")
@@ -118,8 +119,28 @@ def adaptive_case(arrays, seed):
     arrays["adaptive:grad_full"] = g.numpy()
 
 
+def dice_case(arrays, tag, shape, seed, weight, smooth, act):
+    x = fx.det_tensor(shape, seed, scale=3.0)
+    if not act:
+        x = torch.sigmoid(x)
+    x.requires_grad_(True)
+    t = (fx.det_tensor(shape, seed + 1) > 0.3).float()
+    loss = RefDiceBLoss(weight=weight, num_class=shape[1])(x, t, smooth=smooth, act=act)
+    g, = torch.autograd.grad(loss, x)
+    lo, go = T.dice_bce_loss_and_grad(x.detach().numpy(), t.numpy(), weight, smooth, act)
+    assert abs(lo - loss.item()) <= 2e-6 * abs(lo), (lo, loss.item())
+    assert np.abs(go - g.numpy()).max() <= 2e-6 * np.abs(g.numpy()).max()
+    arrays[f"{tag}:loss"] = np.float64(loss.item())
+    arrays[f"{tag}:grad"] = g.numpy()
+
+
+DICE_CASES = {"dice_2c": [[2, 2, 8, 12], 940, 0.5, 1.0, True], "dice_3c_w03": [[1, 3, 6, 10], 950, 0.3, 2.0, True],
+              "dice_probs": [[2, 2, 4, 4], 960, 0.5, 1.0, False]}
+
 if __name__ == "__main__":
     arrays = {}
+    for tag, (shape, seed, w, sm, act) in DICE_CASES.items():
+        dice_case(arrays, tag, tuple(shape), seed, w, sm, act)
     optimizer_case(arrays)
     loss_case(arrays, "mse2d", (2, 3, 8, 12), 4, True, 910)
     loss_case(arrays, "mse3d", (1, 2, 4, 8, 4), 4, False, 920)
@@ -127,6 +148,6 @@ if __name__ == "__main__":
     cfg = {"kind": "host", "param_shapes": {k: list(v) for k, v in PARAM_SHAPES.items()}, "hyper": HYPER,
            "sched": SCHED, "steps": STEPS, "eps": 1e-8,
            "loss_cases": {"mse2d": [[2, 3, 8, 12], 4, True, 910], "mse3d": [[1, 2, 4, 8, 4], 4, False, 920]},
-           "adaptive_seed": 930}
+           "adaptive_seed": 930, "dice_cases": DICE_CASES}
     fx.save_case(OUT, cfg, {}, arrays)
-    print("[golden] host_train_side: AdamW trajectory, masked / full MSE on patchified targets (2-D, 3-D, adaptive)")
+    print("[golden] host_train_side: AdamW trajectory, masked / full MSE on patchified targets (2-D, 3-D, adaptive), DiceBLoss")

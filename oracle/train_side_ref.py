@@ -64,3 +64,21 @@ def mse_loss_and_grad(pred, target, mask=None):
     w = mask.astype(np.float64)
     den = w.sum() * d.shape[-1]
     return ((d * d).sum(-1) * w).sum() / den, 2.0 * d * w[..., None] / den
+
+
+def dice_bce_loss_and_grad(logits, targets, weight=0.5, smooth=1.0, act=True):
+    """utils/metrics.py:95-121 in float64: loss and d loss / d logits (channel 0 gets zeros).  BCE follows
+    torch.nn.functional.binary_cross_entropy: logs clamped at -100, gradient (p - t) / max(p (1 - p), 1e-12)."""
+    x = logits.astype(np.float64)
+    t = targets.astype(np.float64)[:, 1:]
+    s_all = 1.0 / (1.0 + np.exp(-x)) if act else x
+    s = s_all[:, 1:]
+    inter, den = (s * t).sum(), s.sum() + t.sum() + smooth
+    with np.errstate(divide="ignore"):
+        bce = -(t * np.maximum(np.log(s), -100.0) + (1.0 - t) * np.maximum(np.log(1.0 - s), -100.0))
+    loss = weight * bce.mean() + (1.0 - weight) * (1.0 - (2.0 * inter + smooth) / den)
+    ds = weight / s.size * (s - t) / np.maximum(s * (1.0 - s), 1e-12) \
+        + (1.0 - weight) * (-2.0 * t / den + (2.0 * inter + smooth) / den ** 2)
+    grad = np.zeros_like(x)
+    grad[:, 1:] = ds * (s * (1.0 - s) if act else 1.0)
+    return loss, grad

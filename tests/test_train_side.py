@@ -331,3 +331,80 @@ def test_patch_mse_properties_at_mae_size():
     _close(pa.grad.cpu().numpy(), pb.grad.cpu().numpy(), 2e-6)
     # (4) bit-reproducible
     assert metrics.patch_mse(pred, data, p, True, mask).item() == la.item()
+
+
+# ----------------------------------------------------------------------------------------- DiceBLoss
+def _dice_inputs(tag):
+    shape, seed, w, sm, act = CFG["dice_cases"][tag]
+    x = fx.det_tensor(tuple(shape), seed, scale=3.0)
+    if not act:
+        x = torch.sigmoid(x)
+    t = (fx.det_tensor(tuple(shape), seed + 1) > 0.3).float()
+    return x, t, w, sm, act
+
+
+@pytest.mark.parametrize("tag", ["dice_2c", "dice_3c_w03", "dice_probs"])
+def test_oracle_dice_bce_matches_the_reference(tag):
+    x, t, w, sm, act = _dice_inputs(tag)
+    lo, go = T.dice_bce_loss_and_grad(x.numpy(), t.numpy(), w, sm, act)
+    assert abs(lo - float(G[f"{tag}:loss"])) <= 2e-6 * abs(lo)
+    _close(go, G[f"{tag}:grad"], 2e-6)
+
+
+def test_dice_loss_has_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        metrics.DiceBLoss()(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4))
+    lib = L.lib()
+    assert lib.ucf_dice_bce_fwd(1, 0, 1, 0, 2, 1, 16, 0.5, 1.0, 1, 1, 1, None) == -1 and b"C >= 2" in lib.ucf_last_error()
+    assert lib.ucf_dice_bce_bwd(1, 0, 1, 0, None, None, 2, 2, 16, 0.5, 1, None, None) == -1
+
+
+@gpu
+@pytest.mark.parametrize("tag", ["dice_2c", "dice_3c_w03", "dice_probs"])
+def test_dice_bce_matches_the_reference_vectors(tag):
+    x, t, w, sm, act = _dice_inputs(tag)
+    xg = x.cuda().requires_grad_(True)
+    loss = metrics.DiceBLoss(weight=w, num_class=x.shape[1])(xg, t.cuda(), smooth=sm, act=act)
+    loss.backward()
+    assert abs(loss.item() - float(G[f"{tag}:loss"])) <= 4e-6 * abs(loss.item())
+    _close(xg.grad.cpu().numpy(), G[f"{tag}:grad"], 4e-6)
+    assert xg.grad[:, 0].abs().max().item() == 0.0
+
+
+@gpu
+@pytest.mark.parametrize("shape,dt,dtt", [((2, 2, 64, 64), torch.float32, torch.float32),
+                                          ((3, 4, 33, 17), torch.float32, torch.float32),      # plane % 4 != 0: scalar path
+                                          ((2, 2, 32, 32), torch.bfloat16, torch.float32),
+                                          ((1, 3, 16, 24), torch.bfloat16, torch.bfloat16),
+                                          ((2, 2, 8, 8, 8), torch.float32, torch.float32)])     # 3-D volumes flatten the same way
+def test_dice_bce_against_the_oracle(shape, dt, dtt):
+    torch.manual_seed(len(shape) + shape[-1])
+    x = (torch.randn(*shape) * 2).to(dt)                    # |logits| < ~9: fp32 sigmoid is not yet saturated (float64 oracle)
+    t = (torch.rand(*shape) < 0.4).to(dtt)
+    lo, go = T.dice_bce_loss_and_grad(x.float().numpy(), t.float().numpy(), 0.5, 1.0, True)
+    xg = x.cuda().requires_grad_(True)
+    loss = metrics.DiceBLoss()(xg, t.cuda())
+    (2.0 * loss).backward()
+    assert loss.dtype == dt and xg.grad.dtype == dt
+    assert abs(loss.item() - lo) <= (1e-5 if dt == torch.float32 else 4e-3) * abs(lo)
+    _close(xg.grad.float().cpu().numpy(), 2.0 * go, 2e-5 if dt == torch.float32 else 1e-2)
+
+
+@gpu
+def test_dice_bce_at_sap_size_matches_pytorch_on_the_device():
+    """SAP segmentation shape (1024 x 1024 masks, two classes): same value and gradient as the reference's
+    formulation evaluated by PyTorch ops on the device; bit-reproducible."""
+    torch.manual_seed(17)
+    x = torch.randn(4, 2, 1024, 1024, device="cuda") * 3
+    t = (torch.rand(4, 2, 1024, 1024, device="cuda") < 0.3).float()
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    la = metrics.DiceBLoss()(xa, t)
+    la.backward()
+    p = torch.sigmoid(xb)
+    pred, true = torch.flatten(p[:, 1:]), torch.flatten(t[:, 1:])
+    inter = (pred * true).sum()
+    lb = 0.5 * torch.nn.functional.binary_cross_entropy(pred, true) + 0.5 * (1 - (2 * inter + 1) / (pred.sum() + true.sum() + 1))
+    lb.backward()
+    assert abs(la.item() - lb.item()) <= 1e-5 * abs(lb.item())
+    _close(xa.grad.cpu().numpy(), xb.grad.cpu().numpy(), 2e-5)
+    assert metrics.DiceBLoss()(x, t).item() == la.item()

@@ -408,6 +408,127 @@ static int patch_mse_quad_grid(PatchGeom* gm, const void* pred, int pred_dtype, 
   return static_cast<int>((gm->items + per - 1) / per);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dice + binary-cross-entropy loss of the SAP driver (utils/metrics.py:95-121)
+//
+// pred = sigmoid(logits)[:, 1:], true = targets[:, 1:], flattened:
+//   loss = w * mean(BCE(pred, true)) + (1 - w) * (1 - (2 sum(pred*true) + sm) / (sum(pred) + sum(true) + sm))
+// One pass reads both tensors once and carries the four sums; channel 0 is never touched.
+// ------------------------------------------------------------------------------------------------
+struct DiceGeom {
+  long long HW;        // elements of one channel plane
+  long long slab;      // (C - 1) * HW: the elements of one sample that count
+  long long pitch;     // C * HW
+  long long n;         // B * slab
+};
+
+__device__ __forceinline__ float dice_prob(float x, bool act) { return act ? 1.f / (1.f + expf(-x)) : x; }
+// torch.nn.functional.binary_cross_entropy clamps both logarithms at -100
+__device__ __forceinline__ float bce_term(float s, float t) {
+  return -(t * fmaxf(logf(s), -100.f) + (1.f - t) * fmaxf(logf(1.f - s), -100.f));
+}
+
+template <typename TL, typename TT, bool VEC>
+__global__ void __launch_bounds__(256)
+dice_bce_fwd_kernel(const TL* __restrict__ logits, const TT* __restrict__ targets, const DiceGeom gm, int act,
+                    double* __restrict__ partials) {
+  float inter = 0.f, sp = 0.f, st = 0.f, bce = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  const long long tid = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (VEC) {
+    for (long long i = tid * 4; i < gm.n; i += stride * 4) {
+      const long long b = i / gm.slab, off = b * gm.pitch + gm.HW + (i - b * gm.slab);
+      float x[4], t[4];
+      ld4(logits + off, x);
+      ld4(targets + off, t);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float s = dice_prob(x[e], act);
+        inter = fmaf(s, t[e], inter); sp += s; st += t[e]; bce += bce_term(s, t[e]);
+      }
+    }
+  } else {
+    for (long long i = tid; i < gm.n; i += stride) {
+      const long long b = i / gm.slab, off = b * gm.pitch + gm.HW + (i - b * gm.slab);
+      const float s = dice_prob(ldf(logits + off), act), t = ldf(targets + off);
+      inter = fmaf(s, t, inter); sp += s; st += t; bce += bce_term(s, t);
+    }
+  }
+  double a = inter, c = bce, d = sp, e = st;
+  block_sum2(a, c);
+  __syncthreads();
+  block_sum2(d, e);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = a;
+    partials[UCF_PATCH_MSE_MAX_BLOCKS + blockIdx.x] = c;
+    partials[2 * UCF_PATCH_MSE_MAX_BLOCKS + blockIdx.x] = d;
+    partials[3 * UCF_PATCH_MSE_MAX_BLOCKS + blockIdx.x] = e;
+  }
+}
+
+// out[0] = loss, out[1] = 2*I + smooth, out[2] = sum(pred) + sum(true) + smooth, out[3] = 1 / n
+__global__ void __launch_bounds__(256)
+dice_bce_finish_kernel(const double* __restrict__ partials, int n_partials, double n, float weight, float smooth,
+                       float* __restrict__ out) {
+  double a = 0.0, c = 0.0, d = 0.0, e = 0.0;
+  for (int i = threadIdx.x; i < n_partials; i += 256) {
+    a += partials[i];
+    c += partials[UCF_PATCH_MSE_MAX_BLOCKS + i];
+    d += partials[2 * UCF_PATCH_MSE_MAX_BLOCKS + i];
+    e += partials[3 * UCF_PATCH_MSE_MAX_BLOCKS + i];
+  }
+  block_sum2(a, c);
+  __syncthreads();
+  block_sum2(d, e);
+  if (threadIdx.x == 0) {
+    const double num = 2.0 * a + smooth, den = d + e + smooth;
+    out[0] = static_cast<float>(weight * (c / n) + (1.0 - weight) * (1.0 - num / den));
+    out[1] = static_cast<float>(num);
+    out[2] = static_cast<float>(den);
+    out[3] = static_cast<float>(1.0 / n);
+  }
+}
+
+// d loss / d logits; one thread per element of the FULL tensor so channel 0 receives its zeros in the same pass
+template <typename TL, typename TT, bool VEC>
+__global__ void __launch_bounds__(256)
+dice_bce_bwd_kernel(const TL* __restrict__ logits, const TT* __restrict__ targets, const float* __restrict__ fwd_out,
+                    const float* __restrict__ grad_out, const DiceGeom gm, long long total, float weight, int act,
+                    TL* __restrict__ dlogits) {
+  const float g = __ldg(grad_out), num = __ldg(fwd_out + 1), den = __ldg(fwd_out + 2), inv_n = __ldg(fwd_out + 3);
+  const float k_bce = g * weight * inv_n;
+  const float k_t = -g * (1.f - weight) * 2.f / den;           // d dice / d pred = -2 t / den + num / den^2
+  const float k_0 = g * (1.f - weight) * num / (den * den);
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  const long long tid = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  constexpr int W = VEC ? 4 : 1;
+  for (long long i = tid * W; i < total; i += stride * W) {
+    const bool counted = (i % gm.pitch) >= gm.HW;                // HW % 4 == 0 on the vector path: uniform per quad
+    float x[W], t[W], r[W];
+    if (counted) {
+      if (VEC) { ld4(logits + i, x); ld4(targets + i, t); }
+      else { x[0] = ldf(logits + i); t[0] = ldf(targets + i); }
+    }
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      r[e] = 0.f;
+      if (counted) {
+        const float s = dice_prob(x[e], act);
+        const float ds = k_bce * (s - t[e]) / fmaxf(s * (1.f - s), 1e-12f) + k_t * t[e] + k_0;
+        r[e] = act ? ds * s * (1.f - s) : ds;
+      }
+    }
+    if (VEC) st4(dlogits + i, r);
+    else stf(dlogits + i, r[0]);
+  }
+}
+
+static int dice_geom(const char* who, int B, int C, long long HW, DiceGeom* gm) {
+  if (B <= 0 || C < 2 || HW <= 0) { set_last_error("%s: need B >= 1, C >= 2 and a non-empty plane", who); return UCF_ERR_BAD_ARG; }
+  gm->HW = HW; gm->slab = (C - 1) * HW; gm->pitch = C * HW; gm->n = B * gm->slab;
+  return UCF_OK;
+}
+
 }  // namespace ucf
 
 using namespace ucf;
@@ -556,4 +677,80 @@ extern "C" int ucf_patch_mse_bwd(const void* pred, int pred_dtype, const void* i
   if (!quad) grid = BL < patch_mse_max_grid() ? BL : patch_mse_max_grid();
   by_dtypes(BwdLaunch{pred, img, mask, fwd_out, grad_out, gm, dpred, grid, st}, pred_dtype, img_dtype, quad ? C : 0);
   return check_launch(quad ? "patch_mse_bwd_quad_kernel" : "patch_mse_bwd_kernel");
+}
+
+namespace {
+
+template <typename TL, typename TT>
+void dice_fwd_launch(const void* logits, const void* targets, const DiceGeom& gm, int act, double* ws, int grid, bool vec,
+                     cudaStream_t st) {
+  if (vec) dice_bce_fwd_kernel<TL, TT, true><<<grid, 256, 0, st>>>(static_cast<const TL*>(logits), static_cast<const TT*>(targets), gm, act, ws);
+  else dice_bce_fwd_kernel<TL, TT, false><<<grid, 256, 0, st>>>(static_cast<const TL*>(logits), static_cast<const TT*>(targets), gm, act, ws);
+}
+
+template <typename TL, typename TT>
+void dice_bwd_launch(const void* logits, const void* targets, const float* fwd_out, const float* grad_out, const DiceGeom& gm,
+                     long long total, float weight, int act, void* dlogits, int grid, bool vec, cudaStream_t st) {
+  if (vec)
+    dice_bce_bwd_kernel<TL, TT, true><<<grid, 256, 0, st>>>(static_cast<const TL*>(logits), static_cast<const TT*>(targets),
+                                                            fwd_out, grad_out, gm, total, weight, act, static_cast<TL*>(dlogits));
+  else
+    dice_bce_bwd_kernel<TL, TT, false><<<grid, 256, 0, st>>>(static_cast<const TL*>(logits), static_cast<const TT*>(targets),
+                                                             fwd_out, grad_out, gm, total, weight, act, static_cast<TL*>(dlogits));
+}
+
+bool dice_vec_ok(const DiceGeom& gm, const void* a, int a_dtype, const void* b, int b_dtype, const void* c) {
+  if (gm.HW % 4) return false;
+  const uintptr_t ma = a_dtype == UCF_DTYPE_F32 ? 15 : 7, mb = b_dtype == UCF_DTYPE_F32 ? 15 : 7;
+  return !((reinterpret_cast<uintptr_t>(a) & ma) || (reinterpret_cast<uintptr_t>(c) & ma) || (reinterpret_cast<uintptr_t>(b) & mb));
+}
+
+int dice_grid(long long items) {
+  long long g = (items + 255) / 256;
+  if (g > patch_mse_max_grid()) g = patch_mse_max_grid();
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
+}  // namespace
+
+extern "C" int ucf_dice_bce_fwd(const void* logits, int logits_dtype, const void* targets, int targets_dtype, int B, int C,
+                                long long HW, float weight, float smooth, int act, double* workspace, float* out,
+                                void* stream) {
+  DiceGeom gm;
+  int rc = dice_geom("dice_bce_fwd", B, C, HW, &gm);
+  if (rc == UCF_OK) rc = patch_mse_dtypes("dice_bce_fwd", logits_dtype, targets_dtype);
+  if (rc != UCF_OK) return rc;
+  if (!logits || !targets || !workspace || !out) { set_last_error("dice_bce_fwd: null pointer"); return UCF_ERR_BAD_ARG; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool vec = dice_vec_ok(gm, logits, logits_dtype, targets, targets_dtype, nullptr);
+  const int grid = dice_grid(vec ? gm.n / 4 : gm.n);
+  const bool lf = logits_dtype == UCF_DTYPE_F32, tf = targets_dtype == UCF_DTYPE_F32;
+  if (lf && tf) dice_fwd_launch<float, float>(logits, targets, gm, act, workspace, grid, vec, st);
+  else if (lf) dice_fwd_launch<float, __nv_bfloat16>(logits, targets, gm, act, workspace, grid, vec, st);
+  else if (tf) dice_fwd_launch<__nv_bfloat16, float>(logits, targets, gm, act, workspace, grid, vec, st);
+  else dice_fwd_launch<__nv_bfloat16, __nv_bfloat16>(logits, targets, gm, act, workspace, grid, vec, st);
+  rc = check_launch("dice_bce_fwd_kernel");
+  if (rc != UCF_OK) return rc;
+  dice_bce_finish_kernel<<<1, 256, 0, st>>>(workspace, grid, static_cast<double>(gm.n), weight, smooth, out);
+  return check_launch("dice_bce_finish_kernel");
+}
+
+extern "C" int ucf_dice_bce_bwd(const void* logits, int logits_dtype, const void* targets, int targets_dtype,
+                                const float* fwd_out, const float* grad_out, int B, int C, long long HW, float weight,
+                                int act, void* dlogits, void* stream) {
+  DiceGeom gm;
+  int rc = dice_geom("dice_bce_bwd", B, C, HW, &gm);
+  if (rc == UCF_OK) rc = patch_mse_dtypes("dice_bce_bwd", logits_dtype, targets_dtype);
+  if (rc != UCF_OK) return rc;
+  if (!logits || !targets || !fwd_out || !grad_out || !dlogits) { set_last_error("dice_bce_bwd: null pointer"); return UCF_ERR_BAD_ARG; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool vec = dice_vec_ok(gm, logits, logits_dtype, targets, targets_dtype, dlogits);
+  const long long total = static_cast<long long>(B) * gm.pitch;
+  const int grid = dice_grid(vec ? total / 4 : total);
+  const bool lf = logits_dtype == UCF_DTYPE_F32, tf = targets_dtype == UCF_DTYPE_F32;
+  if (lf && tf) dice_bwd_launch<float, float>(logits, targets, fwd_out, grad_out, gm, total, weight, act, dlogits, grid, vec, st);
+  else if (lf) dice_bwd_launch<float, __nv_bfloat16>(logits, targets, fwd_out, grad_out, gm, total, weight, act, dlogits, grid, vec, st);
+  else if (tf) dice_bwd_launch<__nv_bfloat16, float>(logits, targets, fwd_out, grad_out, gm, total, weight, act, dlogits, grid, vec, st);
+  else dice_bwd_launch<__nv_bfloat16, __nv_bfloat16>(logits, targets, fwd_out, grad_out, gm, total, weight, act, dlogits, grid, vec, st);
+  return check_launch("dice_bce_bwd_kernel");
 }

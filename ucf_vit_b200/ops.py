@@ -440,3 +440,35 @@ def add_bcast(x, e):
     L.check(L.lib().ucf_add_bcast(x.data_ptr(), e.data_ptr(), out.data_ptr(), shape[0], shape[1], shape[2], D,
                                   st[0], st[1], st[2], _dt(e), _stream()), "add_bcast")
     return out
+
+
+def _dice_dims(logits, targets):
+    if logits.dim() < 3 or logits.shape != targets.shape or logits.shape[1] < 2:
+        raise ValueError(f"dice_bce: logits and targets must share a [B, C >= 2, ...] shape, got {tuple(logits.shape)} "
+                         f"and {tuple(targets.shape)}")
+    B, C = logits.shape[:2]
+    return B, C, logits[0, 0].numel()
+
+
+def dice_bce_fwd(logits, targets, weight, smooth, act):
+    """fp32 [4] = (loss, 2I + smooth, denominator, 1/n) of DiceBLoss over channels 1.. of [B, C, ...] tensors."""
+    _require_cuda(logits, targets)
+    assert logits.is_contiguous() and targets.is_contiguous()
+    B, C, HW = _dice_dims(logits, targets)
+    ws = torch.empty(4 * L.PATCH_MSE_MAX_BLOCKS, dtype=torch.float64, device=logits.device)
+    out = torch.empty(4, dtype=torch.float32, device=logits.device)
+    L.check(L.lib().ucf_dice_bce_fwd(logits.data_ptr(), _dt(logits), targets.data_ptr(), _dt(targets), B, C, HW,
+                                     float(weight), float(smooth), int(bool(act)), ws.data_ptr(), out.data_ptr(), _stream()),
+            "dice_bce_fwd")
+    return out
+
+
+def dice_bce_bwd(logits, targets, fwd_out, grad_out, weight, act):
+    _require_cuda(logits, targets, fwd_out, grad_out)
+    B, C, HW = _dice_dims(logits, targets)
+    assert fwd_out.dtype == torch.float32 and fwd_out.numel() == 4 and grad_out.dtype == torch.float32 and grad_out.numel() == 1
+    dlogits = torch.empty_like(logits)
+    L.check(L.lib().ucf_dice_bce_bwd(logits.data_ptr(), _dt(logits), targets.data_ptr(), _dt(targets), fwd_out.data_ptr(),
+                                     grad_out.data_ptr(), B, C, HW, float(weight), int(bool(act)), dlogits.data_ptr(),
+                                     _stream()), "dice_bce_bwd")
+    return dlogits

@@ -69,18 +69,39 @@ def adaptive_patch_mse(pred, seq, mask=None):
     return _fused_patch_loss(pred, seq, mask, (1, seq.shape[2], 1), (1, 1, seq.shape[3]))
 
 
+class _DiceBceFn(torch.autograd.Function):
+    """DiceBLoss through ucf_dice_bce_fwd / _bwd.  Only the logits are differentiable."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, weight, smooth, act):
+        out = ops.dice_bce_fwd(logits, targets, weight, smooth, act)
+        ctx.save_for_backward(logits, targets, out)
+        ctx.hyper = (weight, act)
+        return out[0].clone() if logits.dtype == torch.float32 else out[0].to(logits.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        logits, targets, out = ctx.saved_tensors
+        weight, act = ctx.hyper
+        g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        return ops.dice_bce_bwd(logits, targets, out, g, weight, act), None, None, None, None
+
+
 class DiceBLoss(nn.Module):
+    """weight * BCE + (1 - weight) * Dice over channels 1.. (utils/metrics.py:95-121), evaluated by one CUDA
+    reduction pass over logits and targets (and one pass for the gradient) instead of ~10 element-wise kernels."""
+
     def __init__(self, weight=0.5, num_class=2, size_average=True):
         super().__init__()
         self.weight = weight
         self.num_class = num_class
 
     def forward(self, inputs, targets, smooth=1, act=True):
-        if act:
-            inputs = torch.sigmoid(inputs)
-        pred = torch.flatten(inputs[:, 1:, :, :])
-        true = torch.flatten(targets[:, 1:, :, :])
-        inter = (pred * true).sum()
-        dice = 1 - (2. * inter + smooth) / (pred.sum() + true.sum() + smooth)
-        bce = F.binary_cross_entropy(pred, true, reduction='mean')
-        return self.weight * bce + (1 - self.weight) * dice
+        if not inputs.is_cuda:
+            raise RuntimeError("DiceBLoss runs on CUDA tensors only (sm_100a); there is no CPU fallback")
+        if targets.requires_grad:
+            raise NotImplementedError("DiceBLoss: the target is a constant of the loss (no gradient is produced)")
+        if targets.dtype not in (torch.float32, torch.bfloat16):
+            targets = targets.to(torch.float32)
+        return _DiceBceFn.apply(inputs.contiguous(), targets.detach().contiguous(), float(self.weight), float(smooth),
+                                bool(act))
