@@ -323,29 +323,13 @@ def run_gpu_arm(args):
     final_loss = float(loss.item())
 
     # ---------------- end-to-end arm: pinned host batch -> device every step, loss read back every step
-    copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [(torch.empty_like(x_dev), torch.empty_like(y_dev)) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-
-    def prefetch(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[i])
-            bufs[i][0].copy_(x_host, non_blocking=True)
-            bufs[i][1].copy_(y_host, non_blocking=True)
-            ready[i].record(copy_stream)
+    # host batches (pinned) -> DevicePrefetcher (the package's loader hand-off: H2D of batch k+1 on a side stream
+    # under step k) -> step -> loss read back
+    from ucf_vit_b200.dataloaders.prefetch import DevicePrefetcher
 
     def e2e_steps(n):
-        for c in consumed:
-            c.record()
-        prefetch(0)
-        for it in range(n):
-            i = it & 1
-            if it + 1 < n:
-                prefetch(i ^ 1)
-            torch.cuda.current_stream().wait_event(ready[i])
-            l = step(bufs[i][0], bufs[i][1])
-            consumed[i].record()
+        for x, y in DevicePrefetcher(((x_host, y_host) for _ in range(n)), dev):
+            l = step(x, y)
             _ = l.item()                      # device -> host read of the step's result
 
     e2e_steps(2)
