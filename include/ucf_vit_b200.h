@@ -124,11 +124,22 @@ int ucf_var_attention_bwd(const void* q, const void* kv, const void* o, const vo
  * (dataloaders/octree.py:72-102).  domain: [n0, n1] (2-D: rows, cols) or cubic [n0, n1, n2] edge map
  * of dtype u8 / f32 / f64; leaf value = int(sum(domain[box]) / norm_factor).  Greedy: split the FIRST
  * leaf holding the maximum value until fixed_length leaves exist or the chosen leaf is 2 wide.
- * boxes_host: int32 [fixed_length, 4] (x1,x2,y1,y2) or [fixed_length, 6] (+z1,z2) in list order;
- * values_host: int64 [fixed_length] or NULL.  Returns the number of leaves (>= 1) or a negative code. */
+ * Like the reference, the last split may overshoot: the tree ends with fixed_length .. fixed_length + 2 (2-D) /
+ * + 6 (3-D) leaves unless fixed_length = 1 (mod 3 / mod 7), so the buffers hold UCF_SAP_TREE_ROWS(fixed_length,
+ * ndim) rows: boxes_host int32 [rows, 4] (x1,x2,y1,y2) or [rows, 6] (+z1,z2) in list order; values_host int64
+ * [rows] or NULL.  Returns the number of leaves (>= 1) or a negative code. */
+#define UCF_SAP_TREE_ROWS(fixed_length, ndim) ((fixed_length) + ((ndim) == 2 ? 3 : 7) - 1)
 int ucf_sap_build_tree_host(const void* domain_host, int domain_dtype, int ndim, int n0, int n1, int n2,
                             double norm_factor, int fixed_length, int32_t* boxes_host,
                             long long* values_host);
+/* The same for n_images edge maps of one shape on host threads (n_threads <= 0: one per core, at most one per
+ * image): domains_host = HOST array of n_images HOST pointers; boxes_host int32 [n_images, rows, 4|6],
+ * values_host int64 [n_images, rows] or NULL with rows = UCF_SAP_TREE_ROWS(fixed_length, ndim); n_leaves_host
+ * int [n_images] (leaf count per image).
+ * Returns 0, or the (negative) code of the first image that was rejected. */
+int ucf_sap_build_tree_batch_host(const void* const* domains_host, int n_images, int domain_dtype, int ndim,
+                                  int n0, int n1, int n2, double norm_factor, int fixed_length,
+                                  int32_t* boxes_host, long long* values_host, int* n_leaves_host, int n_threads);
 /* Gather = FixedQuadTree.serialize (quadtree.py:144-174; cv.resize INTER_CUBIC per leaf) /
  * FixedOctTree.serialize (octree.py:104-150; align-corners trilinear).  DEVICE pointers.
  * img: [n0, n1, C] u8|f32 (2-D, HWC) or [n0, n1, n2, C] f32 (3-D, ZYXC); boxes: int32 on device;

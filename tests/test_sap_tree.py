@@ -72,6 +72,45 @@ def test_tree_edge_cases():
         ops.sap_build_tree(np.zeros((4, 8, 8), dtype=np.uint8), 8)      # non-cubic octree domain
 
 
+@pytest.mark.parametrize("shape,L", [((227, 203), 150), ((100, 260), 64), ((64, 64), 256), ((8, 8), 16), ((5, 9), 4),
+                                     ((513, 1027), 1000), ((16, 16), 1000)])
+def test_uint8_cell_table_gives_the_per_pixel_sums(shape, L):
+    """The uint8 path (8 x 8 cell table + border strips, SIMD byte sums) against the oracle's per-box numpy sums and
+    against the float64 path (per-pixel summed-area table, exact for integer data): same boxes, order and values
+    on sizes whose box edges are not multiples of 8."""
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    dom = ((rng.random(shape) < 0.2) * 255).astype(np.uint8)
+    dom[: shape[0] // 3, : shape[1] // 2] = 255                      # a dense corner: deep, unbalanced tree
+    b8, v8 = ops.sap_build_tree(dom, L)
+    b64, v64 = ops.sap_build_tree(dom.astype(np.float64), L)
+    assert np.array_equal(b8, b64) and np.array_equal(v8, v64)
+    nodes = Q.build_quadtree(dom, L)
+    assert np.array_equal(b8, np.array([n[:4] for n in nodes], np.int32))
+    assert np.array_equal(v8, np.array([n[4] for n in nodes], np.int64))
+    for (x1, x2, y1, y2), v in zip(b8[:: max(1, len(b8) // 25)], v8[:: max(1, len(b8) // 25)]):
+        assert v == int(dom[y1:y2, x1:x2].astype(np.int64).sum() / 255)
+
+
+def test_batch_tree_builder_matches_single_calls_on_any_thread_count():
+    rng = np.random.default_rng(5)
+    maps = [((rng.random((96, 96)) < d) * 255).astype(np.uint8) for d in (0.01, 0.1, 0.3, 0.6, 0.9)]
+    single = [ops.sap_build_tree(m, 40) for m in maps]
+    for threads in (0, 1, 3, 16):
+        got = ops.sap_build_trees(maps, 40, threads=threads)
+        assert len(got) == len(single)
+        for (b, v), (b0, v0) in zip(got, single):
+            assert np.array_equal(b, b0) and np.array_equal(v, v0)
+    vols = [rng.random((16, 16, 16)).astype(np.float32) * 255 for _ in range(3)]
+    for (b, v), vol in zip(ops.sap_build_trees(vols, 22), vols):
+        b0, v0 = ops.sap_build_tree(vol, 22)
+        assert np.array_equal(b, b0) and np.array_equal(v, v0)
+    assert ops.sap_build_trees([], 8) == []
+    with pytest.raises(ValueError):
+        ops.sap_build_trees([maps[0], maps[1][:50]], 8)
+    with pytest.raises(RuntimeError, match="image 0 was rejected"):
+        ops.sap_build_trees([np.zeros((8, 8), np.uint8)] * 2, 8, norm_factor=0.0)
+
+
 @pytest.mark.parametrize("name", [c for c in CASES if "oct" not in c])
 def test_oracle_serialize_matches_reference_2d(name):
     cfg, a, dom = _load(name)

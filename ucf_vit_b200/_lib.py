@@ -34,6 +34,8 @@ _SIGNATURES = {
     "ucf_var_attention_bwd": (c_int, [c_void_p] * 7 + [_LL, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "ucf_sap_build_tree_host": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_double, c_int, c_void_p,
                                         c_void_p]),
+    "ucf_sap_build_tree_batch_host": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int,
+                                              c_void_p, c_void_p, c_void_p, c_int]),
     "ucf_sap_gather": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p]),
     "ucf_sap_scatter": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,

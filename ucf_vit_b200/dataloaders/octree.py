@@ -50,6 +50,8 @@ class FixedOctTree:
         h2, w2, d2, c2 = size
         assert h2 == w2 == d2
         t = _as_device_image(img, self.device).float()
+        # like the reference's serialize: a fixed_length that the last split overshoots (!= 1 mod 3 / mod 7) is an error
+        assert len(self.nodes) <= self.fixed_length, "Not equal fixed legnth."
         return ops.sap_gather(t, self._dev_boxes(), self.fixed_length, h2)
 
     def deserialize_device(self, seq, patch_size, channel):

@@ -253,14 +253,46 @@ def sap_build_tree(domain, fixed_length, norm_factor=255.0):
     nd = d.ndim
     assert nd in (2, 3)
     nc = 4 if nd == 2 else 6
-    boxes = np.zeros((fixed_length, nc), dtype=np.int32)
-    values = np.zeros((fixed_length,), dtype=np.int64)
+    rows = fixed_length + (3 if nd == 2 else 7) - 1          # UCF_SAP_TREE_ROWS: the last split may overshoot
+    boxes = np.zeros((rows, nc), dtype=np.int32)
+    values = np.zeros((rows,), dtype=np.int64)
     shp = list(d.shape) + [0] * (3 - nd)
     n = L.lib().ucf_sap_build_tree_host(d.ctypes.data, dt, nd, shp[0], shp[1], shp[2], float(norm_factor), fixed_length,
                                         boxes.ctypes.data, values.ctypes.data)
     if n < 0:
         L.check(n, "sap_build_tree_host")
     return boxes[:n].copy(), values[:n].copy()
+
+
+def sap_build_trees(domains, fixed_length, norm_factor=255.0, threads=0):
+    """Trees of several same-shape edge maps built on host threads (`threads` <= 0: one per core).
+    Returns a list of (boxes int32 [n_i, 4|6], values int64 [n_i]) like `sap_build_tree`."""
+    import numpy as np
+    ds = [np.ascontiguousarray(d) for d in domains]
+    if not ds:
+        return []
+    kind = ds[0].dtype
+    if kind not in (np.uint8, np.float32):
+        kind = np.dtype(np.float64)
+    ds = [np.ascontiguousarray(d, dtype=kind) for d in ds]
+    if any(d.shape != ds[0].shape for d in ds):
+        raise ValueError("sap_build_trees: every edge map of a batch must have the same shape")
+    dt = {np.dtype(np.uint8): L.UCF_DTYPE_U8, np.dtype(np.float32): L.UCF_DTYPE_F32,
+          np.dtype(np.float64): L.UCF_DTYPE_F64}[np.dtype(kind)]
+    nd = ds[0].ndim
+    assert nd in (2, 3)
+    nc = 4 if nd == 2 else 6
+    n = len(ds)
+    rows = fixed_length + (3 if nd == 2 else 7) - 1          # UCF_SAP_TREE_ROWS
+    boxes = np.zeros((n, rows, nc), dtype=np.int32)
+    values = np.zeros((n, rows), dtype=np.int64)
+    counts = np.zeros((n,), dtype=np.int32)
+    ptrs = (ctypes.c_void_p * n)(*[d.ctypes.data for d in ds])
+    shp = list(ds[0].shape) + [0] * (3 - nd)
+    rc = L.lib().ucf_sap_build_tree_batch_host(ptrs, n, dt, nd, shp[0], shp[1], shp[2], float(norm_factor), fixed_length,
+                                               boxes.ctypes.data, values.ctypes.data, counts.ctypes.data, int(threads))
+    L.check(rc, "sap_build_tree_batch_host")
+    return [(boxes[i, :counts[i]].copy(), values[i, :counts[i]].copy()) for i in range(n)]
 
 
 def sap_gather(img, boxes, fixed_length, p):
