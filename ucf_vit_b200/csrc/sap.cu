@@ -9,8 +9,8 @@
 // replace their parent in place, so list order == DFS order -- O(L log L) queue work.  Box sums: uint8
 // edge maps (the Canny output the drivers feed) use an integer summed-area table over 8 x 8 pixel cells built
 // in one SIMD pass (psadbw) plus direct sums of the thin unaligned borders of a box -- exact, and 1/64 of the
-// memory of a per-pixel table, which was 134 MB and 135 ms at 4096^2.  Float maps keep the double-precision
-// per-pixel table; uint8 volumes are summed directly.  A batch entry point builds the trees of several images on host
+// memory of a per-pixel table, which was 134 MB and 135 ms at 4096^2.  Float maps use the same cell table in double;
+// volumes keep a per-voxel table (float) or direct sums (uint8).  A batch entry point builds the trees of several images on host
 // threads (the calls release the GIL).
 // Gather/scatter: 2-D = OpenCV INTER_CUBIC (Keys a=-0.75, half-pixel centres, replicated border, NO
 // antialiasing: each output needs 16 taps, so traffic is L*p^2*16*C reads -- latency-, not
@@ -35,26 +35,6 @@ namespace ucf {
 // ------------------------------------------------------------------------------------------------
 // host: tree construction
 // ------------------------------------------------------------------------------------------------
-template <typename Acc>
-struct Sat2 {   // summed-area table, (H+1) x (W+1)
-  int H, W;
-  std::vector<Acc> s;
-  template <typename T>
-  Sat2(const T* d, int h, int w) : H(h), W(w), s(static_cast<size_t>(h + 1) * (w + 1), Acc(0)) {
-    for (int y = 0; y < h; ++y) {
-      Acc row = 0;
-      for (int x = 0; x < w; ++x) {
-        row += static_cast<Acc>(d[static_cast<size_t>(y) * w + x]);
-        s[static_cast<size_t>(y + 1) * (w + 1) + x + 1] = s[static_cast<size_t>(y) * (w + 1) + x + 1] + row;
-      }
-    }
-  }
-  Acc sum(int x1, int x2, int y1, int y2) const {
-    auto at = [&](int y, int x) { return s[static_cast<size_t>(y) * (W + 1) + x]; };
-    return at(y2, x2) - at(y1, x2) - at(y2, x1) + at(y1, x1);
-  }
-};
-
 // Sum of n bytes.  SSE2: psadbw adds 16 bytes per instruction into two 64-bit lanes; elsewhere a SWAR loop
 // over 8-byte words with 16-bit lanes folded every 128 words (128 * 2 * 255 < 2^16).
 static inline unsigned long long sum_bytes(const uint8_t* p, int n) {
@@ -145,6 +125,54 @@ struct CellSatU8 {
     return cells(ax1 >> 3, ax2 >> 3, ay1 >> 3, ay2 >> 3) +
            px.sum2(x1, x2, y1, ay1) + px.sum2(x1, x2, ay2, y2) +        // rows above / below the aligned core
            px.sum2(x1, ax1, ay1, ay2) + px.sum2(ax2, x2, ay1, ay2);     // columns left / right of it
+  }
+};
+
+// Float edge maps, 2-D: the same 8 x 8 cell table in double (the reference sums each box with numpy; any
+// double-precision evaluation order agrees with it to ~1e-9 of a unit at 4096^2, far below the int() step).
+template <typename T>
+struct CellSatF {
+  const T* d;
+  int H, W, ch, cw;
+  std::vector<double> s;                 // (ch + 1) x (cw + 1)
+  CellSatF(const T* dom, int h, int w) : d(dom), H(h), W(w), ch(h / 8), cw(w / 8),
+                                         s(static_cast<size_t>(h / 8 + 1) * (w / 8 + 1), 0.0) {
+    std::vector<double> cell(static_cast<size_t>(cw) + 1);
+    for (int cy = 0; cy < ch; ++cy) {
+      std::fill(cell.begin(), cell.end(), 0.0);
+      for (int r = 0; r < 8; ++r) {
+        const T* row = d + static_cast<size_t>(cy * 8 + r) * W;
+        for (int cx = 0; cx < cw; ++cx) {
+          const T* q = row + cx * 8;
+          cell[cx] += ((static_cast<double>(q[0]) + q[1]) + (static_cast<double>(q[2]) + q[3])) +
+                      ((static_cast<double>(q[4]) + q[5]) + (static_cast<double>(q[6]) + q[7]));
+        }
+      }
+      double run = 0.0;
+      const size_t up = static_cast<size_t>(cy) * (cw + 1), here = up + (cw + 1);
+      for (int cx = 0; cx < cw; ++cx) {
+        run += cell[cx];
+        s[here + cx + 1] = s[up + cx + 1] + run;
+      }
+    }
+  }
+  double direct(int x1, int x2, int y1, int y2) const {
+    double t = 0.0;
+    for (int y = y1; y < y2; ++y) {
+      const T* row = d + static_cast<size_t>(y) * W;
+      double rs = 0.0;
+      for (int x = x1; x < x2; ++x) rs += static_cast<double>(row[x]);
+      t += rs;
+    }
+    return t;
+  }
+  double sum(int x1, int x2, int y1, int y2) const {
+    const int ax1 = (x1 + 7) & ~7, ax2 = x2 & ~7, ay1 = (y1 + 7) & ~7, ay2 = y2 & ~7;
+    if (ax1 >= ax2 || ay1 >= ay2) return direct(x1, x2, y1, y2);
+    auto at = [&](int y, int x) { return s[static_cast<size_t>(y) * (cw + 1) + x]; };
+    const int cx1 = ax1 >> 3, cx2 = ax2 >> 3, cy1 = ay1 >> 3, cy2 = ay2 >> 3;
+    return (at(cy2, cx2) - at(cy1, cx2) - at(cy2, cx1) + at(cy1, cx1)) + direct(x1, x2, y1, ay1) + direct(x1, x2, ay2, y2) +
+           direct(x1, ax1, ay1, ay2) + direct(ax2, x2, ay1, ay2);
   }
 };
 
@@ -490,11 +518,11 @@ extern "C" int ucf_sap_build_tree_host(const void* domain_host, int domain_dtype
       return build_tree(2, root, fixed_length, val, boxes_host, values_host);
     }
     if (domain_dtype == UCF_DTYPE_F32) {
-      Sat2<double> sat(static_cast<const float*>(domain_host), H, W);
+      const CellSatF<float> sat(static_cast<const float*>(domain_host), H, W);
       auto val = [&](const int* c) { return static_cast<long long>(sat.sum(c[0], c[1], c[2], c[3]) / norm_factor); };
       return build_tree(2, root, fixed_length, val, boxes_host, values_host);
     }
-    Sat2<double> sat(static_cast<const double*>(domain_host), H, W);
+    const CellSatF<double> sat(static_cast<const double*>(domain_host), H, W);
     auto val = [&](const int* c) { return static_cast<long long>(sat.sum(c[0], c[1], c[2], c[3]) / norm_factor); };
     return build_tree(2, root, fixed_length, val, boxes_host, values_host);
   }
