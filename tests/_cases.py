@@ -139,7 +139,9 @@ def run_product(cfg, model, inp):
     if k == "mae":
         feats, mask, ids = model.forward_features(inp["x"], VARS3, None, noise=inp["noise"])
         pred = model.forward_head(feats, ids, None)
-        return {"pred": pred, "mask": mask}, R.masked_mse(pred.float(), inp["target"], mask)
+        # the product's own loss: patchify folded into the masked MSE kernel (the target is never materialised)
+        from ucf_vit_b200.utils.metrics import patch_mse
+        return {"pred": pred, "mask": mask}, patch_mse(pred, inp["x"], cfg["patch_size"], True, mask)
     if k == "diffusion":
         o = model(inp["x"], inp["t"], VARS3)
         return {"pred": o}, torch.nn.functional.mse_loss(o.float(), inp["target"])

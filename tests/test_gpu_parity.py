@@ -208,10 +208,12 @@ def test_weights_used_by_kernels_follow_the_optimizer(fused):
         assert _rel_l2(p.detach().float().cpu(), sd[k]) > 1e-3, k
 
 
+@pytest.mark.parametrize("optimizer", ["torch_fused", "ucf"])
 @pytest.mark.parametrize("name", ["vit_cls_hd64", "mae_hd64_dec32"])
-def test_model_trains_like_the_oracle_under_fused_adamw(name):
-    """Five optimizer steps (torch AdamW, fused=True) on a whole model: the loss trajectory must follow the fp32
-    oracle trained with the same optimizer -- every weight the kernels read has to follow its fp32 master."""
+def test_model_trains_like_the_oracle_under_fused_adamw(name, optimizer):
+    """Five optimizer steps (torch AdamW fused=True, or this package's FusedAdamW) on a whole model: the loss
+    trajectory must follow the fp32 oracle trained with torch's AdamW -- every weight the kernels read has to
+    follow its fp32 master.  The MAE case runs the product's fused masking and reconstruction-loss kernels."""
     cfg, shapes, arrays, sd = C.load(name)
     inp = C.inputs(cfg, arrays)
     steps, lr = 5, 2e-3
@@ -231,7 +233,11 @@ def test_model_trains_like_the_oracle_under_fused_adamw(name):
     model = C.build_product(cfg)
     model.load_state_dict(sd, strict=True)
     model = model.cuda().train(cfg.get("train", True))
-    opt = torch.optim.AdamW(model.parameters(), lr=lr, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
+    if optimizer == "ucf":
+        from ucf_vit_b200.utils.optim import FusedAdamW
+        opt = FusedAdamW(model.parameters(), lr=lr, betas=(0.9, 0.95), weight_decay=0.0)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=lr, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
     dinp = _to_dev(inp)
     losses_p = []
     for _ in range(steps):

@@ -26,7 +26,7 @@ class _PatchMseFn(torch.autograd.Function):
         out = ops.patch_mse_fwd(pred, img, grid, patch, mask)
         ctx.save_for_backward(pred, img, mask, out)
         ctx.geometry = (grid, patch)
-        return out[0].clone() if pred.dtype == torch.float32 else out[0].to(pred.dtype)
+        return out[0].clone()          # fp32 whatever the prediction's dtype: the sums are carried in fp32 / double
 
     @staticmethod
     def backward(ctx, grad_loss):
@@ -77,7 +77,7 @@ class _DiceBceFn(torch.autograd.Function):
         out = ops.dice_bce_fwd(logits, targets, weight, smooth, act)
         ctx.save_for_backward(logits, targets, out)
         ctx.hyper = (weight, act)
-        return out[0].clone() if logits.dtype == torch.float32 else out[0].to(logits.dtype)
+        return out[0].clone()          # fp32 whatever the logits' dtype
 
     @staticmethod
     def backward(ctx, grad_loss):
