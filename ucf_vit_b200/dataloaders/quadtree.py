@@ -2,7 +2,7 @@
 (/root/reference/src/UCF_VIT/dataloaders/quadtree.py: Rect :6-82, FixedQuadTree :84-242).
 
 `nodes` keeps the reference's `[[Rect, value], ...]` list (same order, same integers).  The tree
-is built by the C++ host routine `ucf_sap_build_tree_host` (summed-area table + priority queue,
+is built by the C++ host routine `ucf_sap_build_tree_host` (8x8-cell summed-area table + priority queue,
 O(L log L) instead of the reference's O(L^2) Python scans) and `serialize` / `deserialize`
 resample every leaf on the GPU (`ucf_sap_gather` / `ucf_sap_scatter`) instead of one
 `cv.resize` call per leaf.  Drawing helpers (matplotlib) are not part of the hot path and are
