@@ -278,8 +278,17 @@ def host_logic():
     arrays["patchify3d_p4"] = rm.patchify(x3, 4, False).numpy()
     assert torch.equal(rm.unpatchify(rm.patchify(x2, 4, True), x2, 4, True), x2)
     assert torch.equal(rm.unpatchify(rm.patchify(x3, 4, False), x3, 4, False), x3)
+    ck = {"pos_embed": fx.det_tensor((1, 10, 8), 73), "decoder_pos_embed": fx.det_tensor((1, 7, 4), 74),
+          "other": torch.zeros(2)}
+    rm.interpolate_pos_embed_adaptive(None, ck, new_size=7)        # pos_embed 10 -> 7, decoder table already 7
+    arrays["interp_pos_10to7"] = ck["pos_embed"].numpy()
+    arrays["interp_dec_unchanged"] = ck["decoder_pos_embed"].numpy()
+    ck2 = {"decoder_pos_embed": fx.det_tensor((1, 5, 4), 75)}
+    rm.interpolate_pos_embed_adaptive(None, ck2, new_size=12)
+    arrays["interp_dec_5to12"] = ck2["decoder_pos_embed"].numpy()
+    arrays["pow2"] = np.array([int(bool(rm.is_power_of_two(n))) for n in range(0, 70)])
     fx.save_case(os.path.join(OUT, "host_logic.npz"), {"kind": "host"}, {}, arrays)
-    print("[golden] host_logic: pos-embed tables, LR schedule, patchify targets")
+    print("[golden] host_logic: pos-embed tables, LR schedule, patchify targets, pos-embed interpolation")
 
 
 if __name__ == "__main__":

@@ -120,3 +120,15 @@ def test_wgrad_split_factor_fills_whole_rounds():
         assert 1 <= s <= 16 and kb // s >= 8
     finally:
         F._SM_COUNT.pop(0, None)
+
+
+def test_checkpoint_pos_embed_interpolation_and_power_of_two_match_reference():
+    ck = {"pos_embed": fx.det_tensor((1, 10, 8), 73), "decoder_pos_embed": fx.det_tensor((1, 7, 4), 74), "other": torch.zeros(2)}
+    dec_before = ck["decoder_pos_embed"]
+    misc.interpolate_pos_embed_adaptive(None, ck, new_size=7)
+    assert np.array_equal(ck["pos_embed"].numpy(), HOST["interp_pos_10to7"])
+    assert ck["decoder_pos_embed"] is dec_before and np.array_equal(dec_before.numpy(), HOST["interp_dec_unchanged"])
+    ck2 = {"decoder_pos_embed": fx.det_tensor((1, 5, 4), 75)}
+    misc.interpolate_pos_embed_adaptive(None, ck2, new_size=12)
+    assert np.array_equal(ck2["decoder_pos_embed"].numpy(), HOST["interp_dec_5to12"])
+    assert [int(bool(misc.is_power_of_two(n))) for n in range(0, 70)] == HOST["pow2"].tolist()

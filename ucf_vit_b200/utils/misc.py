@@ -54,6 +54,25 @@ def configure_scheduler(optimizer, warmup_steps, max_steps, warmup_start_lr, eta
     return LinearWarmupCosineAnnealingLR(optimizer, warmup_steps, max_steps, warmup_start_lr, eta_min)
 
 
+def interpolate_pos_embed_adaptive(model, checkpoint_model, new_size=127):
+    """Resample the learned position tables of a checkpoint to `new_size` tokens, in place in the state dict
+    (reference utils/misc.py:98-127: 1-D linear interpolation along the token axis, align_corners=False).
+    `model` is unused, as in the reference."""
+    for key in ("pos_embed", "decoder_pos_embed"):
+        table = checkpoint_model.get(key)
+        if table is None or table.shape[-2] == new_size:
+            continue
+        n_tok, width = table.shape[-2], table.shape[-1]
+        as_channels = table.reshape(-1, n_tok, width).transpose(1, 2)           # [1, D, L]: tokens last for interpolate
+        checkpoint_model[key] = torch.nn.functional.interpolate(as_channels, size=new_size, mode="linear",
+                                                                align_corners=False).transpose(1, 2)
+
+
+def is_power_of_two(n):
+    """utils/misc.py:553-554."""
+    return n != 0 and (n & (n - 1)) == 0
+
+
 # ---------------------------------------------------------------------------------------------
 # process groups (reference: utils/misc.py:129-238).  Rank layout: tensor-parallel fastest, then
 # sequence-parallel, then data-parallel; the data-parallel ranks are further cut into contiguous
