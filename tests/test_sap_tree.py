@@ -178,3 +178,38 @@ def test_quadtree_class_api_and_large_image_partition():
     patches, sizes, centres = qt.serialize(img, size=(16, 16, 3))
     assert len(patches) == 1024 and patches[0].shape == (16, 16, 3) and sizes[0] == qt.nodes[0][0].get_size()[0]
     assert centres[0] == qt.nodes[0][0].get_center()
+
+
+def _fake_cv2():
+    """OpenCV is not installed in the build image: a small stand-in with the three calls the edge recipes use
+    (not OpenCV's arithmetic -- enough to drive the host logic around them)."""
+    import types
+    from scipy import ndimage
+    cv = types.ModuleType("cv2")
+    cv.CV_64F = 6
+    cv.Sobel = lambda a, ddepth, dx, dy, ksize=3: ndimage.sobel(a.astype(np.float64), axis=1 if dx else 0)
+    cv.GaussianBlur = lambda a, k, s: ndimage.gaussian_filter(a, sigma=max(k[0], 1) / 3)
+
+    def canny(a, lo, hi):
+        g = np.hypot(ndimage.sobel(a.astype(np.float64), axis=0), ndimage.sobel(a.astype(np.float64), axis=1))
+        return ((g > hi) * 255).astype(np.uint8)
+    cv.Canny = canny
+    return cv
+
+
+def test_patchify_3d_edge_map_feeds_the_octree(monkeypatch):
+    import sys
+    from ucf_vit_b200.dataloaders.transform import Patchify_3D
+    monkeypatch.setitem(sys.modules, "cv2", _fake_cv2())
+    rng = np.random.default_rng(3)
+    vol = rng.random((16, 16, 16, 2)).astype(np.float32)
+    vol[4:12, 4:12, 4:12, :] += 2.0                                   # a block with sharp faces
+    t = Patchify_3D(fixed_length=22, patch_size=4, num_channels=2)
+    t.smooth_factor, t.canny = 1, [60, 110]
+    edges = t._edges(vol)
+    assert edges.dtype == np.uint8 and edges.shape == (16, 16, 16)
+    assert t._norm_factor == 127 and set(np.unique(edges)) <= {0, 127, 254} and edges.any()
+    boxes, values = ops.sap_build_tree(edges, 22, float(t._norm_factor))
+    nodes = Q.build_octree(edges, 22, t._norm_factor)
+    assert np.array_equal(boxes, np.array([n[:6] for n in nodes], np.int32))
+    assert np.array_equal(values, np.array([n[6] for n in nodes], np.int64))

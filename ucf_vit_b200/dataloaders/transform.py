@@ -2,7 +2,8 @@
 (/root/reference/src/UCF_VIT/dataloaders/transform.py:9-54, :56-132).
 
 Edge detection stays on OpenCV / scipy on the host (bit-exactness of the tree depends on it,
-SURVEY.md §0.9, §8f rank 4); the tree build is the C++ host routine and the per-leaf resampling
+SURVEY.md §0.9, §8f rank 4; OpenCV is not installed in the build image, so the edge recipes are
+exercised in tests only through a stand-in `cv2` -- the tree and gather they feed are pinned); the tree build is the C++ host routine and the per-leaf resampling
 gather runs on the GPU.  With `device_output=True` the sequence stays on the device as torch
 tensors (no D2H copy) for direct consumption by the model."""
 import random
@@ -51,3 +52,74 @@ class Patchify(torch.nn.Module):
         if not self.device_output:
             seq, seq_size, seq_pos = seq.cpu().numpy(), seq_size.cpu().numpy(), seq_pos.cpu().numpy()
         return (seq, seq_size, seq_pos, qdt, edges) if self.return_edges else (seq, seq_size, seq_pos, qdt)
+
+
+class Patchify_3D(torch.nn.Module):
+    """Volume [Z, Y, X, C] -> adaptive octree sequence (reference transform.py:56-132).
+
+    Edge map on the host, slice by slice, with the reference's recipe: Gaussian smoothing of the volume, the
+    gradient direction from 5x5 Sobel derivatives, one Canny pass per channel; a voxel votes once per channel that
+    marks it, and it counts when the min-max-normalised direction of an edge voxel exceeds 0.5.  The uint8 map
+    (votes * int(255 / C)) drives the C++ octree build; the per-leaf trilinear gather runs on the GPU."""
+
+    def __init__(self, sths=[0, 1, 3, 5], fixed_length=196, cannys=[50, 100], patch_size=16, num_channels=3,
+                 dataset="basic_ct", return_edges=False, device="cuda", device_output=False) -> None:
+        super().__init__()
+        self.sths = sths
+        self.fixed_length = fixed_length
+        self.cannys = [x for x in range(cannys[0], cannys[1], 1)]
+        self.patch_size = patch_size
+        self.num_channels = num_channels
+        self.dataset = dataset
+        self.return_edges = return_edges
+        self.device, self.device_output = device, device_output
+
+    def _slice_direction(self, planes):
+        """arctan2(dy, dx) of one z-slice.  Channel 0 supplies both derivatives; a later channel takes over dx when its
+        mean gradient magnitude beats channel 0's, and dy when its mean dy beats the current one (:75-90)."""
+        import cv2 as cv
+        dx = cv.Sobel(planes[:, :, 0], cv.CV_64F, 1, 0, ksize=5)
+        dy = cv.Sobel(planes[:, :, 0], cv.CV_64F, 0, 1, ksize=5)
+        strength0 = np.mean(np.sqrt(dx ** 2 + dy ** 2))
+        for c in range(1, self.num_channels):
+            cx = cv.Sobel(planes[:, :, c], cv.CV_64F, 1, 0, ksize=5)
+            cy = cv.Sobel(planes[:, :, c], cv.CV_64F, 0, 1, ksize=5)
+            if np.mean(np.sqrt(cx ** 2 + cy ** 2)) > strength0:
+                dx = cx
+            if np.mean(cy) > np.mean(dy):
+                dy = cy
+        return np.arctan2(dy, dx)
+
+    def _edges(self, img):
+        import cv2 as cv
+        from scipy.ndimage import gaussian_filter
+        s = self.smooth_factor
+        smooth = gaussian_filter(img, sigma=(s, s, s, 0))
+        direction = np.zeros_like(smooth[:, :, :, 0])
+        votes = np.zeros(smooth.shape[:3], dtype=np.uint8)
+        for z in range(smooth.shape[0]):
+            direction[z] = self._slice_direction(smooth[z])
+            for c in range(self.num_channels):
+                marked = cv.Canny((smooth[z, :, :, c] * 255).astype(np.uint8), self.canny[0], self.canny[1]) > 0
+                votes[z] += marked.astype(np.uint8)
+        on_edge = votes > 0                       # the reference ORs the per-channel maps through a wrapping uint8 sum
+        masked = np.zeros_like(direction)
+        masked[on_edge] = direction[on_edge]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            unit = (masked - masked.min()) / (masked.max() - masked.min())
+        self._norm_factor = int(255 / self.num_channels)
+        return (unit > 0.5).astype(np.uint8) * (votes * self._norm_factor)
+
+    def forward(self, img):
+        self.smooth_factor = random.choice(self.sths)
+        c = random.choice(self.cannys)
+        self.canny = [c, c + 50]
+        edges = self._edges(img)
+        tree = FixedOctTree(domain=edges, fixed_length=self.fixed_length, norm_factor=self._norm_factor, device=self.device)
+        p, C = self.patch_size, self.num_channels
+        seq, seq_size, seq_pos = tree.serialize_device(img, size=(p, p, p, C))
+        # raw reshape like the 2-D transform (:121-124): (L,p,p,p,C) -> (C,L,p^3), not a transpose
+        seq = seq.reshape(C, -1, p * p * p) if C > 1 else seq.reshape(-1, p * p * p)
+        if not self.device_output:
+            seq, seq_size, seq_pos = seq.cpu().numpy(), seq_size.cpu().numpy(), seq_pos.cpu().numpy()
+        return (seq, seq_size, seq_pos, tree, edges) if self.return_edges else (seq, seq_size, seq_pos, tree)
