@@ -213,3 +213,22 @@ def test_patchify_3d_edge_map_feeds_the_octree(monkeypatch):
     nodes = Q.build_octree(edges, 22, t._norm_factor)
     assert np.array_equal(boxes, np.array([n[:6] for n in nodes], np.int32))
     assert np.array_equal(values, np.array([n[6] for n in nodes], np.int64))
+
+
+def test_patchify_2d_edge_branches(monkeypatch):
+    import sys
+    from ucf_vit_b200.dataloaders.transform import Patchify
+    monkeypatch.setitem(sys.modules, "cv2", _fake_cv2())
+    rng = np.random.default_rng(4)
+    img = (rng.random((32, 32, 3)) * 255).astype(np.uint8)
+    t = Patchify(fixed_length=16, patch_size=4, num_channels=3, dataset="imagenet")
+    t.smooth_factor, t.canny = 3, [50, 100]
+    e = t._edges(img)
+    assert e.dtype == np.uint8 and e.shape[:2] == (32, 32)
+    t.smooth_factor = 0                                   # the reference's "no smoothing" branch: a random float map
+    np.random.seed(0)
+    e0 = t._edges(img)
+    assert e0.dtype == np.float64 and e0.shape == (32, 32) and 0.0 <= e0.min() and e0.max() <= 1.0
+    boxes, values = ops.sap_build_tree(e0, 16)             # float64 path of the builder
+    nodes = Q.build_quadtree(e0, 16)
+    assert np.array_equal(boxes, np.array([n[:4] for n in nodes], np.int32))
