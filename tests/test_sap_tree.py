@@ -190,8 +190,10 @@ def _fake_cv2():
     cv.Sobel = lambda a, ddepth, dx, dy, ksize=3: ndimage.sobel(a.astype(np.float64), axis=1 if dx else 0)
     cv.GaussianBlur = lambda a, k, s: ndimage.gaussian_filter(a, sigma=max(k[0], 1) / 3)
 
-    def canny(a, lo, hi):
-        g = np.hypot(ndimage.sobel(a.astype(np.float64), axis=0), ndimage.sobel(a.astype(np.float64), axis=1))
+    def canny(a, lo, hi):                                    # multi-channel input -> one 2-D map, like OpenCV
+        a = a.astype(np.float64)
+        g = np.hypot(ndimage.sobel(a, axis=0), ndimage.sobel(a, axis=1))
+        g = g.max(axis=2) if g.ndim == 3 else g
         return ((g > hi) * 255).astype(np.uint8)
     cv.Canny = canny
     return cv
@@ -224,7 +226,7 @@ def test_patchify_2d_edge_branches(monkeypatch):
     t = Patchify(fixed_length=16, patch_size=4, num_channels=3, dataset="imagenet")
     t.smooth_factor, t.canny = 3, [50, 100]
     e = t._edges(img)
-    assert e.dtype == np.uint8 and e.shape[:2] == (32, 32)
+    assert e.dtype == np.uint8 and e.shape == (32, 32)
     t.smooth_factor = 0                                   # the reference's "no smoothing" branch: a random float map
     np.random.seed(0)
     e0 = t._edges(img)
@@ -232,3 +234,35 @@ def test_patchify_2d_edge_branches(monkeypatch):
     boxes, values = ops.sap_build_tree(e0, 16)             # float64 path of the builder
     nodes = Q.build_quadtree(e0, 16)
     assert np.array_equal(boxes, np.array([n[:4] for n in nodes], np.int32))
+
+
+def test_build_many_and_forward_batch_equal_the_per_image_path(monkeypatch):
+    import random
+    import sys
+    from ucf_vit_b200.dataloaders.quadtree import FixedQuadTree
+    from ucf_vit_b200.dataloaders.transform import Patchify
+    rng = np.random.default_rng(8)
+    maps = [((rng.random((64, 64)) < 0.2) * 255).astype(np.uint8), rng.random((64, 64)),            # mixed dtypes and
+            ((rng.random((32, 32)) < 0.5) * 255).astype(np.uint8), ((rng.random((64, 64)) < 0.7) * 255).astype(np.uint8)]
+    many = FixedQuadTree.build_many(maps, 31, device="cpu", threads=3)
+    for m, t in zip(maps, many):
+        one = FixedQuadTree(m, 31, device="cpu")
+        assert np.array_equal(t.boxes, one.boxes) and [v for _, v in t.nodes] == [v for _, v in one.nodes]
+        assert t.encode_nodes() == one.encode_nodes() and t.count_patches() == one.count_patches()
+    # the transform: same random draws, same trees, whether images go one by one or as a batch
+    monkeypatch.setitem(sys.modules, "cv2", _fake_cv2())
+    monkeypatch.setattr(FixedQuadTree, "serialize_device",
+                        lambda self, img, size: (torch.zeros(self.fixed_length, size[0], size[1], size[2]),
+                                                 torch.zeros(self.fixed_length, dtype=torch.int64),
+                                                 torch.zeros(self.fixed_length, 2, dtype=torch.float64)))
+    imgs = [(rng.random((32, 32, 3)) * 255).astype(np.uint8) for _ in range(5)]
+    t = Patchify(fixed_length=16, patch_size=4, num_channels=3, dataset="imagenet", device="cpu")
+    random.seed(11)
+    np.random.seed(11)
+    single = [t(img) for img in imgs]
+    random.seed(11)
+    np.random.seed(11)
+    batch = t.forward_batch(imgs, threads=2)
+    assert len(batch) == len(single)
+    for a, b in zip(single, batch):
+        assert np.array_equal(a[3].boxes, b[3].boxes) and a[0].shape == b[0].shape == (3, 16, 16)

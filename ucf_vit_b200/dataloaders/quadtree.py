@@ -60,8 +60,32 @@ class FixedQuadTree:
     def _build_tree(self):
         h, w = self.domain.shape
         assert h > 0 and w > 0, "Wrong img size."
-        self.boxes, values = ops.sap_build_tree(np.asarray(self.domain), self.fixed_length, 255.0)
-        self.nodes = [[Rect(int(b[0]), int(b[1]), int(b[2]), int(b[3])), int(v)] for b, v in zip(self.boxes, values)]
+        self._adopt(*ops.sap_build_tree(np.asarray(self.domain), self.fixed_length, 255.0))
+
+    def _adopt(self, boxes, values):
+        self.boxes = boxes
+        self.nodes = [[Rect(int(b[0]), int(b[1]), int(b[2]), int(b[3])), int(v)] for b, v in zip(boxes, values)]
+
+    @classmethod
+    def build_many(cls, domains, fixed_length=128, device="cuda", threads=0):
+        """Trees of several edge maps at once: maps of one shape and dtype are built together on host threads
+        (`ucf_sap_build_tree_batch_host`).  Returns one FixedQuadTree per map, in order -- identical to
+        `[FixedQuadTree(d, fixed_length, device=device) for d in domains]`."""
+        doms = [np.asarray(d) for d in domains]
+        groups = {}
+        for i, d in enumerate(doms):
+            groups.setdefault((d.shape, d.dtype.str), []).append(i)
+        trees = [None] * len(doms)
+        for idx in groups.values():
+            built = ops.sap_build_trees([doms[i] for i in idx], fixed_length, 255.0, threads=threads)
+            for i, (boxes, values) in zip(idx, built):
+                t = cls.__new__(cls)
+                t.domain, t.fixed_length, t.device, t._boxes_dev = domains[i], fixed_length, device, None
+                h, w = doms[i].shape
+                assert h > 0 and w > 0, "Wrong img size."
+                t._adopt(boxes, values)
+                trees[i] = t
+        return trees
 
     # ---- bookkeeping helpers with reference semantics
     def nodes_value(self):

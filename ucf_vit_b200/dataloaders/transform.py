@@ -53,6 +53,26 @@ class Patchify(torch.nn.Module):
             seq, seq_size, seq_pos = seq.cpu().numpy(), seq_size.cpu().numpy(), seq_pos.cpu().numpy()
         return (seq, seq_size, seq_pos, qdt, edges) if self.return_edges else (seq, seq_size, seq_pos, qdt)
 
+    def forward_batch(self, imgs, threads=0):
+        """`[self(img) for img in imgs]` with the trees of the whole batch built together on host threads (the
+        random smoothing / Canny draws are consumed in the same order as by repeated `forward` calls)."""
+        edges = []
+        for img in imgs:
+            self.smooth_factor = random.choice(self.sths)
+            c = random.choice(self.cannys)
+            self.canny = [c, c + 50]
+            edges.append(self._edges(img))
+        trees = FixedQuadTree.build_many(edges, self.fixed_length, device=self.device, threads=threads)
+        p, C = self.patch_size, self.num_channels
+        out = []
+        for img, e, qdt in zip(imgs, edges, trees):
+            seq, seq_size, seq_pos = qdt.serialize_device(img, size=(p, p, C))
+            seq = seq.reshape(C, -1, p * p) if C > 1 else seq.reshape(-1, p * p)
+            if not self.device_output:
+                seq, seq_size, seq_pos = seq.cpu().numpy(), seq_size.cpu().numpy(), seq_pos.cpu().numpy()
+            out.append((seq, seq_size, seq_pos, qdt, e) if self.return_edges else (seq, seq_size, seq_pos, qdt))
+        return out
+
 
 class Patchify_3D(torch.nn.Module):
     """Volume [Z, Y, X, C] -> adaptive octree sequence (reference transform.py:56-132).
