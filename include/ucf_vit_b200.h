@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UCF_ABI_VERSION 1
+#define UCF_ABI_VERSION 2
 
 enum { UCF_DTYPE_F32 = 0, UCF_DTYPE_BF16 = 1, UCF_DTYPE_U8 = 2, UCF_DTYPE_F64 = 3 };
 enum { UCF_LAYOUT_K_MAJOR = 0, UCF_LAYOUT_MN_MAJOR = 1 };
@@ -68,7 +68,7 @@ int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* bias, void*
 
 /* ---- LayerNorm (replaces nn.LayerNorm at arch.py:170,266; building_blocks.py:212,226) ------
  * x: [rows, D] (x_dtype), gamma/beta: [D] (param_dtype, may be NULL = 1/0), y: [rows, D] bf16,
- * mean/rstd: [rows] fp32 (saved for backward).  D % 8 == 0, D <= 4096 (fwd) / 2048 (bwd). */
+ * mean/rstd: [rows] fp32 (saved for backward).  D % 8 == 0, D <= 4096. */
 int ucf_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean,
                       float* rstd, long long rows, int D, float eps, int x_dtype, int param_dtype,
                       void* stream);
@@ -167,11 +167,14 @@ int ucf_cast_bf16_to_f32(const void* src, float* dst, long long n, int accumulat
 /* out[n] (+)= sum_m x[m, n]   x bf16 [M, N] pitch ld; out fp32 [N]  (bias gradients) */
 int ucf_colsum_bf16(const void* x, float* out, long long M, int N, long long ld, int accumulate,
                     void* stream);
-/* Conv{2,3}d(k = s = p) input -> GEMM rows (replaces the im2col inside cuDNN, building_blocks.py:89)
- * x: [B, C, G0*p, G1*p (, G2*p)] of x_dtype (fp32 / bf16), contiguous
- * out: bf16 [B*G0*G1(*G2), C*p^dims], K ordered (c, p0, p1(, p2)) == conv weight.view(D, -1) */
+/* Conv{2,3}d(k = s = p) input -> GEMM rows (replaces the im2col inside cuDNN, building_blocks.py:58-60,89)
+ * x: [B, C, S0, S1 (, S2)] of x_dtype (fp32 / bf16), contiguous, S >= G*p: like the strided convolution,
+ *    pixels past the last whole patch are ignored.  Any patch size (16-byte vectors when p % 8 == 0,
+ *    8-byte when p % 4 == 0, scalar otherwise).
+ * out: bf16 [B*G0*G1(*G2), ld_out], ld_out >= K = C*p^dims and a multiple of 8 (the GEMM's K extent; pad
+ *      columns are zero-filled), K ordered (c, p0, p1(, p2)) == conv weight.view(D, -1) */
 int ucf_patchify(const void* x, void* out, int B, int C, int G0, int G1, int G2, int p, int dims,
-                 int x_dtype, void* stream);
+                 int S0, int S1, int S2, long long ld_out, int x_dtype, void* stream);
 
 /* class-token concat + position-embedding add (replaces torch.cat + add in VIT._pos_embed,
  * arch.py:367-393) in one pass: out[b, n] = (n < P ? prefix[n] : tok[b, n - P]) + pos[b * pos_bstride

@@ -69,7 +69,8 @@ def test_gemm_linearity_at_benchmark_size():
     assert ((y1[idx] - ref).abs() <= 0.005 * ref.abs() + 1e-3).all()
 
 
-@pytest.mark.parametrize("rows,D", [(7, 64), (1000, 192), (3000, 1024), (513, 512), (100, 2048), (50432, 768)])
+@pytest.mark.parametrize("rows,D", [(7, 64), (1000, 192), (3000, 1024), (513, 512), (100, 2048), (50432, 768), (333, 4096),
+                                     (40, 3072)])
 def test_layernorm_fwd_bwd(rows, D):
     torch.manual_seed(rows)
     x = torch.randn(rows, D, device=dev) * 2 + 0.5
@@ -114,6 +115,29 @@ def test_attention_fwd_bwd(B, N, H, hd):
     _ok(dqkv[:, :, 0], qf.grad, 2e-2)
     _ok(dqkv[:, :, 1], kf.grad, 2e-2)
     _ok(dqkv[:, :, 2], vf.grad, 2e-2)
+
+
+@pytest.mark.parametrize("B,N,H,hd", [(2, 197, 2, 64), (1, 512, 2, 64), (2, 700, 2, 32), (1, 1100, 1, 64)])
+def test_attention_fwd_stabiliser_jumps(B, N, H, hd):
+    """Rows whose maximum moves by far more than 2^60 inside a key tile and from one tile to the next: the
+    single-sweep forward kernel must take its rescale path (O and l in tensor memory / registers are
+    multiplied by exp2(m_used - m_new) and the tile is swept again) and still return the exact softmax."""
+    torch.manual_seed(N + hd)
+    scale = hd ** -0.5
+    qkv = torch.randn(B, N, 3, H, hd, device=dev)
+    qkv[:, :, 0] *= 6.0
+    for k0, f in ((40, 8.0), (170, 30.0), (300, 90.0), (1000, 200.0)):
+        if k0 < N:
+            qkv[:, k0:k0 + 3, 1] *= f
+    qkv = bf(qkv)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale * 1.4426950408889634
+    first = s[..., :32].max(-1).values
+    assert ((s.max(-1).values - first) > 60.0).any(), "the inputs do not reach the rescale path"
+    o, lse = ops.attention_fwd(q, k, v, scale)
+    oref, lref = _ref_attn(q.float(), k.float(), v.float(), scale)
+    _ok(o, oref, 1.5e-2)
+    _ok(lse, lref, 1e-3)
 
 
 def test_attention_cross_lengths():
@@ -226,6 +250,47 @@ def test_elementwise_helpers():
     ref = vol.reshape(2, 2, 2, 8, 4, 8, 2, 8).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(32, 1024)
     assert torch.equal(ops.patchify(vol, 8), ref.to(torch.bfloat16))
     assert torch.equal(ops.patchify(bf(vol), 8), ref.to(torch.bfloat16))
+
+
+def _conv_rows(x, p):
+    """What Conv(k = s = p) sees: unfold over whole patches only, K ordered (c, p0, p1(, p2))."""
+    nd = x.dim() - 2
+    B, C = x.shape[:2]
+    G = [s // p for s in x.shape[2:]]
+    x = x[(slice(None), slice(None)) + tuple(slice(0, g * p) for g in G)]
+    if nd == 2:
+        return x.reshape(B, C, G[0], p, G[1], p).permute(0, 2, 4, 1, 3, 5).reshape(B * G[0] * G[1], C * p * p)
+    return x.reshape(B, C, G[0], p, G[1], p, G[2], p).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(-1, C * p ** 3)
+
+
+@pytest.mark.parametrize("shape,p", [((2, 1, 64, 64), 4), ((2, 3, 30, 45), 4), ((1, 1, 20, 24, 28), 4), ((2, 1, 18, 18), 2),
+                                     ((2, 3, 21, 35), 7), ((1, 2, 37, 50), 16), ((2, 1, 17, 16, 19), 8)])
+def test_patchify_any_patch_size_and_cropped_images(shape, p):
+    """basic_ct configs use patch_size 4 (reference configs/basic_ct/*/base_config.yaml); Conv(k = s = p) floors
+    a spatial size that is not a multiple of p (building_blocks.py:58-60)."""
+    x = torch.randn(*shape, device=dev)
+    ref = _conv_rows(x, p).to(torch.bfloat16)
+    for xin in (x, bf(x)):
+        got = ops.patchify(xin.contiguous(), p)
+        K = ref.shape[1]
+        assert got.shape == (ref.shape[0], -(-K // 8) * 8)
+        assert torch.equal(got[:, :K], ref)
+        assert not got[:, K:].any()
+
+
+def test_patch_embed_matches_conv_for_small_patches():
+    from ucf_vit_b200.simple.building_blocks import PatchEmbed
+    torch.manual_seed(5)
+    for twoD, img, p, C in ((True, 32, 4, 1), (False, 16, 4, 1), (True, 18, 2, 1)):
+        pe = PatchEmbed(img_size=img, patch_size=p, in_chans=C, embed_dim=64, twoD=twoD).to(dev)
+        x = torch.randn(2, C, *([img] * (2 if twoD else 3)), device=dev)
+        y = pe(x)
+        ref = pe.proj(x).flatten(2).transpose(1, 2)
+        _ok(y, ref, 2e-2)
+        y.float().sum().backward()
+        gref = torch.autograd.grad(pe.proj(x).sum(), pe.proj.weight)[0]
+        _ok(pe.proj.weight.grad, gref, 2e-2)
+        pe.zero_grad()
 
 
 def test_assemble_tokens_fwd_bwd():

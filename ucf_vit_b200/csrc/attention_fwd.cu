@@ -729,6 +729,396 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Single-sweep schedule (round 2; default for every shape).
+//
+// What bounded the two kernels above was tensor-memory READ bandwidth (~64-85 B/clk/SM): the general kernel
+// read 320 columns per row and key tile (S for the row maximum, S again for the exponentials, the PV
+// partial product), the short-key kernel 480 per item.  Here S is read ONCE and O never leaves tensor
+// memory until the item's epilogue:
+//   * optimistic stabiliser: the exponentials of tile j are taken against `m_used`, a value that was a row
+//     maximum at some earlier point (tile 0: the maximum of the first 32 keys).  fp32 / bf16 carry 8 exponent
+//     bits, so P = exp2(s - m_used) stays exact in relative terms as long as s - m_used < ~100; the true row
+//     maximum is tracked on the side (one FMNMX3 per pair) and only when it exceeds m_used by more than
+//     kRescaleThreshold (= 60, i.e. a factor 2^60) does the warp take the slow path: O (in tensor memory) and
+//     l are multiplied by exp2(m_used - m_new) and the tile is swept again.  The result is the exact softmax
+//     either way (lse = m_used + log2 l); the slow path is a correctness net for pathological rows
+//     (tests/test_gpu_kernels.py::test_attention_fwd_stabiliser_jumps drives it).
+//   * O accumulates in tensor memory over the key tiles (PV with accumulate), no per-tile read-back, no
+//     rescaling in the common case, no O registers.
+//   * the MMA warp walks ONE continuous stream of key tiles across work items: S_g(next tile) -- also the
+//     first tile of the NEXT item -- is issued right behind PV_g(this tile), so each warpgroup's
+//     softmax -> PV -> S chain never drains at an item boundary, and warpgroup 1 is started half a
+//     softmax period late once (the offset persists: nothing couples the two chains) so that one
+//     warpgroup's MMAs run under the other's exponentials.
+//   * a fraction of the exponentials is evaluated on the FMA pipe (Cody-Waite + degree-3 minimax
+//     polynomial, rel. error 7.5e-5, far below bf16 rounding of P) to unload the 16-lane MUFU unit.
+// Same shared-memory layout, barriers, producer and tensor maps as the general kernel above.
+// ---------------------------------------------------------------------------------------------
+constexpr float kRescaleThreshold = 60.0f;
+
+// 2^t for t <= ~100 on the FMA / ALU pipes (no MUFU): t = n + f, n = round(t), f in [-0.5, 0.5]
+__device__ __forceinline__ float2 exp2_poly2(float2 t) {
+  t.x = fmaxf(t.x, -125.0f);
+  t.y = fmaxf(t.y, -125.0f);
+  const float2 magic = mk2(12582912.0f);                   // 1.5 * 2^23: low mantissa bits hold round(t)
+  const float2 fi = __fadd2_rn(t, magic);
+  const float2 n = __fadd2_rn(fi, mk2(-12582912.0f));
+  const float2 f = __fadd2_rn(t, make_float2(-n.x, -n.y));
+  float2 q = __ffma2_rn(mk2(0.05517132207751274f), f, mk2(0.24261054396629333f));
+  q = __ffma2_rn(q, f, mk2(0.6932609677314758f));
+  q = __ffma2_rn(q, f, mk2(0.9999281167984009f));
+  return make_float2(__uint_as_float(__float_as_uint(q.x) + (__float_as_uint(fi.x) << 23)),
+                     __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(fi.y) << 23)));
+}
+
+// tcgen05.wait::ld that also names the destination registers of the load in flight, so the compiler cannot
+// schedule a read (or a copy) of them above the wait
+__device__ __forceinline__ void tmem_wait_ld_pin(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+        "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+        "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+        "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+      :: "memory");
+}
+
+template <int HD, int POLY>     // POLY: pairs (of 16) per 32-column chunk whose exp2 runs on the FMA pipe
+__global__ void __launch_bounds__(320, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                 const AttnFwdParams p) {
+  using Cfg = AttnFwdCfg<HD>;
+  constexpr int BQ = Cfg::BQ, BKV = Cfg::BKV, RING = Cfg::RING;
+  constexpr int RB = Cfg::ROW_BYTES, AB = Cfg::ATOM_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* q_s = smem;                                  // [2 buffers][2 tiles]
+  uint8_t* kv_s = q_s + 4 * Cfg::Q_BYTES;               // [RING]
+  uint8_t* p_s = kv_s + RING * Cfg::KV_BYTES;           // [2 warpgroups]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * Cfg::P_BYTES);
+  uint64_t* q_full = bars;                 // [2]
+  uint64_t* q_empty = bars + 2;            // [2]
+  uint64_t* kv_full = bars + 4;            // [RING]
+  uint64_t* kv_empty = bars + 4 + RING;    // [RING]
+  uint64_t* s_full = bars + 4 + 2 * RING;  // [2]   S_g(tile) is in tensor memory
+  uint64_t* p_full = s_full + 4;           // [2]   P_g(tile) is in shared memory (and S_g has been read)
+  uint64_t* pv_full = s_full + 6;          // [2]   the item's last PV_g has retired: O_g is complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NBAR);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const int nkv = (p.Nk + BKV - 1) / BKV;
+  const int nvalid_last = p.Nk - (nkv - 1) * BKV;       // keys of the last tile that exist (1..128)
+  const int ksteps_last = (nvalid_last + 15) >> 4;      // PV k-steps of the last tile (columns past it are never read)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < RING; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 4);
+      mbar_init(&pv_full[g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int item, int& b, int& h, int& q0) {
+    const int qp = item % p.nqp;
+    const int bh = item / p.nqp;
+    h = bh % p.H;
+    b = bh / p.H;
+    q0 = qp * 2 * BQ;
+  };
+  const int my_items = (p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  // first query row of the k-th item of this CTA
+  auto item_q0 = [&](int k) { return ((static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x)) % p.nqp) * 2 * BQ; };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (converged warp, elected lane issues)
+    uint32_t r = 0;
+    for (int k = 0; k < my_items; ++k) {
+      int b, h, q0;
+      decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), b, h, q0);
+      const int qb = k & 1;
+      mbar_wait(&q_empty[qb], ((k >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&q_full[qb], 2 * Cfg::Q_BYTES);
+        tma_load_4d(q_s + (qb * 2 + 0) * Cfg::Q_BYTES, &tmQ, &q_full[qb], 0, h, q0, b);
+        tma_load_4d(q_s + (qb * 2 + 1) * Cfg::Q_BYTES, &tmQ, &q_full[qb], 0, h, q0 + BQ, b);
+      }
+      __syncwarp();
+      for (int j = 0; j < nkv; ++j) {
+        for (int t = 0; t < 2; ++t, ++r) {
+          const int slot = r % RING;
+          mbar_wait(&kv_empty[slot], ((r / RING) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&kv_full[slot], Cfg::KV_BYTES);
+            tma_load_4d(kv_s + slot * Cfg::KV_BYTES, t == 0 ? &tmK : &tmV, &kv_full[slot], 0, h, j * BKV, b);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: one continuous stream of key tiles
+    if (my_items > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, false, false);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, false, true);
+      const uint32_t p_addr0 = smem_u32(p_s);
+      uint32_t pc[2] = {0, 0};       // P tiles consumed per warpgroup (p_full parity)
+
+      auto issue_s = [&](int g, int k, uint32_t k_addr) {      // S_g of a tile of item k
+        const uint32_t q_addr = smem_u32(q_s + ((k & 1) * 2 + g) * Cfg::Q_BYTES);
+        const uint32_t d = tmem_base + g * 256;
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < HD / 16; ++kk)
+            umma_bf16(d, attn_desc<RB>(q_addr + kk * 32, 16, AB), attn_desc<RB>(k_addr + kk * 32, 16, AB), idesc_s,
+                      kk > 0 ? 1u : 0u);
+          umma_commit(&s_full[g]);
+        }
+        __syncwarp();
+      };
+
+      uint32_t r = 0;                // ring position of the current tile's K (V follows at r + 1)
+      // prologue: S of the first tile; warpgroup 1 starts `stagger_cycles` late, once
+      {
+        mbar_wait(&q_full[0], 0);
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(kv_s);
+        const int q0 = item_q0(0);
+        issue_s(0, 0, k_addr);
+        if (q0 + BQ < p.Nq) {
+          const long long t0 = clock64();
+          while (clock64() - t0 < p.stagger_cycles) { }
+          issue_s(1, 0, k_addr);
+        }
+        if (elect_one()) umma_commit(&kv_empty[0]);
+        __syncwarp();
+      }
+      for (int k = 0; k < my_items; ++k) {
+        const int q0 = item_q0(k);
+        const int ng = (q0 + BQ < p.Nq) ? 2 : 1;
+        for (int j = 0; j < nkv; ++j, r += 2) {
+          const bool last_tile = j + 1 == nkv;
+          const bool has_next = !(last_tile && k + 1 == my_items);
+          const int kn = last_tile ? k + 1 : k;                 // item of the next tile
+          const int sv = (r + 1) % RING;
+          mbar_wait(&kv_full[sv], ((r + 1) / RING) & 1);
+          const uint32_t v_addr = smem_u32(kv_s + sv * Cfg::KV_BYTES);
+          int sk = 0, ng_next = 0;
+          uint32_t k_addr = 0;
+          if (has_next) {
+            if (last_tile) mbar_wait(&q_full[kn & 1], (kn >> 1) & 1);
+            sk = (r + 2) % RING;
+            mbar_wait(&kv_full[sk], ((r + 2) / RING) & 1);
+            k_addr = smem_u32(kv_s + sk * Cfg::KV_BYTES);
+            ng_next = last_tile ? ((item_q0(kn) + BQ < p.Nq) ? 2 : 1) : ng;
+          }
+          const int ksteps = last_tile ? ksteps_last : BKV / 16;
+          for (int g = 0; g < 2; ++g) {
+            if (g < ng) {
+              mbar_wait(&p_full[g], pc[g] & 1);
+              ++pc[g];
+              tc_fence_after();
+              const uint32_t d = tmem_base + g * 256 + 128;
+              const uint32_t pa = p_addr0 + g * Cfg::P_BYTES;
+              if (elect_one()) {
+                for (int kk = 0; kk < ksteps; ++kk)
+                  umma_bf16(d, umma_smem_desc(pa + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                            attn_desc<RB>(v_addr + kk * 2 * AB, 0, AB), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                if (last_tile) umma_commit(&pv_full[g]);
+              }
+              __syncwarp();
+            }
+            if (has_next && g < ng_next) issue_s(g, kn, k_addr);
+          }
+          if (elect_one()) {
+            umma_commit(&kv_empty[sv]);
+            if (has_next) umma_commit(&kv_empty[sk]);
+            if (last_tile) umma_commit(&q_empty[k & 1]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int g = (warp - 2) >> 2;
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;                 // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t tmem_s = tmem_base + g * 256, tmem_o = tmem_s + 128;
+    const uint32_t row_sw = row & 7, lrow_sw = lane & 7;
+    uint8_t* p_row = p_s + g * Cfg::P_BYTES + row * 128;
+    uint8_t* o_stage = p_s + g * Cfg::P_BYTES + qd * 4096;   // O staging reuses this warp's own P rows
+    uint32_t tc = 0;         // key tiles processed (s_full parity)
+    uint32_t ic = 0;         // items processed (pv_full parity)
+    const float2 sc2 = mk2(p.scale_log2);
+
+    for (int k = 0; k < my_items; ++k) {
+      int b, h, q0;
+      decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), b, h, q0);
+      const int qt0 = q0 + g * BQ;                  // first query row of this warpgroup's tile
+      if (qt0 >= p.Nq) continue;                    // (only warpgroup 1 can be idle)
+      // a warp whose 32 rows are all past Nq keeps the barrier protocol but does no work (its rows of P / O are
+      // never stored: the TMA store clips them)
+      const bool dead = qt0 + qd * 32 >= p.Nq;
+      float m_used = 0.f, l_run = 0.f;
+      // the previous item's O tile may still be leaving the staging area (== this warp's P rows)
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+
+      for (int j = 0; j < nkv; ++j, ++tc) {
+        mbar_wait(&s_full[g], tc & 1);
+        tc_fence_after();
+        if (!dead) {
+          const int nvalid = j + 1 == nkv ? nvalid_last : BKV;
+          const int nchunk = (nvalid + 31) >> 5;
+          float mx;
+          float2 l2;
+          // one sweep over the tile: exponentials against m_used -> bf16 P in shared memory; returns the row
+          // maximum (raw scores) in mx and the row sum in l2.  `init`: first tile, m_used := max of the first chunk.
+          auto sweep = [&](bool init) {
+            mx = -INFINITY;
+            l2 = make_float2(0.f, 0.f);
+            uint32_t v[2][32];
+            tmem_ld32(tmem_s + lane_addr, v[0]);
+            tmem_wait_ld_pin(v[0]);
+            if (init) {
+              float m0 = -INFINITY;
+              if (nvalid >= 32) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) m0 = fmaxf(m0, fmaxf(__uint_as_float(v[0][e]), __uint_as_float(v[0][e + 1])));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                  if (e < nvalid) m0 = fmaxf(m0, __uint_as_float(v[0][e]));
+              }
+              m_used = m0 * p.scale_log2;
+            }
+            const float2 nm2 = mk2(-m_used);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c < nchunk) {
+                if (c + 1 < 4 && c + 1 < nchunk) tmem_ld32(tmem_s + lane_addr + (c + 1) * 32, v[(c + 1) & 1]);
+                const uint32_t (&vc)[32] = v[c & 1];
+                uint32_t pk[16];
+                const int nv = nvalid - c * 32;
+                if (nv >= 32) {
+#pragma unroll
+                  for (int e = 0; e < 32; e += 2) {
+                    const float2 s2 = make_float2(__uint_as_float(vc[e]), __uint_as_float(vc[e + 1]));
+                    mx = fmaxf(mx, fmaxf(s2.x, s2.y));
+                    const float2 t = __ffma2_rn(s2, sc2, nm2);
+                    const float2 pp = (e >> 1) >= 16 - POLY ? exp2_poly2(t) : make_float2(fast_ex2(t.x), fast_ex2(t.y));
+                    l2 = __fadd2_rn(l2, pp);
+                    pk[e >> 1] = pack_bf16x2(pp.x, pp.y);
+                  }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 32; e += 2) {
+                    const float2 s2 = make_float2(__uint_as_float(vc[e]), __uint_as_float(vc[e + 1]));
+                    const float2 t = __ffma2_rn(s2, sc2, nm2);
+                    float2 pp = make_float2(fast_ex2(t.x), fast_ex2(t.y));
+                    if (e < nv) mx = fmaxf(mx, s2.x); else pp.x = 0.f;
+                    if (e + 1 < nv) mx = fmaxf(mx, s2.y); else pp.y = 0.f;
+                    l2 = __fadd2_rn(l2, pp);
+                    pk[e >> 1] = pack_bf16x2(pp.x, pp.y);
+                  }
+                }
+                uint8_t* blk = p_row + (c >> 1) * 16384;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q4);
+                  *reinterpret_cast<uint4*>(blk + ((chunk ^ row_sw) << 4)) =
+                      make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+                }
+                if (c + 1 < 4 && c + 1 < nchunk) tmem_wait_ld_pin(v[(c + 1) & 1]);
+              }
+            }
+          };
+          sweep(j == 0);
+          const float mt = mx * p.scale_log2;
+          if (__any_sync(0xffffffffu, mt - m_used > kRescaleThreshold)) {
+            // slow path: move the stabiliser up to the row maximum, rescale what has been accumulated, redo the tile
+            const float m_new = fmaxf(m_used, mt);
+            const float alpha = exp2f(m_used - m_new);
+            if (j > 0) {        // O_g is quiescent: PV_g(j-1) retired before S_g(j) was committed
+#pragma unroll
+              for (int c = 0; c < HD / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld32(tmem_o + lane_addr + c * 32, o);
+                tmem_wait_ld_pin(o);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                tmem_st32(tmem_o + lane_addr + c * 32, o);
+              }
+              tmem_wait_st();
+            }
+            l_run *= alpha;
+            m_used = m_new;
+            sweep(false);
+          }
+          l_run += l2.x + l2.y;
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive_warp(&p_full[g]);         // P_g(j) visible to the tensor core; S_g may be overwritten
+      }
+      // ---- epilogue: O / l  (the last PV of the item has retired; it was also the last reader of P)
+      mbar_wait(&pv_full[g], ic & 1);
+      ++ic;
+      tc_fence_after();
+      if (!dead) {
+        const float inv_l = 1.0f / l_run;
+#pragma unroll
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_o + lane_addr + c * 32, v);
+          tmem_wait_ld_pin(v);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q4 * 8 + e]) * inv_l;
+            const uint32_t chunk = static_cast<uint32_t>(c * 4 + q4);
+            uint8_t* dst = (RB == 128) ? o_stage + lane * 128 + ((chunk ^ lrow_sw) << 4)
+                                       : o_stage + lane * 64 + ((chunk ^ ((lane >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                        pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          }
+        }
+        // (the next PV_g that overwrites O_g waits for this warp's next p_full arrival: TMEM reuse is ordered)
+        tc_fence_before();
+        if (qt0 + row < p.Nq)
+          p.lse[(static_cast<long long>(b) * p.H + h) * p.Nq + qt0 + row] = (m_used + log2f(l_run)) * 0.69314718055994531f;
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&tmO, o_stage, 0, h, qt0 + qd * 32, b);
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
 int make_bnhd_tmap(CUtensorMap* tm, const void* ptr, int B, int H, int N, int hd, long long sb, long long sn,
                    long long sh, int box_rows, CUtensorMapDataType dt, int elem_bytes, int box_cols) {
   uint64_t dims[4] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(H), static_cast<uint64_t>(N),
@@ -749,29 +1139,47 @@ static bool strides_ok(long long sb, long long sn, long long sh) {
 }
 
 static int g_fwd_stagger = -1;     // < 0: derived from the problem size
-static bool g_force_general_fwd = false;   // profiling aid: ucf_debug_force_general_attn_fwd
+static int g_fwd_variant = 0;      // 0: single-sweep kernel (default); 1: round-1 kernels (short-key / general); profiling aid
+static int g_fwd_poly = 4;         // single-sweep kernel: exp2 pairs per 16 evaluated on the FMA pipe (0, 4 or 8)
+
+template <typename K>
+static int set_smem_attr(K kernel, int bytes, bool& done) {
+  if (done) return UCF_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_last_error("attention_fwd: smem attr: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  done = true;
+  return UCF_OK;
+}
 
 template <int HD>
 static int launch_attn_fwd(const CUtensorMap& tQ, const CUtensorMap& tK, const CUtensorMap& tV, const CUtensorMap& tO,
-                           const AttnFwdParams& p, cudaStream_t st) {
+                           AttnFwdParams p, cudaStream_t st) {
   using Cfg = AttnFwdCfg<HD>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) { set_last_error("attention_fwd: smem attr: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
-    attr = true;
-  }
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  if (p.Nk <= 2 * Cfg::BKV && !g_force_general_fwd) {
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaError_t e = cudaFuncSetAttribute(attn_fwd_short_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-      if (e != cudaSuccess) { set_last_error("attention_fwd: smem attr: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
-      attr2 = true;
+  int rc;
+  if (g_fwd_variant == 0) {
+    static bool a0 = false, a4 = false, a8 = false;
+    p.stagger_cycles = g_fwd_stagger >= 0 ? g_fwd_stagger : 600;
+    if (g_fwd_poly == 0) {
+      if ((rc = set_smem_attr(attn_fwd2_kernel<HD, 0>, Cfg::SMEM_BYTES, a0))) return rc;
+      attn_fwd2_kernel<HD, 0><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tQ, tK, tV, tO, p);
+    } else if (g_fwd_poly == 8) {
+      if ((rc = set_smem_attr(attn_fwd2_kernel<HD, 8>, Cfg::SMEM_BYTES, a8))) return rc;
+      attn_fwd2_kernel<HD, 8><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tQ, tK, tV, tO, p);
+    } else {
+      if ((rc = set_smem_attr(attn_fwd2_kernel<HD, 4>, Cfg::SMEM_BYTES, a4))) return rc;
+      attn_fwd2_kernel<HD, 4><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tQ, tK, tV, tO, p);
     }
+    return check_launch("attn_fwd2_kernel");
+  }
+  if (p.Nk <= 2 * Cfg::BKV && g_fwd_variant != 2) {
+    static bool attr2 = false;
+    if ((rc = set_smem_attr(attn_fwd_short_kernel<HD>, Cfg::SMEM_BYTES, attr2))) return rc;
     attn_fwd_short_kernel<HD><<<grid, Cfg::THREADS + 32, Cfg::SMEM_BYTES, st>>>(tQ, tK, tV, tO, p);
     return check_launch("attn_fwd_short_kernel");
   }
+  static bool attr = false;
+  if ((rc = set_smem_attr(attn_fwd_kernel<HD>, Cfg::SMEM_BYTES, attr))) return rc;
   attn_fwd_kernel<HD><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tQ, tK, tV, tO, p);
   return check_launch("attn_fwd_kernel");
 }
@@ -783,8 +1191,11 @@ using namespace ucf;
 static long long* g_fwd_timeline = nullptr;
 /* profiling aid (not part of the public header): device buffer of 64 int64 receiving clock64 stamps */
 extern "C" void ucf_debug_set_attn_fwd_timeline(void* dev_ptr) { g_fwd_timeline = static_cast<long long*>(dev_ptr); }
-/* profiling aid: 1 = always run the general (online-softmax) kernel, also for Nk <= 256 */
-extern "C" void ucf_debug_force_general_attn_fwd(int on) { ucf::g_force_general_fwd = on != 0; }
+/* profiling aids: variant 0 = single-sweep kernel (default), 1 = round-1 short-key / general kernels, 2 = round-1 general
+   kernel for every Nk; poly = exp2 pairs per 16 on the FMA pipe in the single-sweep kernel (0, 4, 8) */
+extern "C" void ucf_debug_set_attn_fwd_variant(int variant) { ucf::g_fwd_variant = variant; }
+extern "C" void ucf_debug_set_attn_fwd_poly(int pairs) { ucf::g_fwd_poly = pairs; }
+extern "C" void ucf_debug_force_general_attn_fwd(int on) { ucf::g_fwd_variant = on ? 2 : 0; }
 extern "C" void ucf_debug_set_attn_fwd_stagger(int cycles) { ucf::g_fwd_stagger = cycles; }
 
 extern "C" int ucf_attention_fwd(const void* q, const void* k, const void* v, void* o, float* lse,

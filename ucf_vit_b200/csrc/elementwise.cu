@@ -105,17 +105,22 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
 
 // x [B, C, G0*p, G1*p(, G2*p)] -> out bf16 [B*G0*G1(*G2), C*p^dims].  One thread produces 8
 // consecutive K elements (one 16-byte store); the innermost patch axis (p) is contiguous in x.
-template <bool X_BF16>
+// VEC consecutive elements of one patch row per thread (VEC | p; VEC == 8: one 16-byte store, the layout every
+// ViT-B/16-style model uses; smaller VEC serves patch sizes 4 / 2 / odd and cropped images whose rows are not
+// 16-byte aligned).  S0/S1/S2 are the image's REAL spatial sizes (>= G*p: like the strided convolution, pixels
+// past the last whole patch are ignored); ldo >= K is the output row pitch.
+template <bool X_BF16, int VEC>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int G0, int G1,
-                int G2, int p, int dims, long long total_vec) {
+                int G2, int p, int dims, int S0, int S1, int S2, long long ldo, long long total_vec) {
   const int Kp = (dims == 2) ? p * p : p * p * p;
   const int K = C * Kp;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total_vec; t += stride) {
-    const long long e = t * 8;
+    const long long e = t * VEC;
     const long long row = e / K;
     int k = static_cast<int>(e - row * K);
+    const int kcol = k;
     const int c = k / Kp; k -= c * Kp;
     long long src;
     if (dims == 2) {
@@ -124,8 +129,7 @@ patchify_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int
       const long long r2 = row / G1;
       const int g0 = static_cast<int>(r2 % G0);
       const long long b = r2 / G0;
-      const long long W = static_cast<long long>(G1) * p, Hh = static_cast<long long>(G0) * p;
-      src = ((b * C + c) * Hh + (static_cast<long long>(g0) * p + p0)) * W + static_cast<long long>(g1) * p + p1;
+      src = ((b * C + c) * S0 + (static_cast<long long>(g0) * p + p0)) * S1 + static_cast<long long>(g1) * p + p1;
     } else {
       const int p0 = k / (p * p); k -= p0 * p * p;
       const int p1 = k / p, p2 = k - p1 * p;
@@ -134,20 +138,31 @@ patchify_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int
       const int g1 = static_cast<int>(r2 % G1); r2 /= G1;
       const int g0 = static_cast<int>(r2 % G0);
       const long long b = r2 / G0;
-      const long long Z = static_cast<long long>(G2) * p, W = static_cast<long long>(G1) * p, Hh = static_cast<long long>(G0) * p;
-      src = (((b * C + c) * Hh + (static_cast<long long>(g0) * p + p0)) * W + (static_cast<long long>(g1) * p + p1)) * Z +
+      src = (((b * C + c) * S0 + (static_cast<long long>(g0) * p + p0)) * S1 + (static_cast<long long>(g1) * p + p1)) * S2 +
             static_cast<long long>(g2) * p + p2;
     }
-    float f[8];
-    if (X_BF16) {
-      const uint4 r = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + src));
-      *reinterpret_cast<uint4*>(out + e) = r;
+    __nv_bfloat16* dst = out + row * ldo + kcol;
+    if (VEC == 8) {
+      if (X_BF16) {
+        *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + src));
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + src));
+        const float4 b2 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + src + 4));
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b2.x, b2.y),
+                                                    pack_bf16x2(b2.z, b2.w));
+      }
+    } else if (VEC == 4) {
+      if (X_BF16) {
+        *reinterpret_cast<uint2*>(dst) = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + src));
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + src));
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+      }
     } else {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + src));
-      const float4 b2 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + src + 4));
-      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b2.x; f[5] = b2.y; f[6] = b2.z; f[7] = b2.w;
-      uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-      *reinterpret_cast<uint4*>(out + e) = o;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        dst[i] = X_BF16 ? reinterpret_cast<const __nv_bfloat16*>(x)[src + i]
+                        : __float2bfloat16_rn(reinterpret_cast<const float*>(x)[src + i]);
     }
   }
 }
@@ -315,20 +330,42 @@ extern "C" int ucf_colsum_bf16(const void* x, float* out, long long M, int N, lo
 }
 
 extern "C" int ucf_patchify(const void* x, void* out, int B, int C, int G0, int G1, int G2, int p, int dims,
-                            int x_dtype, void* stream) {
+                            int S0, int S1, int S2, long long ld_out, int x_dtype, void* stream) {
   if (dims != 2 && dims != 3) { set_last_error("patchify: dims must be 2 or 3"); return UCF_ERR_BAD_ARG; }
-  if (p % 8 != 0) { set_last_error("patchify: patch size %d must be a multiple of 8", p); return UCF_ERR_BAD_ARG; }
-  if (dims == 2) G2 = 1;
+  if (p <= 0 || B < 0 || C <= 0 || G0 < 0 || G1 < 0 || G2 < 0) { set_last_error("patchify: bad shape"); return UCF_ERR_BAD_ARG; }
+  if (dims == 2) { G2 = 1; S2 = 1; }
+  if (S0 < G0 * p || S1 < G1 * p || (dims == 3 && S2 < G2 * p)) {
+    set_last_error("patchify: image %dx%dx%d is smaller than grid x patch", S0, S1, S2); return UCF_ERR_BAD_ARG;
+  }
   const long long Kp = (dims == 2) ? 1LL * p * p : 1LL * p * p * p;
-  const long long total = 1LL * B * G0 * G1 * G2 * C * Kp;
+  const long long K = C * Kp;
+  if (ld_out < K || ld_out % 8) { set_last_error("patchify: ld_out must be >= K and a multiple of 8"); return UCF_ERR_BAD_ARG; }
+  const long long rows = 1LL * B * G0 * G1 * G2;
+  const long long total = rows * K;
   if (total <= 0) return UCF_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const long long nvec = total / 8;
+  if (ld_out > K) {      // zero the pad columns (the GEMM's K extent is ld_out)
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(rows) * ld_out, st);
+    if (e != cudaSuccess) { set_last_error("patchify: memset: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  }
+  // widest vector that divides the patch row and keeps every source / destination address aligned
+  const int esz = x_dtype == UCF_DTYPE_BF16 ? 2 : 4;
+  const long long inner = dims == 2 ? S1 : S2;
+  int vec = 1;
+  for (int v = 8; v >= 4; v >>= 1) {
+    const uintptr_t align = v * esz > 16 ? 16 : v * esz;          // widest single load the kernel issues
+    if (p % v == 0 && inner % v == 0 && reinterpret_cast<uintptr_t>(x) % align == 0) { vec = v; break; }
+  }
+  if ((reinterpret_cast<uintptr_t>(out) & 15)) { set_last_error("patchify: out must be 16-byte aligned"); return UCF_ERR_BAD_ARG; }
+  const long long nvec = total / vec;
   const int grid = ew_grid(nvec, 256);
-  if (x_dtype == UCF_DTYPE_BF16)
-    patchify_kernel<true><<<grid, 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(out), B, C, G0, G1, G2, p, dims, nvec);
-  else
-    patchify_kernel<false><<<grid, 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(out), B, C, G0, G1, G2, p, dims, nvec);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+#define UCF_PATCHIFY(BF_, V_) patchify_kernel<BF_, V_><<<grid, 256, 0, st>>>(x, o, B, C, G0, G1, G2, p, dims, S0, S1, S2, ld_out, nvec)
+  const bool bf = x_dtype == UCF_DTYPE_BF16;
+  if (vec == 8) { if (bf) UCF_PATCHIFY(true, 8); else UCF_PATCHIFY(false, 8); }
+  else if (vec == 4) { if (bf) UCF_PATCHIFY(true, 4); else UCF_PATCHIFY(false, 4); }
+  else { if (bf) UCF_PATCHIFY(true, 1); else UCF_PATCHIFY(false, 1); }
+#undef UCF_PATCHIFY
   return check_launch("patchify_kernel");
 }
 

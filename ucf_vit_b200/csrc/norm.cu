@@ -322,6 +322,88 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
   }
 }
 
+// Wide rows (2048 < D <= 8192: the adaptive token_embeds' LayerNorm over patch_dim = C*p^d, 4096 for 3-D p = 16,
+// arch.py:282-289).  Same algebra as above, but the row no longer fits in registers: a warp walks its row in 256-column
+// steps twice (the second pass hits L1/L2) and the per-column dgamma / dbeta partials live in shared memory
+// (shared atomics: different warps of the CTA hit the same column).  One LayerNorm per step on this path.
+template <bool P_BF16>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_wide_kernel(const void* __restrict__ dy, const void* __restrict__ x, const void* __restrict__ gamma,
+                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                          const void* __restrict__ dres, void* __restrict__ dx, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, long long rows, int D) {
+  extern __shared__ float red[];   // [2][D] dgamma / dbeta partials, then [D] gamma as fp32
+  float* red_g = red;
+  float* red_b = red + D;
+  float* gam_s = red + 2 * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    red_g[i] = 0.f; red_b[i] = 0.f;
+    gam_s[i] = gamma ? (P_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(gamma)[i])
+                               : reinterpret_cast<const float*>(gamma)[i])
+                     : 1.0f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const float inv_d = 1.0f / static_cast<float>(D);
+  const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(dres);
+  __nv_bfloat16* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
+  const bool want_pg = dgamma != nullptr || dbeta != nullptr;
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    const float mu = mean[row], rs = rstd[row];
+    const long long base = row * D;
+    float s1 = 0.f, s2 = 0.f;
+    for (int col = lane * 8; col < D; col += 256) {
+      float2 dyv[4], xv[4];
+      unpack4(__ldg(reinterpret_cast<const uint4*>(dyp + base + col)), dyv);
+      unpack4(__ldg(reinterpret_cast<const uint4*>(xp + base + col)), xv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float g0 = gam_s[col + 2 * e], g1 = gam_s[col + 2 * e + 1];
+        const float t0 = dyv[e].x * g0, t1 = dyv[e].y * g1;
+        s1 += t0 + t1;
+        s2 = fmaf(t0, xv[e].x, fmaf(t1, xv[e].y, s2));
+        if (want_pg) {
+          atomicAdd(&red_g[col + 2 * e], rs * (dyv[e].x * xv[e].x) - rs * mu * dyv[e].x);
+          atomicAdd(&red_g[col + 2 * e + 1], rs * (dyv[e].y * xv[e].y) - rs * mu * dyv[e].y);
+          atomicAdd(&red_b[col + 2 * e], dyv[e].x);
+          atomicAdd(&red_b[col + 2 * e + 1], dyv[e].y);
+        }
+      }
+    }
+    const float S1 = warp_sum(s1);
+    const float S2 = rs * (warp_sum(s2) - mu * S1);
+    const float Bc = -rs * rs * S2 * inv_d;
+    const float Cc = -Bc * mu - rs * S1 * inv_d;
+    for (int col = lane * 8; col < D; col += 256) {
+      float2 dyv[4], xv[4], o[4];
+      unpack4(__ldg(reinterpret_cast<const uint4*>(dyp + base + col)), dyv);
+      unpack4(__ldg(reinterpret_cast<const uint4*>(xp + base + col)), xv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        o[e].x = fmaf(dyv[e].x * gam_s[col + 2 * e], rs, fmaf(xv[e].x, Bc, Cc));
+        o[e].y = fmaf(dyv[e].y * gam_s[col + 2 * e + 1], rs, fmaf(xv[e].y, Bc, Cc));
+      }
+      if (dres) {
+        float2 r[4];
+        unpack4(__ldg(reinterpret_cast<const uint4*>(rp + base + col)), r);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { o[e].x += r[e].x; o[e].y += r[e].y; }
+      }
+      *reinterpret_cast<uint4*>(dxp + base + col) = pack4(o);
+    }
+  }
+  if (!want_pg) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    if (dgamma) atomicAdd(&dgamma[i], red_g[i]);
+    if (dbeta) atomicAdd(&dbeta[i], red_b[i]);
+  }
+}
+
 static int ln_grid(long long rows) {
   const long long warps_per_block = 8;
   long long blocks = (rows + warps_per_block - 1) / warps_per_block;
@@ -367,12 +449,26 @@ extern "C" int ucf_layernorm_bwd(const void* dy, const void* x, const void* gamm
                                  const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
                                  long long rows, int D, int param_dtype, void* stream) {
   if (rows <= 0) return UCF_OK;
-  if (D <= 0 || D % 8 != 0 || D > 2048) {
-    set_last_error("layernorm_bwd: D=%d must be a multiple of 8 and <= 2048", D);
+  if (D <= 0 || D % 8 != 0 || D > 8192) {
+    set_last_error("layernorm_bwd: D=%d must be a multiple of 8 and <= 8192", D);
     return UCF_ERR_BAD_ARG;
   }
   if (!dy || !x || !mean || !rstd || !dx) { set_last_error("layernorm_bwd: null pointer"); return UCF_ERR_BAD_ARG; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (D > 2048) {
+    long long wblocks = (rows + 7) / 8;
+    const long long wcap = static_cast<long long>(ucf::num_sms()) * 2;
+    if (wblocks > wcap) wblocks = wcap;
+    const size_t wsmem = 3 * static_cast<size_t>(D) * sizeof(float);
+    if (param_dtype == UCF_DTYPE_BF16) {
+      cudaFuncSetAttribute(layernorm_bwd_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wsmem));
+      layernorm_bwd_wide_kernel<true><<<static_cast<int>(wblocks), 256, wsmem, st>>>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, D);
+    } else {
+      cudaFuncSetAttribute(layernorm_bwd_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(wsmem));
+      layernorm_bwd_wide_kernel<false><<<static_cast<int>(wblocks), 256, wsmem, st>>>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, D);
+    }
+    return check_launch("layernorm_bwd_wide_kernel");
+  }
   // fewer, fatter blocks than forward: every block ends with 2*D global atomics
   long long blocks = (rows + 7) / 8;
   const long long cap = static_cast<long long>(ucf::num_sms()) * (D <= 768 ? 2 : 1);   // resident CTAs per SM, persistent

@@ -471,15 +471,23 @@ class _PatchifyFn(torch.autograd.Function):
         shp, p = ctx.shape, ctx.p
         B, C = shp[:2]
         G = [s // p for s in shp[2:]]
-        if len(G) == 2:
-            dx = g.view(B, G[0], G[1], C, p, p).permute(0, 3, 1, 4, 2, 5).reshape(shp)
+        nd = len(G)
+        g = g[:, :C * p ** nd]                                   # drop the K pad columns
+        if nd == 2:
+            core = g.reshape(B, G[0], G[1], C, p, p).permute(0, 3, 1, 4, 2, 5).reshape(B, C, G[0] * p, G[1] * p)
         else:
-            dx = g.view(B, G[0], G[1], G[2], C, p, p, p).permute(0, 4, 1, 5, 2, 6, 3, 7).reshape(shp)
-        return dx.to(ctx.dt), None
+            core = g.reshape(B, G[0], G[1], G[2], C, p, p, p).permute(0, 4, 1, 5, 2, 6, 3, 7).reshape(
+                B, C, G[0] * p, G[1] * p, G[2] * p)
+        if tuple(core.shape) != tuple(shp):                      # cropped border pixels get no gradient
+            dx = core.new_zeros(shp)
+            dx[(slice(None), slice(None)) + tuple(slice(0, gi * p) for gi in G)] = core
+            core = dx
+        return core.to(ctx.dt), None
 
 
 def patchify(x, p):
-    """[B,C,H,W(,Z)] -> bf16 [B*L, C*p^d], K ordered (c, p0, p1(, p2)) like conv.weight.view(D,-1)."""
+    """[B,C,H,W(,Z)] -> bf16 [B*L, K8], K = C*p^d ordered (c, p0, p1(, p2)) like conv.weight.view(D,-1), zero-padded to
+    K8 = ceil(K/8)*8 columns; pixels past the last whole patch are ignored (like the strided convolution)."""
     if x.requires_grad:
         return _PatchifyFn.apply(x, p)
     with torch.no_grad():

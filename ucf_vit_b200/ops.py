@@ -146,19 +146,23 @@ def colsum(x, out=None, accumulate=False):
 
 
 def patchify(x, p):
-    """x [B,C,H,W] or [B,C,H,W,Z] (fp32/bf16, contiguous) -> bf16 [B*L, C*p^dims], K order (c,p0,p1[,p2])."""
+    """x [B,C,H,W] or [B,C,H,W,Z] (fp32/bf16, contiguous) -> bf16 [B*L, K8], K = C*p^dims ordered (c,p0,p1[,p2]) and
+    K8 = K rounded up to a multiple of 8 (zero pad columns; the GEMM's K extent).  Like Conv(k = s = p), pixels past
+    the last whole patch are ignored."""
     _require_cuda(x)
     assert x.is_contiguous()
     dims = x.dim() - 2
     B, C = x.shape[:2]
-    G = [s // p for s in x.shape[2:]]
-    assert all(g * p == s for g, s in zip(G, x.shape[2:])), "spatial size must be a multiple of the patch size"
+    S = list(x.shape[2:])
+    G = [s // p for s in S]
     L_ = 1
     for g in G:
         L_ *= g
-    out = torch.empty((B * L_, C * p ** dims), dtype=torch.bfloat16, device=x.device)
+    K = C * p ** dims
+    K8 = -(-K // 8) * 8
+    out = torch.empty((B * L_, K8), dtype=torch.bfloat16, device=x.device)
     L.check(L.lib().ucf_patchify(x.data_ptr(), out.data_ptr(), B, C, G[0], G[1], G[2] if dims == 3 else 1, p, dims,
-                                 _dt(x), _stream()), "patchify")
+                                 S[0], S[1], S[2] if dims == 3 else 1, K8, _dt(x), _stream()), "patchify")
     return out
 
 

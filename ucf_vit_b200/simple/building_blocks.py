@@ -70,8 +70,11 @@ class PatchEmbed(nn.Module):
         p = _uniform(self.patch_size)
         D = self.proj.out_channels
         B = x.shape[0]
-        rows = UF.patchify(x, p)                                   # [B*L, C*p^d] bf16
-        y = UF.linear(rows, self.proj.weight.view(D, -1), self.proj.bias)
+        rows = UF.patchify(x, p)                                   # [B*L, K8] bf16, K8 = C*p^d rounded up to 8
+        w = self.proj.weight.view(D, -1)
+        if rows.shape[1] != w.shape[1]:                            # K not a multiple of 8 (e.g. C = 1, p = 2): zero columns
+            w = nn.functional.pad(w, (0, rows.shape[1] - w.shape[1]))
+        y = UF.linear(rows, w, self.proj.bias)
         y = y.view(B, -1, D)
         if not isinstance(self.norm, nn.Identity):
             y = _apply_norm(self.norm, y)
