@@ -71,9 +71,12 @@ def case(B, N, H, hd, packed=True, do_bwd=True, Nk=None, jump=False):
             dq, dk, dv = ops.attention_bwd(q, k, v, o, do, lse, scale)
         torch.cuda.synchronize()
         oref.backward(do.float())
-        report(f"attn bwd dq  {tag}", dq, qf.grad, 2e-2)
-        report(f"attn bwd dk  {tag}", dk, kf.grad, 2e-2)
-        report(f"attn bwd dv  {tag}", dv, vf.grad, 2e-2)
+        # jump rows are nearly one-hot: dS = P o (dP - delta) cancels to a few ulps of the bf16-rounded O that delta is
+        # taken from, so the gate is wider there (the same holds for any kernel that keeps O in bf16)
+        tol = 4e-2 if jump else 2e-2
+        report(f"attn bwd dq  {tag}", dq, qf.grad, tol)
+        report(f"attn bwd dk  {tag}", dk, kf.grad, tol)
+        report(f"attn bwd dv  {tag}", dv, vf.grad, tol)
 
 
 _flush = None
@@ -115,12 +118,12 @@ def bench(B, N, H, hd, variants=False):
     ms = timeit(f2); res["ucf bwd"] = ms
     print(f"ucf  bwd {shape}: {ms*1e3:8.1f} us  {bfl/ms/1e9:7.1f} TFLOP/s  (delta + dq-cast passes included)", flush=True)
     if variants:
-        for var, poly in ((0, 0), (0, 8), (1, 4)):
-            lib.ucf_debug_set_attn_fwd_variant(var); lib.ucf_debug_set_attn_fwd_poly(poly)
+        for poly in (0, 8):
+            lib.ucf_debug_set_attn_fwd_poly(poly)
             ms = timeit(f1)
-            print(f"ucf  fwd {shape} variant={var} poly={poly}: {ms*1e3:8.1f} us  {ffl/ms/1e9:7.1f} TFLOP/s", flush=True)
-        lib.ucf_debug_set_attn_fwd_variant(0); lib.ucf_debug_set_attn_fwd_poly(4)
-        for st in (0, 300, 1000, 1500):
+            print(f"ucf  fwd {shape} poly={poly}: {ms*1e3:8.1f} us  {ffl/ms/1e9:7.1f} TFLOP/s", flush=True)
+        lib.ucf_debug_set_attn_fwd_poly(4)
+        for st in (0, 250, 1000):
             lib.ucf_debug_set_attn_fwd_stagger(st)
             ms = timeit(f1)
             print(f"ucf  fwd {shape} stagger={st}: {ms*1e3:8.1f} us", flush=True)
