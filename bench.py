@@ -1,15 +1,17 @@
 #!/usr/bin/env python
-"""Headline benchmark: ViT-B/16 ImageNet-shape classification training step (BASELINE.json
-configs[1]) on N B200s, data-parallel, through the reference's module API backed by this
-package's sm_100a kernels.
+"""Benchmarks of the B200-native ViT training hot path, one workload per BASELINE.json config.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--config NAME] [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = forward + cross-entropy + backward + AdamW update on one synthetic batch of
-256 images per GPU (224x224x3), bf16 tensor-core math with fp32 accumulation and fp32 master
-weights.  Prints ONE JSON line (see DESIGN.md "Measurement").
+Default (--config vit_b16) is the headline: BASELINE.json configs[1], the ViT-B/16 ImageNet-shape classification
+training step on N B200s, data-parallel, through the reference's module API backed by this package's sm_100a kernels.
+Other configs (bench_workloads.py): vit_tiny (configs[0]), mae_vitl_fsdp (configs[2]), unetr_128 (configs[3]),
+sap_4096_L4096 / sap_4096_L1024 and diffusion_fsdp (configs[4]).
 
-  value     whole-job images/s, inputs resident in HBM, K steps timed with CUDA events between
+One "step" = forward + loss + backward + AdamW update on one synthetic batch per GPU, bf16 tensor-core math with fp32
+accumulation and fp32 master weights.  Prints ONE JSON line (see DESIGN.md "Measurement").
+
+  value     whole-job samples/s, inputs resident in HBM, K steps timed with CUDA events between
             barrier + synchronize pairs, max over ranks
   e2e       same metric through the public module API from pinned HOST buffers: every step
             copies its batch host->device (prefetched on a side stream) and reads the loss back
@@ -34,21 +36,12 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-WORKLOAD = "ViT-B/16 ImageNet-shape classification train step (fwd+CE+bwd+AdamW), 224x224x3, batch 256/GPU"
+import bench_workloads  # noqa: E402
+
+METRIC = "ViT train imgs/s at 1/2/4/8 B200; attn+MLP TFLOP/s vs bf16 peak"
+# kept for scripts that import them (the headline workload)
 CFG = dict(img_size=[224, 224], patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12)
 PER_GPU_BATCH = 256
-METRIC = "ViT train imgs/s at 1/2/4/8 B200; attn+MLP TFLOP/s vs bf16 peak"
-
-
-def flops_per_image_train(cfg=CFG):
-    """F_block = 24 N D^2 + 4 N^2 D, F_pe = 2 L K D, train = 3 x forward."""
-    D, depth = cfg["embed_dim"], cfg["depth"]
-    L = (cfg["img_size"][0] // cfg["patch_size"]) ** 2
-    N = L + 1
-    K = cfg["in_chans"] * cfg["patch_size"] ** 2
-    f_block = 24 * N * D * D + 4 * N * N * D
-    f_model = 2 * L * K * D + depth * f_block + 2 * D * cfg["num_classes"]
-    return 3 * f_model, 3 * depth * f_block
 
 
 def measured_peaks():
@@ -62,52 +55,20 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: oracle restatement of the reference path on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_rate(batch, steps, warmup):
-    """imgs/s of the reference algorithm (oracle port, fp32, torch CPU kernels, all threads)."""
-    from oracle import vit_ref as R
-    from ucf_vit_b200.simple import arch as A      # used ONLY to obtain reference-shaped initial weights on CPU
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    shapes_model = A.VIT(**CFG, mlp_ratio=4, class_token=True, twoD=True, default_vars=["r", "g", "b"])
-    sd = {k: v.detach().clone().requires_grad_(True) for k, v in shapes_model.state_dict().items()
-          if not k.startswith("token_embeds.")}
-    del shapes_model
-    cfg = dict(CFG)
-    opt = torch.optim.AdamW([v for v in sd.values()], lr=1e-4, betas=(0.9, 0.95), weight_decay=1e-5)
-    g = torch.Generator().manual_seed(0)
-    x = torch.rand(batch, 3, 224, 224, generator=g) * 255.0
-    y = torch.randint(0, CFG["num_classes"], (batch,), generator=g)
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        logits = R.vit_forward(x, sd, cfg)
-        loss = torch.nn.functional.cross_entropy(logits, y)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    return batch / statistics.median(times), cores, statistics.median(times)
-
-
-def run_reference_arm(args):
+def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 16
     steps = max(1, min(args.steps, 3))
     warm = 1
-    rate, cores, sec = cpu_reference_step_rate(batch, steps, warm)
+    rate, cores, sec, sample = wl.cpu_rate(steps, warm)
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": wl.unit, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"batch {batch} per step on the host CPU"},
-        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} timed + {warm} warm-up steps of batch {batch} (same model, fp32, oracle/vit_ref.py + torch autograd + AdamW)"},
-        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": wl.workload, "name": wl.name, "sample": f"batch {wl.cpu_batch} per step on the host CPU"},
+        "cpu_baseline": {"value": rate, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -219,36 +180,39 @@ class ClockSampler:
 
 
 class GemmTimer:
-    """Wraps ops.gemm: brackets every launch with CUDA events on the launching (current) stream."""
+    """Per-launch CUDA-event timing of the GEMM family, taken inside the library on the launching stream (the launches
+    come from ucf_block_fwd / ucf_block_bwd in C++ as well as from the Python op wrappers)."""
 
     def __init__(self):
-        from ucf_vit_b200 import ops
-        self.ops, self.orig, self.records, self.enabled = ops, ops.gemm, [], False
+        import ctypes
+        from ucf_vit_b200 import _lib
+        self.lib, self.ct, self.enabled_ = _lib.lib(), ctypes, False
+        self.lib.ucf_debug_gemm_timing.argtypes = [ctypes.c_int]
+        self.lib.ucf_debug_gemm_timing_summary.argtypes = [ctypes.c_void_p] * 3
 
     def install(self):
-        def timed(a, b, *, M, N, K, **kw):
-            if not self.enabled:
-                return self.orig(a, b, M=M, N=N, K=K, **kw)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = self.orig(a, b, M=M, N=N, K=K, **kw)
-            e1.record()
-            self.records.append((2.0 * M * N * K, e0, e1))
-            return r
-        self.ops.gemm = timed
+        pass
+
+    @property
+    def enabled(self):
+        return self.enabled_
+
+    @enabled.setter
+    def enabled(self, v):
+        self.enabled_ = bool(v)
+        self.lib.ucf_debug_gemm_timing(int(bool(v)))
 
     def summary(self):
-        fl = sum(r[0] for r in self.records)
-        ms = sum(r[1].elapsed_time(r[2]) for r in self.records)
-        return fl, ms, len(self.records)
+        ct = self.ct
+        fl, ms, n = ct.c_double(0), ct.c_double(0), ct.c_longlong(0)
+        self.lib.ucf_debug_gemm_timing_summary(ct.byref(fl), ct.byref(ms), ct.byref(n))
+        return fl.value, ms.value, n.value
 
 
-def run_gpu_arm(args):
+def run_gpu_arm(args, wl):
     import torch.distributed as dist
     from ucf_vit_b200 import _lib
-    from ucf_vit_b200.simple.arch import VIT
-    from ucf_vit_b200.utils.fused_attn import FusedAttn
-    from ucf_vit_b200.utils.misc import configure_optimizer
+    from ucf_vit_b200.dataloaders.prefetch import DevicePrefetcher
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -257,34 +221,25 @@ def run_gpu_arm(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    need_pg = world > 1 or wl.uses_fsdp
+    if need_pg:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        os.environ.setdefault("MASTER_PORT", "29533")
+        if world == 1:
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+        else:
+            dist.init_process_group("nccl", device_id=dev)
 
-    torch.manual_seed(0)
-    model = VIT(**CFG, mlp_ratio=4, class_token=True, twoD=True, default_vars=["r", "g", "b"],
-                FusedAttn_option=FusedAttn.FLASH).to(dev).train()
-    net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
-                                                        bucket_cap_mb=64)
-    opt = configure_optimizer(model, 1e-4, 0.9, 0.95, 1e-5, fused="ucf" if args.optimizer == "ucf" else True)
-    variables = ["r", "g", "b"]
-    B = PER_GPU_BATCH
-    g = torch.Generator().manual_seed(1234 + rank)
-    x_host = (torch.rand(B, 3, 224, 224, generator=g) * 255.0).pin_memory()      # raw 0..255 pixels as float (catsdogs path)
-    y_host = torch.randint(0, CFG["num_classes"], (B,), generator=g).pin_memory()
-    x_dev = x_host.to(dev)
-    y_dev = y_host.to(dev)
-    lossf = torch.nn.CrossEntropyLoss()
+    wl.build(dev, world, local, rank, args)
+    host = wl.host_batch(rank)
+    resident = tuple(t.to(dev) for t in host)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if getattr(wl, "flush_l2", False) else None
 
-    def step(x, y):
-        logits = net(x, variables)
-        loss = lossf(logits.float(), y)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        return loss
+    def step(batch):
+        if flush is not None:
+            flush.zero_()
+        return wl.step(*batch)
 
     def fence():
         if world > 1:
@@ -292,18 +247,16 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     timer = GemmTimer()
-    if rank == 0:
-        timer.install()
 
     # ---------------- resident-input arm
     sampler = ClockSampler(local)
     sampler.start()
     for _ in range(args.warmup):
-        step(x_dev, y_dev)
+        step(resident)
     fence()
     # host cost of enqueueing ONE (untimed) step into an empty launch queue: is the step launch-bound?
     t_host0 = time.perf_counter()
-    step(x_dev, y_dev)
+    step(resident)
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
     fence()
     n0 = _lib.launch_count()
@@ -313,7 +266,7 @@ def run_gpu_arm(args):
     sampler.mark()
     e0.record()
     for _ in range(args.steps):
-        loss = step(x_dev, y_dev)
+        loss = step(resident)
     e1.record()
     fence()
     timer.enabled = False
@@ -325,11 +278,9 @@ def run_gpu_arm(args):
     # ---------------- end-to-end arm: pinned host batch -> device every step, loss read back every step
     # host batches (pinned) -> DevicePrefetcher (the package's loader hand-off: H2D of batch k+1 on a side stream
     # under step k) -> step -> loss read back
-    from ucf_vit_b200.dataloaders.prefetch import DevicePrefetcher
-
     def e2e_steps(n):
-        for x, y in DevicePrefetcher(((x_host, y_host) for _ in range(n)), dev):
-            l = step(x, y)
+        for batch in DevicePrefetcher((host for _ in range(n)), dev):
+            l = step(tuple(batch))
             _ = l.item()                      # device -> host read of the step's result
 
     e2e_steps(2)
@@ -346,42 +297,43 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = t.tolist()
+    extras = wl.extras(dev, args) if rank == 0 else {}
     if rank != 0:
-        if world > 1:
+        if need_pg:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
     ms_step = ms_total / args.steps
-    imgs = B * world
-    value = imgs / (ms_step * 1e-3)
-    e2e_value = imgs / (ms_e2e / args.steps * 1e-3)
-    f_img, f_blocks = flops_per_image_train()
+    samples = wl.batch * world
+    value = samples / (ms_step * 1e-3)
+    e2e_value = samples / (ms_e2e / args.steps * 1e-3)
+    f_sample, f_blocks = wl.flops()
     gemm_fl, gemm_ms, gemm_n = timer.summary()
     peak, peak_src = measured_peaks()
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(tpath):
+    if wl.name == "vit_b16" and os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             traffic = None
 
     line = {
-        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": imgs, "parallelism": f"dp{world}",
-                   "l2_policy": "per-step inputs (154 MB) and activations (>10 GB) exceed the 126 MB L2",
-                   "optimizer": ("AdamW, ucf_adamw_multi kernel" if args.optimizer == "ucf" else "AdamW, torch fused kernel") +
+        "config": {"workload": wl.workload, "name": wl.name, "global_batch": samples, "parallelism": wl.parallelism(world),
+                   "l2_policy": wl.l2_policy,
+                   "optimizer": ("AdamW, ucf_adamw_multi kernel" if args.optimizer == "ucf" else "AdamW, torch kernel") +
                                 ", fp32 master weights", "loss_final": final_loss},
-        "model_tflops": value * f_img / 1e12,
+        "model_tflops": value * f_sample / 1e12,
         "attn_mlp_tflops": value * f_blocks / 1e12,
         "attn_mlp_frac_of_peak": value * f_blocks / 1e12 / (peak * world),
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                    "samples": clocks["samples"], "power_w_max": clocks.get("power_w_max")},
-        "e2e": {"value": e2e_value, "unit": "images/s",
-                "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8) * world,
+        "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": int(h2d_bytes) * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
@@ -390,33 +342,42 @@ def run_gpu_arm(args):
                      "traffic": traffic, "peak_source": peak_src, "launches_timed": gemm_n,
                      "share_of_step": gemm_ms / ms_total if ms_total > 0 else None},
     }
+    if extras:
+        line["extras"] = extras
+        if wl.name == "unetr_128":       # the decoder's FLOPs are known only after the counter ran
+            f_sample, _ = wl.flops()
+            line["model_tflops"] = value * f_sample / 1e12
     if world == 1 and not args.no_cpu_baseline:
         try:
-            rate, cores, sec = cpu_reference_step_rate(16, 2, 1)
-            line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
-                                    "sample": "2 timed + 1 warm-up steps of batch 16 of the same model (fp32, oracle/vit_ref.py + torch autograd + AdamW) on the GPU box host"}
+            rate, cores, sec, sample = wl.cpu_rate(2 if wl.name.startswith("vit") else 1, 1 if wl.name.startswith("vit") else 0)
+            line["cpu_baseline"] = {"value": rate, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample + " on the GPU box host"}
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
     print(json.dumps(line), flush=True)
-    if world > 1:
+    if need_pg:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    reg = bench_workloads.registry()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="vit_b16", choices=sorted(reg))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bf16-allreduce", action="store_true", help="DDP gradient all-reduce in bf16 (torch's bf16_compress_hook)")
     ap.add_argument("--optimizer", default="ucf", choices=["torch", "ucf"],
-                    help="AdamW update: torch's fused CUDA kernel or this package's ucf_adamw_multi")
+                    help="AdamW update: torch's kernel or this package's ucf_adamw_multi")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    wl = reg[args.config]
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, wl)
     else:
-        run_gpu_arm(args)
+        run_gpu_arm(args, wl)
 
 
 if __name__ == "__main__":

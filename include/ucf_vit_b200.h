@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UCF_ABI_VERSION 2
+#define UCF_ABI_VERSION 3
 
 enum { UCF_DTYPE_F32 = 0, UCF_DTYPE_BF16 = 1, UCF_DTYPE_U8 = 2, UCF_DTYPE_F64 = 3 };
 enum { UCF_LAYOUT_K_MAJOR = 0, UCF_LAYOUT_MN_MAJOR = 1 };
@@ -104,6 +104,46 @@ int ucf_attention_bwd(const void* q, const void* k, const void* v, const void* o
                       long long dk_sb, long long dk_sn, long long dk_sh,
                       long long dv_sb, long long dv_sn, long long dv_sh,
                       float scale, void* stream);
+
+/* ---- one C call per transformer block and direction ------------------------------------------
+ * Replaces Block.forward (simple/building_blocks.py:236-239: x + attn(norm1(x)), then + mlp(norm2(.))) and the
+ * autograd graph torch builds for it, in the configuration every reference driver uses (no qk_norm, no LayerScale,
+ * drop rates 0, GELU(erf), head_dim 32 or 64).  The kernels are the ones behind ucf_layernorm_*, ucf_gemm_bf16 and
+ * ucf_attention_*; what these entry points remove is the per-kernel host cost of a Python caller (one foreign call
+ * instead of 8 forward / 15 backward).  M = B*N tokens.  Every buffer is caller-provided. */
+typedef struct {
+  int B, N, D, H, hidden;        /* batch, tokens per sample, width, heads, MLP width; head_dim = D/H */
+  float eps1, eps2;              /* LayerNorm epsilons */
+  int ln_dtype, bias_dtype;      /* UCF_DTYPE_F32 | UCF_DTYPE_BF16 of the LayerNorm parameters / of the Linear biases */
+  const void *n1_w, *n1_b, *n2_w, *n2_b;           /* [D] (biases may be NULL) */
+  const void *qkv_b, *proj_b, *fc1_b, *fc2_b;      /* [3D], [D], [hidden], [D] or NULL */
+  const void *qkv_w, *proj_w, *fc1_w, *fc2_w;      /* bf16 compute copies [3D,D], [D,D], [hidden,D], [D,hidden] */
+  /* fp32 master weights or NULL.  Non-NULL: ucf_block_fwd first refreshes the bf16 copy above from it (the per-step
+   * cast of mixed-precision training, one launch for all four); ucf_block_bwd ignores these. */
+  const void *qkv_w_master, *proj_w_master, *fc1_w_master, *fc2_w_master;
+} ucf_block_params;
+typedef struct {                 /* activations: written by ucf_block_fwd, read by ucf_block_bwd (all but y) */
+  const void* x;                 /* bf16 [M, D] block input */
+  void *h1, *qkv, *o, *x1, *h2;  /* bf16 [M,D] LN1(x) | [M,3D] packed q,k,v | [M,D] attention out | [M,D] x + proj | [M,D] LN2(x1) */
+  void *z, *u;                   /* bf16 [M,hidden] fc1 pre-activation | GELU(z) */
+  void* y;                       /* bf16 [M, D] block output */
+  float *mean1, *rstd1, *mean2, *rstd2;   /* fp32 [M] */
+  float* lse;                    /* fp32 [B, H, N] */
+} ucf_block_acts;
+typedef struct {
+  const void* dy;                /* bf16 [M, D] gradient of the block output */
+  void* dx;                      /* bf16 [M, D] gradient of the block input (written) */
+  /* fp32 gradients, ACCUMULATED into (caller zero-fills or carries .grad); the bias entries may be NULL */
+  float *g_n1_w, *g_n1_b, *g_qkv_w, *g_qkv_b, *g_proj_w, *g_proj_b, *g_n2_w, *g_n2_b, *g_fc1_w, *g_fc1_b, *g_fc2_w, *g_fc2_b;
+  void* ws_a;                    /* bf16 workspace, M * max(hidden, 3D) elements */
+  void *ws_b, *ws_c;             /* bf16 workspaces, M * D elements each */
+  float* dq_acc;                 /* fp32 [B,N,H,hd] workspace; may be NULL when N <= 256 */
+  float* delta;                  /* fp32 [B,H,N] workspace */
+} ucf_block_grads;
+int ucf_block_fwd(const ucf_block_params* params, const ucf_block_acts* acts, void* stream);
+int ucf_block_bwd(const ucf_block_params* params, const ucf_block_acts* acts, const ucf_block_grads* grads, void* stream);
+/* split-K factor ucf_block_bwd uses for the weight-gradient GEMM dW[n_out, k_in] over M tokens (host arithmetic only) */
+int ucf_wgrad_splits(int n_out, int k_in, long long M);
 
 /* ---- channel variable-aggregation cross-attention core (replaces the SDPA call inside
  * VariableMapping_Attention.forward, building_blocks.py:339-367; Nq = Na (1), Nk = V) ---------

@@ -17,7 +17,34 @@ EPI_BIAS, EPI_BIAS_RESIDUAL, EPI_BIAS_GELU_AUX, EPI_DGELU, EPI_F32_ADD = 0, 1, 2
 PATCH_MSE_MAX_BLOCKS = 4096
 
 _LL = c_longlong
+
+
+class BlockParams(ctypes.Structure):
+    """ucf_block_params (include/ucf_vit_b200.h)."""
+    _fields_ = ([(n, c_int) for n in ("B", "N", "D", "H", "hidden")] + [("eps1", c_float), ("eps2", c_float),
+                ("ln_dtype", c_int), ("bias_dtype", c_int)] +
+                [(n, c_void_p) for n in ("n1_w", "n1_b", "n2_w", "n2_b", "qkv_b", "proj_b", "fc1_b", "fc2_b",
+                                         "qkv_w", "proj_w", "fc1_w", "fc2_w",
+                                         "qkv_w_master", "proj_w_master", "fc1_w_master", "fc2_w_master")])
+
+
+class BlockActs(ctypes.Structure):
+    """ucf_block_acts."""
+    _fields_ = [(n, c_void_p) for n in ("x", "h1", "qkv", "o", "x1", "h2", "z", "u", "y", "mean1", "rstd1", "mean2",
+                                        "rstd2", "lse")]
+
+
+class BlockGrads(ctypes.Structure):
+    """ucf_block_grads."""
+    _fields_ = [(n, c_void_p) for n in ("dy", "dx", "g_n1_w", "g_n1_b", "g_qkv_w", "g_qkv_b", "g_proj_w", "g_proj_b",
+                                        "g_n2_w", "g_n2_b", "g_fc1_w", "g_fc1_b", "g_fc2_w", "g_fc2_b",
+                                        "ws_a", "ws_b", "ws_c", "dq_acc", "delta")]
+
+
 _SIGNATURES = {
+    "ucf_block_fwd": (c_int, [ctypes.POINTER(BlockParams), ctypes.POINTER(BlockActs), c_void_p]),
+    "ucf_block_bwd": (c_int, [ctypes.POINTER(BlockParams), ctypes.POINTER(BlockActs), ctypes.POINTER(BlockGrads), c_void_p]),
+    "ucf_wgrad_splits": (c_int, [c_int, c_int, _LL]),
     "ucf_abi_version": (c_int, []),
     "ucf_last_error": (c_char_p, []),
     "ucf_launch_count": (c_ulonglong, []),

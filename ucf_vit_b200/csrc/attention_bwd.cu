@@ -1052,7 +1052,7 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
   const int grid = p.items < num_sms() ? p.items : num_sms();
 #define UCF_ATTN_BWD_LAUNCH(HD_, SHORT_)                                                                        \
   {                                                                                                             \
-    static bool attr = false;                                                                                   \
+    static DeviceOnce once; bool& attr = once.flag();                                                           \
     if (!attr) {                                                                                                \
       e = cudaFuncSetAttribute(attn_bwd_kernel<HD_, SHORT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                AttnBwdCfg<HD_>::SMEM_BYTES);                                                    \
@@ -1063,7 +1063,7 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
   }
 #define UCF_ATTN_BWD2_LAUNCH(HD_, SHORT_)                                                                       \
   {                                                                                                             \
-    static bool attr = false;                                                                                   \
+    static DeviceOnce once; bool& attr = once.flag();                                                           \
     if (!attr) {                                                                                                \
       e = cudaFuncSetAttribute(attn_bwd2_kernel<HD_, SHORT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                AttnBwd2Cfg<HD_>::SMEM_BYTES);                                                   \

@@ -504,7 +504,7 @@ static int launch_attn_fwd(const CUtensorMap& tQ, const CUtensorMap& tK, const C
   p.stagger_cycles = g_fwd_stagger >= 0 ? g_fwd_stagger : 600;
 #define UCF_FWD(POLY_)                                                                                            \
   {                                                                                                               \
-    static bool done = false;                                                                                     \
+    static DeviceOnce once; bool& done = once.flag();                                                                                     \
     if ((rc = set_smem_attr(attn_fwd_kernel<HD, POLY_, true>, Cfg::SMEM_BYTES, done))) return rc;                 \
     attn_fwd_kernel<HD, POLY_, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tQ, tK, tV, tO, p);             \
   }

@@ -22,7 +22,13 @@ enum : int {
 };
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError -> code (positive cudaError_t)
-int num_sms();                        // SM count of the current device (cached)
+int num_sms();                        // SM count of the current device (cached per device)
+// "has this been done on the CURRENT device?": function attributes (max dynamic shared memory) are per device, so a
+// process that drives several GPUs must set them once on each
+struct DeviceOnce {
+  bool done[64] = {};
+  bool& flag() { int d = 0; cudaGetDevice(&d); return done[d & 63]; }
+};
 
 // host: encode a 2-D/3-D/4-D tiled tensor map. dims/strides innermost first; strides in bytes
 // for dims 1..rank-1 (dim 0 is contiguous).

@@ -6,6 +6,7 @@ tensor-memory accumulators through the TMA reduce-add epilogue).
 Reference semantics: /root/reference/src/UCF_VIT/simple/building_blocks.py
   Mlp.forward :122-129, Attention.forward :157-192, Block.forward :236-239.
 """
+import ctypes
 import math
 
 import torch
@@ -309,8 +310,29 @@ class _AttnPackedFn(torch.autograd.Function):
         return dqkv, None
 
 
+def _padded_head_dim(hd):
+    """Head width the tcgen05 attention kernels run a head of `hd` columns at (zero columns appended to q, k and v
+    change neither the scores nor the output columns that are kept)."""
+    if hd in (32, 64):
+        return hd
+    if hd < 32:
+        return 32
+    if hd < 64:
+        return 64
+    raise NotImplementedError(f"attention: head_dim {hd} > 64 has no kernel (32 and 64 run natively, narrower heads "
+                              "zero-padded; e.g. ViT-H's 80 is not supported)")
+
+
 def attention_packed(qkv, scale):
-    return _AttnPackedFn.apply(qkv, scale)
+    """qkv [B, N, 3, H, hd] -> [B, N, H*hd].  head_dim 36 (decoder_embed_dim 576 / 16 heads in the reference's
+    configs/basic_ct MAE and diffusion YAMLs) and other widths below 64 run zero-padded to 32 / 64."""
+    hd = qkv.shape[-1]
+    hp = _padded_head_dim(hd)
+    if hp == hd:
+        return _AttnPackedFn.apply(qkv, scale)
+    B, N, _, H, _ = qkv.shape
+    o = _AttnPackedFn.apply(torch.nn.functional.pad(qkv, (0, hp - hd)), scale)
+    return o.view(B, N, H, hp)[..., :hd].reshape(B, N, H * hd)
 
 
 class _AttnFn(torch.autograd.Function):
@@ -331,7 +353,12 @@ class _AttnFn(torch.autograd.Function):
 
 
 def attention(q, k, v, scale):
-    return _AttnFn.apply(q, k, v, scale)
+    hd = q.shape[-1]
+    hp = _padded_head_dim(hd)
+    if hp == hd:
+        return _AttnFn.apply(q, k, v, scale)
+    pad = torch.nn.functional.pad
+    return _AttnFn.apply(pad(q, (0, hp - hd)), pad(k, (0, hp - hd)), pad(v, (0, hp - hd)), scale)[..., :hd]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -351,32 +378,54 @@ class _BlockFn(torch.autograd.Function):
         B, N, D = x.shape
         M = B * N
         H = num_heads
-        hd = D // H
+        Hd = fc1_w.shape[0]
+        dev = x.device
         x2 = x.reshape(M, D)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        h1, mean1, rstd1 = ops.layernorm_fwd(x2, n1w, n1b, eps1)
-        wq, wp, w1h, w2h = bf16_params(qkv_w, proj_w, fc1_w, fc2_w)
-        qkv = ops.gemm(h1, wq, M=M, N=3 * D, K=D, bias=qkv_b)
-        qkv5 = qkv.view(B, N, 3, H, hd)
-        o, lse = ops.attention_fwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], hd ** -0.5)
-        o2 = o.view(M, D)
-        x1 = ops.gemm(o2, wp, M=M, N=D, K=D, bias=proj_b, aux=x2, epilogue=L.EPI_BIAS_RESIDUAL)
-        h2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b, eps2)
-        Hd = fc1_w.shape[0]
-        u, z = ops.gemm(h2, w1h, M=M, N=Hd, K=D, bias=fc1_b, epilogue=L.EPI_BIAS_GELU_AUX)
-        y = ops.gemm(u, w2h, M=M, N=D, K=Hd, bias=fc2_b, aux=x1, epilogue=L.EPI_BIAS_RESIDUAL)
-        ctx.w16 = (wq, wp, w1h, w2h)     # this call's bf16 weight copies, reused by its backward
-        ctx.save_for_backward(x2, mean1, rstd1, h1, qkv, o, lse, x1, mean2, rstd2, h2, z, u,
-                              n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
-        ctx.dims = (B, N, D, H, hd, Hd)
-        return y.view(B, N, D)
+        # one bf16 slab for everything backward re-reads, one fp32 slab for the statistics, one for the weights
+        sizes = (M * D, 3 * M * D, M * D, M * D, M * D, M * Hd, M * Hd)
+        slab = torch.empty(sum(sizes), dtype=BF16, device=dev)
+        h1, qkv, o, x1, h2, z, u = torch.split(slab, sizes)
+        Mp = -(-M // 64) * 64
+        stats = torch.empty(4 * Mp + B * H * N, dtype=torch.float32, device=dev)
+        y = torch.empty((B, N, D), dtype=BF16, device=dev)
+        ws, masters, w16 = (qkv_w, proj_w, fc1_w, fc2_w), [], []
+        cast = [w for w in ws if w.dtype != BF16]
+        if cast:
+            if any(w.dtype != torch.float32 or not w.is_contiguous() for w in cast):
+                raise TypeError("fused_block: weights must be contiguous fp32 or bf16 tensors")
+            wslab = torch.empty(sum(-(-w.numel() // 64) * 64 for w in cast), dtype=BF16, device=dev)
+            off = 0
+        for w in ws:
+            if w.dtype == BF16:
+                w16.append(w.detach() if w.is_contiguous() else w.detach().contiguous())
+                masters.append(None)
+            else:
+                w16.append(wslab[off:off + w.numel()].view(w.shape))
+                masters.append(w.data_ptr())
+                off += -(-w.numel() // 64) * 64
+        ptr = lambda t: None if t is None else t.data_ptr()
+        biases = (qkv_b, proj_b, fc1_b, fc2_b)
+        bdt = next((ops._dt(b) for b in biases if b is not None), 0)
+        prm = L.BlockParams(B, N, D, H, Hd, float(eps1), float(eps2), ops._dt(n1w), bdt,
+                            ptr(n1w), ptr(n1b), ptr(n2w), ptr(n2b), ptr(qkv_b), ptr(proj_b), ptr(fc1_b), ptr(fc2_b),
+                            *[w.data_ptr() for w in w16], *masters)
+        acts = L.BlockActs(x2.data_ptr(), h1.data_ptr(), qkv.data_ptr(), o.data_ptr(), x1.data_ptr(), h2.data_ptr(),
+                           z.data_ptr(), u.data_ptr(), y.data_ptr(), stats.data_ptr(), stats.data_ptr() + 4 * Mp,
+                           stats.data_ptr() + 8 * Mp, stats.data_ptr() + 12 * Mp, stats.data_ptr() + 16 * Mp)
+        ops._require_cuda(x2, n1w, qkv_w, proj_w, fc1_w, fc2_w)
+        L.check(L.lib().ucf_block_fwd(ctypes.byref(prm), ctypes.byref(acts), ops._stream()), "block_fwd")
+        ctx.w16 = w16                    # this call's bf16 weight copies, reused by its backward
+        ctx.eps = (float(eps1), float(eps2))
+        ctx.save_for_backward(x2, slab, stats, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b)
+        ctx.dims = (B, N, D, H, Hd)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
-        (x2, mean1, rstd1, h1, qkv, o, lse, x1, mean2, rstd2, h2, z, u,
-         n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b) = ctx.saved_tensors
-        B, N, D, H, hd, Hd = ctx.dims
+        (x2, slab, stats, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b) = ctx.saved_tensors
+        B, N, D, H, Hd = ctx.dims
         M = B * N
         dev = dy.device
         dy2 = dy.reshape(M, D)
@@ -392,35 +441,36 @@ class _BlockFn(torch.autograd.Function):
         def opt(b, shape):
             return shape if b is not None else None
 
-        (g_fc2_w, g_fc2_b, g_fc1_w, g_fc1_b, d_n2w, d_n2b, g_proj_w, g_proj_b, g_qkv_w, g_qkv_b, d_n1w,
-         d_n1b) = _zeros_f32(dev, (D, Hd), opt(fc2_b, (D,)), (Hd, D), opt(fc1_b, (Hd,)), (D,), opt(n2b, (D,)),
-                             (D, D), opt(proj_b, (D,)), (3 * D, D), opt(qkv_b, (3 * D,)), (D,), opt(n1b, (D,)))
-        # ---- MLP
-        d_fc2_w, d_fc2_b = _wgrad(dy2, u, D, Hd, fc2_w, fc2_b, g_fc2_w, g_fc2_b)
-        wq, wp, w1h, w2h = ctx.w16
-        dz = ops.gemm(dy2, w2h, M=M, N=Hd, K=D, b_mn=True, aux=z, epilogue=L.EPI_DGELU)
-        d_fc1_w, d_fc1_b = _wgrad(dz, h2, Hd, D, fc1_w, fc1_b, g_fc1_w, g_fc1_b)
-        dh2 = ops.gemm(dz, w1h, M=M, N=D, K=Hd, b_mn=True)
-        del dz
-        dx1 = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dy2, dgamma=d_n2w, dbeta=d_n2b)
-        del dh2
-        # ---- attention
-        d_proj_w, d_proj_b = _wgrad(dx1, o.view(M, D), D, D, proj_w, proj_b, g_proj_w, g_proj_b)
-        d_o = ops.gemm(dx1, wp, M=M, N=D, K=D, b_mn=True)
-        dqkv = torch.empty_like(qkv)
-        qkv5 = qkv.view(B, N, 3, H, hd)
-        dqkv5 = dqkv.view(B, N, 3, H, hd)
-        ops.attention_bwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], o, d_o.view(B, N, H, hd), lse, hd ** -0.5,
-                          dq=dqkv5[:, :, 0], dk=dqkv5[:, :, 1], dv=dqkv5[:, :, 2])
-        del d_o
-        d_qkv_w, d_qkv_b = _wgrad(dqkv, h1, 3 * D, D, qkv_w, qkv_b, g_qkv_w, g_qkv_b)
-        dh1 = ops.gemm(dqkv, wq, M=M, N=D, K=3 * D, b_mn=True)
-        del dqkv
-        dx = ops.layernorm_bwd(dh1, x2, n1w, mean1, rstd1, dres=dx1, dgamma=d_n1w, dbeta=d_n1b)
-        return (dx.view(B, N, D), cast_like(d_n1w, n1w), cast_like(d_n1b, n1b) if n1b is not None else None,
-                d_qkv_w, d_qkv_b, d_proj_w, d_proj_b,
-                cast_like(d_n2w, n2w), cast_like(d_n2b, n2b) if n2b is not None else None,
-                d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b, None, None, None)
+        grads = _zeros_f32(dev, (D,), opt(n1b, (D,)), (3 * D, D), opt(qkv_b, (3 * D,)), (D, D), opt(proj_b, (D,)),
+                           (D,), opt(n2b, (D,)), (Hd, D), opt(fc1_b, (Hd,)), (D, Hd), opt(fc2_b, (D,)))
+        wsa = max(Hd, 3 * D)
+        ws = torch.empty(M * (wsa + 2 * D), dtype=BF16, device=dev)
+        dx = torch.empty((B, N, D), dtype=BF16, device=dev)
+        nlse = B * H * N
+        f32ws = torch.empty(nlse + (M * D if N > 256 else 0), dtype=f32, device=dev)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        g = L.BlockGrads(dy2.data_ptr(), dx.data_ptr(), *[ptr(t) for t in grads],
+                         ws.data_ptr(), ws.data_ptr() + 2 * M * wsa, ws.data_ptr() + 2 * M * (wsa + D),
+                         (f32ws.data_ptr() + 4 * nlse) if N > 256 else None, f32ws.data_ptr())
+        # the descriptors are rebuilt from the saved tensors: under activation checkpointing these are the RECOMPUTED
+        # buffers, not the ones the original forward call wrote
+        h1, qkv, o, x1, h2, z, u = torch.split(slab, (M * D, 3 * M * D, M * D, M * D, M * D, M * Hd, M * Hd))
+        Mp = -(-M // 64) * 64
+        biases = (qkv_b, proj_b, fc1_b, fc2_b)
+        bdt = next((ops._dt(b) for b in biases if b is not None), 0)
+        prm = L.BlockParams(B, N, D, H, Hd, ctx.eps[0], ctx.eps[1], ops._dt(n1w), bdt,
+                            ptr(n1w), ptr(n1b), ptr(n2w), ptr(n2b), ptr(qkv_b), ptr(proj_b), ptr(fc1_b), ptr(fc2_b),
+                            *[w.data_ptr() for w in ctx.w16], None, None, None, None)
+        acts = L.BlockActs(x2.data_ptr(), h1.data_ptr(), qkv.data_ptr(), o.data_ptr(), x1.data_ptr(), h2.data_ptr(),
+                           z.data_ptr(), u.data_ptr(), None, stats.data_ptr(), stats.data_ptr() + 4 * Mp,
+                           stats.data_ptr() + 8 * Mp, stats.data_ptr() + 12 * Mp, stats.data_ptr() + 16 * Mp)
+        L.check(L.lib().ucf_block_bwd(ctypes.byref(prm), ctypes.byref(acts), ctypes.byref(g), ops._stream()), "block_bwd")
+        (d_n1w, d_n1b, d_qkv_w, d_qkv_b, d_proj_w, d_proj_b, d_n2w, d_n2b, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b) = grads
+        return (dx, cast_like(d_n1w, n1w), cast_like(d_n1b, n1b),
+                cast_like(d_qkv_w, qkv_w), cast_like(d_qkv_b, qkv_b), cast_like(d_proj_w, proj_w), cast_like(d_proj_b, proj_b),
+                cast_like(d_n2w, n2w), cast_like(d_n2b, n2b),
+                cast_like(d_fc1_w, fc1_w), cast_like(d_fc1_b, fc1_b), cast_like(d_fc2_w, fc2_w), cast_like(d_fc2_b, fc2_b),
+                None, None, None)
 
 
 def fused_block(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,

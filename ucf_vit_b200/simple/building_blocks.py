@@ -158,7 +158,7 @@ class Attention(nn.Module):
         else:
             q = _apply_norm(self.q_norm, qkv[:, :, 0].contiguous())
             k = _apply_norm(self.k_norm, qkv[:, :, 1].contiguous())
-            o = UF.attention(q, k, qkv[:, :, 2], self.scale).view(B, N, C)
+            o = UF.attention(q, k, qkv[:, :, 2], self.scale).reshape(B, N, C)
         if _dropout_active(self.proj_drop):
             y = self.proj_drop(UF.linear(o, self.proj.weight, self.proj.bias))
             return y if residual is None else y + residual
@@ -196,7 +196,7 @@ class Block(nn.Module):
     def _fully_fused(self):
         a, m = self.attn, self.mlp
         return (self._plain() and type(m) is Mlp and m._fusable() and m.fc1.bias is not None
-                and isinstance(a.q_norm, nn.Identity) and isinstance(a.k_norm, nn.Identity)
+                and a.head_dim in (32, 64) and isinstance(a.q_norm, nn.Identity) and isinstance(a.k_norm, nn.Identity)
                 and not _dropout_active(a.attn_drop) and not _dropout_active(a.proj_drop))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

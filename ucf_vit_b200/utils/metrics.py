@@ -105,3 +105,39 @@ class DiceBLoss(nn.Module):
             targets = targets.to(torch.float32)
         return _DiceBceFn.apply(inputs.contiguous(), targets.detach().contiguous(), float(self.weight), float(smooth),
                                 bool(act))
+
+
+class DiceCELoss(nn.Module):
+    """Dice + cross-entropy loss of the UNETR driver (training_scripts/train_unetr_simple.py:38,51:
+    `monai.losses.DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)`).
+
+    MONAI is not in the image and not vendored in the reference, so this restates its published definition
+    (PARITY UNPINNED: no MONAI output was available to check it against):
+      p = softmax(logits, 1);  t = one_hot(target);  per (b, c) over the spatial axes
+      dice = 1 - (2 sum(p t) + smooth_nr) / (sum(t^2) + sum(p^2) + smooth_dr)   [squared_pred; background included]
+      loss = lambda_dice * mean_{b,c}(dice) + lambda_ce * CrossEntropy(logits, target)
+    logits [B, C, ...] (any float dtype, evaluated in fp32), target [B, 1, ...] class indices (to_onehot_y=True)."""
+
+    def __init__(self, to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6,
+                 lambda_dice=1.0, lambda_ce=1.0, include_background=True):
+        super().__init__()
+        if not (to_onehot_y and softmax and include_background):
+            raise NotImplementedError("DiceCELoss: only the configuration of the reference's UNETR driver is implemented "
+                                      "(to_onehot_y=True, softmax=True, include_background=True)")
+        self.squared_pred, self.smooth_nr, self.smooth_dr = squared_pred, float(smooth_nr), float(smooth_dr)
+        self.lambda_dice, self.lambda_ce = float(lambda_dice), float(lambda_ce)
+
+    def forward(self, logits, target):
+        C = logits.shape[1]
+        if target.dim() == logits.dim() and target.shape[1] == 1:
+            target = target[:, 0]
+        t = target.long()
+        lf = logits.float()
+        ce = F.cross_entropy(lf, t)
+        p = torch.softmax(lf, dim=1)
+        oh = F.one_hot(t, C).movedim(-1, 1).to(p.dtype)
+        dims = tuple(range(2, lf.dim()))
+        inter = (p * oh).sum(dims)
+        den = ((p * p).sum(dims) + oh.sum(dims)) if self.squared_pred else (p.sum(dims) + oh.sum(dims))
+        dice = 1.0 - (2.0 * inter + self.smooth_nr) / (den + self.smooth_dr)
+        return self.lambda_dice * dice.mean() + self.lambda_ce * ce
