@@ -236,10 +236,17 @@ def run_gpu_arm(args, wl):
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if getattr(wl, "flush_l2", False) else None
 
+    graphed = None
+    if args.cuda_graph:
+        if world > 1 or wl.uses_fsdp:
+            raise SystemExit("--cuda-graph: single-GPU, non-FSDP workloads only")
+        from ucf_vit_b200.utils.graph import GraphedTrainStep
+        graphed = GraphedTrainStep(wl.step, resident, warmup=3)
+
     def step(batch):
         if flush is not None:
             flush.zero_()
-        return wl.step(*batch)
+        return graphed(*batch) if graphed is not None else wl.step(*batch)
 
     def fence():
         if world > 1:
@@ -273,6 +280,15 @@ def run_gpu_arm(args, wl):
     ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n0
     clocks = sampler.stop()
+    if graphed is not None:
+        # a replayed graph makes no library calls: count the kernels of one eager step, and time the GEMM family there
+        n1 = _lib.launch_count()
+        timer.enabled = rank == 0
+        for _ in range(args.steps):
+            wl.step(*resident)
+        torch.cuda.synchronize()
+        timer.enabled = False
+        launches = _lib.launch_count() - n1
     final_loss = float(loss.item())
 
     # ---------------- end-to-end arm: pinned host batch -> device every step, loss read back every step
@@ -325,7 +341,7 @@ def run_gpu_arm(args, wl):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl.workload, "name": wl.name, "global_batch": samples, "parallelism": wl.parallelism(world),
-                   "l2_policy": wl.l2_policy,
+                   "l2_policy": wl.l2_policy, "cuda_graph": bool(args.cuda_graph),
                    "optimizer": ("AdamW, ucf_adamw_multi kernel" if args.optimizer == "ucf" else "AdamW, torch kernel") +
                                 ", fp32 master weights", "loss_final": final_loss},
         "model_tflops": value * f_sample / 1e12,
@@ -340,7 +356,8 @@ def run_gpu_arm(args, wl):
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all layouts/epilogues)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "launches_timed": gemm_n,
-                     "share_of_step": gemm_ms / ms_total if ms_total > 0 else None},
+                     "share_of_step": gemm_ms / ms_total if ms_total > 0 else None,
+                     "timed_in": "eager pass after the graph-replay region" if args.cuda_graph else "the timed region"},
     }
     if extras:
         line["extras"] = extras
@@ -368,6 +385,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="vit_b16", choices=sorted(reg))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="capture the whole training step in a CUDA graph (utils/graph.py) and replay it; the GEMM roofline "
+                         "is then taken from an eager pass after the timed region")
     ap.add_argument("--bf16-allreduce", action="store_true", help="DDP gradient all-reduce in bf16 (torch's bf16_compress_hook)")
     ap.add_argument("--optimizer", default="ucf", choices=["torch", "ucf"],
                     help="AdamW update: torch's kernel or this package's ucf_adamw_multi")

@@ -88,6 +88,12 @@ class Workload:
         return net
 
 
+def _opt_kind(args, torch_default):
+    if args.optimizer != "ucf":
+        return torch_default
+    return "ucf_capturable" if getattr(args, "cuda_graph", False) else "ucf"
+
+
 def _cpu_state(model):
     return {k: v.detach().clone().float().requires_grad_(True) for k, v in model.state_dict().items()
             if not k.startswith("token_embeds.") and v.dtype.is_floating_point}
@@ -115,7 +121,7 @@ class VitClassification(Workload):
         torch.manual_seed(0)
         self.model = self._model().to(dev).train()
         self.net = self._wrap_ddp(self.model, world, local, args)
-        self.opt = configure_optimizer(self.model, 1e-4, 0.9, 0.95, 1e-5, fused="ucf" if args.optimizer == "ucf" else True)
+        self.opt = configure_optimizer(self.model, 1e-4, 0.9, 0.95, 1e-5, fused=_opt_kind(args, True))
         self.lossf = torch.nn.CrossEntropyLoss()
 
     def host_batch(self, rank):
@@ -188,7 +194,7 @@ class _FsdpWorkload(Workload):
         from torch.distributed.fsdp.sharded_grad_scaler import ShardedGradScaler
         from ucf_vit_b200.utils.misc import configure_optimizer
         self.net = fsdp_wrap(model.to(dev), world, local).train()
-        self.opt = configure_optimizer(self.net, 1e-4, 0.9, 0.95, 1e-5, fused="ucf" if args.optimizer == "ucf" else None)
+        self.opt = configure_optimizer(self.net, 1e-4, 0.9, 0.95, 1e-5, fused=_opt_kind(args, None))
         self.scaler = ShardedGradScaler(init_scale=8192, growth_interval=100)
 
     def _backward_and_update(self, loss):
@@ -203,8 +209,8 @@ class MaeVitLFsdp(_FsdpWorkload):
     scaler.scale(loss).backward(); scaler.step; scaler.update)."""
     name = "mae_vitl_fsdp"
     workload = ("MAE ViT-L/16 masked pretraining train step (75 % mask, fwd+MSE+bwd+AdamW), 224x224x3 bf16 images, "
-                "batch 256/GPU, FSDP + activation checkpointing + grad scaler")
-    batch = 256
+                "batch 512/GPU, FSDP + activation checkpointing + grad scaler")
+    batch = 512
     cpu_batch = 4
     cfg = dict(img_size=[224, 224], patch_size=16, in_chans=3, embed_dim=1024, depth=24, num_heads=16,
                decoder_embed_dim=512, decoder_depth=8, decoder_num_heads=16, mask_ratio=0.75, class_token=False)
@@ -380,7 +386,7 @@ class Unetr128(Workload):
         torch.manual_seed(0)
         self.model = self._model().to(dev).train()
         self.net = self._wrap_ddp(self.model, world, local, args)
-        self.opt = configure_optimizer(self.model, 1e-5, 0.9, 0.95, 1e-5, fused="ucf" if args.optimizer == "ucf" else True)
+        self.opt = configure_optimizer(self.model, 1e-5, 0.9, 0.95, 1e-5, fused=_opt_kind(args, True))
         self.lossf = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)
 
     def host_batch(self, rank):
@@ -496,7 +502,7 @@ class Sap4096(Workload):
         self.dev = dev
         self.model = self._model().to(dev).train()
         self.net = self._wrap_ddp(self.model, world, local, args)
-        self.opt = configure_optimizer(self.model, 1e-4, 0.9, 0.95, 1e-5, fused="ucf" if args.optimizer == "ucf" else True)
+        self.opt = configure_optimizer(self.model, 1e-4, 0.9, 0.95, 1e-5, fused=_opt_kind(args, True))
         self.lossf = DiceBLoss(num_class=self.cfg["num_classes"])
         g = torch.Generator().manual_seed(77 + rank)
         self.edges = [self._edge_map(g) for _ in range(self.batch)]
@@ -523,7 +529,11 @@ class Sap4096(Workload):
     def front_end(self, imgs):
         """Patchify.forward_batch minus the OpenCV edge detection: trees on host threads, gather on the device."""
         from ucf_vit_b200.dataloaders.quadtree import FixedQuadTree
-        trees = FixedQuadTree.build_many(self.edges, self.L, device=self.dev)
+        # the trees of THIS batch were submitted during the previous step (a loader knows batch k+1 while the GPU works on
+        # batch k); the trees of the next batch are submitted now and built on a host thread under this step's GPU work
+        fut = getattr(self, "_next_trees", None) or FixedQuadTree.build_many_async(self.edges, self.L, device=self.dev)
+        trees = fut.result()
+        self._next_trees = FixedQuadTree.build_many_async(self.edges, self.L, device=self.dev)
         p = self.p
         seqs, ps = [], []
         for i, qdt in enumerate(trees):

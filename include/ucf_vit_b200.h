@@ -208,7 +208,7 @@ int ucf_cast_bf16_to_f32(const void* src, float* dst, long long n, int accumulat
 int ucf_colsum_bf16(const void* x, float* out, long long M, int N, long long ld, int accumulate,
                     void* stream);
 /* Conv{2,3}d(k = s = p) input -> GEMM rows (replaces the im2col inside cuDNN, building_blocks.py:58-60,89)
- * x: [B, C, S0, S1 (, S2)] of x_dtype (fp32 / bf16), contiguous, S >= G*p: like the strided convolution,
+ * x: [B, C, S0, S1 (, S2)] of x_dtype (fp32 / bf16 / uint8 raw pixels), contiguous, S >= G*p: like the strided convolution,
  *    pixels past the last whole patch are ignored.  Any patch size (16-byte vectors when p % 8 == 0,
  *    8-byte when p % 4 == 0, scalar otherwise).
  * out: bf16 [B*G0*G1(*G2), ld_out], ld_out >= K = C*p^dims and a multiple of 8 (the GEMM's K extent; pad
@@ -305,6 +305,14 @@ int ucf_dice_bce_bwd(const void* logits, int logits_dtype, const void* targets, 
 int ucf_adamw_multi(int n, float* const* params, const float* const* grads, float* const* exp_avg,
                     float* const* exp_avg_sq, const long long* counts, double lr, double beta1, double beta2,
                     double eps, double weight_decay, long long step, int maximize, void* stream);
+/* The same update with the learning rate and the step count read from DEVICE memory (fp32 scalars; *step_dev is the
+ * 1-based count of this update), so the launch can be captured in a CUDA graph and replayed while a scheduler rewrites
+ * *lr_dev and the caller increments *step_dev on the stream between replays.  Bias corrections are evaluated in fp32
+ * inside the kernel (the host form above evaluates them in double): updates agree to ~1e-6 relative. */
+int ucf_adamw_multi_dev(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                        float* const* exp_avg_sq, const long long* counts, const float* lr_dev, double beta1,
+                        double beta2, double eps, double weight_decay, const float* step_dev, int maximize,
+                        void* stream);
 
 #ifdef __cplusplus
 }

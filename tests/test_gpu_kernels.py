@@ -276,6 +276,10 @@ def test_patchify_any_patch_size_and_cropped_images(shape, p):
         assert got.shape == (ref.shape[0], -(-K // 8) * 8)
         assert torch.equal(got[:, :K], ref)
         assert not got[:, K:].any()
+    # raw uint8 pixels (a quarter of the fp32 host->device bytes): exact, 0..255 are bf16-representable
+    xu = torch.randint(0, 256, shape, device=dev, dtype=torch.uint8)
+    got = ops.patchify(xu, p)
+    assert torch.equal(got[:, :K], _conv_rows(xu.float(), p).to(torch.bfloat16))
 
 
 def test_patch_embed_matches_conv_for_small_patches():

@@ -85,6 +85,7 @@ _SIGNATURES = {
     "ucf_dice_bce_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, _LL, c_float, c_int,
                                  c_void_p, c_void_p]),
     "ucf_adamw_multi": (c_int, [c_int] + [c_void_p] * 5 + [c_double] * 5 + [_LL, c_int, c_void_p]),
+    "ucf_adamw_multi_dev": (c_int, [c_int] + [c_void_p] * 6 + [c_double] * 4 + [c_void_p, c_int, c_void_p]),
     "ucf_patchify": (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [_LL, c_int, c_void_p]),
 }
 

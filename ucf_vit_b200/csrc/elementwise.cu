@@ -109,7 +109,8 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
 // ViT-B/16-style model uses; smaller VEC serves patch sizes 4 / 2 / odd and cropped images whose rows are not
 // 16-byte aligned).  S0/S1/S2 are the image's REAL spatial sizes (>= G*p: like the strided convolution, pixels
 // past the last whole patch are ignored); ldo >= K is the output row pitch.
-template <bool X_BF16, int VEC>
+// XT: element type of x -- 0 fp32, 1 bf16, 2 uint8 (raw pixels: a quarter of the fp32 host->device bytes)
+template <int XT, int VEC>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int G0, int G1,
                 int G2, int p, int dims, int S0, int S1, int S2, long long ldo, long long total_vec) {
@@ -143,26 +144,39 @@ patchify_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, int
     }
     __nv_bfloat16* dst = out + row * ldo + kcol;
     if (VEC == 8) {
-      if (X_BF16) {
+      if (XT == 1) {
         *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + src));
-      } else {
+      } else if (XT == 0) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + src));
         const float4 b2 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + src + 4));
         *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b2.x, b2.y),
                                                     pack_bf16x2(b2.z, b2.w));
+      } else {
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(x) + src));
+        *reinterpret_cast<uint4*>(dst) = make_uint4(
+            pack_bf16x2(static_cast<float>(q.x & 255u), static_cast<float>((q.x >> 8) & 255u)),
+            pack_bf16x2(static_cast<float>((q.x >> 16) & 255u), static_cast<float>(q.x >> 24)),
+            pack_bf16x2(static_cast<float>(q.y & 255u), static_cast<float>((q.y >> 8) & 255u)),
+            pack_bf16x2(static_cast<float>((q.y >> 16) & 255u), static_cast<float>(q.y >> 24)));
       }
     } else if (VEC == 4) {
-      if (X_BF16) {
+      if (XT == 1) {
         *reinterpret_cast<uint2*>(dst) = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + src));
-      } else {
+      } else if (XT == 0) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + src));
         *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+      } else {
+        const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(x) + src));
+        *reinterpret_cast<uint2*>(dst) = make_uint2(
+            pack_bf16x2(static_cast<float>(q & 255u), static_cast<float>((q >> 8) & 255u)),
+            pack_bf16x2(static_cast<float>((q >> 16) & 255u), static_cast<float>(q >> 24)));
       }
     } else {
 #pragma unroll
       for (int i = 0; i < VEC; ++i)
-        dst[i] = X_BF16 ? reinterpret_cast<const __nv_bfloat16*>(x)[src + i]
-                        : __float2bfloat16_rn(reinterpret_cast<const float*>(x)[src + i]);
+        dst[i] = XT == 1 ? reinterpret_cast<const __nv_bfloat16*>(x)[src + i]
+               : XT == 0 ? __float2bfloat16_rn(reinterpret_cast<const float*>(x)[src + i])
+                         : __float2bfloat16_rn(static_cast<float>(reinterpret_cast<const uint8_t*>(x)[src + i]));
     }
   }
 }
@@ -349,7 +363,10 @@ extern "C" int ucf_patchify(const void* x, void* out, int B, int C, int G0, int 
     if (e != cudaSuccess) { set_last_error("patchify: memset: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
   }
   // widest vector that divides the patch row and keeps every source / destination address aligned
-  const int esz = x_dtype == UCF_DTYPE_BF16 ? 2 : 4;
+  if (x_dtype != UCF_DTYPE_F32 && x_dtype != UCF_DTYPE_BF16 && x_dtype != UCF_DTYPE_U8) {
+    set_last_error("patchify: x_dtype must be f32, bf16 or u8"); return UCF_ERR_BAD_ARG;
+  }
+  const int esz = x_dtype == UCF_DTYPE_BF16 ? 2 : x_dtype == UCF_DTYPE_U8 ? 1 : 4;
   const long long inner = dims == 2 ? S1 : S2;
   int vec = 1;
   for (int v = 8; v >= 4; v >>= 1) {
@@ -360,11 +377,17 @@ extern "C" int ucf_patchify(const void* x, void* out, int B, int C, int G0, int 
   const long long nvec = total / vec;
   const int grid = ew_grid(nvec, 256);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-#define UCF_PATCHIFY(BF_, V_) patchify_kernel<BF_, V_><<<grid, 256, 0, st>>>(x, o, B, C, G0, G1, G2, p, dims, S0, S1, S2, ld_out, nvec)
-  const bool bf = x_dtype == UCF_DTYPE_BF16;
-  if (vec == 8) { if (bf) UCF_PATCHIFY(true, 8); else UCF_PATCHIFY(false, 8); }
-  else if (vec == 4) { if (bf) UCF_PATCHIFY(true, 4); else UCF_PATCHIFY(false, 4); }
-  else { if (bf) UCF_PATCHIFY(true, 1); else UCF_PATCHIFY(false, 1); }
+#define UCF_PATCHIFY(T_, V_) patchify_kernel<T_, V_><<<grid, 256, 0, st>>>(x, o, B, C, G0, G1, G2, p, dims, S0, S1, S2, ld_out, nvec)
+#define UCF_PATCHIFY_T(V_)                                                  \
+  {                                                                         \
+    if (x_dtype == UCF_DTYPE_BF16) UCF_PATCHIFY(1, V_);                     \
+    else if (x_dtype == UCF_DTYPE_U8) UCF_PATCHIFY(2, V_);                  \
+    else UCF_PATCHIFY(0, V_);                                               \
+  }
+  if (vec == 8) UCF_PATCHIFY_T(8)
+  else if (vec == 4) UCF_PATCHIFY_T(4)
+  else UCF_PATCHIFY_T(1)
+#undef UCF_PATCHIFY_T
 #undef UCF_PATCHIFY
   return check_launch("patchify_kernel");
 }

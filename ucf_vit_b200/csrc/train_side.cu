@@ -32,7 +32,22 @@ struct AdamWScalars {
   float inv_bc2_sqrt; // 1 / sqrt(1 - beta2^t)
   float eps;
   float gsign;        // -1 when maximizing
+  // CUDA-graph capturable form (ucf_adamw_multi_dev): learning rate and step count live in device memory and the three
+  // step-dependent scalars above are derived from them inside the kernel, so a captured launch stays valid as both change
+  const float* lr_dev;
+  const float* step_dev;
+  float weight_decay;
 };
+
+__device__ __forceinline__ AdamWScalars adamw_resolve(AdamWScalars s) {
+  if (s.lr_dev != nullptr) {
+    const float lr = *s.lr_dev, t = *s.step_dev;
+    s.decay = 1.0f - lr * s.weight_decay;
+    s.step_size = lr / (1.0f - powf(s.beta1, t));
+    s.inv_bc2_sqrt = rsqrtf(1.0f - powf(s.beta2, t));
+  }
+  return s;
+}
 
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamWScalars& s) {
   g *= s.gsign;
@@ -47,7 +62,8 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
 // VEC: all four streams of every tensor are 16-byte aligned -> float4, four independent chunks of loads in
 // flight per thread; otherwise a scalar walk over the same chunk.
 template <bool VEC>
-__global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamWArgs a, const AdamWScalars s) {
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamWArgs a, const AdamWScalars s_in) {
+  const AdamWScalars s = adamw_resolve(s_in);
   int t = 0;
 #pragma unroll
   for (int i = 1; i < kAdamTensors; ++i) t += (static_cast<int>(blockIdx.x) >= a.first_chunk[i]) ? 1 : 0;
@@ -533,14 +549,14 @@ static int dice_geom(const char* who, int B, int C, long long HW, DiceGeom* gm) 
 
 using namespace ucf;
 
+static int adamw_launch(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                        float* const* exp_avg_sq, const long long* counts, const AdamWScalars& s, void* stream);
+
 extern "C" int ucf_adamw_multi(int n, float* const* params, const float* const* grads, float* const* exp_avg,
                                float* const* exp_avg_sq, const long long* counts, double lr, double beta1,
                                double beta2, double eps, double weight_decay, long long step, int maximize,
                                void* stream) {
   if (n <= 0) return UCF_OK;
-  if (!params || !grads || !exp_avg || !exp_avg_sq || !counts) {
-    set_last_error("adamw_multi: null pointer table"); return UCF_ERR_BAD_ARG;
-  }
   if (step < 1) { set_last_error("adamw_multi: step must be >= 1 (got %lld)", step); return UCF_ERR_BAD_ARG; }
   if (!(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0)) {
     set_last_error("adamw_multi: betas must lie in [0, 1)"); return UCF_ERR_BAD_ARG;
@@ -553,6 +569,34 @@ extern "C" int ucf_adamw_multi(int n, float* const* params, const float* const* 
   s.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(1.0 - pow(beta2, static_cast<double>(step))));
   s.eps = static_cast<float>(eps);
   s.gsign = maximize ? -1.f : 1.f;
+  s.lr_dev = nullptr; s.step_dev = nullptr; s.weight_decay = static_cast<float>(weight_decay);
+  return adamw_launch(n, params, grads, exp_avg, exp_avg_sq, counts, s, stream);
+}
+
+extern "C" int ucf_adamw_multi_dev(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                                   float* const* exp_avg_sq, const long long* counts, const float* lr_dev, double beta1,
+                                   double beta2, double eps, double weight_decay, const float* step_dev, int maximize,
+                                   void* stream) {
+  if (n <= 0) return UCF_OK;
+  if (!lr_dev || !step_dev) { set_last_error("adamw_multi_dev: null lr / step pointer"); return UCF_ERR_BAD_ARG; }
+  if (!(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0)) {
+    set_last_error("adamw_multi_dev: betas must lie in [0, 1)"); return UCF_ERR_BAD_ARG;
+  }
+  AdamWScalars s;
+  s.decay = 1.f; s.step_size = 0.f; s.inv_bc2_sqrt = 1.f;      // derived from *lr_dev / *step_dev inside the kernel
+  s.beta1 = static_cast<float>(beta1); s.beta2 = static_cast<float>(beta2);
+  s.one_m_beta1 = static_cast<float>(1.0 - beta1); s.one_m_beta2 = static_cast<float>(1.0 - beta2);
+  s.eps = static_cast<float>(eps);
+  s.gsign = maximize ? -1.f : 1.f;
+  s.lr_dev = lr_dev; s.step_dev = step_dev; s.weight_decay = static_cast<float>(weight_decay);
+  return adamw_launch(n, params, grads, exp_avg, exp_avg_sq, counts, s, stream);
+}
+
+static int adamw_launch(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                        float* const* exp_avg_sq, const long long* counts, const AdamWScalars& s, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !counts) {
+    set_last_error("adamw_multi: null pointer table"); return UCF_ERR_BAD_ARG;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   for (int base = 0; base < n; base += kAdamTensors) {
     const int cnt = n - base < kAdamTensors ? n - base : kAdamTensors;

@@ -64,7 +64,31 @@ class FixedQuadTree:
 
     def _adopt(self, boxes, values):
         self.boxes = boxes
-        self.nodes = [[Rect(int(b[0]), int(b[1]), int(b[2]), int(b[3])), int(v)] for b, v in zip(boxes, values)]
+        self._values = values
+        self._nodes = None            # the reference's `nodes` list ([[Rect, value], ...]) is materialised on first access:
+                                      # 4096 Python objects per tree that the training path (boxes -> device gather) never reads
+
+    @property
+    def nodes(self):
+        if self._nodes is None:
+            self._nodes = [[Rect(int(b[0]), int(b[1]), int(b[2]), int(b[3])), int(v)] for b, v in zip(self.boxes, self._values)]
+        return self._nodes
+
+    @nodes.setter
+    def nodes(self, value):
+        self._nodes = value
+
+    _pool = None
+
+    @classmethod
+    def build_many_async(cls, domains, fixed_length=128, device="cuda", threads=0):
+        """`build_many` on a background host thread (the C++ builder runs without the GIL): returns a
+        concurrent.futures.Future whose result() is the list of trees.  A loader submits batch k+1 here while the GPU
+        works on batch k, which takes the ~5 ms per 4096^2 image of integer work off the step's critical path."""
+        from concurrent.futures import ThreadPoolExecutor
+        if cls._pool is None:
+            cls._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="ucf_sap_tree")
+        return cls._pool.submit(cls.build_many, domains, fixed_length, device, threads)
 
     @classmethod
     def build_many(cls, domains, fixed_length=128, device="cuda", threads=0):
@@ -102,7 +126,7 @@ class FixedQuadTree:
         return out
 
     def count_patches(self):
-        return len(self.nodes)
+        return len(self.boxes)
 
     def _dev_boxes(self):
         if self._boxes_dev is None:
@@ -118,7 +142,7 @@ class FixedQuadTree:
         t = _as_device_image(img, self.device)
         assert t.dim() == 3 and t.shape[2] == c2
         # like the reference's serialize: a fixed_length that the last split overshoots (!= 1 mod 3 / mod 7) is an error
-        assert len(self.nodes) <= self.fixed_length, "Not equal fixed legnth."
+        assert len(self.boxes) <= self.fixed_length, "Not equal fixed legnth."
         return ops.sap_gather(t, self._dev_boxes(), self.fixed_length, h2)
 
     def deserialize_device(self, seq, patch_size, channel):

@@ -37,11 +37,13 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-def _dt(t):
+def _dt(t, allow_u8=False):
     if t.dtype == torch.bfloat16:
         return L.UCF_DTYPE_BF16
     if t.dtype == torch.float32:
         return L.UCF_DTYPE_F32
+    if allow_u8 and t.dtype == torch.uint8:
+        return L.UCF_DTYPE_U8
     raise TypeError(f"unsupported dtype {t.dtype}")
 
 
@@ -162,7 +164,7 @@ def colsum(x, out=None, accumulate=False):
 
 
 def patchify(x, p):
-    """x [B,C,H,W] or [B,C,H,W,Z] (fp32/bf16, contiguous) -> bf16 [B*L, K8], K = C*p^dims ordered (c,p0,p1[,p2]) and
+    """x [B,C,H,W] or [B,C,H,W,Z] (fp32 / bf16 / uint8 raw pixels, contiguous) -> bf16 [B*L, K8], K = C*p^dims ordered (c,p0,p1[,p2]) and
     K8 = K rounded up to a multiple of 8 (zero pad columns; the GEMM's K extent).  Like Conv(k = s = p), pixels past
     the last whole patch are ignored."""
     _require_cuda(x)
@@ -178,7 +180,7 @@ def patchify(x, p):
     K8 = -(-K // 8) * 8
     out = torch.empty((B * L_, K8), dtype=torch.bfloat16, device=x.device)
     L.check(L.lib().ucf_patchify(x.data_ptr(), out.data_ptr(), B, C, G[0], G[1], G[2] if dims == 3 else 1, p, dims,
-                                 S[0], S[1], S[2] if dims == 3 else 1, K8, _dt(x), _stream()), "patchify")
+                                 S[0], S[1], S[2] if dims == 3 else 1, K8, _dt(x, allow_u8=True), _stream()), "patchify")
     return out
 
 
@@ -411,7 +413,8 @@ def patch_mse_bwd(pred, img, grid, patch, mask, fwd_out, grad_out):
 
 
 def adamw_multi(params, grads, exp_avgs, exp_avg_sqs, *, lr, beta1, beta2, eps, weight_decay, step, maximize=False):
-    """One in-place AdamW update of the fp32 tensors `params` (+ both moments) that share a step count."""
+    """One in-place AdamW update of the fp32 tensors `params` (+ both moments) that share a step count.
+    `lr` and `step` are host numbers, or BOTH fp32 CUDA scalars (the CUDA-graph capturable form)."""
     n = len(params)
     if n == 0:
         return
@@ -426,6 +429,14 @@ def adamw_multi(params, grads, exp_avgs, exp_avg_sqs, *, lr, beta1, beta2, eps, 
             raise ValueError("adamw_multi: parameter, gradient and moments differ in size")
     tbl = [(ctypes.c_void_p * n)(*[t.data_ptr() for t in ts]) for ts in (params, grads, exp_avgs, exp_avg_sqs)]
     cnts = (ctypes.c_longlong * n)(*[p.numel() for p in params])
+    if torch.is_tensor(lr) or (torch.is_tensor(step) and step.is_cuda):
+        if not (torch.is_tensor(lr) and torch.is_tensor(step) and lr.is_cuda and step.is_cuda and
+                lr.dtype == torch.float32 and step.dtype == torch.float32 and lr.numel() == 1 and step.numel() == 1):
+            raise TypeError("adamw_multi: device-resident lr and step must both be fp32 CUDA scalars")
+        L.check(L.lib().ucf_adamw_multi_dev(n, *tbl, cnts, lr.data_ptr(), float(beta1), float(beta2), float(eps),
+                                            float(weight_decay), step.data_ptr(), int(bool(maximize)), _stream()),
+                "adamw_multi_dev")
+        return
     L.check(L.lib().ucf_adamw_multi(n, *tbl, cnts, float(lr), float(beta1), float(beta2), float(eps),
                                     float(weight_decay), int(step), int(bool(maximize)), _stream()), "adamw_multi")
 

@@ -35,7 +35,8 @@ def configure_optimizer(model, lr, beta_1, beta_2, weight_decay, fused=None):
     """AdamW with two groups: weight decay everywhere except var/pos/time embeddings.
 
     `fused`: None = stock torch.optim.AdamW defaults (what the reference builds), True / False = torch's own
-    `fused` flag, "ucf" = this package's `FusedAdamW` (same state layout, multi-tensor CUDA update)."""
+    `fused` flag, "ucf" = this package's `FusedAdamW` (same state layout, multi-tensor CUDA update), "ucf_capturable" = the same with
+    device-resident step / learning rate so the training step can be captured in a CUDA graph (utils/graph.py)."""
     decay, no_decay = [], []
     for name, prm in model.named_parameters():
         (no_decay if ("var_embed" in name or "pos_embed" in name or "time_pos_embed" in name) else decay).append(prm)
@@ -43,9 +44,9 @@ def configure_optimizer(model, lr, beta_1, beta_2, weight_decay, fused=None):
         {"params": decay, "lr": lr, "betas": (beta_1, beta_2), "weight_decay": weight_decay},
         {"params": no_decay, "lr": lr, "betas": (beta_1, beta_2), "weight_decay": 0},
     ]
-    if fused == "ucf":
+    if fused in ("ucf", "ucf_capturable"):
         from .optim import FusedAdamW
-        return FusedAdamW(groups)
+        return FusedAdamW(groups, capturable=(fused == "ucf_capturable"))
     kw = {} if fused is None else {"fused": fused}
     return torch.optim.AdamW(groups, **kw)
 
