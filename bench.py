@@ -67,7 +67,7 @@ def run_reference_arm(args, wl):
         "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl.workload, "name": wl.name, "sample": f"batch {wl.cpu_batch} per step on the host CPU"},
-        "cpu_baseline": {"value": rate, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": wl.unit, "cores": cores, "kind": wl.cpu_kind, "sample": sample},
         "e2e": {"value": rate, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -367,7 +367,7 @@ def run_gpu_arm(args, wl):
     if world == 1 and not args.no_cpu_baseline:
         try:
             rate, cores, sec, sample = wl.cpu_rate(2 if wl.name.startswith("vit") else 1, 1 if wl.name.startswith("vit") else 0)
-            line["cpu_baseline"] = {"value": rate, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample + " on the GPU box host"}
+            line["cpu_baseline"] = {"value": rate, "unit": wl.unit, "cores": cores, "kind": wl.cpu_kind, "sample": sample + " on the GPU box host"}
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
     print(json.dumps(line), flush=True)
@@ -388,7 +388,10 @@ def main():
     ap.add_argument("--cuda-graph", action="store_true",
                     help="capture the whole training step in a CUDA graph (utils/graph.py) and replay it; the GEMM roofline "
                          "is then taken from an eager pass after the timed region")
-    ap.add_argument("--bf16-allreduce", action="store_true", help="DDP gradient all-reduce in bf16 (torch's bf16_compress_hook)")
+    ap.add_argument("--fp32-pixels", action="store_true", help="vit configs: host batches as fp32 pixels (round-1 form) instead of uint8")
+    ap.add_argument("--fp32-allreduce", action="store_true",
+                    help="DDP gradient all-reduce in fp32 (round-1 form); default: bf16 (torch's bf16_compress_hook -- the "
+                         "reference's FSDP drivers likewise reduce in bf16, MixedPrecision(reduce_dtype=bf16))")
     ap.add_argument("--optimizer", default="ucf", choices=["torch", "ucf"],
                     help="AdamW update: torch's kernel or this package's ucf_adamw_multi")
     args = ap.parse_args()

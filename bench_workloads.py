@@ -43,10 +43,12 @@ class Workload:
     batch = 1                   # samples per GPU and step
     cpu_batch = 2               # samples per step of the bounded CPU sample
     uses_fsdp = False
+    cpu_kind = "port"           # "reference" when the CPU arm ran the reference's own modules from baseline/_ref
+    find_unused = False         # the reference's SAP / UNETR drivers wrap with find_unused_parameters=True
     l2_policy = "per-step activations exceed the 126 MB L2"
 
     def parallelism(self, world):
-        return f"dp{world}"
+        return f"dp{world}" + (" (DDP, bf16 gradient all-reduce)" if world > 1 else "")
 
     # -- GPU side
     def build(self, dev, world, local, rank, args):
@@ -81,8 +83,8 @@ class Workload:
         if world <= 1:
             return model
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
-                                                        bucket_cap_mb=64)
-        if getattr(args, "bf16_allreduce", False):
+                                                        bucket_cap_mb=64, find_unused_parameters=self.find_unused)
+        if not getattr(args, "fp32_allreduce", False):
             from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
             net.register_comm_hook(None, default_hooks.bf16_compress_hook)
         return net
@@ -92,6 +94,25 @@ def _opt_kind(args, torch_default):
     if args.optimizer != "ucf":
         return torch_default
     return "ucf_capturable" if getattr(args, "cuda_graph", False) else "ucf"
+
+
+def import_reference():
+    """The UNMODIFIED reference package from baseline/_ref (installed by baseline/install_ref.sh; git-ignored, travels to
+    the GPU box) behind the third-party stand-ins of oracle/shims.  Returns the `UCF_VIT.simple.arch` module or None."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.abspath(__file__))
+    ref = os.path.join(root, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "UCF_VIT")):
+        return None
+    for p_ in (ref, os.path.join(root, "oracle", "shims")):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    try:
+        return importlib.import_module("UCF_VIT.simple.arch")
+    except Exception as ex:  # noqa: BLE001
+        print(f"[bench] reference import failed, using the oracle port: {ex}", file=sys.stderr)
+        return None
 
 
 def _cpu_state(model):
@@ -107,7 +128,7 @@ class VitClassification(Workload):
         self.name, self.workload, self.batch, self.cpu_batch = name, workload, batch, cpu_batch
         self.cfg = dict(img_size=[224, 224], patch_size=16, in_chans=3, num_classes=classes, embed_dim=embed_dim,
                         depth=depth, num_heads=heads)
-        self.l2_policy = (f"per-step inputs ({batch * 3 * 224 * 224 * 4 / 1e6:.0f} MB) and activations exceed the 126 MB L2"
+        self.l2_policy = ("per-step activations (>10 GB) exceed the 126 MB L2"
                           if batch >= 128 else "256 MB L2 flush write before every timed step")
         self.flush_l2 = batch < 128
 
@@ -119,14 +140,20 @@ class VitClassification(Workload):
     def build(self, dev, world, local, rank, args):
         from ucf_vit_b200.utils.misc import configure_optimizer
         torch.manual_seed(0)
+        self.fp32_pixels = bool(getattr(args, "fp32_pixels", False))
         self.model = self._model().to(dev).train()
         self.net = self._wrap_ddp(self.model, world, local, args)
         self.opt = configure_optimizer(self.model, 1e-4, 0.9, 0.95, 1e-5, fused=_opt_kind(args, True))
         self.lossf = torch.nn.CrossEntropyLoss()
 
+    fp32_pixels = False
+
     def host_batch(self, rank):
         g = torch.Generator().manual_seed(1234 + rank)
-        x = torch.rand(self.batch, 3, 224, 224, generator=g) * 255.0          # raw 0..255 pixels as float (catsdogs path)
+        if self.fp32_pixels:      # round-1 form: the reference's loader hands float tensors over (154 MB per 256 images)
+            x = torch.rand(self.batch, 3, 224, 224, generator=g) * 255.0
+        else:                     # decoded uint8 pixels cross the host link; ucf_patchify widens them to bf16 (exact)
+            x = torch.randint(0, 256, (self.batch, 3, 224, 224), generator=g, dtype=torch.uint8)
         y = torch.randint(0, self.cfg["num_classes"], (self.batch,), generator=g)
         return _pin(x), _pin(y)
 
@@ -146,13 +173,32 @@ class VitClassification(Workload):
         return 3 * (2 * L * K * D + blocks + 2 * D * c["num_classes"]), 3 * blocks
 
     def cpu_step_fn(self):
+        g = torch.Generator().manual_seed(0)
+        x = torch.rand(self.cpu_batch, 3, 224, 224, generator=g) * 255.0
+        y = torch.randint(0, self.cfg["num_classes"], (self.cpu_batch,), generator=g)
+        ref = import_reference()
+        if ref is not None:
+            # the reference's own VIT + configure_optimizer + training_step (train_class_simple.py:37-46,343-357), fp32
+            from UCF_VIT.utils.fused_attn import FusedAttn as RefFusedAttn
+            from UCF_VIT.utils.misc import configure_optimizer as ref_configure_optimizer
+            torch.manual_seed(0)
+            model = ref.VIT(**self.cfg, mlp_ratio=4, class_token=True, twoD=True, default_vars=VARS3,
+                            FusedAttn_option=RefFusedAttn.DEFAULT).train()
+            opt = ref_configure_optimizer(model, 1e-4, 0.9, 0.95, 1e-5)
+            lossf = torch.nn.CrossEntropyLoss()
+            self.cpu_kind = "reference"
+
+            def fn_ref():
+                loss = lossf(model.forward(x, VARS3, None), y)
+                loss.backward()
+                opt.step()
+                opt.zero_grad()
+            return fn_ref, ("the UNMODIFIED reference (baseline/_ref: UCF_VIT.simple.arch.VIT, SDPA attention, "
+                            "utils.misc.configure_optimizer AdamW), fp32 on the host cores")
         from oracle import vit_ref as R
         torch.manual_seed(0)
         sd = _cpu_state(self._model())
         opt = torch.optim.AdamW(list(sd.values()), lr=1e-4, betas=(0.9, 0.95), weight_decay=1e-5)
-        g = torch.Generator().manual_seed(0)
-        x = torch.rand(self.cpu_batch, 3, 224, 224, generator=g) * 255.0
-        y = torch.randint(0, self.cfg["num_classes"], (self.cpu_batch,), generator=g)
         cfg = dict(self.cfg)
 
         def fn():
@@ -254,12 +300,35 @@ class MaeVitLFsdp(_FsdpWorkload):
         return 3 * (blocks + other), 3 * blocks
 
     def cpu_step_fn(self):
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(self.cpu_batch, 3, 224, 224, generator=g)
+        ref = import_reference()
+        if ref is not None:
+            # the reference's own MAE and training_step (train_masked_fsdp.py:47-62, default full-MSE loss), fp32, unsharded
+            from UCF_VIT.utils.misc import configure_optimizer as ref_configure_optimizer
+            from UCF_VIT.utils.misc import patchify as ref_patchify
+            c = self.cfg
+            torch.manual_seed(0)
+            model = ref.MAE(img_size=c["img_size"], patch_size=c["patch_size"], in_chans=3, embed_dim=c["embed_dim"],
+                            depth=c["depth"], num_heads=c["num_heads"], decoder_embed_dim=c["decoder_embed_dim"],
+                            decoder_depth=c["decoder_depth"], decoder_num_heads=c["decoder_num_heads"], mlp_ratio=4,
+                            mlp_ratio_decoder=4, mask_ratio=c["mask_ratio"], linear_decoder=False, class_token=False,
+                            weight_init="skip", twoD=True, default_vars=VARS3, adaptive_patching=False).train()
+            opt = ref_configure_optimizer(model, 1e-4, 0.9, 0.95, 1e-5)
+            self.cpu_kind = "reference"
+
+            def fn_ref():
+                output, _ = model.forward(x, VARS3, None)
+                loss = torch.nn.MSELoss()(output, ref_patchify(x, 16, True))
+                loss.backward()
+                opt.step()
+                opt.zero_grad()
+            return fn_ref, ("the UNMODIFIED reference (baseline/_ref: UCF_VIT.simple.arch.MAE + utils.misc.patchify / "
+                            "configure_optimizer), fp32, unsharded, no recompute, on the host cores")
         from oracle import vit_ref as R
         torch.manual_seed(0)
         sd = _cpu_state(self._model(fsdp=False))
         opt = torch.optim.AdamW(list(sd.values()), lr=1e-4, betas=(0.9, 0.95), weight_decay=1e-5)
-        g = torch.Generator().manual_seed(0)
-        x = torch.randn(self.cpu_batch, 3, 224, 224, generator=g)
         noise = torch.rand(self.cpu_batch, 196, generator=g)
         cfg = dict(self.cfg, kind="mae")
         target = R.patchify_target(x, 16, True)
@@ -361,6 +430,7 @@ class DiffusionFsdp(_FsdpWorkload):
 # configs[3]: UNETR 3-D with variable aggregation, training_scripts/train_unetr_simple.py:34-41,447-452
 # ------------------------------------------------------------------------------------------------
 class Unetr128(Workload):
+    find_unused = True          # train_unetr_simple.py:273
     name = "unetr_128"
     unit = "volumes/s"
     workload = ("UNETR 3-D segmentation train step (fwd+DiceCE+bwd+AdamW), 128^3 volumes, 4 variable channels aggregated by "
@@ -471,6 +541,7 @@ class Unetr128(Workload):
 # front end dataloaders/transform.py:21-54 (Patchify.forward) that produces its sequences
 # ------------------------------------------------------------------------------------------------
 class Sap4096(Workload):
+    find_unused = True          # train_sap_simple.py:255,331
     unit = "images/s"
     cpu_batch = 1
 

@@ -1,0 +1,200 @@
+"""Drop-in proof through the reference's own configuration files and driver code.
+
+* every `configs/*/*/base_config.yaml` the reference ships is turned into the product model exactly the way the
+  matching reference driver does it (`model.net.init_args` + `data` -> constructor kwargs; citations per driver below);
+  the YAML contents are pinned in tests/golden/reference_yaml_configs.json (oracle/gen_ref_configs.py) and re-read from
+  /root/reference when it is present
+* (-m gpu) the loop body of training_scripts/train_class_simple_torchDataloader.py:172-199,274-293 runs verbatim in
+  structure with `UCF_VIT` aliased to this package (`ucf_vit_b200.install_as`), single-rank NCCL group, synthetic data
+* (-m gpu) the basic_ct configs (patch 4, head_dim 36 decoder, 3-D adaptive sequences) take a forward/backward step
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CFGS = json.load(open(os.path.join(HERE, "golden", "reference_yaml_configs.json")))
+
+
+def _common(ia, data):
+    """the kwargs every driver derives the same way (e.g. train_unetr_simple.py:126-146,205-243)"""
+    adaptive = ia["adaptive_patching"]
+    twoD = ia["twoD"]
+    fixed_length = ia["fixed_length"] if adaptive else None
+    sqrt_len = None
+    if adaptive:
+        sqrt_len = int(math.sqrt(fixed_length)) if twoD else int(np.rint(math.pow(fixed_length, 1 / 3)))
+    single = data.get("single_channel", False)
+    max_channels = 1
+    if not single:
+        for v in data.get("num_channels_used", {}).values():
+            if v > 1:
+                max_channels = v
+    return adaptive, twoD, fixed_length, sqrt_len, single, max_channels
+
+
+def build_from_yaml(key, pkg="ucf_vit_b200"):
+    import importlib
+    A = importlib.import_module(pkg + ".simple.arch")
+    FusedAttn = importlib.import_module(pkg + ".utils.fused_attn").FusedAttn
+    c = CFGS[key]
+    ia, data = c["init_args"], c["data"]
+    adaptive, twoD, fixed_length, sqrt_len, single, max_channels = _common(ia, data)
+    kind = key.split("/")[1]
+    base = dict(img_size=ia["tile_size"], patch_size=ia["patch_size"], embed_dim=ia["embed_dim"], depth=ia["depth"],
+                num_heads=ia["num_heads"], mlp_ratio=ia["mlp_ratio"], drop_path_rate=ia["drop_path"], twoD=twoD,
+                default_vars=ia["default_vars"], use_varemb=ia["use_varemb"], adaptive_patching=adaptive,
+                fixed_length=fixed_length, FusedAttn_option=FusedAttn.DEFAULT)
+    dec = {k: ia[k] for k in ("decoder_depth", "decoder_embed_dim", "decoder_num_heads", "mlp_ratio_decoder") if k in ia}
+    if kind == "classification":       # train_class_simple_torchDataloader.py:172-192
+        in_ch = len(next(iter(data["dict_in_variables"].values())))
+        return A.VIT(num_classes=data.get("num_classes", 1000), in_chans=in_ch, drop_rate=ia.get("drop_rate", 0.0),
+                     weight_init='', use_adaptive_pos_emb=ia.get("use_adaptive_pos_emb") if adaptive else None, **base)
+    if kind == "mae":                  # train_masked_simple.py (model = MAE(...))
+        return A.MAE(in_chans=max_channels, mask_ratio=ia["mask_ratio"], linear_decoder=ia["linear_decoder"],
+                     single_channel=single, use_adaptive_pos_emb=ia.get("use_adaptive_pos_emb") if adaptive else None,
+                     class_token=False, weight_init='skip', **dec, **base)
+    if kind == "diffusion":            # train_diffusion_simple.py (model = DiffusionVIT(...))
+        return A.DiffusionVIT(in_chans=max_channels, linear_decoder=ia["linear_decoder"], single_channel=single,
+                              time_steps=ia["num_time_steps"], class_token=False, weight_init='skip', **dec, **base)
+    if kind == "unetr":                # train_unetr_simple.py:245-270
+        return A.UNETR(in_chans=max_channels, num_classes=data["num_classes"], linear_decoder=ia["linear_decoder"],
+                       feature_size=ia["feature_size"], skip_connection=ia["skip_connection"], single_channel=single,
+                       sqrt_len=sqrt_len, use_adaptive_pos_emb=ia.get("use_adaptive_pos_emb") if adaptive else None,
+                       sqrt_len_method=bool(adaptive), class_token=False, weight_init='skip', **base)
+    if kind == "sap":                  # train_sap_simple.py:228-250
+        return A.SAP(in_chans=max_channels, num_classes=data["num_classes"], single_channel=single, sqrt_len=sqrt_len,
+                     use_adaptive_pos_emb=ia.get("use_adaptive_pos_emb") if adaptive else None, sqrt_len_method=True,
+                     class_token=False, weight_init='skip', **base)
+    raise KeyError(key)
+
+
+def test_fixture_matches_the_reference_yaml_files():
+    if not os.path.isdir("/root/reference/configs"):
+        pytest.skip("/root/reference is not present on this machine; the committed fixture is used as is")
+    from oracle.gen_ref_configs import load_all
+    assert json.loads(json.dumps(load_all(), sort_keys=True)) == CFGS
+
+
+@pytest.mark.parametrize("key", sorted(CFGS))
+def test_every_reference_yaml_builds_the_product_model(key):
+    m = build_from_yaml(key)
+    n = sum(p.numel() for p in m.parameters())
+    assert n > 1e6, (key, n)
+    ia = CFGS[key]["init_args"]
+    assert len(m.blocks) == ia["depth"] and m.embed_dim == ia["embed_dim"]
+    if "decoder_depth" in ia and key.split("/")[1] in ("mae", "diffusion"):
+        assert len(m.decoder_blocks) == ia["decoder_depth"]
+        assert m.decoder_blocks[0].attn.head_dim == ia["decoder_embed_dim"] // ia["decoder_num_heads"]
+
+
+def test_install_as_aliases_the_reference_import_paths():
+    import sys
+    import ucf_vit_b200
+    ucf_vit_b200.install_as("UCF_VIT_alias_test")
+    from UCF_VIT_alias_test.simple.arch import VIT          # noqa: F401
+    from UCF_VIT_alias_test.fsdp.building_blocks import Block   # noqa: F401
+    from UCF_VIT_alias_test.utils.misc import configure_optimizer, configure_scheduler   # noqa: F401
+    from UCF_VIT_alias_test.utils.fused_attn import FusedAttn   # noqa: F401
+    from UCF_VIT_alias_test.dataloaders.transform import Patchify   # noqa: F401
+    assert sys.modules["UCF_VIT_alias_test.simple.arch"] is sys.modules["ucf_vit_b200.simple.arch"]
+
+
+@pytest.mark.gpu
+def test_reference_class_driver_loop_runs_on_the_product_package():
+    """train_class_simple_torchDataloader.py: model construction :172-192, DDP wrap :196, optimizer / scheduler :198-199,
+    training_step :37-46 (CrossEntropy on net.forward(data, variables, seq_ps)), loop body :274-293."""
+    import socket
+    import torch.distributed as dist
+    import ucf_vit_b200
+    ucf_vit_b200.install_as("UCF_VIT")
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from UCF_VIT.simple.arch import VIT
+    from UCF_VIT.utils.fused_attn import FusedAttn
+    from UCF_VIT.utils.misc import configure_optimizer, configure_scheduler
+    c = CFGS["catsdogs/classification"]
+    ia, data, mc = c["init_args"], c["data"], c["model"]
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    device = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=device)
+    try:
+        torch.manual_seed(0)
+        model = VIT(img_size=ia["tile_size"], patch_size=ia["patch_size"], num_classes=data["num_classes"],
+                    in_chans=len(data["dict_in_variables"]["catsdogs"]), embed_dim=ia["embed_dim"], depth=ia["depth"],
+                    num_heads=ia["num_heads"], mlp_ratio=ia["mlp_ratio"], drop_path_rate=ia["drop_path"],
+                    drop_rate=ia["drop_rate"], twoD=ia["twoD"], weight_init='', default_vars=ia["default_vars"],
+                    use_varemb=ia["use_varemb"], adaptive_patching=ia["adaptive_patching"], fixed_length=None,
+                    FusedAttn_option=FusedAttn.DEFAULT, use_adaptive_pos_emb=None).to(device)
+        model = DDP(model, device_ids=[0], output_device=[0], find_unused_parameters=True)
+        optimizer = configure_optimizer(model, float(mc["lr"]) * 30, float(mc["beta_1"]), float(mc["beta_2"]), float(mc["weight_decay"]))
+        scheduler = configure_scheduler(optimizer, 2, 20, float(mc["warmup_start_lr"]), float(mc["eta_min"]))
+
+        def training_step(data_, variables, label, net, seq_ps):
+            output = net.forward(data_, variables, seq_ps)
+            loss = torch.nn.CrossEntropyLoss()(output, label)
+            return loss, output
+
+        g = torch.Generator().manual_seed(0)
+        B = 8
+        data_ = torch.rand(B, 3, *ia["tile_size"], generator=g).to(device).to(torch.float32)
+        label = torch.randint(0, data["num_classes"], (B,), generator=g).to(device)
+        variables = ia["default_vars"]
+        model.train()
+        losses = []
+        for it in range(8):
+            loss, output = training_step(data_, variables, label, model, None)
+            acc = (output.argmax(dim=1) == label).float().mean()
+            losses.append(loss.item())
+            loss.backward()
+            optimizer.step()
+            optimizer.zero_grad()
+            scheduler.step()
+        assert all(math.isfinite(l) for l in losses)
+        assert losses[-1] < losses[0], losses
+        assert 0.0 <= acc.item() <= 1.0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["basic_ct/mae", "basic_ct/diffusion", "basic_ct/sap", "imagenet/mae"])
+def test_reference_yaml_models_take_a_training_step(key):
+    """patch_size 4, 3-D adaptive sequences and the head_dim-36 decoder (576 / 16) of configs/basic_ct; the adaptive
+    2-D imagenet MAE.  Inputs follow the drivers' shapes (train_masked_simple.py training_step_adaptive: seq [B, C, L, p^d],
+    seq_ps [B, L, 1 + d])."""
+    c = CFGS[key]
+    ia = c["init_args"]
+    model = build_from_yaml(key).cuda().train()
+    kind = key.split("/")[1]
+    adaptive, twoD, L, sqrt_len, single, C = _common(ia, c["data"])
+    p, nd = ia["patch_size"], 2 if twoD else 3
+    variables = ia["default_vars"]
+    g = torch.Generator().manual_seed(0)
+    B = 2
+    if kind == "mae":
+        seq = torch.randn(B, C, L, p ** nd, generator=g).cuda()
+        seq_ps = torch.rand(B, L, 1 + nd, generator=g).cuda() if ia.get("use_adaptive_pos_emb") else None
+        out, mask = model(seq.squeeze(1) if single and False else seq, variables, seq_ps)
+        assert out.shape == (B, L, p ** nd * C)
+    elif kind == "diffusion":
+        x = torch.randn(B, C, L, p ** nd, generator=g).cuda() if adaptive else torch.randn(B, C, *ia["tile_size"], generator=g).cuda()
+        t = torch.randint(0, ia["num_time_steps"], (B,), generator=g).cuda()
+        out = model(x, t, variables)
+    else:
+        side = p * sqrt_len
+        x = torch.randn(B, C, *([side] * nd), generator=g).cuda()
+        seq_ps = torch.rand(B, L, 1 + nd, generator=g).cuda()
+        out = model(x, variables, seq_ps)
+        assert out.shape == (B, c["data"]["num_classes"], *([side] * nd))
+    loss = out.float().pow(2).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    assert math.isfinite(loss.item())
+    grads = [q.grad for q in model.parameters() if q.grad is not None]
+    assert len(grads) > 50 and all(torch.isfinite(gq).all() for gq in grads)

@@ -56,18 +56,41 @@ def _worker(rank, world, port, ret):
         apply_activation_checkpointing(model, checkpoint_wrapper_fn=checkpoint_wrapper,
                                        check_fn=lambda m: isinstance(m, Block))
         opt = configure_optimizer(model, 1e-3, 0.9, 0.95, 1e-5)
-        g = torch.Generator().manual_seed(100 + rank)
-        x = torch.randn(8, 3, 64, 64, generator=g).cuda().to(torch.bfloat16)
+        xs = [torch.randn(8, 3, 64, 64, generator=torch.Generator().manual_seed(100 + r)).cuda().to(torch.bfloat16)
+              for r in range(world)]
+        x = xs[rank]
         target = patchify(x.float(), 8, True)
+        # the random masking must be the same in the sharded and the unsharded run: the device generator is re-seeded
+        # per step and rank right before the forward pass
         losses = []
-        for _ in range(6):
+        for st in range(6):
+            torch.manual_seed(1000 * st + rank)           # MAE.random_masking draws torch.rand on the device
             pred, mask = model(x, ["r", "g", "b"])
             loss = torch.nn.functional.mse_loss(pred.float(), target)
             opt.zero_grad(set_to_none=True)
             loss.backward()
             opt.step()
-            losses.append(loss.item())
-        ret[rank] = losses
+            l = loss.detach().clone()
+            dist.all_reduce(l)
+            losses.append(l.item() / world)
+        # the same training run WITHOUT FSDP / sharding / checkpointing: the plain product model on the global batch
+        # (equal per-rank batches: the mean of the per-rank losses is the global-batch loss, and FSDP averages gradients)
+        plain = _build().cuda().train()
+        opt_p = configure_optimizer(plain, 1e-3, 0.9, 0.95, 1e-5)
+        xg = torch.cat(xs)
+        tg = patchify(xg.float(), 8, True)
+        losses_plain = []
+        for st in range(6):
+            preds = []
+            for r in range(world):                          # same per-rank masking draws as above
+                torch.manual_seed(1000 * st + r)
+                preds.append(plain(xs[r], ["r", "g", "b"])[0])
+            loss = torch.nn.functional.mse_loss(torch.cat(preds).float(), tg)
+            opt_p.zero_grad(set_to_none=True)
+            loss.backward()
+            opt_p.step()
+            losses_plain.append(loss.item())
+        ret[rank] = (losses, losses_plain)
     finally:
         dist.barrier()
         dist.destroy_process_group()
@@ -79,6 +102,9 @@ def test_fsdp_mixed_precision_activation_checkpointing_trains():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     for r in range(world):
-        losses = ret[r]
+        losses, losses_plain = ret[r]
         assert all(l == l and abs(l) < 1e4 for l in losses), losses          # finite
         assert losses[-1] < losses[0], losses                                # it learns the fixed batch
+        # sharded (bf16 parameters / bf16 gradient reduction / recompute) vs unsharded product: same trajectory
+        for a, b in zip(losses, losses_plain):
+            assert abs(a - b) <= 1e-2 * abs(b), (losses, losses_plain)
