@@ -1,5 +1,5 @@
 """Run ONE hot kernel a few times so that ncu can capture it in isolation.
-python scripts/gpu_one_kernel.py {fc1_gelu|fc2_dgelu|fc1_plain|attn_fwd|attn_bwd|ln_fwd|ln_bwd|wgrad}"""
+python scripts/gpu_one_kernel.py {fc1_gelu|fc2_dgelu|fc1_plain|attn_fwd|attn_bwd|ln_fwd|ln_bwd|wgrad|sap_gather|var_attn} [B N H hd]"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -20,8 +20,25 @@ elif which == "wgrad":
     dz = bf(torch.randn(M, Hd, device=dev)); x = bf(torch.randn(M, D, device=dev))
     dw = torch.zeros(Hd, D, device=dev); db = torch.zeros(Hd, device=dev)
     f = lambda: ops.gemm(dz, x, M=Hd, N=D, K=M, a_mn=True, b_mn=True, epilogue=L.EPI_F32_ADD, out=dw, splits=8, bias_grad=db)
+elif which == "sap_gather":
+    import numpy as np
+    from ucf_vit_b200.dataloaders.quadtree import FixedQuadTree
+    import bench_workloads
+    g = torch.Generator().manual_seed(0)
+    edge = bench_workloads.Sap4096._edge_map(g)
+    img = torch.randint(0, 256, (4096, 4096, 3), generator=g, dtype=torch.uint8).to(dev)
+    qdt = FixedQuadTree(edge, 4096, device=dev)
+    f = lambda: qdt.serialize_device(img, size=(16, 16, 3))
+elif which == "var_attn":
+    rows, V, H, hd = 16 * 512, 4, 12, 64          # UNETR 128^3 / patch 16, batch 16, 4 variables
+    q = bf(torch.randn(1, 1, H, hd, device=dev)); kv = bf(torch.randn(rows, V, 2, H, hd, device=dev))
+    o, lse = ops.var_attention_fwd(q, kv, hd ** -0.5)
+    do = torch.randn_like(o)
+    def f():
+        ops.var_attention_fwd(q, kv, hd ** -0.5)
+        ops.var_attention_bwd(q, kv, o, do, lse, hd ** -0.5)
 elif which in ("attn_fwd", "attn_bwd"):
-    B, N, H, hd = 256, 197, 12, 64
+    B, N, H, hd = [int(a) for a in sys.argv[2:6]] if len(sys.argv) >= 6 else (256, 197, 12, 64)
     qkv = bf(torch.randn(B, N, 3, H, hd, device=dev))
     q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
     o, lse = ops.attention_fwd(q, k, v, hd ** -0.5)
