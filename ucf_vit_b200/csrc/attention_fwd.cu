@@ -83,7 +83,7 @@ struct AttnFwdCfg {
   static constexpr int TMEM_COLS = 512;                // WG g: S at g*256 (128), O at +128 (HD), P (bf16 pairs) at +192 (64)
   static constexpr int ROW_BYTES = HD * 2;
   static constexpr int ATOM_BYTES = 8 * ROW_BYTES;
-  static constexpr int THREADS = 64 + 256 + 32;        // producer, MMA 0, 8 softmax warps, MMA 1
+  static constexpr int THREADS = 64 + 256;             // producer, MMA issuer, 8 softmax warps
   static_assert(SMEM_BYTES <= 232448, "smem");
 };
 
@@ -135,7 +135,7 @@ __device__ __forceinline__ uint32_t pack_p(float2 pp) {
 }
 
 template <int HD, int POLY, bool TRUNC>     // POLY: pairs (of 16) per 32-column chunk whose exp2 runs on the FMA pipe; TRUNC: see pack_p
-__global__ void __launch_bounds__(352, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                  const AttnFwdParams p) {
@@ -165,8 +165,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
-    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 2); }      // (2: one commit per MMA stream)
-    for (int i = 0; i < RING; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < RING; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
       mbar_init(&p_full[g], 4);
@@ -217,26 +217,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1 || warp == 10) {
-    // ------------------------------------------------------------------ MMA issuers: one warp per warpgroup, each walking its own
-    // continuous stream of key tiles across work items (S_g(next tile) -- also the first tile of the NEXT item -- goes out
-    // right behind the hand-over of P_g(this tile), ahead of PV_g(this tile)).  With one shared issuer a warpgroup's
-    // hand-over sat ~400 cycles behind the other warpgroup's blocking waits and MMA issue (profiles/r02_attn_fwd_timeline.txt).
-    // An idle stream (query tile g past Nq) still walks the ring and releases every slot.
-    const int g = warp == 1 ? 0 : 1;
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer: one continuous stream of key tiles
     if (my_items > 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, false, false);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, false, true);
-      const uint32_t d_s = tmem_base + g * 256, d_o = d_s + 128, d_p = d_s + 192;
-      auto valid = [&](int k) { return item_q0(k) + g * BQ < p.Nq; };
-      uint32_t pc = 0;               // P tiles consumed (p_full parity)
+      uint32_t pc[2] = {0, 0};       // P tiles consumed per warpgroup (p_full parity)
 
-      auto issue_s = [&](int k, uint32_t k_addr) {      // S_g of a tile of item k
+      auto issue_s = [&](int g, int k, uint32_t k_addr) {      // S_g of a tile of item k
         const uint32_t q_addr = smem_u32(q_s + ((k & 1) * 2 + g) * Cfg::Q_BYTES);
+        const uint32_t d = tmem_base + g * 256;
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < HD / 16; ++kk)
-            umma_bf16(d_s, attn_desc<RB>(q_addr + kk * 32, 16, AB), attn_desc<RB>(k_addr + kk * 32, 16, AB), idesc_s,
+            umma_bf16(d, attn_desc<RB>(q_addr + kk * 32, 16, AB), attn_desc<RB>(k_addr + kk * 32, 16, AB), idesc_s,
                       kk > 0 ? 1u : 0u);
           umma_commit(&s_full[g]);
         }
@@ -244,20 +238,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       };
 
       uint32_t r = 0;                // ring position of the current tile's K (V follows at r + 1)
-      if (g == 1) {                  // warpgroup 1 starts out of phase, once
-        const long long t0 = clock64();
-        while (clock64() - t0 < p.stagger_cycles) { }
-      }
+      // prologue: S of the first tile; warpgroup 1 starts `stagger_cycles` late, once
       {
         mbar_wait(&q_full[0], 0);
         mbar_wait(&kv_full[0], 0);
         tc_fence_after();
-        if (valid(0)) issue_s(0, smem_u32(kv_s));
+        const uint32_t k_addr = smem_u32(kv_s);
+        const int q0 = item_q0(0);
+        issue_s(0, 0, k_addr);
+        if (q0 + BQ < p.Nq) {
+          const long long t0 = clock64();
+          while (clock64() - t0 < p.stagger_cycles) { }
+          issue_s(1, 0, k_addr);
+        }
         if (elect_one()) umma_commit(&kv_empty[0]);
         __syncwarp();
       }
       for (int k = 0; k < my_items; ++k) {
-        const bool v = valid(k);
+        const int q0 = item_q0(k);
+        const int ng = (q0 + BQ < p.Nq) ? 2 : 1;
         for (int j = 0; j < nkv; ++j, r += 2) {
           const bool last_tile = j + 1 == nkv;
           const bool has_next = !(last_tile && k + 1 == my_items);
@@ -265,35 +264,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const int sv = (r + 1) % RING;
           mbar_wait(&kv_full[sv], ((r + 1) / RING) & 1);
           const uint32_t v_addr = smem_u32(kv_s + sv * Cfg::KV_BYTES);
-          int sk = 0;
+          int sk = 0, ng_next = 0;
           uint32_t k_addr = 0;
           if (has_next) {
             if (last_tile) mbar_wait(&q_full[kn & 1], (kn >> 1) & 1);
             sk = (r + 2) % RING;
             mbar_wait(&kv_full[sk], ((r + 2) / RING) & 1);
             k_addr = smem_u32(kv_s + sk * Cfg::KV_BYTES);
+            ng_next = last_tile ? ((item_q0(kn) + BQ < p.Nq) ? 2 : 1) : ng;
           }
           const int ksteps = last_tile ? ksteps_last : BKV / 16;
-          if (v) {
-            mbar_wait(&p_full[g], pc & 1);       // P_g(j) is in tensor memory and S_g(j) has been read
-            UCF_F2TL(pc, g, 3);
-            ++pc;
-            tc_fence_after();
-          }
-          // S_g of the NEXT tile first: it does not depend on P, and it is what the warpgroup is waiting for
-          if (has_next && valid(kn)) issue_s(kn, k_addr);
-          if (elect_one()) {
-            if (v) {
-              for (int kk = 0; kk < ksteps; ++kk)
-                umma_bf16_ts(d_o, d_p + kk * 8, attn_desc<RB>(v_addr + kk * 2 * AB, 0, AB), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-              umma_commit(&pv_full[g]);             // PV_g(j) retired: P_g may be rewritten (and, last tile: O_g is complete)
+          for (int g = 0; g < 2; ++g) {
+            if (g < ng) {
+              mbar_wait(&p_full[g], pc[g] & 1);       // P_g(j) is in tensor memory and S_g(j) has been read
+              UCF_F2TL(pc[g], g, 3);
+              ++pc[g];
+              tc_fence_after();
             }
+            // S_g of the NEXT tile first: it does not depend on P, and it is what the warpgroup is waiting for
+            if (has_next && g < ng_next) issue_s(g, kn, k_addr);
+            if (g < ng) {
+              const uint32_t d = tmem_base + g * 256 + 128;
+              const uint32_t pt = tmem_base + g * 256 + 192;          // P_g: bf16 pairs, 8 columns per 16 keys
+              if (elect_one()) {
+                for (int kk = 0; kk < ksteps; ++kk)
+                  umma_bf16_ts(d, pt + kk * 8, attn_desc<RB>(v_addr + kk * 2 * AB, 0, AB), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(&pv_full[g]);             // PV_g(j) retired: P_g may be rewritten (and, last tile: O_g is complete)
+              }
+              __syncwarp();
+            }
+            UCF_F2TL(pc[g] - 1, g, 4);
+          }
+          if (elect_one()) {
             umma_commit(&kv_empty[sv]);
             if (has_next) umma_commit(&kv_empty[sk]);
             if (last_tile) umma_commit(&q_empty[k & 1]);
           }
           __syncwarp();
-          UCF_F2TL(pc - 1, g, 4);
         }
       }
     }
