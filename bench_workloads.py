@@ -455,6 +455,9 @@ class Unetr128(Workload):
         from ucf_vit_b200.utils.misc import configure_optimizer
         torch.manual_seed(0)
         self.model = self._model().to(dev).train()
+        if getattr(args, "bf16_decoder", False):
+            self.model.conv_autocast_dtype = torch.bfloat16
+            self.workload = self.workload.replace("conv decoder (feature_size 16)", "conv decoder (feature_size 16) under bf16 autocast")
         self.net = self._wrap_ddp(self.model, world, local, args)
         self.opt = configure_optimizer(self.model, 1e-5, 0.9, 0.95, 1e-5, fused=_opt_kind(args, True))
         self.lossf = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)

@@ -4,7 +4,7 @@ N=${1:-1}
 TAG=${2:-r02}
 STEPS=${3:-10}
 mkdir -p gpurun_out
-for c in vit_b16 vit_tiny mae_vitl_fsdp diffusion_fsdp unetr_128 sap_4096_L1024 sap_4096_L4096; do
+for c in ${CONFIGS:-vit_b16 vit_tiny mae_vitl_fsdp diffusion_fsdp unetr_128 sap_4096_L1024 sap_4096_L4096}; do
   if [ "$N" = "1" ]; then
     timeout 600 python bench.py --config $c --steps $STEPS --warmup 3 > gpurun_out/${TAG}_bench_${c}_n${N}.json 2> gpurun_out/${TAG}_bench_${c}_n${N}.err
   else

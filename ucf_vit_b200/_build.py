@@ -51,7 +51,11 @@ def build(force: bool = False, verbose: bool = True) -> str:
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         res = list(ex.map(lambda s: _compile(s, force, hdr_m), _sources()))
     objs = [o for o, _ in res]
-    if force or any(c for _, c in res) or not os.path.exists(LIB):
+    stale = [f for f in os.listdir(OBJ) if f.endswith(".o") and os.path.join(OBJ, f) not in objs]
+    for f in stale:                      # object of a source file that no longer exists: drop it and relink
+        os.remove(os.path.join(OBJ, f))
+    if force or stale or any(c for _, c in res) or not os.path.exists(LIB) or \
+            any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

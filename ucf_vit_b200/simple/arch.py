@@ -614,13 +614,28 @@ class UNETR(VIT):
     def forward_head(self, x: torch.Tensor, intermediates, enc1):
         return self.unetr_head(self.pool(x), intermediates, enc1)
 
+    # Convolutional decoder precision.  None (default): cuDNN in the parameter dtype, like the reference.  torch.bfloat16:
+    # the decoder's convolutions run under autocast in bf16 (fp32 accumulate; InstanceNorm statistics stay fp32) -- not the
+    # reference's arithmetic, opt-in for throughput (bench.py --config unetr_128 states which one it timed).
+    conv_autocast_dtype = None
+
+    def _conv_ctx(self):
+        import contextlib
+        if self.conv_autocast_dtype is None:
+            return contextlib.nullcontext()
+        return torch.autocast("cuda", dtype=self.conv_autocast_dtype)
+
     def forward(self, x: torch.Tensor, variables, seq_ps=None, x_seq=None) -> torch.Tensor:
         tokens_in = x_seq if self.adaptive_patching else x
         if self.skip_connection:
-            enc1 = _torch_head(self.encoder1, x)
+            with self._conv_ctx():
+                enc1 = _torch_head(self.encoder1, x)
             feats, inter = self.forward_intermediates(tokens_in, variables, seq_ps, indices=self.skip_indices)
-            return self.forward_head(feats, inter, enc1)
-        return self.forward_head(self.forward_features(tokens_in, variables, seq_ps), None, None)
+            with self._conv_ctx():
+                return self.forward_head(feats, inter, enc1)
+        feats = self.forward_features(tokens_in, variables, seq_ps)
+        with self._conv_ctx():
+            return self.forward_head(feats, None, None)
 
 
 # ---------------------------------------------------------------------------------------------
