@@ -66,6 +66,17 @@ int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* bias, void*
                   int a_layout, int b_layout, int epilogue, int bias_dtype, int splits, int tile_n,
                   void* bias_grad, void* stream);
 
+/* The attention-output dgrad with the attention backward's row statistic fused into its epilogue:
+ *   dX[M, N] = dY[M, K] * W[K, N]   (W = Attention.proj.weight [out = K, in = N], read MN-major in place)
+ *   delta[b, h, n] = sum_{d < N/heads} dX[b*tokens + n, h*hd + d] * O[b*tokens + n, h*hd + d]
+ * i.e. `d_o = d_x1 @ proj.weight` of Attention.proj's backward (building_blocks.py:154,189) plus the
+ * rowsum(dO o O) pass a flash-attention backward starts with (replaces a separate 2 x M x N read).  delta is taken from
+ * the fp32 accumulator tile.  O: bf16 [M, N] (pitch ldo), delta: fp32 [M / tokens, heads, tokens].  Shapes the fused
+ * kernel serves: ucf_gemm_dgrad_delta_supported() != 0 (head_dim 32 / 64, N a multiple of 128 in 512..4096, M >= 512). */
+int ucf_gemm_dgrad_delta_supported(int M, int N, int K, int heads);
+int ucf_gemm_dgrad_delta(const void* dY, const void* W, void* dX, const void* O, float* delta, int M, int N, int K,
+                         long long lddy, long long ldw, long long lddx, long long ldo, int tokens, int heads, void* stream);
+
 /* ---- LayerNorm (replaces nn.LayerNorm at arch.py:170,266; building_blocks.py:212,226) ------
  * x: [rows, D] (x_dtype), gamma/beta: [D] (param_dtype, may be NULL = 1/0), y: [rows, D] bf16,
  * mean/rstd: [rows] fp32 (saved for backward).  D % 8 == 0, D <= 4096. */
@@ -95,6 +106,18 @@ int ucf_attention_fwd(const void* q, const void* k, const void* v, void* o, floa
  * dq/dk/dv: bf16, addressed like q/k/v (may alias a packed dqkv buffer). */
 int ucf_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                       const float* lse, void* dq, void* dk, void* dv, float* dq_acc, float* delta,
+                      int B, int H, int Nq, int Nk, int hd,
+                      long long q_sb, long long q_sn, long long q_sh,
+                      long long k_sb, long long k_sn, long long k_sh,
+                      long long v_sb, long long v_sn, long long v_sh,
+                      long long o_sb, long long o_sn, long long o_sh,
+                      long long dq_sb, long long dq_sn, long long dq_sh,
+                      long long dk_sb, long long dk_sn, long long dk_sh,
+                      long long dv_sb, long long dv_sn, long long dv_sh,
+                      float scale, void* stream);
+/* The same with `delta` already holding rowsum(dO o O) (written by ucf_gemm_dgrad_delta): skips the delta pass. */
+int ucf_attention_bwd_with_delta(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                      const float* lse, void* dq, void* dk, void* dv, float* dq_acc, const float* delta,
                       int B, int H, int Nq, int Nk, int hd,
                       long long q_sb, long long q_sn, long long q_sh,
                       long long k_sb, long long k_sn, long long k_sh,

@@ -413,3 +413,19 @@ def test_add_bcast_fwd_bwd(xs, es, edt):
     assert torch.equal(x.grad.float(), x32.grad)
     assert e.grad.dtype == edt and e.grad.shape == e.shape
     _ok(e.grad, e32.grad, 1e-2 if edt == torch.bfloat16 else 2e-3)
+
+
+@pytest.mark.parametrize("B,N,D,H", [(256, 197, 768, 12), (5, 300, 512, 16), (3, 1000, 1024, 16)])
+def test_dgrad_with_fused_attention_delta(B, N, D, H):
+    """ucf_gemm_dgrad_delta: the attention-output dgrad whose epilogue also leaves rowsum(dO o O) per head."""
+    torch.manual_seed(B + N)
+    M, hd = B * N, D // H
+    dy = bf(torch.randn(M, D, device=dev))
+    w = bf(torch.randn(D, D, device=dev) * 0.05)
+    o = bf(torch.randn(M, D, device=dev))
+    dx, delta = ops.gemm_dgrad_delta(dy, w, o, N, H)
+    ref = dy.float() @ w.float()
+    _ok(dx, ref, 1e-2)
+    assert torch.equal(dx, ops.gemm(dy, w, M=M, N=D, K=D, b_mn=True))          # same product as the plain dgrad kernel
+    dref = (ref * o.float()).view(B, N, H, hd).sum(-1).permute(0, 2, 1)
+    _ok(delta, dref, 2e-3)

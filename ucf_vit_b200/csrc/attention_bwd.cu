@@ -975,6 +975,18 @@ extern "C" void ucf_debug_set_attn_bwd_variant(int v) { g_bwd_variant = v; }
 /* profiling aid (not part of the public header): device buffer of 64 int64 receiving clock64 stamps */
 extern "C" void ucf_debug_set_attn_bwd_timeline(void* dev_ptr) { g_bwd_timeline = static_cast<long long*>(dev_ptr); }
 
+static int attention_bwd_impl(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                 const float* lse, void* dq, void* dk, void* dv, float* dq_acc, float* delta,
+                                 int B, int H, int Nq, int Nk, int hd,
+                                 long long q_sb, long long q_sn, long long q_sh,
+                                 long long k_sb, long long k_sn, long long k_sh,
+                                 long long v_sb, long long v_sn, long long v_sh,
+                                 long long o_sb, long long o_sn, long long o_sh,
+                                 long long dq_sb, long long dq_sn, long long dq_sh,
+                                 long long dk_sb, long long dk_sn, long long dk_sh,
+                                 long long dv_sb, long long dv_sn, long long dv_sh,
+                                 float scale, void* stream, bool delta_ready);
+
 extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                                  const float* lse, void* dq, void* dk, void* dv, float* dq_acc, float* delta,
                                  int B, int H, int Nq, int Nk, int hd,
@@ -986,6 +998,38 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
                                  long long dk_sb, long long dk_sn, long long dk_sh,
                                  long long dv_sb, long long dv_sn, long long dv_sh,
                                  float scale, void* stream) {
+  return attention_bwd_impl(q, k, v, o, d_o, lse, dq, dk, dv, dq_acc, delta, B, H, Nq, Nk, hd, q_sb, q_sn, q_sh, k_sb, k_sn, k_sh,
+                            v_sb, v_sn, v_sh, o_sb, o_sn, o_sh, dq_sb, dq_sn, dq_sh, dk_sb, dk_sn, dk_sh, dv_sb, dv_sn, dv_sh,
+                            scale, stream, false);
+}
+
+extern "C" int ucf_attention_bwd_with_delta(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                 const float* lse, void* dq, void* dk, void* dv, float* dq_acc, const float* delta,
+                                 int B, int H, int Nq, int Nk, int hd,
+                                 long long q_sb, long long q_sn, long long q_sh,
+                                 long long k_sb, long long k_sn, long long k_sh,
+                                 long long v_sb, long long v_sn, long long v_sh,
+                                 long long o_sb, long long o_sn, long long o_sh,
+                                 long long dq_sb, long long dq_sn, long long dq_sh,
+                                 long long dk_sb, long long dk_sn, long long dk_sh,
+                                 long long dv_sb, long long dv_sn, long long dv_sh,
+                                 float scale, void* stream) {
+  return attention_bwd_impl(q, k, v, o, d_o, lse, dq, dk, dv, dq_acc, const_cast<float*>(delta), B, H, Nq, Nk, hd, q_sb, q_sn, q_sh,
+                            k_sb, k_sn, k_sh, v_sb, v_sn, v_sh, o_sb, o_sn, o_sh, dq_sb, dq_sn, dq_sh, dk_sb, dk_sn, dk_sh,
+                            dv_sb, dv_sn, dv_sh, scale, stream, true);
+}
+
+static int attention_bwd_impl(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                 const float* lse, void* dq, void* dk, void* dv, float* dq_acc, float* delta,
+                                 int B, int H, int Nq, int Nk, int hd,
+                                 long long q_sb, long long q_sn, long long q_sh,
+                                 long long k_sb, long long k_sn, long long k_sh,
+                                 long long v_sb, long long v_sn, long long v_sh,
+                                 long long o_sb, long long o_sn, long long o_sh,
+                                 long long dq_sb, long long dq_sn, long long dq_sh,
+                                 long long dk_sb, long long dk_sn, long long dk_sh,
+                                 long long dv_sb, long long dv_sn, long long dv_sh,
+                                 float scale, void* stream, bool delta_ready) {
   if (B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) { set_last_error("attention_bwd: empty problem"); return UCF_ERR_BAD_ARG; }
   if (hd != 64 && hd != 32) { set_last_error("attention_bwd: head_dim %d not supported (32 or 64)", hd); return UCF_ERR_UNSUPPORTED; }
   const bool short_q = Nq <= 256;      // dQ accumulates in tensor memory: dq_acc is not touched (may be NULL)
@@ -1005,7 +1049,7 @@ extern "C" int ucf_attention_bwd(const void* q, const void* k, const void* v, co
 
   // d_o is addressed with o's strides (both are (B,N,H*hd) activations produced by this library)
   const long long items = static_cast<long long>(B) * Nq * H;
-  {
+  if (!delta_ready) {
     const int G = hd / 8;
     long long threads = items * G;
     long long blocks = (threads + 255) / 256;

@@ -147,15 +147,29 @@ extern "C" int ucf_block_bwd(const ucf_block_params* p, const ucf_block_acts* a,
   UCF_TRY(ucf_layernorm_bwd(dh, a->x1, p->n2_w, a->mean2, a->rstd2, g->dy, dx1, g->g_n2_w, g->g_n2_b, M, D, p->ln_dtype, stream));
   // ---- attention
   UCF_TRY(wgrad(dx1, a->o, D, D, M, g->g_proj_w, g->g_proj_b, stream));
-  UCF_TRY(ucf_gemm_bf16(dx1, p->proj_w, dh, nullptr, nullptr, Mi, D, D, D, D, D, 0, UCF_LAYOUT_K_MAJOR, UCF_LAYOUT_MN_MAJOR,
-                        UCF_EPI_BIAS, 0, 1, 0, nullptr, stream));
+  // d_o = dx1 * Wproj; where the fused kernel applies, its epilogue also leaves delta = rowsum(d_o o O) per head for the
+  // attention backward (otherwise ucf_attention_bwd runs its own pass over d_o and O)
+  const bool fused_delta = ucf_gemm_dgrad_delta_supported(Mi, D, D, H) != 0;
+  if (fused_delta) {
+    UCF_TRY(ucf_gemm_dgrad_delta(dx1, p->proj_w, dh, a->o, g->delta, Mi, D, D, D, D, D, D, N, H, stream));
+  } else {
+    UCF_TRY(ucf_gemm_bf16(dx1, p->proj_w, dh, nullptr, nullptr, Mi, D, D, D, D, D, 0, UCF_LAYOUT_K_MAJOR, UCF_LAYOUT_MN_MAJOR,
+                          UCF_EPI_BIAS, 0, 1, 0, nullptr, stream));
+  }
   {
     const uint16_t* q = static_cast<const uint16_t*>(a->qkv);
     uint16_t* dq = static_cast<uint16_t*>(dqkv);
     const long long sb = 3LL * N * D, sn = 3LL * D, sh = hd;
-    UCF_TRY(ucf_attention_bwd(q, q + D, q + 2 * D, a->o, dh, a->lse, dq, dq + D, dq + 2 * D, g->dq_acc, g->delta, B, H, N, N, hd,
-                              sb, sn, sh, sb, sn, sh, sb, sn, sh, 1LL * N * D, D, hd, sb, sn, sh, sb, sn, sh, sb, sn, sh,
-                              1.0f / sqrtf(static_cast<float>(hd)), stream));
+    const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+    if (fused_delta) {
+      UCF_TRY(ucf_attention_bwd_with_delta(q, q + D, q + 2 * D, a->o, dh, a->lse, dq, dq + D, dq + 2 * D, g->dq_acc, g->delta, B, H,
+                                           N, N, hd, sb, sn, sh, sb, sn, sh, sb, sn, sh, 1LL * N * D, D, hd, sb, sn, sh, sb, sn, sh,
+                                           sb, sn, sh, scale, stream));
+    } else {
+      UCF_TRY(ucf_attention_bwd(q, q + D, q + 2 * D, a->o, dh, a->lse, dq, dq + D, dq + 2 * D, g->dq_acc, g->delta, B, H, N, N, hd,
+                                sb, sn, sh, sb, sn, sh, sb, sn, sh, 1LL * N * D, D, hd, sb, sn, sh, sb, sn, sh, sb, sn, sh,
+                                scale, stream));
+    }
   }
   UCF_TRY(wgrad(dqkv, a->h1, 3 * D, D, M, g->g_qkv_w, g->g_qkv_b, stream));
   UCF_TRY(ucf_gemm_bf16(dqkv, p->qkv_w, dh, nullptr, nullptr, Mi, D, 3 * D, 3 * D, D, D, 0, UCF_LAYOUT_K_MAJOR, UCF_LAYOUT_MN_MAJOR,

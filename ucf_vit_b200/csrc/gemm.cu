@@ -29,9 +29,13 @@ struct GemmParams {
   const void* bias;   // length N or null
   int bias_is_bf16;
   float* bias_grad;   // wgrad only (A MN-major, fp32 reduce-add): [M] += row sums of A, i.e. the bias gradient
+  // EPI_DELTA only (the attention-output dgrad dO = dX1 * Wproj, aux = O): delta[b, h, n] = sum_d dO * O per head,
+  // the row statistic the attention backward kernel needs -- taken from the accumulator tile in the epilogue
+  float* delta;       // [M / tokens, heads, tokens] fp32
+  int tokens, heads, head_dim;
 };
 
-enum { EPI_BIAS = 0, EPI_BIAS_RESIDUAL = 1, EPI_BIAS_GELU_AUX = 2, EPI_DGELU = 3, EPI_F32_ADD = 4 };
+enum { EPI_BIAS = 0, EPI_BIAS_RESIDUAL = 1, EPI_BIAS_GELU_AUX = 2, EPI_DGELU = 3, EPI_F32_ADD = 4, EPI_DELTA = 5 };
 
 // Bias-gradient warps of the wgrad kernels.  In wgrad, A = dY^T (MN-major: 64 token rows x 128
 // channels per stage, two 64-channel boxes of 128-byte swizzled rows), so the bias gradient
@@ -415,8 +419,8 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;          // this CTA's half of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr bool HAS_AUX = (EPI == EPI_BIAS_RESIDUAL || EPI == EPI_BIAS_GELU_AUX || EPI == EPI_DGELU);
-  static constexpr bool AUX_IN = (EPI == EPI_BIAS_RESIDUAL || EPI == EPI_DGELU);
+  static constexpr bool HAS_AUX = (EPI == EPI_BIAS_RESIDUAL || EPI == EPI_BIAS_GELU_AUX || EPI == EPI_DGELU || EPI == EPI_DELTA);
+  static constexpr bool AUX_IN = (EPI == EPI_BIAS_RESIDUAL || EPI == EPI_DGELU || EPI == EPI_DELTA);
   // The GELU / GELU' epilogues carry ~20 issue slots per element pair plus a second tensor: with two
   // warps per scheduler the epilogue of tile i did not fit under the MMAs of tile i+1 (measured 234 us
   // against 178 us for the plain kernel, issue slots 40 % busy -- latency-, not throughput-bound).
@@ -614,7 +618,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int r0 = m0 + q * 32;
       const int cbase = grp * (BN / G);
 
-      if (EPI != EPI_F32_ADD && EPI != EPI_DGELU) {
+      if (EPI != EPI_F32_ADD && EPI != EPI_DGELU && EPI != EPI_DELTA) {
         named_bar_sync(1, 32 * Cfg::EPI_WARPS);
         for (int i = etid; i < BN; i += 32 * Cfg::EPI_WARPS) {
           float b = 0.f;
@@ -634,6 +638,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + buf * BN + cbase + (static_cast<uint32_t>(q * 32) << 16);
 
+      float dsum = 0.f;      // EPI_DELTA: running sum_d dO * O of this thread's row over the current head
       if (active) {
 #pragma unroll 1
         for (int c = 0; c < NCHUNK; ++c) {
@@ -669,7 +674,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 4; ++e)
                 f[e] = make_float2(__uint_as_float(v[8 * j + 2 * e]), __uint_as_float(v[8 * j + 2 * e + 1]));
-              if (EPI != EPI_DGELU) {
+              if (EPI != EPI_DGELU && EPI != EPI_DELTA) {
                 const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[cbase + c * CW + 8 * j]);
                 const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[cbase + c * CW + 8 * j + 4]);
                 f[0] = __fadd2_rn(f[0], make_float2(b0.x, b0.y));
@@ -684,6 +689,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 f[1] = __fadd2_rn(f[1], bf16x2_to_f32x2(r.y));
                 f[2] = __fadd2_rn(f[2], bf16x2_to_f32x2(r.z));
                 f[3] = __fadd2_rn(f[3], bf16x2_to_f32x2(r.w));
+              } else if (EPI == EPI_DELTA) {
+                const uint4 r = *reinterpret_cast<const uint4*>(aux_row + sw);
+                float2 d2 = __fmul2_rn(f[0], bf16x2_to_f32x2(r.x));
+                d2 = __ffma2_rn(f[1], bf16x2_to_f32x2(r.y), d2);
+                d2 = __ffma2_rn(f[2], bf16x2_to_f32x2(r.z), d2);
+                d2 = __ffma2_rn(f[3], bf16x2_to_f32x2(r.w), d2);
+                dsum += d2.x + d2.y;
               } else if (EPI == EPI_DGELU) {
                 const uint4 r = *reinterpret_cast<const uint4*>(aux_row + sw);
                 // half of the elements on the MUFU form (2 MUFU + 8 FMA-pipe ops), half on the polynomial
@@ -711,6 +723,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint32_t sw = (static_cast<uint32_t>(j) ^ sw64) << 4;
               *reinterpret_cast<uint4*>(out_row + sw) = o_pk[j];
               if (EPI == EPI_BIAS_GELU_AUX) *reinterpret_cast<uint4*>(aux_row + sw) = z_pk[j];
+            }
+          }
+          if (EPI == EPI_DELTA) {
+            // a head's columns end with this chunk (head_dim 32: every chunk, 64: every second; column groups start on
+            // multiples of 128, so heads never straddle warps): store the row's delta for that head
+            const int cend = col0 + CW;
+            if (cend % p.head_dim == 0) {
+              const int r = r0 + lane;
+              if (r < p.M) {
+                const int bi = r / p.tokens, n = r - bi * p.tokens;
+                const int hh = cend / p.head_dim - 1;
+                p.delta[(static_cast<long long>(bi) * p.heads + hh) * p.tokens + n] = dsum;
+              }
+              dsum = 0.f;
             }
           }
           fence_proxy_async_smem();
@@ -814,10 +840,12 @@ using namespace ucf;
 /* profiling aid (not part of the public header): limit the CTA-pair kernels to n clusters (0 = all SMs) */
 extern "C" void ucf_debug_set_gemm_max_clusters(int n) { ucf::g_debug_max_clusters = n; }
 
+struct DeltaArgs { float* delta; int tokens, heads; };
 static int gemm_bf16_impl(const void* A, const void* B, void* C, const void* bias, void* aux,
                              int M, int N, int K, long long lda, long long ldb, long long ldc,
                              long long ldaux, int a_layout, int b_layout, int epilogue,
-                             int bias_dtype, int splits, int tile_n, void* bias_grad, void* stream);
+                             int bias_dtype, int splits, int tile_n, void* bias_grad, void* stream,
+                             const DeltaArgs* dargs = nullptr);
 
 // ---- profiling aid of bench.py (not part of the public header): CUDA-event timing of every GEMM launch on the
 // launching stream, so the roofline figure is measured live inside the timed region wherever the launch comes from
@@ -865,15 +893,46 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
   return rc;
 }
 
+extern "C" int ucf_gemm_dgrad_delta_supported(int M, int N, int K, int heads) {
+  if (heads <= 0 || N % heads) return 0;
+  const int hd = N / heads;
+  return (hd == 32 || hd == 64) && N % 128 == 0 && M >= 512 && N >= 512 && N <= 4096 && K > 0;
+}
+
+extern "C" int ucf_gemm_dgrad_delta(const void* dY, const void* W, void* dX, const void* O, float* delta, int M, int N, int K,
+                                    long long lddy, long long ldw, long long lddx, long long ldo, int tokens, int heads,
+                                    void* stream) {
+  if (!delta || !O || tokens <= 0 || M % tokens) {
+    set_last_error("gemm_dgrad_delta: delta / O null or M not a multiple of tokens"); return UCF_ERR_BAD_ARG;
+  }
+  if (!ucf_gemm_dgrad_delta_supported(M, N, K, heads)) {
+    set_last_error("gemm_dgrad_delta: shape M=%d N=%d heads=%d has no fused kernel (ucf_gemm_dgrad_delta_supported)", M, N, heads);
+    return UCF_ERR_UNSUPPORTED;
+  }
+  DeltaArgs d{delta, tokens, heads};
+  GemmTimingRec r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (g_gemm_timing) {
+    r.flops = 2.0 * M * N * K;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+  }
+  const int rc = gemm_bf16_impl(dY, W, dX, nullptr, const_cast<void*>(O), M, N, K, lddy, ldw, lddx, ldo, UCF_LAYOUT_K_MAJOR,
+                                UCF_LAYOUT_MN_MAJOR, EPI_DELTA, 0, 1, 512, nullptr, stream, &d);
+  if (g_gemm_timing) { cudaEventRecord(r.e1, st); g_gemm_recs.push_back(r); }
+  return rc;
+}
+
 static int gemm_bf16_impl(const void* A, const void* B, void* C, const void* bias, void* aux,
                              int M, int N, int K, long long lda, long long ldb, long long ldc,
                              long long ldaux, int a_layout, int b_layout, int epilogue,
-                             int bias_dtype, int splits, int tile_n, void* bias_grad, void* stream) {
+                             int bias_dtype, int splits, int tile_n, void* bias_grad, void* stream,
+                             const DeltaArgs* dargs) {
   if (M <= 0 || N <= 0 || K <= 0) { set_last_error("gemm: empty problem M=%d N=%d K=%d", M, N, K); return UCF_ERR_BAD_ARG; }
   if (!A || !B || !C) { set_last_error("gemm: null operand"); return UCF_ERR_BAD_ARG; }
-  if (epilogue < 0 || epilogue > 4) { set_last_error("gemm: bad epilogue %d", epilogue); return UCF_ERR_BAD_ARG; }
+  if (epilogue < 0 || epilogue > 5 || (epilogue == EPI_DELTA && !dargs)) { set_last_error("gemm: bad epilogue %d", epilogue); return UCF_ERR_BAD_ARG; }
   const bool a_mn = a_layout == UCF_LAYOUT_MN_MAJOR, b_mn = b_layout == UCF_LAYOUT_MN_MAJOR;
-  const bool has_aux = epilogue == EPI_BIAS_RESIDUAL || epilogue == EPI_BIAS_GELU_AUX || epilogue == EPI_DGELU;
+  const bool has_aux = epilogue == EPI_BIAS_RESIDUAL || epilogue == EPI_BIAS_GELU_AUX || epilogue == EPI_DGELU || epilogue == EPI_DELTA;
   if (has_aux && !aux) { set_last_error("gemm: epilogue %d needs aux", epilogue); return UCF_ERR_BAD_ARG; }
   const int out_es = (epilogue == EPI_F32_ADD) ? 4 : 2;
   if ((lda * 2) % 16 || (ldb * 2) % 16 || (ldc * out_es) % 16 || (has_aux && (ldaux * 2) % 16) ||
@@ -891,7 +950,7 @@ static int gemm_bf16_impl(const void* A, const void* B, void* C, const void* bia
   // (measured +7..11 % on the ViT-B shapes); everything else to the single-CTA kernels.
   const bool pair_supported =
       (!a_mn && !b_mn && (epilogue == EPI_BIAS || epilogue == EPI_BIAS_RESIDUAL || epilogue == EPI_BIAS_GELU_AUX)) ||
-      (!a_mn && b_mn && (epilogue == EPI_BIAS || epilogue == EPI_DGELU)) || (a_mn && b_mn && epilogue == EPI_F32_ADD);
+      (!a_mn && b_mn && (epilogue == EPI_BIAS || epilogue == EPI_DGELU || epilogue == EPI_DELTA)) || (a_mn && b_mn && epilogue == EPI_F32_ADD);
   if (tile_n == 0 && pair_supported && M >= 512 && N >= 512 && N <= 4096) tile_n = 512;
   const bool pair = tile_n == 512;
   int BN = pair ? 256 : tile_n;
@@ -908,6 +967,10 @@ static int gemm_bf16_impl(const void* A, const void* B, void* C, const void* bia
   p.bias = bias;
   p.bias_is_bf16 = bias_dtype == UCF_DTYPE_BF16;
   p.bias_grad = static_cast<float*>(bias_grad);
+  p.delta = nullptr; p.tokens = 1; p.heads = 1; p.head_dim = 64;
+  if (epilogue == EPI_DELTA) {
+    p.delta = dargs->delta; p.tokens = dargs->tokens; p.heads = dargs->heads; p.head_dim = N / dargs->heads;
+  }
   if (bias_grad && !(a_mn && epilogue == EPI_F32_ADD)) {
     set_last_error("gemm: bias_grad is only produced by the wgrad form (A MN-major, UCF_EPI_F32_ADD)");
     return UCF_ERR_BAD_ARG;
@@ -952,6 +1015,7 @@ static int gemm_bf16_impl(const void* A, const void* B, void* C, const void* bia
   UCF_GEMM2_CASE(5, false, false, EPI_BIAS_GELU_AUX)
   UCF_GEMM2_CASE(6, false, true, EPI_BIAS)
   UCF_GEMM2_CASE(4, false, true, EPI_DGELU)
+  UCF_GEMM2_CASE(5, false, true, EPI_DELTA)
   UCF_GEMM2_CASE(6, true, true, EPI_F32_ADD)
 #undef UCF_GEMM2_CASE
   if (pair) {

@@ -76,6 +76,24 @@ def gemm(a, b, *, M, N, K, a_mn=False, b_mn=False, epilogue=L.EPI_BIAS, bias=Non
     return (out, aux) if epilogue == L.EPI_BIAS_GELU_AUX else out
 
 
+def gemm_dgrad_delta(dy, w, o, tokens, heads):
+    """dX = dy @ w (w = nn.Linear weight [out, in] read in place) and delta[b, h, n] = sum_d dX * o per head, from the GEMM's
+    epilogue.  dy bf16 [M, out], w bf16 [out, in], o bf16 [M, in] -> (dX bf16 [M, in], delta fp32 [M // tokens, heads, tokens])."""
+    _require_cuda(dy, w, o)
+    M, K = dy.shape
+    N = w.shape[1]
+    assert w.shape[0] == K and tuple(o.shape) == (M, N) and M % tokens == 0
+    assert dy.dtype == w.dtype == o.dtype == torch.bfloat16 and dy.stride(1) == 1 and w.stride(1) == 1 and o.stride(1) == 1
+    if not L.lib().ucf_gemm_dgrad_delta_supported(M, N, K, heads):
+        raise RuntimeError(f"gemm_dgrad_delta: no fused kernel for M={M} N={N} heads={heads}")
+    dx = torch.empty((M, N), dtype=torch.bfloat16, device=dy.device)
+    delta = torch.empty((M // tokens, heads, tokens), dtype=torch.float32, device=dy.device)
+    L.check(L.lib().ucf_gemm_dgrad_delta(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), o.data_ptr(), delta.data_ptr(), M, N, K,
+                                         dy.stride(0), w.stride(0), dx.stride(0), o.stride(0), tokens, heads, _stream()),
+            "gemm_dgrad_delta")
+    return dx, delta
+
+
 def layernorm_fwd(x, gamma, beta, eps):
     _require_cuda(x, gamma, beta)
     D = x.shape[-1]
