@@ -653,8 +653,9 @@ class Sap4096(Workload):
         e1.record()
         torch.cuda.synchronize()
         gather_ms = e0.elapsed_time(e1) / n
-        # algorithmic bytes of one gather: every source pixel under a leaf is read once (4096^2 * 3 B) and L*p*p*3 fp32 written
-        alg = 4096 * 4096 * 3 + self.L * self.p * self.p * 3 * 4
+        # algorithmic bytes of one gather: INTER_CUBIC without antialiasing reads 16 taps (1 B each, uint8) per
+        # output sample whatever the leaf size, and writes one fp32: L * p^2 * C * (16 + 4) bytes
+        alg = self.L * self.p * self.p * 3 * (16 + 4)
         return {"tree_build_ms_per_batch_host": tree_ms, "gather_ms_per_image": gather_ms,
                 "gather_algorithmic_GBps": alg / (gather_ms * 1e-3) / 1e9}
 
