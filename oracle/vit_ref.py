@@ -254,6 +254,12 @@ def unetr_forward(x, sd: SD, cfg: dict, var_ids=None):
     inc = depth // 4
     take = [(i + 1) * inc for i in range(3)]
     f, inter = vit_features(x, sd, cfg, var_ids, None, take)
+    return unetr_decode(x, f, inter, sd, cfg)
+
+
+def unetr_decode(x, f, inter, sd: SD, cfg: dict):
+    """The convolutional half of UNETR.forward (simple/arch.py:1040-1113) on given encoder features `f` (final, normed)
+    and `inter` (the three skip features): lets a test feed the decoder exactly the features another encoder produced."""
     nsp = x.dim() - 2
     g = [s // cfg["patch_size"] for s in x.shape[2:]]
 

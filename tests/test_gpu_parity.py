@@ -124,6 +124,54 @@ def test_unetr_encoder_var_aggregation_tight():
     assert n >= 50
 
 
+def test_unetr_decoder_matches_oracle_on_the_product_encoder_features():
+    """The conv decoder alone, tightly: the oracle's decoder is fed the SAME (bf16-rounded) encoder features the product's
+    kernels produced, so the 0.5 % bf16 rounding of the encoder -- which the InstanceNorm layers amplify into the wide
+    end-to-end UNETR gate above -- is taken out of the comparison.  fp32 cuDNN (TF32 off) against fp32 CPU."""
+    from oracle import vit_ref as R
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        cfg, shapes, arrays, sd = C.load("unetr_3d_var2")
+        inp = C.inputs(cfg, arrays)
+        model = C.build_product(cfg)
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda().train()
+        x = inp["x"].cuda()
+        with torch.no_grad():
+            feats, inter = model.forward_intermediates(x, ["v0", "v1"], None, indices=model.skip_indices)
+        f_p = feats.detach().clone().requires_grad_(True)
+        i_p = [t.detach().clone().requires_grad_(True) for t in inter]
+        enc1 = model.encoder1(x)
+        out_p = model.forward_head(f_p, i_p, enc1).float()
+        probe = (torch.arange(out_p.numel(), device="cuda").reshape(out_p.shape) % 7 - 3).float() / out_p.numel()
+        (out_p * probe).sum().backward()
+        # oracle decoder on the same features (fp32 copies of the bf16 values)
+        sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        f_o = f_p.detach().float().cpu().requires_grad_(True)
+        i_o = [t.detach().float().cpu().requires_grad_(True) for t in i_p]
+        out_o = R.unetr_decode(inp["x"], f_o, i_o, sdg, cfg)
+        (out_o * probe.cpu()).sum().backward()
+        assert _rel_l2(out_p.detach().cpu(), out_o.detach()) <= 1e-4
+        assert _rel_l2(f_p.grad.float().cpu(), f_o.grad) <= 1e-2          # (gradient leaves the decoder as bf16)
+        for a, b in zip(i_p, i_o):
+            assert _rel_l2(a.grad.float().cpu(), b.grad) <= 1e-2
+        named = dict(model.named_parameters())
+        n = 0
+        for k, v in sdg.items():
+            if v.grad is None or k not in named or named[k].grad is None:
+                continue
+            if k.split(".")[0] not in ("encoder1", "encoder2", "encoder3", "encoder4", "decoder2", "decoder3", "decoder4",
+                                       "decoder5", "out"):
+                continue
+            rel = _rel_l2(named[k].grad.float().cpu(), v.grad)
+            assert rel <= 2e-3, f"{k}: rel {rel:.3e}"
+            n += 1
+        assert n >= 20
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
 def test_block_module_matches_oracle_with_odd_token_count():
     """Block alone, N = 197 (ViT-B/16 @224 incl. cls token): tail masking in attention, M not a
     multiple of the GEMM tile."""

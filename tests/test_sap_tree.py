@@ -266,3 +266,46 @@ def test_build_many_and_forward_batch_equal_the_per_image_path(monkeypatch):
     assert len(batch) == len(single)
     for a, b in zip(single, batch):
         assert np.array_equal(a[3].boxes, b[3].boxes) and a[0].shape == b[0].shape == (3, 16, 16)
+
+
+def test_serialize_labels_nearest_2d_and_3d():
+    """serialize_labels (reference quadtree.py:176-207, octree.py:152-199): label patches are resampled with nearest
+    neighbour.  2-D witness: torch's legacy 'nearest' mode (the documented twin of cv.INTER_NEAREST: floor(dst * scale));
+    3-D witness: scipy's RegularGridInterpolator(method='nearest') driven exactly as the reference drives it."""
+    import torch
+    from scipy.interpolate import RegularGridInterpolator
+    from ucf_vit_b200.dataloaders.octree import FixedOctTree
+    from ucf_vit_b200.dataloaders.quadtree import FixedQuadTree, Rect
+    rng = np.random.default_rng(5)
+    edge = (rng.random((128, 128)) < 0.05).astype(np.uint8) * 255
+    edge[:32, :32] = 255
+    qdt = FixedQuadTree(edge, fixed_length=46, device="cpu")
+    lab = rng.integers(0, 5, size=(128, 128, 3)).astype(np.uint8)
+    patches, sizes, pos = qdt.serialize_labels(lab, size=(8, 8, 3))
+    assert len(patches) == len(sizes) == len(pos) == 46
+    for (r, _), pt, sz, ps in zip(qdt.nodes, patches, sizes, pos):
+        src = torch.from_numpy(r.get_area(lab).astype(np.float32)).permute(2, 0, 1)[None]
+        ref = torch.nn.functional.interpolate(src, size=(8, 8), mode="nearest")[0].permute(1, 2, 0).numpy()
+        assert np.array_equal(pt.astype(np.float32), ref) and pt.dtype == lab.dtype
+        assert sz == r.get_size()[0] and ps == r.get_center()
+    one = qdt.serialize_labels(lab[:, :, :1], size=(4, 4, 1))[0]
+    assert one[0].shape == (4, 4)                       # cv.resize drops a single channel axis
+    short = FixedQuadTree(np.zeros((4, 4), np.uint8), fixed_length=7, device="cpu")      # four 2x2 leaves cannot split: 3 pad slots
+    p2, s2, o2 = short.serialize_labels(np.ones((4, 4, 2), np.uint8), size=(2, 2, 2))
+    assert len(p2) == 7 and s2 == [2, 2, 2, 2, 0, 0, 0] and o2[-1] == (-1, -1) and not p2[-1].any() and p2[0].all()
+    assert hash(Rect(0, 4, 0, 4)) == hash(Rect(0, 4, 0, 4)) and len({Rect(0, 4, 0, 4), Rect(0, 4, 0, 4)}) == 1
+
+    vol_edge = (rng.random((32, 32, 32)) < 0.03).astype(np.float32)
+    oct_ = FixedOctTree(vol_edge, fixed_length=22, norm_factor=1, device="cpu")
+    labv = rng.integers(0, 4, size=(32, 32, 32, 1)).astype(np.float64)
+    patches, sizes, pos = oct_.serialize_labels(labv, size=(4, 4, 4, 1))
+    assert len(patches) == 22
+    for (c, _), pt in zip(oct_.nodes, patches):
+        area = c.get_area(labv)
+        h1 = area.shape[0]
+        g1 = np.linspace(0, h1, h1)
+        f = RegularGridInterpolator(points=[g1, g1, g1], values=area[:, :, :, 0], method="nearest")
+        q = np.linspace(0, h1, 4)
+        H, W, D = np.meshgrid(q, q, q, indexing="ij")
+        ref = f(np.vstack([H.ravel(), W.ravel(), D.ravel()]).T).reshape(4, 4, 4)
+        assert np.array_equal(pt[:, :, :, 0], ref)

@@ -29,6 +29,18 @@ class Cube:
         return (self.x2 + self.x1) / 2, (self.y2 + self.y1) / 2, (self.z2 + self.z1) / 2
 
 
+def _nearest_grid_index(src, dst):
+    """scipy RegularGridInterpolator(method='nearest') on the reference's grids (octree.py:167-185): source points
+    linspace(0, src, src), queries linspace(0, src, dst); ties (normalised distance exactly 0.5) go to the lower index."""
+    if src == 1:
+        return np.zeros(dst, dtype=np.int64)
+    grid = np.linspace(0, src, src)
+    q = np.linspace(0, src, dst)
+    lo = np.clip(np.searchsorted(grid, q) - 1, 0, src - 2)
+    frac = (q - grid[lo]) / (grid[lo + 1] - grid[lo])
+    return np.where(frac <= 0.5, lo, lo + 1).astype(np.int64)
+
+
 class FixedOctTree:
     def __init__(self, domain, fixed_length=128, norm_factor=255, device="cuda") -> None:
         self.domain, self.fixed_length, self.norm_factor, self.device = domain, fixed_length, norm_factor, device
@@ -58,6 +70,29 @@ class FixedOctTree:
         s = seq if torch.is_tensor(seq) else torch.from_numpy(np.asarray(seq, dtype=np.float32))
         s = s.to(self.device).float().reshape(self.fixed_length, patch_size, patch_size, patch_size, channel)
         return ops.sap_scatter(s, self._dev_boxes(), tuple(self.domain.shape), patch_size, channel)
+
+    def serialize_labels(self, img, size=(8, 8, 8, 1)):
+        """FixedOctTree.serialize_labels, octree.py:152-199: nearest-neighbour resampling of every leaf of the label
+        volume (scipy RegularGridInterpolator(method='nearest') in the reference) as an integer gather on the host."""
+        h2, w2, d2, c2 = size
+        assert len(self.boxes) <= self.fixed_length, "Not equal fixed legnth."
+        img = np.asarray(img)
+        patches, sizes, pos = [], [], []
+        for x1, x2, y1, y2, z1, z2 in np.asarray(self.boxes).tolist():
+            h1, w1, d1 = z2 - z1, y2 - y1, x2 - x1
+            assert h1 == w1 == d1, "Need squared input."
+            zi = z1 + _nearest_grid_index(h1, h2)
+            yi = y1 + _nearest_grid_index(w1, w2)
+            xi = x1 + _nearest_grid_index(d1, d2)
+            patches.append(img[zi[:, None, None], yi[None, :, None], xi[None, None, :], :].astype(np.float64))
+            sizes.append(x2 - x1)
+            pos.append(((x2 + x1) / 2, (y2 + y1) / 2, (z2 + z1) / 2))
+        pad = self.fixed_length - len(patches)
+        if pad > 0:
+            patches += [np.zeros(shape=(h2, w2, d2, c2))] * pad
+            sizes += [0] * pad
+            pos += [(-1, -1, -1)] * pad
+        return patches, sizes, pos
 
     def serialize(self, img, size=(8, 8, 8, 1)):
         seq, ssize, spos = self.serialize_device(img, size)

@@ -34,8 +34,31 @@ class Rect:
     def get_center(self):
         return (self.x2 + self.x1) / 2, (self.y2 + self.y1) / 2
 
+    def set_area(self, mask, patch):
+        """Paste `patch` ([p, p, C]), cubic-resampled to this box, into `mask` ([H, W, C] numpy, modified in place and returned):
+        Rect.set_area, quadtree.py:25-36 (cv.resize INTER_CUBIC of the float32 patch), on the device scatter kernel."""
+        p_ = np.asarray(patch, dtype=np.float32)
+        if p_.ndim == 2:
+            p_ = p_[:, :, None]
+        C = p_.shape[2]
+        seq = torch.from_numpy(np.ascontiguousarray(p_)).cuda().reshape(1, p_.shape[0], p_.shape[1], C)
+        box = torch.tensor([[self.x1, self.x2, self.y1, self.y2]], dtype=torch.int32, device="cuda")
+        full = ops.sap_scatter(seq, box, (mask.shape[0], mask.shape[1]), p_.shape[0], C)
+        mask[self.y1:self.y2, self.x1:self.x2, :] = full[self.y1:self.y2, self.x1:self.x2, :].cpu().numpy()
+        return mask
+
     def __eq__(self, other):
         return isinstance(other, Rect) and self.get_coord() == other.get_coord()
+
+    def __hash__(self):
+        return hash(self.get_coord())
+
+
+def _nearest_index(src, dst):
+    """Source index of every destination sample of cv.resize(..., interpolation=cv.INTER_NEAREST): floor(x * (1 / (dst / src)))
+    in double, clamped to src - 1 (OpenCV resizeNN; the same rule as torch's legacy 'nearest' mode)."""
+    inv = 1.0 / (np.float64(dst) / np.float64(src))
+    return np.minimum(np.floor(np.arange(dst, dtype=np.float64) * inv).astype(np.int64), src - 1)
 
 
 def _as_device_image(img, device):
@@ -150,6 +173,33 @@ class FixedQuadTree:
         s = seq if torch.is_tensor(seq) else torch.from_numpy(np.asarray(seq, dtype=np.float32))
         s = s.to(self.device).float().reshape(self.fixed_length, patch_size, patch_size, channel)
         return ops.sap_scatter(s, self._dev_boxes(), (H, W), patch_size, channel, truncate_to_int=True)
+
+    def serialize_labels(self, img, size=(8, 8, 3)):
+        """FixedQuadTree.serialize_labels, quadtree.py:176-207: every leaf of the label image resampled with
+        cv.INTER_NEAREST to `size` (labels must not be interpolated).  Index arithmetic on the host (integer gather, a few
+        KB per image); returns the reference's three lists.  A single-channel image yields 2-D patches, like cv.resize."""
+        h2, w2, c2 = size
+        assert len(self.boxes) <= self.fixed_length, "Not equal fixed legnth."
+        img = np.asarray(img)
+        if img.ndim == 2:
+            img = img[:, :, None]
+        patches, sizes, pos = [], [], []
+        for x1, x2, y1, y2 in np.asarray(self.boxes).tolist():
+            h1, w1 = y2 - y1, x2 - x1
+            assert h1 == w1, "Need squared input."
+            # cv.resize(patch, (h2, w2)): dsize = (width, height) -> w2 rows, h2 columns
+            ys = y1 + _nearest_index(h1, w2)
+            xs = x1 + _nearest_index(w1, h2)
+            pt = img[ys[:, None], xs[None, :], :]
+            patches.append(pt[:, :, 0] if img.shape[2] == 1 else pt)
+            sizes.append(x2 - x1)
+            pos.append(((x2 + x1) / 2, (y2 + y1) / 2))
+        pad = self.fixed_length - len(patches)
+        if pad > 0:
+            patches += [np.zeros(shape=(h2, w2, c2)) if c2 > 1 else np.zeros(shape=(h2, w2))] * pad
+            sizes += [0] * pad
+            pos += [(-1, -1)] * pad
+        return patches, sizes, pos
 
     # ---- reference-typed API (lists / numpy back on the host)
     def serialize(self, img, size=(8, 8, 3)):
