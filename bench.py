@@ -390,7 +390,6 @@ def main():
                          "is then taken from an eager pass after the timed region")
     ap.add_argument("--bf16-decoder", action="store_true",
                     help="unetr_128: run the cuDNN conv decoder under bf16 autocast (default: fp32 like the reference)")
-    ap.add_argument("--channels-last", action="store_true", help="unetr_128 with --bf16-decoder: NDHWC conv weights")
     ap.add_argument("--fp32-pixels", action="store_true", help="vit configs: host batches as fp32 pixels (round-1 form) instead of uint8")
     ap.add_argument("--fp32-allreduce", action="store_true",
                     help="DDP gradient all-reduce in fp32 (round-1 form); default: bf16 (torch's bf16_compress_hook -- the "

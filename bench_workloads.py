@@ -457,8 +457,6 @@ class Unetr128(Workload):
         self.model = self._model().to(dev).train()
         if getattr(args, "bf16_decoder", False):
             self.model.conv_autocast_dtype = torch.bfloat16
-            if getattr(args, "channels_last", False):
-                self.model = self.model.to(memory_format=torch.channels_last_3d)
             self.workload = self.workload.replace("conv decoder (feature_size 16)", "conv decoder (feature_size 16) under bf16 autocast")
         self.net = self._wrap_ddp(self.model, world, local, args)
         self.opt = configure_optimizer(self.model, 1e-5, 0.9, 0.95, 1e-5, fused=_opt_kind(args, True))
