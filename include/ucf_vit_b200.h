@@ -31,7 +31,7 @@ extern "C" {
 
 #define UCF_ABI_VERSION 3
 
-enum { UCF_DTYPE_F32 = 0, UCF_DTYPE_BF16 = 1, UCF_DTYPE_U8 = 2, UCF_DTYPE_F64 = 3 };
+enum { UCF_DTYPE_F32 = 0, UCF_DTYPE_BF16 = 1, UCF_DTYPE_U8 = 2, UCF_DTYPE_F64 = 3, UCF_DTYPE_I64 = 4 };
 enum { UCF_LAYOUT_K_MAJOR = 0, UCF_LAYOUT_MN_MAJOR = 1 };
 /* GEMM epilogues */
 enum {
@@ -315,6 +315,23 @@ int ucf_dice_bce_fwd(const void* logits, int logits_dtype, const void* targets, 
 int ucf_dice_bce_bwd(const void* logits, int logits_dtype, const void* targets, int targets_dtype,
                      const float* fwd_out, const float* grad_out, int B, int C, long long HW, float weight, int act,
                      void* dlogits, void* stream);
+
+/* Dice + cross-entropy loss of the UNETR driver: replaces `monai.losses.DiceCELoss(to_onehot_y=True, softmax=True,
+ * squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)(output, label)` (training_scripts/train_unetr_simple.py:38-39,51-52;
+ * MONAI 1.4 is a dependency that is not vendored in the reference: restated from its published definition, parity unpinned).
+ *   p = softmax(logits, 1), t = one_hot(target); per (b, c) over the S positions: I = sum p t, Q = sum p^2 (squared_pred
+ *   != 0) or sum p, T = sum t;  loss = lambda_dice * mean_{b,c}(1 - (2I + smooth_nr) / (Q + T + smooth_dr))
+ *                                      + lambda_ce * mean_{b,s}(-log p[b, target[b,s], s])
+ * logits [B, C, S] f32|bf16 contiguous, 2 <= C <= 8; target [B, S] class indices as u8, i64 or f32; workspace
+ * B * ucf_dice_ce_blocks_per_sample(B, S) * 25 doubles; out f32 [2 + 2 B C]: out[0] = loss, the rest are the per-(b, c)
+ * coefficients and the cross-entropy scale the backward call reads.  One read of both tensors; reproducible (fixed order). */
+int ucf_dice_ce_blocks_per_sample(int B, long long S);
+int ucf_dice_ce_fwd(const void* logits, int logits_dtype, const void* target, int target_dtype, int B, int C, long long S,
+                    int squared_pred, float smooth_nr, float smooth_dr, float lambda_dice, float lambda_ce,
+                    double* workspace, float* out, void* stream);
+/* dlogits [B, C, S] (dtype of logits) = grad_out * d loss / d logits; grad_out a DEVICE f32 scalar. */
+int ucf_dice_ce_bwd(const void* logits, int logits_dtype, const void* target, int target_dtype, const float* fwd_out,
+                    const float* grad_out, int B, int C, long long S, int squared_pred, void* dlogits, void* stream);
 
 /* One AdamW step (decoupled weight decay, no amsgrad) over n fp32 tensors that share the same
  * hyper-parameters and step count: the arithmetic of torch.optim.AdamW as configured by

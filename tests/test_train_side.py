@@ -408,3 +408,26 @@ def test_dice_bce_at_sap_size_matches_pytorch_on_the_device():
     assert abs(la.item() - lb.item()) <= 1e-5 * abs(lb.item())
     _close(xa.grad.cpu().numpy(), xb.grad.cpu().numpy(), 2e-5)
     assert metrics.DiceBLoss()(x, t).item() == la.item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dt,tdt", [((2, 4, 16, 16, 16), torch.float32, torch.uint8), ((3, 2, 40, 33), torch.float32, torch.int64),
+                                           ((2, 5, 9, 7, 11), torch.bfloat16, torch.float32), ((1, 8, 64, 64, 64), torch.float32, torch.uint8)])
+def test_dice_ce_kernels_match_the_torch_formulation(shape, dt, tdt):
+    """ucf_dice_ce_fwd / _bwd against the PyTorch formulation of the same loss (DiceCELoss.forward_torch, fp32)."""
+    from ucf_vit_b200.utils.metrics import DiceCELoss
+    g = torch.Generator().manual_seed(sum(shape))
+    logits = (torch.randn(shape, generator=g) * 2).cuda()
+    target = torch.randint(0, shape[1], (shape[0], 1) + shape[2:], generator=g).to(tdt).cuda()
+    for squared in (True, False):
+        lossf = DiceCELoss(squared_pred=squared, smooth_nr=0.0, smooth_dr=1e-6)
+        a = logits.to(dt).detach().requires_grad_(True)
+        b = a.detach().float().requires_grad_(True)
+        la = lossf(a, target)
+        lb = lossf.forward_torch(b, target)
+        (la * 1.7).backward()
+        (lb * 1.7).backward()
+        assert abs(la.item() - lb.item()) <= 2e-5 * abs(lb.item()) + 1e-6, (la.item(), lb.item())
+        tol = 2e-5 if dt == torch.float32 else 1e-2
+        err = (a.grad.float() - b.grad).abs().max().item()
+        assert err <= tol * b.grad.abs().max().item() + 1e-9, err

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libucfvit_b200.so")
 _lib = None
 
-UCF_DTYPE_F32, UCF_DTYPE_BF16, UCF_DTYPE_U8, UCF_DTYPE_F64 = 0, 1, 2, 3
+UCF_DTYPE_F32, UCF_DTYPE_BF16, UCF_DTYPE_U8, UCF_DTYPE_F64, UCF_DTYPE_I64 = 0, 1, 2, 3, 4
 UCF_LAYOUT_K_MAJOR, UCF_LAYOUT_MN_MAJOR = 0, 1
 EPI_BIAS, EPI_BIAS_RESIDUAL, EPI_BIAS_GELU_AUX, EPI_DGELU, EPI_F32_ADD = 0, 1, 2, 3, 4
 PATCH_MSE_MAX_BLOCKS = 4096
@@ -87,6 +87,10 @@ _SIGNATURES = {
                                  c_void_p, c_void_p]),
     "ucf_dice_bce_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, _LL, c_float, c_int,
                                  c_void_p, c_void_p]),
+    "ucf_dice_ce_blocks_per_sample": (c_int, [c_int, _LL]),
+    "ucf_dice_ce_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, _LL, c_int, c_float, c_float, c_float, c_float,
+                                c_void_p, c_void_p, c_void_p]),
+    "ucf_dice_ce_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, _LL, c_int, c_void_p, c_void_p]),
     "ucf_adamw_multi": (c_int, [c_int] + [c_void_p] * 5 + [c_double] * 5 + [_LL, c_int, c_void_p]),
     "ucf_adamw_multi_dev": (c_int, [c_int] + [c_void_p] * 6 + [c_double] * 4 + [c_void_p, c_int, c_void_p]),
     "ucf_patchify": (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [_LL, c_int, c_void_p]),

@@ -545,6 +545,137 @@ static int dice_geom(const char* who, int B, int C, long long HW, DiceGeom* gm) 
   return UCF_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Dice + cross-entropy loss of the UNETR driver: monai.losses.DiceCELoss(to_onehot_y=True,
+// softmax=True, squared_pred=..., smooth_nr, smooth_dr) as configured at training_scripts/train_unetr_simple.py:38.
+//   p = softmax(logits, 1); t = one_hot(target); per (b, c) over the S spatial positions
+//   I = sum p t,  Q = sum p^2 (squared_pred) or sum p,  T = sum t
+//   loss = ld * mean_{b,c}(1 - (2 I + snr) / (Q + T + sdr)) + lce * mean_{b,s}(-log p[target])
+// logits [B, C, S] (C planes of S contiguous values), target [B, S] class indices.  One read of both tensors in each
+// direction; a CTA works on voxels of ONE sample, so it carries 3 C + 1 partial sums (fp32 per thread, double across
+// threads and CTAs, fixed order).  The finish kernel leaves, per (b, c), the two coefficients of d dice / d p = a t + b p
+// (b p^(squared ? 1 : 0)) and the cross-entropy scale on the device for the backward pass.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDiceCeMaxC = 8;
+
+__device__ __forceinline__ int ld_class(const uint8_t* p) { return *p; }
+__device__ __forceinline__ int ld_class(const long long* p) { return static_cast<int>(*p); }
+__device__ __forceinline__ int ld_class(const float* p) { return static_cast<int>(*p); }
+
+template <typename TL, typename TT>
+__global__ void __launch_bounds__(256)
+dice_ce_fwd_kernel(const TL* __restrict__ logits, const TT* __restrict__ target, int C, long long S, int nb, int squared,
+                   double* __restrict__ partials) {
+  const int b = blockIdx.x / nb, j = blockIdx.x - b * nb;
+  const long long per = (S + nb - 1) / nb;
+  const long long s0 = j * per, s1 = s0 + per < S ? s0 + per : S;
+  float si[kDiceCeMaxC], sq[kDiceCeMaxC], st[kDiceCeMaxC], ce = 0.f;
+#pragma unroll
+  for (int c = 0; c < kDiceCeMaxC; ++c) si[c] = sq[c] = st[c] = 0.f;
+  const TL* lg = logits + static_cast<long long>(b) * C * S;
+  const TT* tg = target + static_cast<long long>(b) * S;
+  for (long long s = s0 + threadIdx.x; s < s1; s += 256) {
+    float z[kDiceCeMaxC], m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kDiceCeMaxC; ++c)
+      if (c < C) { z[c] = ldf(lg + c * S + s); m = fmaxf(m, z[c]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kDiceCeMaxC; ++c)
+      if (c < C) { z[c] = __expf(z[c] - m); sum += z[c]; }
+    const float inv = 1.f / sum;
+    const int t = ld_class(tg + s);
+#pragma unroll
+    for (int c = 0; c < kDiceCeMaxC; ++c)
+      if (c < C) {
+        const float pc = z[c] * inv;
+        sq[c] += squared ? pc * pc : pc;
+        if (c == t) { si[c] += pc; st[c] += 1.f; ce -= logf(fmaxf(pc, 1e-38f)); }
+      }
+  }
+  double* out = partials + static_cast<long long>(blockIdx.x) * (3 * kDiceCeMaxC + 1);
+#pragma unroll
+  for (int c = 0; c < kDiceCeMaxC; ++c) {
+    double a = si[c], q = sq[c];
+    block_sum2(a, q);
+    __syncthreads();
+    double t2 = st[c], e = (c == 0) ? ce : 0.0;
+    block_sum2(t2, e);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      out[c] = a; out[kDiceCeMaxC + c] = q; out[2 * kDiceCeMaxC + c] = t2;
+      if (c == 0) out[3 * kDiceCeMaxC] = e;
+    }
+  }
+}
+
+// out[0] = loss; out[1 + (b C + c)] = a_bc; out[1 + B C + (b C + c)] = b_bc; out[1 + 2 B C] = lambda_ce / (B S)
+__global__ void __launch_bounds__(256)
+dice_ce_finish_kernel(const double* __restrict__ partials, int B, int C, int nb, double S, int squared, float snr, float sdr,
+                      float ld, float lce, float* __restrict__ out) {
+  __shared__ double dice_s[256], ce_s[256];
+  double dice = 0.0, ce = 0.0;
+  for (int bc = threadIdx.x; bc < B * C; bc += 256) {
+    const int b = bc / C, c = bc - b * C;
+    double I = 0.0, Q = 0.0, T = 0.0;
+    for (int j = 0; j < nb; ++j) {
+      const double* pp = partials + static_cast<long long>(b * nb + j) * (3 * kDiceCeMaxC + 1);
+      I += pp[c]; Q += pp[kDiceCeMaxC + c]; T += pp[2 * kDiceCeMaxC + c];
+      if (c == 0) ce += pp[3 * kDiceCeMaxC];
+    }
+    const double num = 2.0 * I + snr, den = Q + T + sdr, w = static_cast<double>(ld) / (B * C);
+    dice += 1.0 - num / den;
+    out[1 + bc] = static_cast<float>(-2.0 / den * w);                                  // d dice / d p: coefficient of t
+    out[1 + B * C + bc] = static_cast<float>((squared ? 2.0 : 1.0) * num / (den * den) * w);   // coefficient of p (squared) or 1
+  }
+  dice_s[threadIdx.x] = dice; ce_s[threadIdx.x] = ce;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double d = 0.0, e = 0.0;
+    for (int i = 0; i < 256; ++i) { d += dice_s[i]; e += ce_s[i]; }
+    out[0] = static_cast<float>(ld * d / (B * C) + lce * e / (B * S));
+    out[1 + 2 * B * C] = static_cast<float>(lce / (B * S));
+  }
+}
+
+template <typename TL, typename TT>
+__global__ void __launch_bounds__(256)
+dice_ce_bwd_kernel(const TL* __restrict__ logits, const TT* __restrict__ target, const float* __restrict__ fwd_out,
+                   const float* __restrict__ grad_out, int B, int C, long long S, int squared, TL* __restrict__ dlogits) {
+  const float g = *grad_out, ces = fwd_out[1 + 2 * B * C];
+  const long long total = static_cast<long long>(B) * S;
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += stride) {
+    const int b = static_cast<int>(i / S);
+    const long long s = i - b * S;
+    const TL* lg = logits + static_cast<long long>(b) * C * S + s;
+    float z[kDiceCeMaxC], m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kDiceCeMaxC; ++c)
+      if (c < C) { z[c] = ldf(lg + c * S); m = fmaxf(m, z[c]); }
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kDiceCeMaxC; ++c)
+      if (c < C) { z[c] = __expf(z[c] - m); sum += z[c]; }
+    const float inv = 1.f / sum;
+    const int t = ld_class(target + i);
+    float G[kDiceCeMaxC], dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kDiceCeMaxC; ++c)
+      if (c < C) {
+        z[c] *= inv;                                                     // p_c
+        const float a = fwd_out[1 + b * C + c], bb = fwd_out[1 + B * C + b * C + c];
+        G[c] = (c == t ? a : 0.f) + (squared ? bb * z[c] : bb);         // d(dice term) / d p_c
+        dot = fmaf(z[c], G[c], dot);
+      }
+    TL* dl = dlogits + static_cast<long long>(b) * C * S + s;
+#pragma unroll
+    for (int c = 0; c < kDiceCeMaxC; ++c)
+      if (c < C) stf(dl + c * S, g * (z[c] * (G[c] - dot) + ces * (z[c] - (c == t ? 1.f : 0.f))));
+  }
+}
+
 }  // namespace ucf
 
 using namespace ucf;
@@ -797,4 +928,67 @@ extern "C" int ucf_dice_bce_bwd(const void* logits, int logits_dtype, const void
   else if (tf) dice_bwd_launch<__nv_bfloat16, float>(logits, targets, fwd_out, grad_out, gm, total, weight, act, dlogits, grid, vec, st);
   else dice_bwd_launch<__nv_bfloat16, __nv_bfloat16>(logits, targets, fwd_out, grad_out, gm, total, weight, act, dlogits, grid, vec, st);
   return check_launch("dice_bce_bwd_kernel");
+}
+
+namespace {
+template <typename TL>
+int dice_ce_dispatch_fwd(const void* logits, const void* target, int tdt, int C, long long S, int nb, int squared, double* ws,
+                         int grid, cudaStream_t st) {
+  const TL* lg = static_cast<const TL*>(logits);
+  if (tdt == UCF_DTYPE_U8) dice_ce_fwd_kernel<TL, uint8_t><<<grid, 256, 0, st>>>(lg, static_cast<const uint8_t*>(target), C, S, nb, squared, ws);
+  else if (tdt == UCF_DTYPE_I64) dice_ce_fwd_kernel<TL, long long><<<grid, 256, 0, st>>>(lg, static_cast<const long long*>(target), C, S, nb, squared, ws);
+  else dice_ce_fwd_kernel<TL, float><<<grid, 256, 0, st>>>(lg, static_cast<const float*>(target), C, S, nb, squared, ws);
+  return check_launch("dice_ce_fwd_kernel");
+}
+template <typename TL>
+int dice_ce_dispatch_bwd(const void* logits, const void* target, int tdt, const float* fwd_out, const float* grad_out, int B, int C,
+                         long long S, int squared, void* dlogits, int grid, cudaStream_t st) {
+  const TL* lg = static_cast<const TL*>(logits);
+  TL* dl = static_cast<TL*>(dlogits);
+  if (tdt == UCF_DTYPE_U8) dice_ce_bwd_kernel<TL, uint8_t><<<grid, 256, 0, st>>>(lg, static_cast<const uint8_t*>(target), fwd_out, grad_out, B, C, S, squared, dl);
+  else if (tdt == UCF_DTYPE_I64) dice_ce_bwd_kernel<TL, long long><<<grid, 256, 0, st>>>(lg, static_cast<const long long*>(target), fwd_out, grad_out, B, C, S, squared, dl);
+  else dice_ce_bwd_kernel<TL, float><<<grid, 256, 0, st>>>(lg, static_cast<const float*>(target), fwd_out, grad_out, B, C, S, squared, dl);
+  return check_launch("dice_ce_bwd_kernel");
+}
+int dice_ce_check(const char* who, int ldt, int tdt, int B, int C, long long S) {
+  if (B <= 0 || C < 2 || C > kDiceCeMaxC || S <= 0) { set_last_error("%s: need B > 0, 2 <= C <= %d, S > 0 (got B=%d C=%d S=%lld)", who, kDiceCeMaxC, B, C, S); return UCF_ERR_BAD_ARG; }
+  if (ldt != UCF_DTYPE_F32 && ldt != UCF_DTYPE_BF16) { set_last_error("%s: logits must be f32 or bf16", who); return UCF_ERR_BAD_ARG; }
+  if (tdt != UCF_DTYPE_U8 && tdt != UCF_DTYPE_I64 && tdt != UCF_DTYPE_F32) { set_last_error("%s: target must hold class indices as u8, i64 or f32", who); return UCF_ERR_BAD_ARG; }
+  return UCF_OK;
+}
+}  // namespace
+
+extern "C" int ucf_dice_ce_blocks_per_sample(int B, long long S) {
+  long long nb = (S + 8191) / 8192;
+  const long long cap = B > 0 ? (2048 / B > 1 ? 2048 / B : 1) : 1;
+  if (nb > cap) nb = cap;
+  return static_cast<int>(nb < 1 ? 1 : nb);
+}
+
+extern "C" int ucf_dice_ce_fwd(const void* logits, int logits_dtype, const void* target, int target_dtype, int B, int C,
+                               long long S, int squared_pred, float smooth_nr, float smooth_dr, float lambda_dice,
+                               float lambda_ce, double* workspace, float* out, void* stream) {
+  int rc = dice_ce_check("dice_ce_fwd", logits_dtype, target_dtype, B, C, S);
+  if (rc != UCF_OK) return rc;
+  if (!logits || !target || !workspace || !out) { set_last_error("dice_ce_fwd: null pointer"); return UCF_ERR_BAD_ARG; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nb = ucf_dice_ce_blocks_per_sample(B, S);
+  rc = logits_dtype == UCF_DTYPE_F32 ? dice_ce_dispatch_fwd<float>(logits, target, target_dtype, C, S, nb, squared_pred, workspace, B * nb, st)
+                                     : dice_ce_dispatch_fwd<__nv_bfloat16>(logits, target, target_dtype, C, S, nb, squared_pred, workspace, B * nb, st);
+  if (rc != UCF_OK) return rc;
+  dice_ce_finish_kernel<<<1, 256, 0, st>>>(workspace, B, C, nb, static_cast<double>(S), squared_pred, smooth_nr, smooth_dr, lambda_dice,
+                                           lambda_ce, out);
+  return check_launch("dice_ce_finish_kernel");
+}
+
+extern "C" int ucf_dice_ce_bwd(const void* logits, int logits_dtype, const void* target, int target_dtype, const float* fwd_out,
+                               const float* grad_out, int B, int C, long long S, int squared_pred, void* dlogits, void* stream) {
+  int rc = dice_ce_check("dice_ce_bwd", logits_dtype, target_dtype, B, C, S);
+  if (rc != UCF_OK) return rc;
+  if (!logits || !target || !fwd_out || !grad_out || !dlogits) { set_last_error("dice_ce_bwd: null pointer"); return UCF_ERR_BAD_ARG; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = dice_grid(static_cast<long long>(B) * S);
+  return logits_dtype == UCF_DTYPE_F32
+             ? dice_ce_dispatch_bwd<float>(logits, target, target_dtype, fwd_out, grad_out, B, C, S, squared_pred, dlogits, grid, st)
+             : dice_ce_dispatch_bwd<__nv_bfloat16>(logits, target, target_dtype, fwd_out, grad_out, B, C, S, squared_pred, dlogits, grid, st);
 }

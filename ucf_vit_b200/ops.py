@@ -553,3 +553,41 @@ def dice_bce_bwd(logits, targets, fwd_out, grad_out, weight, act):
                                      grad_out.data_ptr(), B, C, HW, float(weight), int(bool(act)), dlogits.data_ptr(),
                                      _stream()), "dice_bce_bwd")
     return dlogits
+
+
+def _class_dtype(t):
+    if t.dtype == torch.uint8:
+        return L.UCF_DTYPE_U8
+    if t.dtype == torch.int64:
+        return L.UCF_DTYPE_I64
+    if t.dtype == torch.float32:
+        return L.UCF_DTYPE_F32
+    raise TypeError(f"dice_ce: class indices must be uint8, int64 or float32, got {t.dtype}")
+
+
+def dice_ce_fwd(logits, target, squared_pred, smooth_nr, smooth_dr, lambda_dice, lambda_ce):
+    """fp32 [2 + 2 B C]: [0] = DiceCE loss of logits [B, C, ...] against class indices target [B, ...]; the rest feeds dice_ce_bwd."""
+    _require_cuda(logits, target)
+    assert logits.is_contiguous() and target.is_contiguous()
+    B, C = logits.shape[:2]
+    S = logits[0, 0].numel()
+    assert target.numel() == B * S, (tuple(logits.shape), tuple(target.shape))
+    nb = L.lib().ucf_dice_ce_blocks_per_sample(B, S)
+    ws = torch.empty(B * nb * 25, dtype=torch.float64, device=logits.device)
+    out = torch.empty(2 + 2 * B * C, dtype=torch.float32, device=logits.device)
+    L.check(L.lib().ucf_dice_ce_fwd(logits.data_ptr(), _dt(logits), target.data_ptr(), _class_dtype(target), B, C, S,
+                                    int(bool(squared_pred)), float(smooth_nr), float(smooth_dr), float(lambda_dice),
+                                    float(lambda_ce), ws.data_ptr(), out.data_ptr(), _stream()), "dice_ce_fwd")
+    return out
+
+
+def dice_ce_bwd(logits, target, fwd_out, grad_out, squared_pred):
+    _require_cuda(logits, target, fwd_out, grad_out)
+    B, C = logits.shape[:2]
+    S = logits[0, 0].numel()
+    assert grad_out.dtype == torch.float32 and grad_out.numel() == 1
+    dlogits = torch.empty_like(logits)
+    L.check(L.lib().ucf_dice_ce_bwd(logits.data_ptr(), _dt(logits), target.data_ptr(), _class_dtype(target), fwd_out.data_ptr(),
+                                    grad_out.data_ptr(), B, C, S, int(bool(squared_pred)), dlogits.data_ptr(), _stream()),
+            "dice_ce_bwd")
+    return dlogits

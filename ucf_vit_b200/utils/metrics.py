@@ -107,10 +107,29 @@ class DiceBLoss(nn.Module):
                                 bool(act))
 
 
+class _DiceCEFn(torch.autograd.Function):
+    """DiceCELoss through ucf_dice_ce_fwd / _bwd (one pass over logits + labels each way).  Only the logits are differentiable."""
+
+    @staticmethod
+    def forward(ctx, logits, target, squared, snr, sdr, ld, lce):
+        out = ops.dice_ce_fwd(logits, target, squared, snr, sdr, ld, lce)
+        ctx.save_for_backward(logits, target, out)
+        ctx.squared = squared
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        logits, target, out = ctx.saved_tensors
+        g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        return ops.dice_ce_bwd(logits, target, out, g, ctx.squared), None, None, None, None, None, None
+
+
 class DiceCELoss(nn.Module):
     """Dice + cross-entropy loss of the UNETR driver (training_scripts/train_unetr_simple.py:38,51:
     `monai.losses.DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)`).
 
+    On CUDA the loss and its gradient are one pass each over logits + labels (`ucf_dice_ce_fwd / _bwd`) instead of ~15
+    element-wise / reduction kernels and a one-hot tensor 4 x the size of the labels.
     MONAI is not in the image and not vendored in the reference, so this restates its published definition
     (PARITY UNPINNED: no MONAI output was available to check it against):
       p = softmax(logits, 1);  t = one_hot(target);  per (b, c) over the spatial axes
@@ -128,6 +147,17 @@ class DiceCELoss(nn.Module):
         self.lambda_dice, self.lambda_ce = float(lambda_dice), float(lambda_ce)
 
     def forward(self, logits, target):
+        C = logits.shape[1]
+        if target.dim() == logits.dim() and target.shape[1] == 1:
+            target = target[:, 0]
+        if logits.is_cuda and 2 <= C <= 8 and logits.dtype in (torch.float32, torch.bfloat16):
+            t = target if target.dtype in (torch.uint8, torch.int64, torch.float32) else target.long()
+            return _DiceCEFn.apply(logits.contiguous(), t.contiguous(), self.squared_pred, self.smooth_nr, self.smooth_dr,
+                                   self.lambda_dice, self.lambda_ce)
+        return self.forward_torch(logits, target)
+
+    def forward_torch(self, logits, target):
+        """The same loss as PyTorch ops (any device; the formulation the CUDA kernels are tested against)."""
         C = logits.shape[1]
         if target.dim() == logits.dim() and target.shape[1] == 1:
             target = target[:, 0]
