@@ -384,6 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="vit_b16", choices=sorted(reg))
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (the line's config.workload says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="capture the whole training step in a CUDA graph (utils/graph.py) and replay it; the GEMM roofline "
@@ -399,6 +400,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = reg[args.config]
+    if args.batch > 0 and args.batch != wl.batch:
+        wl.workload += f" [per-GPU batch overridden: {args.batch} instead of {wl.batch}]"
+        wl.batch = args.batch
     if args.impl == "reference":
         run_reference_arm(args, wl)
     else:
