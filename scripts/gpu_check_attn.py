@@ -184,6 +184,7 @@ if __name__ == "__main__":
         bench(16, 1024, 12, 64, variants)
         bench(4, 4096, 12, 64, variants)
         bench(64, 197, 16, 32, False)
+        bench(512, 49, 16, 64, False)       # MAE ViT-L encoder on the 25 % kept tokens, batch 512
         bench(4, 4096, 24, 32, False)
     print("FAILS", fails)
     sys.exit(1 if fails else 0)

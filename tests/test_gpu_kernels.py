@@ -97,7 +97,9 @@ def _ref_attn(q, k, v, scale):
 
 
 @pytest.mark.parametrize("B,N,H,hd", [(1, 128, 1, 64), (2, 197, 3, 64), (2, 50, 2, 64), (1, 512, 2, 64), (1, 1000, 1, 64),
-                                      (2, 197, 2, 32), (1, 384, 2, 32), (3, 1, 2, 64)])
+                                      (2, 197, 2, 32), (1, 384, 2, 32), (3, 1, 2, 64),
+                                      # Nq <= 128: the two warpgroups take two consecutive (b, h); odd and large item counts
+                                      (3, 49, 3, 64), (64, 49, 16, 64), (5, 128, 7, 32), (1, 100, 1, 64), (37, 33, 5, 32)])
 def test_attention_fwd_bwd(B, N, H, hd):
     torch.manual_seed(N)
     scale = hd ** -0.5

@@ -27,7 +27,8 @@ struct AttnFwdParams {
   float scale_log2;   // scale * log2(e)
   float* lse;         // [B, H, Nq]
   long long* timeline;   // optional clock64 stamps of CTA 0 (profiling aid; NULL in production)
-  int stagger_cycles;    // short-key kernel: start offset of warpgroup 1
+  int stagger_cycles;    // start offset of warpgroup 1
+  int pair_bh;           // Nq <= 128: the two warpgroups take the single query tile of two consecutive (b, h)
 };
 
 // shared-memory descriptor for a tile whose rows are ROW_BYTES wide (128 -> SWIZZLE_128B,
@@ -180,40 +181,59 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto decode = [&](int item, int& b, int& h, int& q0) {
+  // Work item -> (batch, head, first query row) of warpgroup g; returns whether that warpgroup has rows to compute.
+  // Normal mode: the two warpgroups take the two 128-query tiles of one (b, h, tile pair) and share its K/V tiles.
+  // pair_bh mode (Nq <= 128, i.e. one query tile per (b, h) -- the MAE encoder's 49 kept tokens): they take the tiles of two
+  // CONSECUTIVE (b, h), each with its own K/V tiles in the ring (kvsets = 2), so that warpgroup 1 is not idle and the two
+  // items' load -> S -> softmax -> PV -> store chains overlap.
+  const int kvsets = p.pair_bh ? 2 : 1;
+  auto wg_coords = [&](int item, int g, int& b, int& h, int& q0) -> bool {
+    if (p.pair_bh) {
+      int bh = item * 2 + g;
+      const bool ok = bh < p.B * p.H;
+      if (!ok) bh = item * 2;        // an idle warpgroup's loads repeat its neighbour's tiles; nothing is computed or stored
+      h = bh % p.H;
+      b = bh / p.H;
+      q0 = 0;
+      return ok;
+    }
     const int qp = item % p.nqp;
     const int bh = item / p.nqp;
     h = bh % p.H;
     b = bh / p.H;
-    q0 = qp * 2 * BQ;
+    q0 = qp * 2 * BQ + g * BQ;
+    return q0 < p.Nq;
   };
   const int my_items = (p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  // first query row of the k-th item of this CTA
-  auto item_q0 = [&](int k) { return ((static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x)) % p.nqp) * 2 * BQ; };
+  auto item_of = [&](int k) { return static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x); };
+  auto wg1_valid = [&](int k) { int b, h, q0; return wg_coords(item_of(k), 1, b, h, q0); };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (converged warp, elected lane issues)
     uint32_t r = 0;
     for (int k = 0; k < my_items; ++k) {
-      int b, h, q0;
-      decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), b, h, q0);
+      int bb[2], hh[2], qq[2];
+      wg_coords(item_of(k), 0, bb[0], hh[0], qq[0]);
+      wg_coords(item_of(k), 1, bb[1], hh[1], qq[1]);
       const int qb = k & 1;
       mbar_wait(&q_empty[qb], ((k >> 1) & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(&q_full[qb], 2 * Cfg::Q_BYTES);
-        tma_load_4d(q_s + (qb * 2 + 0) * Cfg::Q_BYTES, &tmQ, &q_full[qb], 0, h, q0, b);
-        tma_load_4d(q_s + (qb * 2 + 1) * Cfg::Q_BYTES, &tmQ, &q_full[qb], 0, h, q0 + BQ, b);
+        tma_load_4d(q_s + (qb * 2 + 0) * Cfg::Q_BYTES, &tmQ, &q_full[qb], 0, hh[0], qq[0], bb[0]);
+        tma_load_4d(q_s + (qb * 2 + 1) * Cfg::Q_BYTES, &tmQ, &q_full[qb], 0, hh[1], qq[1], bb[1]);
       }
       __syncwarp();
       for (int j = 0; j < nkv; ++j) {
-        for (int t = 0; t < 2; ++t, ++r) {
-          const int slot = r % RING;
-          mbar_wait(&kv_empty[slot], ((r / RING) & 1) ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&kv_full[slot], Cfg::KV_BYTES);
-            tma_load_4d(kv_s + slot * Cfg::KV_BYTES, t == 0 ? &tmK : &tmV, &kv_full[slot], 0, h, j * BKV, b);
+        for (int set = 0; set < kvsets; ++set) {
+          for (int t = 0; t < 2; ++t, ++r) {
+            const int slot = r % RING;
+            mbar_wait(&kv_empty[slot], ((r / RING) & 1) ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&kv_full[slot], Cfg::KV_BYTES);
+              tma_load_4d(kv_s + slot * Cfg::KV_BYTES, t == 0 ? &tmK : &tmV, &kv_full[slot], 0, hh[set], j * BKV, bb[set]);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
@@ -237,44 +257,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
       };
 
-      uint32_t r = 0;                // ring position of the current tile's K (V follows at r + 1)
+      // ring position of the current tile's K of K/V set 0 (its V follows at r + 1; set 1, pair_bh mode, at r + 2 / r + 3)
+      uint32_t r = 0;
+      const uint32_t tile_slots = 2 * kvsets;
       // prologue: S of the first tile; warpgroup 1 starts `stagger_cycles` late, once
       {
         mbar_wait(&q_full[0], 0);
         mbar_wait(&kv_full[0], 0);
+        if (kvsets == 2) mbar_wait(&kv_full[2], 0);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(kv_s);
-        const int q0 = item_q0(0);
-        issue_s(0, 0, k_addr);
-        if (q0 + BQ < p.Nq) {
+        issue_s(0, 0, smem_u32(kv_s));
+        if (wg1_valid(0)) {
           const long long t0 = clock64();
           while (clock64() - t0 < p.stagger_cycles) { }
-          issue_s(1, 0, k_addr);
+          issue_s(1, 0, smem_u32(kv_s + (kvsets == 2 ? 2 : 0) * Cfg::KV_BYTES));
         }
-        if (elect_one()) umma_commit(&kv_empty[0]);
+        if (elect_one()) {
+          umma_commit(&kv_empty[0]);
+          if (kvsets == 2) umma_commit(&kv_empty[2]);
+        }
         __syncwarp();
       }
       for (int k = 0; k < my_items; ++k) {
-        const int q0 = item_q0(k);
-        const int ng = (q0 + BQ < p.Nq) ? 2 : 1;
-        for (int j = 0; j < nkv; ++j, r += 2) {
+        const int ng = wg1_valid(k) ? 2 : 1;
+        for (int j = 0; j < nkv; ++j, r += tile_slots) {
           const bool last_tile = j + 1 == nkv;
           const bool has_next = !(last_tile && k + 1 == my_items);
           const int kn = last_tile ? k + 1 : k;                 // item of the next tile
-          const int sv = (r + 1) % RING;
-          mbar_wait(&kv_full[sv], ((r + 1) / RING) & 1);
-          const uint32_t v_addr = smem_u32(kv_s + sv * Cfg::KV_BYTES);
-          int sk = 0, ng_next = 0;
-          uint32_t k_addr = 0;
+          int svs[2], sks[2] = {0, 0}, ng_next = 0;
+          uint32_t v_addrs[2], k_addrs[2] = {0, 0};
+          for (int set = 0; set < kvsets; ++set) {
+            const uint32_t rv = r + 2 * set + 1;
+            svs[set] = rv % RING;
+            mbar_wait(&kv_full[svs[set]], (rv / RING) & 1);
+            v_addrs[set] = smem_u32(kv_s + svs[set] * Cfg::KV_BYTES);
+          }
           if (has_next) {
             if (last_tile) mbar_wait(&q_full[kn & 1], (kn >> 1) & 1);
-            sk = (r + 2) % RING;
-            mbar_wait(&kv_full[sk], ((r + 2) / RING) & 1);
-            k_addr = smem_u32(kv_s + sk * Cfg::KV_BYTES);
-            ng_next = last_tile ? ((item_q0(kn) + BQ < p.Nq) ? 2 : 1) : ng;
+            for (int set = 0; set < kvsets; ++set) {
+              const uint32_t rk = r + tile_slots + 2 * set;
+              sks[set] = rk % RING;
+              mbar_wait(&kv_full[sks[set]], (rk / RING) & 1);
+              k_addrs[set] = smem_u32(kv_s + sks[set] * Cfg::KV_BYTES);
+            }
+            ng_next = last_tile ? (wg1_valid(kn) ? 2 : 1) : ng;
           }
+          if (kvsets == 1) { v_addrs[1] = v_addrs[0]; k_addrs[1] = k_addrs[0]; }
           const int ksteps = last_tile ? ksteps_last : BKV / 16;
           for (int g = 0; g < 2; ++g) {
+            const uint32_t v_addr = v_addrs[g], k_addr = k_addrs[g];
             if (g < ng) {
               mbar_wait(&p_full[g], pc[g] & 1);       // P_g(j) is in tensor memory and S_g(j) has been read
               UCF_F2TL(pc[g], g, 3);
@@ -296,8 +327,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             UCF_F2TL(pc[g] - 1, g, 4);
           }
           if (elect_one()) {
-            umma_commit(&kv_empty[sv]);
-            if (has_next) umma_commit(&kv_empty[sk]);
+            for (int set = 0; set < kvsets; ++set) {
+              umma_commit(&kv_empty[svs[set]]);
+              if (has_next) umma_commit(&kv_empty[sks[set]]);
+            }
             if (last_tile) umma_commit(&q_empty[k & 1]);
           }
           __syncwarp();
@@ -318,10 +351,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool stamp_thread = (threadIdx.x & 127) == 64;
 
     for (int k = 0; k < my_items; ++k) {
-      int b, h, q0;
-      decode(static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x), b, h, q0);
-      const int qt0 = q0 + g * BQ;                  // first query row of this warpgroup's tile
-      if (qt0 >= p.Nq) continue;                    // (only warpgroup 1 can be idle)
+      int b, h, qt0;                                // qt0: first query row of this warpgroup's tile
+      if (!wg_coords(item_of(k), g, b, h, qt0)) continue;      // (only warpgroup 1 can be idle)
       // a warp whose 32 rows are all past Nq keeps the barrier protocol but does no work (its rows of P / O are
       // never stored: the TMA store clips them)
       const bool dead = qt0 + qd * 32 >= p.Nq;
@@ -563,7 +594,8 @@ extern "C" int ucf_attention_fwd(const void* q, const void* k, const void* v, vo
   AttnFwdParams p;
   p.B = B; p.H = H; p.Nq = Nq; p.Nk = Nk;
   p.nqp = (Nq + 255) / 256;
-  const long long items = static_cast<long long>(B) * H * p.nqp;
+  p.pair_bh = (Nq <= 128 && static_cast<long long>(B) * H >= 2) ? 1 : 0;
+  const long long items = p.pair_bh ? (static_cast<long long>(B) * H + 1) / 2 : static_cast<long long>(B) * H * p.nqp;
   if (items > 0x7fffffffLL) { set_last_error("attention_fwd: too many work items"); return UCF_ERR_BAD_ARG; }
   p.items = static_cast<int>(items);
   p.scale_log2 = scale * 1.4426950408889634f;
