@@ -951,7 +951,28 @@ static int gemm_bf16_impl(const void* A, const void* B, void* C, const void* bia
   const bool pair_supported =
       (!a_mn && !b_mn && (epilogue == EPI_BIAS || epilogue == EPI_BIAS_RESIDUAL || epilogue == EPI_BIAS_GELU_AUX)) ||
       (!a_mn && b_mn && (epilogue == EPI_BIAS || epilogue == EPI_DGELU || epilogue == EPI_DELTA)) || (a_mn && b_mn && epilogue == EPI_F32_ADD);
-  if (tile_n == 0 && pair_supported && M >= 512 && N >= 512 && N <= 4096) tile_n = 512;
+  if (tile_n == 0 && epilogue != EPI_F32_ADD && epilogue != EPI_DELTA) {
+    // Persistent kernels work through their tiles in rounds of one tile per SM (pair kernel: per 2-SM cluster), so a
+    // small problem is decided by how well its tile count fills whole rounds, not by the per-tile efficiency alone:
+    // M = 8192 x N = 768 is 96 pair tiles on 74 clusters (2 rounds, 65 % busy) but 384 128x128 tiles on 148 SMs (3 rounds
+    // of a quarter of the work each).  Predicted time = rounds x tile area per SM / relative tile efficiency (pair 1.0,
+    // 128x256 0.92, 128x128 0.80: measured on the ViT-B shapes, profiles/r01_gemm_pair_vs_single.log).  The wgrad form keeps
+    // its own round-filling split-K choice (ucf_wgrad_splits).
+    const long long sms = num_sms();
+    auto rounds = [](long long tiles, long long workers) { return (tiles + workers - 1) / workers; };
+    const long long tm128 = (M + 127) / 128, tm256 = (M + 255) / 256, tn128 = (N + 127) / 128, tn256 = (N + 255) / 256;
+    double best = 1e300;
+    if (pair_supported && M >= 512 && N >= 512 && N <= 4096) {
+      best = static_cast<double>(rounds(tm256 * tn256, sms / 2 > 0 ? sms / 2 : 1)) * (128.0 * 256.0);
+      tile_n = 512;
+    }
+    const double c256 = static_cast<double>(rounds(tm128 * tn256, sms)) * (128.0 * 256.0) / 0.92;
+    const double c128 = static_cast<double>(rounds(tm128 * tn128, sms)) * (128.0 * 128.0) / 0.80;
+    if (c256 < best * 0.97) { best = c256; tile_n = 256; }
+    if (c128 < best * 0.97) { best = c128; tile_n = 128; }
+  } else if (tile_n == 0 && pair_supported && M >= 512 && N >= 512 && N <= 4096) {
+    tile_n = 512;
+  }
   const bool pair = tile_n == 512;
   int BN = pair ? 256 : tile_n;
   if (BN != 128 && BN != 256) BN = (N <= 128 || (N % 256 != 0 && N % 128 == 0 && N < 1024)) ? 128 : 256;
