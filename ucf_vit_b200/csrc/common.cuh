@@ -485,6 +485,22 @@ __device__ __forceinline__ float gelu_erf_grad(float z) {
 }
 // ---- packed fp32x2 forms (FFMA2 / FMUL2 / FADD2 process two lanes per instruction; MUFU stays scalar)
 __device__ __forceinline__ float2 mk2(float a) { return make_float2(a, a); }
+
+// 2^t for t <= ~100 on the FMA / ALU pipes (no MUFU): t = n + f, n = round(t), f in [-0.5, 0.5]
+__device__ __forceinline__ float2 exp2_poly2(float2 t) {
+  t.x = fmaxf(t.x, -125.0f);
+  t.y = fmaxf(t.y, -125.0f);
+  const float2 magic = mk2(12582912.0f);                   // 1.5 * 2^23: low mantissa bits hold round(t)
+  const float2 fi = __fadd2_rn(t, magic);
+  const float2 n = __fadd2_rn(fi, mk2(-12582912.0f));
+  const float2 f = __fadd2_rn(t, make_float2(-n.x, -n.y));
+  float2 q = __ffma2_rn(mk2(0.05517132207751274f), f, mk2(0.24261054396629333f));
+  q = __ffma2_rn(q, f, mk2(0.6932609677314758f));
+  q = __ffma2_rn(q, f, mk2(0.9999281167984009f));
+  return make_float2(__uint_as_float(__float_as_uint(q.x) + (__float_as_uint(fi.x) << 23)),
+                     __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(fi.y) << 23)));
+}
+
 __device__ __forceinline__ float2 bf16x2_to_f32x2(uint32_t v) {
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }
