@@ -7,7 +7,7 @@ tiles, which drives the single-sweep kernel's rescale path).  Bench: this packag
 scaled_dot_product_attention (whatever backend torch picks on this box, plus each backend forced) forward AND
 backward at the three shapes VERDICT r01 names, L2 flushed between timed calls.
 """
-import sys
+import ctypes, sys
 import torch
 sys.path.insert(0, ".")
 from ucf_vit_b200 import ops, _lib as L
@@ -158,6 +158,11 @@ SHAPES = [(1, 128, 1, 64), (2, 197, 3, 64), (1, 256, 2, 64), (2, 50, 2, 64), (1,
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
+    import os
+    if os.environ.get("UCF_BWD_VARIANT"):        # 0: kernel in use, 1: round-1 kernel, 2: experimental
+        lib.ucf_debug_set_attn_bwd_variant.argtypes = [ctypes.c_int]
+        lib.ucf_debug_set_attn_bwd_variant(int(os.environ["UCF_BWD_VARIANT"]))
+        print("attention backward variant", os.environ["UCF_BWD_VARIANT"])
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     stage = args[0] if args else "all"
     variants = "--variants" in sys.argv
