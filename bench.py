@@ -230,6 +230,8 @@ def run_gpu_arm(args, wl):
         else:
             dist.init_process_group("nccl", device_id=dev)
 
+    if getattr(wl, "default_cuda_graph", False) and world == 1 and not args.eager:
+        args.cuda_graph = True
     wl.build(dev, world, local, rank, args)
     host = wl.host_batch(rank)
     resident = tuple(t.to(dev) for t in host)
@@ -294,10 +296,28 @@ def run_gpu_arm(args, wl):
     # ---------------- end-to-end arm: pinned host batch -> device every step, loss read back every step
     # host batches (pinned) -> DevicePrefetcher (the package's loader hand-off: H2D of batch k+1 on a side stream
     # under step k) -> step -> loss read back
+    # The loss of EVERY step is copied device -> host (4 bytes into pinned memory, asynchronously behind the step) and read on
+    # the host one step later, so the read of step k does not drain the launch queue before step k + 1 is enqueued (a
+    # blocking `.item()` per step idles the GPU for the host's whole inter-step latency, which grows with 8 ranks on one box).
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+
     def e2e_steps(n):
+        seen = []
+        k = 0
         for batch in DevicePrefetcher((host for _ in range(n)), dev):
             l = step(tuple(batch))
-            _ = l.item()                      # device -> host read of the step's result
+            loss_host[k & 1].copy_(l.detach().reshape(1).float(), non_blocking=True)
+            loss_ev[k & 1].record()
+            if k > 0:
+                loss_ev[(k - 1) & 1].synchronize()
+                seen.append(float(loss_host[(k - 1) & 1][0]))      # device -> host read of step k - 1's result
+            k += 1
+        if k > 0:
+            loss_ev[(k - 1) & 1].synchronize()
+            seen.append(float(loss_host[(k - 1) & 1][0]))
+        assert len(seen) == n
+        return seen
 
     e2e_steps(2)
     fence()
@@ -386,6 +406,7 @@ def main():
     ap.add_argument("--config", default="vit_b16", choices=sorted(reg))
     ap.add_argument("--batch", type=int, default=0, help="override the workload's per-GPU batch (the line's config.workload says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="vit_tiny: do not use the CUDA-graph step it defaults to on one GPU")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="capture the whole training step in a CUDA graph (utils/graph.py) and replay it; the GEMM roofline "
                          "is then taken from an eager pass after the timed region")

@@ -131,6 +131,7 @@ class VitClassification(Workload):
         self.l2_policy = ("per-step activations (>10 GB) exceed the 126 MB L2"
                           if batch >= 128 else "256 MB L2 flush write before every timed step")
         self.flush_l2 = batch < 128
+        self.default_cuda_graph = batch < 128      # launch-bound at small batch: replay the captured step (single GPU)
 
     def _model(self):
         from ucf_vit_b200.simple.arch import VIT
