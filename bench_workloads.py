@@ -555,7 +555,7 @@ class Sap4096(Workload):
         self.p = 16
         self.side = self.p * self.s
         self.name = f"sap_4096_L{L}"
-        self.batch = 4 if L <= 1024 else 2
+        self.batch = 16 if L <= 1024 else 8
         self.workload = (f"SAP adaptive-patching ViT-B segmentation train step on 4096x4096x3 uint8 images: quadtree of {L} leaves "
                          f"per image (host C++ build) + device cubic gather to {self.p}x{self.p} patches + fwd + DiceBCE + bwd + AdamW, "
                          f"batch {self.batch}/GPU; edge maps are synthetic (OpenCV is not in the image)")

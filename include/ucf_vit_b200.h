@@ -77,6 +77,18 @@ int ucf_gemm_dgrad_delta_supported(int M, int N, int K, int heads);
 int ucf_gemm_dgrad_delta(const void* dY, const void* W, void* dX, const void* O, float* delta, int M, int N, int K,
                          long long lddy, long long ldw, long long lddx, long long ldo, int tokens, int heads, void* stream);
 
+/* LayerNorm folded into the projection that consumes it (north-star "fused LayerNorm+QKV projection"; replaces the pair
+ * `self.attn(self.norm1(x))` -> `self.qkv(x)`, building_blocks.py:236-237 -> :150,159, when the normalised activations are
+ * not needed afterwards, i.e. in forward-only / no-grad execution -- training keeps them for the weight gradient):
+ *   y[r, n] = rstd[r] * (sum_k x[r, k] * Wg[n, k] - mean[r] * colsum[n]) + bias_folded[n]   ==   LN(x) W^T + b
+ * with Wg = W * diag(gamma) (bf16 [N, K]), colsum[n] = sum_k Wg[n, k], bias_folded = W beta + b (both fp32 [N]), and
+ * mean / rstd from ucf_layernorm_stats (one read of x, 8 bytes out per row -- instead of a read and a write of x).
+ * x: bf16 [M, K] raw rows; y: bf16 [M, N].  Shapes served: ucf_ln_gemm_supported() != 0. */
+int ucf_layernorm_stats(const void* x, float* mean, float* rstd, long long rows, int D, float eps, int x_dtype, void* stream);
+int ucf_ln_gemm_supported(int M, int N, int K);
+int ucf_ln_gemm(const void* x, const void* w_gamma, void* y, const float* bias_folded, const float* colsum, const float* mean,
+                const float* rstd, int M, int N, int K, long long ldx, long long ldw, long long ldy, void* stream);
+
 /* ---- LayerNorm (replaces nn.LayerNorm at arch.py:170,266; building_blocks.py:212,226) ------
  * x: [rows, D] (x_dtype), gamma/beta: [D] (param_dtype, may be NULL = 1/0), y: [rows, D] bf16,
  * mean/rstd: [rows] fp32 (saved for backward).  D % 8 == 0, D <= 4096. */

@@ -431,3 +431,47 @@ def test_dgrad_with_fused_attention_delta(B, N, D, H):
     assert torch.equal(dx, ops.gemm(dy, w, M=M, N=D, K=D, b_mn=True))          # same product as the plain dgrad kernel
     dref = (ref * o.float()).view(B, N, H, hd).sum(-1).permute(0, 2, 1)
     _ok(delta, dref, 2e-3)
+
+
+@pytest.mark.parametrize("M,D,N", [(50432, 768, 2304), (1000, 512, 1536), (4096, 1024, 3072)])
+def test_layernorm_folded_into_gemm(M, D, N):
+    """ucf_layernorm_stats + ucf_ln_gemm (LayerNorm folded into the projection that consumes it) against LN -> Linear."""
+    from ucf_vit_b200 import functional as UF
+    torch.manual_seed(M % 97)
+    x = bf(torch.randn(M, D, device=dev) * 1.5 + 0.7)            # rows with a non-zero mean: the rank-1 correction matters
+    ln_w = torch.randn(D, device=dev) * 0.3 + 1.0
+    ln_b = torch.randn(D, device=dev) * 0.2
+    w = torch.randn(N, D, device=dev) * 0.03
+    b = torch.randn(N, device=dev) * 0.1
+    mean, rstd = ops.layernorm_stats(x, 1e-6)
+    xf = x.float()
+    _ok(mean, xf.mean(-1), 1e-4)
+    _ok(rstd, (xf.var(-1, unbiased=False) + 1e-6).rsqrt(), 1e-4)
+    wg, colsum, bfold = UF.fold_layernorm(w, b, ln_w, ln_b)
+    y = ops.ln_gemm(x, wg, bfold, colsum, mean, rstd)
+    ref = torch.nn.functional.layer_norm(xf, (D,), ln_w, ln_b, 1e-6) @ w.t() + b
+    _ok(y, ref, 1.5e-2)
+
+
+def test_block_eval_path_matches_training_path():
+    """Block in eval mode under no_grad (LayerNorm1 folded into QKV) == the training-mode forward of the same weights."""
+    from functools import partial
+    from ucf_vit_b200.simple.building_blocks import Block
+    torch.manual_seed(1)
+    blk = Block(dim=768, num_heads=12, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6)).to(dev)
+    with torch.no_grad():
+        blk.norm1.weight.add_(torch.randn_like(blk.norm1.weight) * 0.2)
+        blk.norm1.bias.add_(torch.randn_like(blk.norm1.bias) * 0.2)
+    x = torch.randn(8, 197, 768, device=dev)
+    blk.train()
+    y_train = blk(x).detach()
+    blk.eval()
+    with torch.no_grad():
+        y_eval = blk(x)
+        assert blk._ln_fold is not None
+        _ok(y_eval, y_train.float(), 1e-2)
+        blk.norm1.weight.mul_(1.5)                       # an in-place edit bumps the version: the fold is redone
+        y2 = blk(x)
+    blk.train()
+    assert blk._ln_fold is None
+    _ok(y2, blk(x).detach().float(), 1e-2)

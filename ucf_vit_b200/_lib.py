@@ -53,6 +53,9 @@ _SIGNATURES = {
     "ucf_gemm_dgrad_delta_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "ucf_gemm_dgrad_delta": (c_int, [c_void_p] * 5 + [c_int] * 3 + [_LL] * 4 + [c_int, c_int, c_void_p]),
     "ucf_attention_bwd_with_delta": (c_int, [c_void_p] * 11 + [c_int] * 5 + [_LL] * 21 + [c_float, c_void_p]),
+    "ucf_layernorm_stats": (c_int, [c_void_p, c_void_p, c_void_p, _LL, c_int, c_float, c_int, c_void_p]),
+    "ucf_ln_gemm_supported": (c_int, [c_int, c_int, c_int]),
+    "ucf_ln_gemm": (c_int, [c_void_p] * 7 + [c_int] * 3 + [_LL] * 3 + [c_void_p]),
     "ucf_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, _LL, c_int,
                                   c_float, c_int, c_int, c_void_p]),
     "ucf_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -33,9 +33,14 @@ struct GemmParams {
   // the row statistic the attention backward kernel needs -- taken from the accumulator tile in the epilogue
   float* delta;       // [M / tokens, heads, tokens] fp32
   int tokens, heads, head_dim;
+  // EPI_LN only (LayerNorm folded into the GEMM that consumes it): C[r, n] = rstd[r] * (acc[r, n] - mean[r] * colsum[n]) + bias[n]
+  // with A = the RAW (un-normalised) rows, B = W * diag(gamma), colsum[n] = sum_k B[n, k], bias = W beta + b
+  const float* ln_mean;     // [M]
+  const float* ln_rstd;     // [M]
+  const float* ln_colsum;   // [N]
 };
 
-enum { EPI_BIAS = 0, EPI_BIAS_RESIDUAL = 1, EPI_BIAS_GELU_AUX = 2, EPI_DGELU = 3, EPI_F32_ADD = 4, EPI_DELTA = 5 };
+enum { EPI_BIAS = 0, EPI_BIAS_RESIDUAL = 1, EPI_BIAS_GELU_AUX = 2, EPI_DGELU = 3, EPI_F32_ADD = 4, EPI_DELTA = 5, EPI_LN = 6 };
 
 // Bias-gradient warps of the wgrad kernels.  In wgrad, A = dY^T (MN-major: 64 token rows x 128
 // channels per stage, two 64-channel boxes of 128-byte swizzled rows), so the bias gradient
@@ -443,7 +448,7 @@ struct Gemm2Cfg {
   static constexpr int PRODUCER2_WARP = 2 + EPI_WARPS + (BIASW ? BIAS_WARPS : 0);
   static constexpr int THREADS = 32 * (PRODUCER2_WARP + 1);
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_STAGE_BYTES + AUX_STAGE_BYTES + BN * 4 +
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_STAGE_BYTES + AUX_STAGE_BYTES + BN * 4 * (EPI == EPI_LN ? 2 : 1) +
                                     (3 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
   static_assert(BN == 256, "pair kernel is instantiated for BN = 256");
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
@@ -464,7 +469,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* epi_out = smem + STAGES * STAGE_BYTES;
   uint8_t* epi_aux = epi_out + Cfg::OUT_STAGE_BYTES;
   float* bias_s = reinterpret_cast<float*>(epi_aux + Cfg::AUX_STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + BN);
+  float* csum_s = bias_s + BN;                                  // EPI_LN: column sums of the gamma-scaled weight
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + BN * (EPI == EPI_LN ? 2 : 1));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -626,10 +632,17 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             b = p.bias_is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[n0 + i])
                                : reinterpret_cast<const float*>(p.bias)[n0 + i];
           bias_s[i] = b;
+          if (EPI == EPI_LN) csum_s[i] = n0 + i < p.N ? p.ln_colsum[n0 + i] : 0.f;
         }
         named_bar_sync(1, 32 * Cfg::EPI_WARPS);
       }
       const bool active = r0 < p.M && n0 + cbase < p.N;
+      float2 ln_rs2 = make_float2(1.f, 1.f), ln_nm2 = make_float2(0.f, 0.f);      // EPI_LN: this thread's row statistics
+      if (EPI == EPI_LN && r0 + lane < p.M) {
+        const float rs = p.ln_rstd[r0 + lane], mu = p.ln_mean[r0 + lane];
+        ln_rs2 = make_float2(rs, rs);
+        ln_nm2 = make_float2(-mu * rs, -mu * rs);
+      }
       if (Cfg::AUX_IN && lane == 0 && active) {
         mbar_expect_tx(&my_aux_bar[cc & 1], AUX_BUF);
         tma_load_2d(my_aux + (cc & 1) * AUX_BUF, &tmAux, &my_aux_bar[cc & 1], n0 + cbase, r0);
@@ -674,6 +687,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 4; ++e)
                 f[e] = make_float2(__uint_as_float(v[8 * j + 2 * e]), __uint_as_float(v[8 * j + 2 * e + 1]));
+              if (EPI == EPI_LN) {          // rstd * acc - (mean * rstd) * colsum, then the folded bias below
+                const float4 c0 = *reinterpret_cast<const float4*>(&csum_s[cbase + c * CW + 8 * j]);
+                const float4 c1 = *reinterpret_cast<const float4*>(&csum_s[cbase + c * CW + 8 * j + 4]);
+                f[0] = __ffma2_rn(f[0], ln_rs2, __fmul2_rn(ln_nm2, make_float2(c0.x, c0.y)));
+                f[1] = __ffma2_rn(f[1], ln_rs2, __fmul2_rn(ln_nm2, make_float2(c0.z, c0.w)));
+                f[2] = __ffma2_rn(f[2], ln_rs2, __fmul2_rn(ln_nm2, make_float2(c1.x, c1.y)));
+                f[3] = __ffma2_rn(f[3], ln_rs2, __fmul2_rn(ln_nm2, make_float2(c1.z, c1.w)));
+              }
               if (EPI != EPI_DGELU && EPI != EPI_DELTA) {
                 const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[cbase + c * CW + 8 * j]);
                 const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[cbase + c * CW + 8 * j + 4]);
@@ -840,7 +861,7 @@ using namespace ucf;
 /* profiling aid (not part of the public header): limit the CTA-pair kernels to n clusters (0 = all SMs) */
 extern "C" void ucf_debug_set_gemm_max_clusters(int n) { ucf::g_debug_max_clusters = n; }
 
-struct DeltaArgs { float* delta; int tokens, heads; };
+struct DeltaArgs { float* delta; int tokens, heads; const float* ln_mean; const float* ln_rstd; const float* ln_colsum; };
 static int gemm_bf16_impl(const void* A, const void* B, void* C, const void* bias, void* aux,
                              int M, int N, int K, long long lda, long long ldb, long long ldc,
                              long long ldaux, int a_layout, int b_layout, int epilogue,
@@ -893,6 +914,30 @@ extern "C" int ucf_gemm_bf16(const void* A, const void* B, void* C, const void* 
   return rc;
 }
 
+extern "C" int ucf_ln_gemm_supported(int M, int N, int K) { return M >= 512 && N >= 512 && N <= 4096 && K > 0 && K % 8 == 0; }
+
+extern "C" int ucf_ln_gemm(const void* x, const void* w_gamma, void* y, const float* bias_folded, const float* colsum,
+                           const float* mean, const float* rstd, int M, int N, int K, long long ldx, long long ldw, long long ldy,
+                           void* stream) {
+  if (!bias_folded || !colsum || !mean || !rstd) { set_last_error("ln_gemm: null vector"); return UCF_ERR_BAD_ARG; }
+  if (!ucf_ln_gemm_supported(M, N, K)) {
+    set_last_error("ln_gemm: shape M=%d N=%d K=%d has no fused kernel (ucf_ln_gemm_supported)", M, N, K);
+    return UCF_ERR_UNSUPPORTED;
+  }
+  DeltaArgs d{nullptr, 0, 0, mean, rstd, colsum};
+  GemmTimingRec r;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (g_gemm_timing) {
+    r.flops = 2.0 * M * N * K;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+  }
+  const int rc = gemm_bf16_impl(x, w_gamma, y, bias_folded, nullptr, M, N, K, ldx, ldw, ldy, 0, UCF_LAYOUT_K_MAJOR, UCF_LAYOUT_K_MAJOR,
+                                EPI_LN, UCF_DTYPE_F32, 1, 512, nullptr, stream, &d);
+  if (g_gemm_timing) { cudaEventRecord(r.e1, st); g_gemm_recs.push_back(r); }
+  return rc;
+}
+
 extern "C" int ucf_gemm_dgrad_delta_supported(int M, int N, int K, int heads) {
   if (heads <= 0 || N % heads) return 0;
   const int hd = N / heads;
@@ -909,7 +954,7 @@ extern "C" int ucf_gemm_dgrad_delta(const void* dY, const void* W, void* dX, con
     set_last_error("gemm_dgrad_delta: shape M=%d N=%d heads=%d has no fused kernel (ucf_gemm_dgrad_delta_supported)", M, N, heads);
     return UCF_ERR_UNSUPPORTED;
   }
-  DeltaArgs d{delta, tokens, heads};
+  DeltaArgs d{delta, tokens, heads, nullptr, nullptr, nullptr};
   GemmTimingRec r;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (g_gemm_timing) {
@@ -930,7 +975,7 @@ static int gemm_bf16_impl(const void* A, const void* B, void* C, const void* bia
                              const DeltaArgs* dargs) {
   if (M <= 0 || N <= 0 || K <= 0) { set_last_error("gemm: empty problem M=%d N=%d K=%d", M, N, K); return UCF_ERR_BAD_ARG; }
   if (!A || !B || !C) { set_last_error("gemm: null operand"); return UCF_ERR_BAD_ARG; }
-  if (epilogue < 0 || epilogue > 5 || (epilogue == EPI_DELTA && !dargs)) { set_last_error("gemm: bad epilogue %d", epilogue); return UCF_ERR_BAD_ARG; }
+  if (epilogue < 0 || epilogue > 6 || ((epilogue == EPI_DELTA || epilogue == EPI_LN) && !dargs)) { set_last_error("gemm: bad epilogue %d", epilogue); return UCF_ERR_BAD_ARG; }
   const bool a_mn = a_layout == UCF_LAYOUT_MN_MAJOR, b_mn = b_layout == UCF_LAYOUT_MN_MAJOR;
   const bool has_aux = epilogue == EPI_BIAS_RESIDUAL || epilogue == EPI_BIAS_GELU_AUX || epilogue == EPI_DGELU || epilogue == EPI_DELTA;
   if (has_aux && !aux) { set_last_error("gemm: epilogue %d needs aux", epilogue); return UCF_ERR_BAD_ARG; }
@@ -949,9 +994,9 @@ static int gemm_bf16_impl(const void* A, const void* B, void* C, const void* bia
   // auto (tile_n == 0): tall problems with several 256-wide column tiles go to the CTA-pair kernel
   // (measured +7..11 % on the ViT-B shapes); everything else to the single-CTA kernels.
   const bool pair_supported =
-      (!a_mn && !b_mn && (epilogue == EPI_BIAS || epilogue == EPI_BIAS_RESIDUAL || epilogue == EPI_BIAS_GELU_AUX)) ||
+      (!a_mn && !b_mn && (epilogue == EPI_BIAS || epilogue == EPI_BIAS_RESIDUAL || epilogue == EPI_BIAS_GELU_AUX || epilogue == EPI_LN)) ||
       (!a_mn && b_mn && (epilogue == EPI_BIAS || epilogue == EPI_DGELU || epilogue == EPI_DELTA)) || (a_mn && b_mn && epilogue == EPI_F32_ADD);
-  if (tile_n == 0 && epilogue != EPI_F32_ADD && epilogue != EPI_DELTA) {
+  if (tile_n == 0 && epilogue != EPI_F32_ADD && epilogue != EPI_DELTA && epilogue != EPI_LN) {
     // Persistent kernels work through their tiles in rounds of one tile per SM (pair kernel: per 2-SM cluster), so a
     // small problem is decided by how well its tile count fills whole rounds, not by the per-tile efficiency alone:
     // M = 8192 x N = 768 is 96 pair tiles on 74 clusters (2 rounds, 65 % busy) but 384 128x128 tiles on 148 SMs (3 rounds
@@ -989,9 +1034,11 @@ static int gemm_bf16_impl(const void* A, const void* B, void* C, const void* bia
   p.bias_is_bf16 = bias_dtype == UCF_DTYPE_BF16;
   p.bias_grad = static_cast<float*>(bias_grad);
   p.delta = nullptr; p.tokens = 1; p.heads = 1; p.head_dim = 64;
+  p.ln_mean = p.ln_rstd = p.ln_colsum = nullptr;
   if (epilogue == EPI_DELTA) {
     p.delta = dargs->delta; p.tokens = dargs->tokens; p.heads = dargs->heads; p.head_dim = N / dargs->heads;
   }
+  if (epilogue == EPI_LN) { p.ln_mean = dargs->ln_mean; p.ln_rstd = dargs->ln_rstd; p.ln_colsum = dargs->ln_colsum; }
   if (bias_grad && !(a_mn && epilogue == EPI_F32_ADD)) {
     set_last_error("gemm: bias_grad is only produced by the wgrad form (A MN-major, UCF_EPI_F32_ADD)");
     return UCF_ERR_BAD_ARG;
@@ -1037,6 +1084,7 @@ static int gemm_bf16_impl(const void* A, const void* B, void* C, const void* bia
   UCF_GEMM2_CASE(6, false, true, EPI_BIAS)
   UCF_GEMM2_CASE(4, false, true, EPI_DGELU)
   UCF_GEMM2_CASE(5, false, true, EPI_DELTA)
+  UCF_GEMM2_CASE(5, false, false, EPI_LN)
   UCF_GEMM2_CASE(6, true, true, EPI_F32_ADD)
 #undef UCF_GEMM2_CASE
   if (pair) {

@@ -111,6 +111,7 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ gamma,
       if (mean_out) mean_out[row] = mu;
       if (rstd_out) rstd_out[row] = rs;
     }
+    if (y == nullptr) continue;          // statistics-only pass (ucf_layernorm_stats: the LayerNorm -> GEMM fusion)
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
@@ -443,6 +444,27 @@ extern "C" int ucf_layernorm_fwd(const void* x, const void* gamma, const void* b
   UCF_LN_DISPATCH_NCH(D, LAUNCH)
 #undef LAUNCH
   return check_launch("layernorm_fwd_kernel");
+}
+
+extern "C" int ucf_layernorm_stats(const void* x, float* mean, float* rstd, long long rows, int D, float eps, int x_dtype,
+                                   void* stream) {
+  if (rows <= 0) return UCF_OK;
+  if (D <= 0 || D % 8 != 0 || D > 4096) {
+    set_last_error("layernorm_stats: D=%d must be a multiple of 8 and <= 4096", D);
+    return UCF_ERR_BAD_ARG;
+  }
+  if (!x || !mean || !rstd) { set_last_error("layernorm_stats: null pointer"); return UCF_ERR_BAD_ARG; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ln_grid(rows);
+  const bool xb = x_dtype == UCF_DTYPE_BF16;
+  const void* none = nullptr;
+  void* no_y = nullptr;
+#define LAUNCH(NCH)                                                                                              \
+  if (xb) layernorm_fwd_kernel<NCH, true, false><<<grid, 256, 0, st>>>(x, none, none, no_y, mean, rstd, rows, D, eps);  \
+  else layernorm_fwd_kernel<NCH, false, false><<<grid, 256, 0, st>>>(x, none, none, no_y, mean, rstd, rows, D, eps);
+  UCF_LN_DISPATCH_NCH(D, LAUNCH)
+#undef LAUNCH
+  return check_launch("layernorm_fwd_kernel(stats)");
 }
 
 extern "C" int ucf_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,

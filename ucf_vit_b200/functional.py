@@ -488,6 +488,47 @@ class _BlockFn(torch.autograd.Function):
                 None, None, None)
 
 
+# ---------------------------------------------------------------------------------------------
+# forward-only block: LayerNorm folded into the QKV projection (no normalised activations are written)
+# ---------------------------------------------------------------------------------------------
+def fold_layernorm(weight, bias, ln_weight, ln_bias):
+    """Constants of `LN(x) W^T + b == rstd * (x Wg^T - mean * colsum) + b_folded` (ops.ln_gemm):
+    Wg = W diag(gamma) rounded to bf16, colsum = row sums of THAT rounded matrix (so the mean term cancels exactly what
+    the tensor cores accumulated), b_folded = W beta + b in fp32."""
+    w32 = weight.detach().float()
+    g = ln_weight.detach().float() if ln_weight is not None else torch.ones(w32.shape[1], device=w32.device)
+    wg = (w32 * g[None, :]).to(BF16).contiguous()
+    colsum = wg.float().sum(1).contiguous()
+    bf = torch.zeros(w32.shape[0], device=w32.device) if bias is None else bias.detach().float().clone()
+    if ln_bias is not None:
+        bf = bf + w32 @ ln_bias.detach().float()
+    return wg, colsum, bf.contiguous()
+
+
+@torch.no_grad()
+def block_forward_nograd(x, folded, n1_eps, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, num_heads, eps2):
+    """Block.forward when no gradient is wanted (eval / inference): statistics pass + ONE GEMM for LayerNorm1 + QKV
+    (`ucf_layernorm_stats` + `ucf_ln_gemm`), nothing saved for backward.  `folded` = fold_layernorm(qkv.weight, qkv.bias,
+    norm1.weight, norm1.bias)."""
+    B, N, D = x.shape
+    M, H = B * N, num_heads
+    hd = D // H
+    x2 = x.reshape(M, D)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    wg, colsum, bfold = folded
+    mean, rstd = ops.layernorm_stats(x2, n1_eps)
+    qkv5 = ops.ln_gemm(x2, wg, bfold, colsum, mean, rstd).view(B, N, 3, H, hd)
+    o, _ = ops.attention_fwd(qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2], hd ** -0.5)
+    wp, w1h, w2h = bf16_params(proj_w, fc1_w, fc2_w)
+    x1 = ops.gemm(o.view(M, D), wp, M=M, N=D, K=D, bias=proj_b, aux=x2, epilogue=L.EPI_BIAS_RESIDUAL)
+    h2, _, _ = ops.layernorm_fwd(x1, n2w, n2b, eps2)
+    Hd = fc1_w.shape[0]
+    u, _ = ops.gemm(h2, w1h, M=M, N=Hd, K=D, bias=fc1_b, epilogue=L.EPI_BIAS_GELU_AUX)
+    y = ops.gemm(u, w2h, M=M, N=D, K=Hd, bias=fc2_b, aux=x1, epilogue=L.EPI_BIAS_RESIDUAL)
+    return y.view(B, N, D)
+
+
 def fused_block(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
                 num_heads, eps1, eps2):
     return _BlockFn.apply(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,

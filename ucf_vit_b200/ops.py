@@ -110,6 +110,40 @@ def layernorm_fwd(x, gamma, beta, eps):
     return y.view(*x.shape[:-1], D), mean, rstd
 
 
+def layernorm_stats(x, eps):
+    """(mean, rstd) fp32 [rows] of LayerNorm over the last dim: one read of x, nothing else written."""
+    _require_cuda(x)
+    D = x.shape[-1]
+    x2 = x.reshape(-1, D)
+    assert x2.is_contiguous()
+    rows = x2.shape[0]
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    L.check(L.lib().ucf_layernorm_stats(x2.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, D, float(eps), _dt(x2), _stream()),
+            "layernorm_stats")
+    return mean, rstd
+
+
+def ln_gemm_supported(M, N, K):
+    return bool(L.lib().ucf_ln_gemm_supported(M, N, K))
+
+
+def ln_gemm(x, w_gamma, bias_folded, colsum, mean, rstd):
+    """y = LayerNorm(x) W^T + b from the RAW rows x: y[r, n] = rstd[r] * (x[r] . Wg[n] - mean[r] * colsum[n]) + bias_folded[n]
+    (Wg = W diag(gamma) in bf16, colsum = Wg.sum(1), bias_folded = W beta + b: see functional.fold_layernorm)."""
+    _require_cuda(x, w_gamma, bias_folded, colsum, mean, rstd)
+    M, K = x.shape
+    N = w_gamma.shape[0]
+    assert x.dtype == torch.bfloat16 and w_gamma.dtype == torch.bfloat16 and x.stride(1) == 1 and w_gamma.stride(1) == 1
+    assert bias_folded.dtype == colsum.dtype == mean.dtype == rstd.dtype == torch.float32
+    assert bias_folded.numel() == N and colsum.numel() == N and mean.numel() == M and rstd.numel() == M
+    y = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().ucf_ln_gemm(x.data_ptr(), w_gamma.data_ptr(), y.data_ptr(), bias_folded.data_ptr(), colsum.data_ptr(),
+                                mean.data_ptr(), rstd.data_ptr(), M, N, K, x.stride(0), w_gamma.stride(0), y.stride(0), _stream()),
+            "ln_gemm")
+    return y
+
+
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, dgamma=None, dbeta=None):
     """Returns dx (bf16).  dgamma/dbeta (fp32 [D]) are accumulated into when given."""
     _require_cuda(dy, x, gamma, dres)

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as UF
+from .. import ops
 from ..utils.fused_attn import FusedAttn
 from ..utils.layers import DropPath, LayerScale, to_2tuple, to_3tuple, trunc_normal_  # noqa: F401 (re-exported)
 from ..utils.unetr_blocks import get_conv_layer
@@ -199,8 +200,31 @@ class Block(nn.Module):
                 and a.head_dim in (32, 64) and isinstance(a.q_norm, nn.Identity) and isinstance(a.k_norm, nn.Identity)
                 and not _dropout_active(a.attn_drop) and not _dropout_active(a.proj_drop))
 
+    def train(self, mode: bool = True):
+        self._ln_fold = None            # folded LayerNorm1 -> QKV constants belong to one set of eval-time weights
+        return super().train(mode)
+
+    def _folded_qkv(self):
+        """(Wg, colsum, b_folded) of functional.fold_layernorm for norm1 -> attn.qkv, cached while the module stays in eval
+        mode and the four tensors keep their versions and storage (load_state_dict / in-place edits re-fold)."""
+        a = self.attn
+        src = (a.qkv.weight, a.qkv.bias, self.norm1.weight, self.norm1.bias)
+        key = tuple((t.data_ptr(), t._version) for t in src if t is not None)
+        cached = getattr(self, "_ln_fold", None)
+        if cached is None or cached[0] != key:
+            cached = (key, UF.fold_layernorm(*src))
+            self._ln_fold = cached
+        return cached[1]
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         x = UF.to_bf16(x)
+        if (not self.training and not torch.is_grad_enabled() and x.dim() == 3 and self._fully_fused()
+                and ops.ln_gemm_supported(x.shape[0] * x.shape[1], 3 * x.shape[2], x.shape[2])):
+            # forward-only execution: LayerNorm1 is folded into the QKV projection (no normalised copy of x is written)
+            a, m = self.attn, self.mlp
+            return UF.block_forward_nograd(x, self._folded_qkv(), self.norm1.eps, a.proj.weight, a.proj.bias,
+                                           self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias,
+                                           m.fc2.weight, m.fc2.bias, a.num_heads, self.norm2.eps)
         if self._fully_fused():
             a, m = self.attn, self.mlp
             return UF.fused_block(x, self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias,
