@@ -405,6 +405,51 @@ layernorm_bwd_wide_kernel(const void* __restrict__ dy, const void* __restrict__ 
   }
 }
 
+// Statistics only (bf16 rows): one pass, sum and sum of squares together, two rows in flight per warp.  8 bytes out
+// per row; the whole kernel is one read of x.  var = E[x^2] - mean^2 in fp32 over bf16 data (|x| of activations is O(1..100)).
+__global__ void __launch_bounds__(256)
+layernorm_stats_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                            long long rows, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const float inv_d = 1.0f / static_cast<float>(D);
+  const int nvec = D >> 3;                                   // 16-byte vectors per row
+  for (long long row = warp_global * 2; row < rows; row += nwarps * 2) {
+    const bool two = row + 1 < rows;
+    const uint4* r0 = reinterpret_cast<const uint4*>(x + row * D);
+    const uint4* r1 = reinterpret_cast<const uint4*>(x + (row + (two ? 1 : 0)) * D);
+    float2 s0 = f2(0.f, 0.f), q0 = f2(0.f, 0.f), s1 = f2(0.f, 0.f), q1 = f2(0.f, 0.f);
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 a = __ldg(r0 + v), b = __ldg(r1 + v);
+      float2 fa[4], fb[4];
+      unpack4(a, fa);
+      unpack4(b, fb);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s0 = __fadd2_rn(s0, fa[e]); q0 = __ffma2_rn(fa[e], fa[e], q0);
+        s1 = __fadd2_rn(s1, fb[e]); q1 = __ffma2_rn(fb[e], fb[e], q1);
+      }
+    }
+    float a0 = s0.x + s0.y, b0 = q0.x + q0.y, a1 = s1.x + s1.y, b1 = q1.x + q1.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o); b0 += __shfl_xor_sync(0xffffffffu, b0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o); b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+    }
+    if (lane == 0) {
+      const float m0 = a0 * inv_d;
+      mean_out[row] = m0;
+      rstd_out[row] = rsqrtf(fmaxf(b0 * inv_d - m0 * m0, 0.f) + eps);
+      if (two) {
+        const float m1 = a1 * inv_d;
+        mean_out[row + 1] = m1;
+        rstd_out[row + 1] = rsqrtf(fmaxf(b1 * inv_d - m1 * m1, 0.f) + eps);
+      }
+    }
+  }
+}
+
 static int ln_grid(long long rows) {
   const long long warps_per_block = 8;
   long long blocks = (rows + warps_per_block - 1) / warps_per_block;
@@ -455,8 +500,15 @@ extern "C" int ucf_layernorm_stats(const void* x, float* mean, float* rstd, long
   }
   if (!x || !mean || !rstd) { set_last_error("layernorm_stats: null pointer"); return UCF_ERR_BAD_ARG; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = ln_grid(rows);
   const bool xb = x_dtype == UCF_DTYPE_BF16;
+  if (xb && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    long long blocks = (rows + 15) / 16;                        // 8 warps x 2 rows per block
+    const long long cap = static_cast<long long>(num_sms()) * 8;
+    if (blocks > cap) blocks = cap;
+    layernorm_stats_bf16_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), mean, rstd, rows, D, eps);
+    return check_launch("layernorm_stats_bf16_kernel");
+  }
+  const int grid = ln_grid(rows);
   const void* none = nullptr;
   void* no_y = nullptr;
 #define LAUNCH(NCH)                                                                                              \
