@@ -459,6 +459,10 @@ class Unetr128(Workload):
         if getattr(args, "bf16_decoder", False):
             self.model.conv_autocast_dtype = torch.bfloat16
             self.workload = self.workload.replace("conv decoder (feature_size 16)", "conv decoder (feature_size 16) under bf16 autocast")
+        if getattr(args, "fused_decoder", False):
+            self.model.use_fused_decoder()
+            self.workload = self.workload.replace("conv decoder (feature_size 16)", "channels-last bf16 conv decoder (feature_size "
+                                                  "16; cuDNN convolutions, fused InstanceNorm + LeakyReLU kernels)")
         self.net = self._wrap_ddp(self.model, world, local, args)
         self.opt = configure_optimizer(self.model, 1e-5, 0.9, 0.95, 1e-5, fused=_opt_kind(args, True))
         self.lossf = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define UCF_ABI_VERSION 3
+#define UCF_ABI_VERSION 4
 
 enum { UCF_DTYPE_F32 = 0, UCF_DTYPE_BF16 = 1, UCF_DTYPE_U8 = 2, UCF_DTYPE_F64 = 3, UCF_DTYPE_I64 = 4 };
 enum { UCF_LAYOUT_K_MAJOR = 0, UCF_LAYOUT_MN_MAJOR = 1 };
@@ -344,6 +344,24 @@ int ucf_dice_ce_fwd(const void* logits, int logits_dtype, const void* target, in
 /* dlogits [B, C, S] (dtype of logits) = grad_out * d loss / d logits; grad_out a DEVICE f32 scalar. */
 int ucf_dice_ce_bwd(const void* logits, int logits_dtype, const void* target, int target_dtype, const float* fwd_out,
                     const float* grad_out, int B, int C, long long S, int squared_pred, void* dlogits, void* stream);
+
+/* ---- UNETR convolutional decoder: InstanceNorm (+ residual) + LeakyReLU on channels-last bf16 -------------------------
+ * One call per MONAI block body the reference builds its decoder from (simple/arch.py:808-940 ->
+ * monai.networks.blocks.dynunet_block.UnetResBlock / UnetBasicBlock; MONAI 1.4 is not vendored: restated from its published
+ * definition, the arithmetic is pinned to torch.nn.InstanceNorm3d + LeakyReLU by tests):
+ *     y = lrelu_slope( IN(a)  [ + IN(b)  |  + b ] ),   IN(x)[n, s, c] = (x - mean[n, c]) * rstd[n, c]
+ * (nn.InstanceNorm{2,3}d: affine=False, biased variance, eps inside the square root; slope = 1 disables the activation).
+ * Tensors are bf16 [N, S, C] with C fastest (torch.channels_last / channels_last_3d of [N, C, ...]); C even, C <= 2048.
+ * stats: fp32 [N, 2, C] = (mean, rstd); workspace: fp32 [N * ucf_inorm_chunks(N, S, C) * 3 * C]; coef: fp32 [N, 3, C].
+ * b == NULL: no second operand; b != NULL and stats_b == NULL: raw residual; both: normalised residual.
+ * Reductions are two-stage and fixed-order (reproducible run to run). */
+int ucf_inorm_chunks(int N, long long S, int C);
+int ucf_inorm_stats(const void* x, int N, long long S, int C, float eps, float* workspace, float* stats, void* stream);
+int ucf_inorm_apply(const void* a, const float* stats_a, const void* b, const float* stats_b, void* y, int N, long long S,
+                    int C, float slope, void* stream);
+/* da (and db when b took part: pass db != NULL exactly then) from dy; y is the forward output (NULL when slope == 1). */
+int ucf_inorm_bwd(const void* dy, const void* y, const void* a, const float* stats_a, const void* b, const float* stats_b,
+                  void* da, void* db, int N, long long S, int C, float slope, float* workspace, float* coef, void* stream);
 
 /* One AdamW step (decoupled weight decay, no amsgrad) over n fp32 tensors that share the same
  * hyper-parameters and step count: the arithmetic of torch.optim.AdamW as configured by

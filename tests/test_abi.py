@@ -28,7 +28,7 @@ def test_python_binding_covers_header():
 
 def test_abi_version_and_error_string():
     lib = _lib.lib()
-    assert lib.ucf_abi_version() == 3
+    assert lib.ucf_abi_version() == 4
     assert isinstance(lib.ucf_last_error(), (bytes, type(None)))
     assert lib.ucf_launch_count() == 0 or lib.ucf_launch_count() > 0
 

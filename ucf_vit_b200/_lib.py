@@ -90,6 +90,11 @@ _SIGNATURES = {
                                  c_void_p, c_void_p]),
     "ucf_dice_bce_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, _LL, c_float, c_int,
                                  c_void_p, c_void_p]),
+    "ucf_inorm_chunks": (c_int, [c_int, _LL, c_int]),
+    "ucf_inorm_stats": (c_int, [c_void_p, c_int, _LL, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "ucf_inorm_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, _LL, c_int, c_float, c_void_p]),
+    "ucf_inorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, _LL, c_int,
+                      c_float, c_void_p, c_void_p, c_void_p]),
     "ucf_dice_ce_blocks_per_sample": (c_int, [c_int, _LL]),
     "ucf_dice_ce_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, _LL, c_int, c_float, c_float, c_float, c_float,
                                 c_void_p, c_void_p, c_void_p]),

@@ -709,3 +709,44 @@ def gather_tokens(src, idx, fill=None, pos=None, complete=False):
 def assemble_tokens(tok, prefix=None, pos=None, pos_has_prefix=True):
     """concat(prefix tokens, tok) + pos  ->  bf16 [B, P+L, D]  (VIT._pos_embed, arch.py:367-393)."""
     return _AssembleFn.apply(tok, prefix, pos, pos_has_prefix)
+
+
+# ---- UNETR decoder block bodies (channels-last bf16) ------------------------------------------------------------------------
+class _InstNormActFn(torch.autograd.Function):
+    """y = lrelu(IN(a) [+ IN(b) | + b]): MONAI UnetResBlock / UnetBasicBlock bodies between the convolutions
+    (/root/reference/src/UCF_VIT/simple/arch.py:808-940 build them; InstanceNorm affine=False, LeakyReLU 0.01)."""
+
+    @staticmethod
+    def forward(ctx, a, b, norm_b, slope, eps):
+        stats_a = ops.inorm_stats(a, eps)
+        stats_b = ops.inorm_stats(b, eps) if (b is not None and norm_b) else None
+        y = ops.inorm_apply(a, stats_a, b, stats_b, slope)
+        ctx.save_for_backward(a, b, y if slope != 1.0 else None, stats_a, stats_b)
+        ctx.slope = slope
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b, y, stats_a, stats_b = ctx.saved_tensors
+        if dy.stride() != a.stride():
+            dy = torch.empty_like(a, memory_format=torch.preserve_format).copy_(dy)
+        da, db = ops.inorm_bwd(dy, y, a, stats_a, b, stats_b, ctx.slope)
+        return da, db, None, None, None
+
+
+def channels_last(x):
+    """x [N, C, *spatial] in channels-last memory ([N, *spatial, C]); a no-op when it already is."""
+    if x.movedim(1, -1).is_contiguous():
+        return x
+    return x.contiguous(memory_format=torch.channels_last if x.dim() == 4 else torch.channels_last_3d)
+
+
+def instance_norm_act(a, residual=None, norm_residual=False, negative_slope=0.01, eps=1e-5):
+    """LeakyReLU(InstanceNorm(a) + [InstanceNorm(residual) | residual]) on channels-last bf16 CUDA tensors [N, C, ...];
+    negative_slope = 1 leaves the activation out."""
+    if a.dtype != torch.bfloat16 or not a.is_cuda:
+        raise RuntimeError("ucf_vit_b200: instance_norm_act takes bf16 CUDA tensors (no CPU fallback)")
+    a = channels_last(a)
+    if residual is not None:
+        residual = channels_last(residual.to(torch.bfloat16))
+    return _InstNormActFn.apply(a, residual, bool(norm_residual), float(negative_slope), float(eps))

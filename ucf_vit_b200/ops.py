@@ -464,6 +464,18 @@ def patch_mse_bwd(pred, img, grid, patch, mask, fwd_out, grad_out):
     return dpred
 
 
+def _is_dense(t):
+    """Non-overlapping and dense in some dimension order (e.g. channels_last): an elementwise kernel may walk the storage."""
+    n = 1
+    for size, stride in sorted(zip(t.shape, t.stride()), key=lambda ss: ss[1]):
+        if size == 1:
+            continue
+        if stride != n:
+            return False
+        n *= size
+    return True
+
+
 def adamw_multi(params, grads, exp_avgs, exp_avg_sqs, *, lr, beta1, beta2, eps, weight_decay, step, maximize=False):
     """One in-place AdamW update of the fp32 tensors `params` (+ both moments) that share a step count.
     `lr` and `step` are host numbers, or BOTH fp32 CUDA scalars (the CUDA-graph capturable form)."""
@@ -473,9 +485,10 @@ def adamw_multi(params, grads, exp_avgs, exp_avg_sqs, *, lr, beta1, beta2, eps, 
     assert len(grads) == n and len(exp_avgs) == n and len(exp_avg_sqs) == n
     for ts in (params, grads, exp_avgs, exp_avg_sqs):
         _require_cuda(*ts)
-        for t in ts:
-            if t.dtype != torch.float32 or not t.is_contiguous():
-                raise TypeError("adamw_multi: every tensor must be a contiguous fp32 CUDA tensor")
+        for t, p in zip(ts, params):
+            if t.dtype != torch.float32 or not ((t.is_contiguous() and p.is_contiguous()) or
+                                                (t.stride() == p.stride() and _is_dense(t))):
+                raise TypeError("adamw_multi: every tensor must be a dense fp32 CUDA tensor laid out like its parameter")
     for p, g, m, v in zip(params, grads, exp_avgs, exp_avg_sqs):
         if not (p.numel() == g.numel() == m.numel() == v.numel()):
             raise ValueError("adamw_multi: parameter, gradient and moments differ in size")
@@ -625,3 +638,56 @@ def dice_ce_bwd(logits, target, fwd_out, grad_out, squared_pred):
                                     grad_out.data_ptr(), B, C, S, int(bool(squared_pred)), dlogits.data_ptr(), _stream()),
             "dice_ce_bwd")
     return dlogits
+
+
+# ---- UNETR decoder: InstanceNorm (+ residual) + LeakyReLU on channels-last bf16 ---------------------------------------------
+def _nsc(t):
+    """(N, S, C) of a [N, C, *spatial] bf16 tensor whose memory is [N, *spatial, C] (channels_last / channels_last_3d)."""
+    if t.dtype != torch.bfloat16 or t.dim() < 3:
+        raise TypeError(f"instance norm kernels take bf16 [N, C, ...] tensors, got {t.dtype} {tuple(t.shape)}")
+    if not t.movedim(1, -1).is_contiguous():
+        raise TypeError("instance norm kernels take channels-last tensors (memory [N, ..., C]); "
+                        f"got shape {tuple(t.shape)} strides {t.stride()}")
+    N, C = t.shape[:2]
+    return N, t[0, 0].numel(), C
+
+
+def inorm_stats(x, eps=1e-5):
+    """fp32 [N, 2, C]: per-(sample, channel) mean and 1/sqrt(biased var + eps) of channels-last bf16 x [N, C, ...]."""
+    _require_cuda(x)
+    N, S, C = _nsc(x)
+    ws = torch.empty(N * L.lib().ucf_inorm_chunks(N, S, C) * 2 * C, dtype=torch.float32, device=x.device)
+    stats = torch.empty(N, 2, C, dtype=torch.float32, device=x.device)
+    L.check(L.lib().ucf_inorm_stats(x.data_ptr(), N, S, C, float(eps), ws.data_ptr(), stats.data_ptr(), _stream()), "inorm_stats")
+    return stats
+
+
+def inorm_apply(a, stats_a, b=None, stats_b=None, slope=0.01):
+    """lrelu_slope(IN(a) [+ IN(b) | + b]) in a's layout; slope 1 = no activation."""
+    _require_cuda(a, stats_a)
+    N, S, C = _nsc(a)
+    if b is not None:
+        _require_cuda(b)
+        assert _nsc(b) == (N, S, C), "inorm_apply: operands differ in shape"
+    assert stats_b is None or b is not None
+    y = torch.empty_like(a, memory_format=torch.preserve_format)
+    L.check(L.lib().ucf_inorm_apply(a.data_ptr(), stats_a.data_ptr(), b.data_ptr() if b is not None else None,
+                                    stats_b.data_ptr() if stats_b is not None else None, y.data_ptr(), N, S, C, float(slope),
+                                    _stream()), "inorm_apply")
+    return y
+
+
+def inorm_bwd(dy, y, a, stats_a, b=None, stats_b=None, slope=0.01):
+    """(da, db) of inorm_apply; db is None when there was no second operand."""
+    _require_cuda(dy, a, stats_a)
+    N, S, C = _nsc(a)
+    assert _nsc(dy) == (N, S, C) and (y is None or _nsc(y) == (N, S, C))
+    assert y is not None or slope == 1.0
+    da = torch.empty_like(a, memory_format=torch.preserve_format)
+    db = torch.empty_like(a, memory_format=torch.preserve_format) if b is not None else None
+    ws = torch.empty(N * L.lib().ucf_inorm_chunks(N, S, C) * 3 * C, dtype=torch.float32, device=a.device)
+    coef = torch.empty(N, 3, C, dtype=torch.float32, device=a.device)
+    ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+    L.check(L.lib().ucf_inorm_bwd(dy.data_ptr(), ptr(y), a.data_ptr(), stats_a.data_ptr(), ptr(b), ptr(stats_b), da.data_ptr(),
+                                  ptr(db), N, S, C, float(slope), ws.data_ptr(), coef.data_ptr(), _stream()), "inorm_bwd")
+    return da, db

@@ -619,6 +619,15 @@ class UNETR(VIT):
     # reference's arithmetic, opt-in for throughput (bench.py --config unetr_128 states which one it timed).
     conv_autocast_dtype = None
 
+    def use_fused_decoder(self, on: bool = True):
+        """Channels-last bf16 decoder: cuDNN convolutions under bf16 autocast (fp32 accumulate) with this package's fused
+        InstanceNorm + residual + LeakyReLU kernels between them (`utils/unetr_blocks.py`, `csrc/instnorm.cu`)."""
+        self.conv_autocast_dtype = torch.bfloat16 if on else None
+        for m in self.modules():
+            if hasattr(m, "ndhwc_bf16"):
+                m.ndhwc_bf16 = bool(on)
+        return self
+
     def _conv_ctx(self):
         import contextlib
         if self.conv_autocast_dtype is None:

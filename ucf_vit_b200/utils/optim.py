@@ -15,6 +15,15 @@ import torch
 from .. import ops
 
 
+def _grad_like(p, g):
+    """The gradient in the parameter's own dense layout (the kernel walks both storages in step)."""
+    if g.stride() == p.stride() or (p.is_contiguous() and g.is_contiguous()):
+        return g
+    out = torch.empty_like(p, memory_format=torch.preserve_format)
+    out.copy_(g)
+    return out
+
+
 class FusedAdamW(torch.optim.AdamW):
     """`capturable=True`: the step count and every group's learning rate live in fp32 CUDA scalars (`group["lr"]` becomes
     a tensor; torch's LR schedulers `fill_` tensor learning rates in place), the kernel derives its bias corrections from
@@ -65,8 +74,8 @@ class FusedAdamW(torch.optim.AdamW):
         if not p.is_cuda or p.dtype != torch.float32 or g.dtype != torch.float32:
             raise RuntimeError("FusedAdamW updates fp32 CUDA parameters with fp32 gradients only "
                                f"(got {p.dtype} on {p.device}, grad {g.dtype}); there is no CPU fallback")
-        if not p.is_contiguous():
-            raise RuntimeError("FusedAdamW needs contiguous parameters")
+        if not (p.is_contiguous() or ops._is_dense(p)):
+            raise RuntimeError("FusedAdamW needs dense parameters (contiguous or a permuted-dense layout such as channels_last)")
 
     @torch.no_grad()
     def _step_capturable(self):
@@ -87,7 +96,7 @@ class FusedAdamW(torch.optim.AdamW):
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] = self._step_dev[0]           # a view: every parameter shares the device counter
                 ps.append(p)
-                gs.append(g if g.is_contiguous() else g.contiguous())
+                gs.append(_grad_like(p, g))
                 ms.append(st["exp_avg"])
                 vs.append(st["exp_avg_sq"])
             if ps:
@@ -120,7 +129,7 @@ class FusedAdamW(torch.optim.AdamW):
                 st["step"] += 1
                 ps, gs, ms, vs = by_step[int(st["step"].item())]
                 ps.append(p)
-                gs.append(g if g.is_contiguous() else g.contiguous())
+                gs.append(_grad_like(p, g))
                 ms.append(st["exp_avg"])
                 vs.append(st["exp_avg_sq"])
             for step, (ps, gs, ms, vs) in by_step.items():

@@ -9,13 +9,20 @@ behaviour, keeping every sub-module name so reference checkpoints load with ``st
 (e.g. ``decoder5.transp_conv.conv.weight``, ``encoder1.layer.conv1.conv.weight``,
 ``out.conv.conv.bias``).  Parity against a real MONAI install is UNPINNED.
 
-These blocks are SURVEY.md §8(f) rank-1 "next" work: they stay on cuDNN this round.
+Two execution modes:
+* default -- PyTorch / cuDNN in the parameter dtype, the reference's arithmetic;
+* ``ndhwc_bf16`` (``UNETR.use_fused_decoder()``) -- channels-last bf16 activations end to end: the convolutions stay cuDNN
+  calls (under autocast, fp32 accumulate), everything between them -- InstanceNorm, residual add, LeakyReLU, forward and
+  backward -- is one ``ucf_inorm_*`` kernel sequence per block body (``csrc/instnorm.cu``) instead of PyTorch's batch-norm
+  kernels, layout copies and element-wise passes (60 % of the bf16 decoder step before).
 """
 from typing import Sequence, Union
 
 import numpy as np
 import torch
 import torch.nn as nn
+
+from .. import functional as UF
 
 __all__ = [
     "get_conv_layer", "UnetResBlock", "UnetBasicBlock", "UnetrBasicBlock",
@@ -85,6 +92,13 @@ def _norm(norm_name, spatial_dims, channels):
     raise NotImplementedError(f"norm {norm_name!r}")
 
 
+def _fused_norm_args(norm, lrelu):
+    """(eps, slope) for the fused InstanceNorm + LeakyReLU kernels; anything else has no fused form."""
+    if not isinstance(norm, tuple(_INORM.values())) or norm.affine or norm.track_running_stats:
+        raise NotImplementedError("ndhwc_bf16 decoder: only parameter-free InstanceNorm (norm_name='instance') is fused")
+    return norm.eps, lrelu.negative_slope
+
+
 class UnetResBlock(nn.Module):
     def __init__(self, spatial_dims, in_channels, out_channels, kernel_size, stride, norm_name,
                  act_name=None, dropout=None):
@@ -101,7 +115,20 @@ class UnetResBlock(nn.Module):
             self.conv3 = get_conv_layer(spatial_dims, in_channels, out_channels, 1, stride, conv_only=False)
             self.norm3 = _norm(norm_name, spatial_dims, out_channels)
 
+    ndhwc_bf16 = False
+
+    def _forward_fused(self, inp):
+        eps, slope = _fused_norm_args(self.norm1, self.lrelu)
+        inp = UF.channels_last(inp.to(torch.bfloat16))
+        out = UF.instance_norm_act(self.conv1(inp), negative_slope=slope, eps=eps)
+        out = self.conv2(out)
+        if hasattr(self, "conv3"):
+            return UF.instance_norm_act(out, self.conv3(inp), norm_residual=True, negative_slope=slope, eps=eps)
+        return UF.instance_norm_act(out, inp, norm_residual=False, negative_slope=slope, eps=eps)
+
     def forward(self, inp):
+        if self.ndhwc_bf16:
+            return self._forward_fused(inp)
         residual = inp
         out = self.lrelu(self.norm1(self.conv1(inp)))
         out = self.norm2(self.conv2(out))
@@ -121,7 +148,13 @@ class UnetBasicBlock(nn.Module):
         self.norm1 = _norm(norm_name, spatial_dims, out_channels)
         self.norm2 = _norm(norm_name, spatial_dims, out_channels)
 
+    ndhwc_bf16 = False
+
     def forward(self, inp):
+        if self.ndhwc_bf16:
+            eps, slope = _fused_norm_args(self.norm1, self.lrelu)
+            out = UF.instance_norm_act(self.conv1(UF.channels_last(inp.to(torch.bfloat16))), negative_slope=slope, eps=eps)
+            return UF.instance_norm_act(self.conv2(out), negative_slope=slope, eps=eps)
         out = self.lrelu(self.norm1(self.conv1(inp)))
         return self.lrelu(self.norm2(self.conv2(out)))
 
