@@ -659,8 +659,35 @@ class Sap4096(Workload):
         # algorithmic bytes of one gather: INTER_CUBIC without antialiasing reads 16 taps (1 B each, uint8) per
         # output sample whatever the leaf size, and writes one fp32: L * p^2 * C * (16 + 4) bytes
         alg = self.L * self.p * self.p * 3 * (16 + 4)
-        return {"tree_build_ms_per_batch_host": tree_ms, "gather_ms_per_image": gather_ms,
-                "gather_algorithmic_GBps": alg / (gather_ms * 1e-3) / 1e9}
+        out = {"tree_build_ms_per_batch_host": tree_ms, "gather_ms_per_image": gather_ms,
+               "gather_algorithmic_GBps": alg / (gather_ms * 1e-3) / 1e9}
+        out.update(self._edge_front_end(imgs[0]))
+        return out
+
+    @staticmethod
+    def _edge_front_end(img):
+        """Edge detection of one 4096^2 image (the reference's cv.GaussianBlur(5x5) + cv.Canny, transform.py:33-34): device
+        kernels (ucf_gaussian_blur_u8 + ucf_canny_u8, wall clock of the call: the hysteresis loop synchronises) against OpenCV
+        on the host cores when cv2 is importable.  Not part of the timed step: the step uses fixed synthetic edge maps."""
+        from ucf_vit_b200 import ops
+        run = lambda: ops.canny_u8(ops.gaussian_blur_u8(img, 5), 60, 110)   # noqa: E731
+        run()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            e = run()
+        torch.cuda.synchronize()
+        out = {"edges_device_ms_per_image": (time.perf_counter() - t0) / 5 * 1e3}
+        try:
+            import cv2
+            h = img.cpu().numpy()
+            t0 = time.perf_counter()
+            he = cv2.Canny(cv2.GaussianBlur(h, (5, 5), 0), 60, 110)
+            out["edges_opencv_host_ms_per_image"] = (time.perf_counter() - t0) * 1e3
+            out["edges_identical_to_opencv"] = bool((torch.as_tensor(he) == e.cpu()).all())
+        except ImportError:
+            pass
+        return out
 
     CPU_SAMPLE_L = 256
 

@@ -345,6 +345,22 @@ int ucf_dice_ce_fwd(const void* logits, int logits_dtype, const void* target, in
 int ucf_dice_ce_bwd(const void* logits, int logits_dtype, const void* target, int target_dtype, const float* fwd_out,
                     const float* grad_out, int B, int C, long long S, int squared_pred, void* dlogits, void* stream);
 
+/* ---- SAP front end on the device: edge map of a natural (uint8) image -------------------------------
+ * Replace `grey_img = cv.GaussianBlur(img, (k, k), 0)` and `edges = cv.Canny(grey_img, c, c + 50)`
+ * (dataloaders/transform.py:33-34; opencv-python is a dependency of the reference that is not vendored in it: restated
+ * from its published algorithm in oracle/canny_np.py, pinned bit-for-bit against cv2 4.13 by the tests).  Integer arithmetic,
+ * results identical to OpenCV's byte for byte.
+ * img / dst: u8 [H, W, C] (C interleaved, 1..4), ksize in {1, 3, 5} (sigma 0: taps [1], [1 2 1]/4, [1 4 6 4 1]/16,
+ * BORDER_REFLECT_101, one round-half-up). */
+int ucf_gaussian_blur_u8(const void* src, void* dst, int H, int W, int C, int ksize, void* stream);
+/* Canny, aperture 3, L1 gradient norm: per pixel the channel with the largest |dx| + |dy|, non-maximum suppression,
+ * thresholds floor(low) / floor(high), hysteresis over 8-neighbours.  class_map: u8 [H, W] workspace (2 strong, 0 candidate,
+ * 1 none); edges: u8 [H, W] out (0 / 255); flag_dev: one device int; flag_host_pinned: one int of page-locked host memory.
+ * The hysteresis repeats whole-image sweeps until none changes the map and reads the flag back after each, so this
+ * launcher SYNCHRONISES `stream` (run it on a side stream / host thread); *sweeps_out (may be NULL) = sweeps taken. */
+int ucf_canny_u8(const void* img, int H, int W, int C, double low_thresh, double high_thresh, void* class_map, void* edges,
+                 int* flag_dev, int* flag_host_pinned, int* sweeps_out, void* stream);
+
 /* ---- UNETR convolutional decoder: InstanceNorm (+ residual) + LeakyReLU on channels-last bf16 -------------------------
  * One call per MONAI block body the reference builds its decoder from (simple/arch.py:808-940 ->
  * monai.networks.blocks.dynunet_block.UnetResBlock / UnetBasicBlock; MONAI 1.4 is not vendored: restated from its published

@@ -90,6 +90,9 @@ _SIGNATURES = {
                                  c_void_p, c_void_p]),
     "ucf_dice_bce_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, _LL, c_float, c_int,
                                  c_void_p, c_void_p]),
+    "ucf_gaussian_blur_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ucf_canny_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
+                     c_void_p, c_void_p]),
     "ucf_inorm_chunks": (c_int, [c_int, _LL, c_int]),
     "ucf_inorm_stats": (c_int, [c_void_p, c_int, _LL, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "ucf_inorm_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, _LL, c_int, c_float, c_void_p]),

@@ -1,10 +1,12 @@
 """`Patchify` / `Patchify_3D` data transforms with the reference's constructor and return values
 (/root/reference/src/UCF_VIT/dataloaders/transform.py:9-54, :56-132).
 
-Edge detection stays on OpenCV / scipy on the host (bit-exactness of the tree depends on it,
-SURVEY.md §0.9, §8f rank 4; OpenCV is not installed in the build image, so the edge recipes are
-exercised in tests only through a stand-in `cv2` -- the tree and gather they feed are pinned); the tree build is the C++ host routine and the per-leaf resampling
-gather runs on the GPU.  With `device_output=True` the sequence stays on the device as torch
+Edge detection (bit-exactness of the tree depends on it): for natural uint8 images --
+the imagenet / catsdogs branch, `cv.GaussianBlur` + `cv.Canny` -- `Patchify(edges="device")` runs both on the GPU
+(`ucf_gaussian_blur_u8`, `ucf_canny_u8`: integer arithmetic, byte-identical to OpenCV, tests/test_gpu_canny.py) on the copy
+of the image the gather needs anyway and hands the host tree builder the uint8 map; `edges="host"` (default, the reference's
+own calls) and every other branch (float images, the 3-D recipe) use OpenCV / scipy on the host.  The tree build is the C++
+host routine and the per-leaf resampling gather runs on the GPU.  With `device_output=True` the sequence stays on the device as torch
 tensors (no D2H copy) for direct consumption by the model."""
 import random
 
@@ -17,8 +19,11 @@ from .quadtree import FixedQuadTree
 
 class Patchify(torch.nn.Module):
     def __init__(self, sths=[0, 1, 3, 5], fixed_length=196, cannys=[50, 100], patch_size=16, num_channels=3,
-                 dataset="imagenet", return_edges=False, device="cuda", device_output=False) -> None:
+                 dataset="imagenet", return_edges=False, device="cuda", device_output=False, edges="host") -> None:
         super().__init__()
+        if edges not in ("host", "device"):
+            raise ValueError("edges must be 'host' (OpenCV) or 'device' (ucf_gaussian_blur_u8 + ucf_canny_u8)")
+        self.edges = edges
         self.sths = sths
         self.fixed_length = fixed_length
         self.cannys = [x for x in range(cannys[0], cannys[1], 1)]
@@ -28,9 +33,21 @@ class Patchify(torch.nn.Module):
         self.return_edges = return_edges
         self.device, self.device_output = device, device_output
 
+    def _edges_device(self, img):
+        """The natural-image branch on the GPU: same bytes as cv.Canny(cv.GaussianBlur(img, (k, k), 0), c, c + 50)."""
+        from .. import ops
+        dev = torch.device(self.device)
+        with torch.cuda.device(dev):
+            x = torch.as_tensor(np.ascontiguousarray(img)).to(dev, non_blocking=True)
+            e = ops.canny_u8(ops.gaussian_blur_u8(x, self.smooth_factor), self.canny[0], self.canny[1])
+            return e.cpu().numpy()
+
     def _edges(self, img):
-        import cv2 as cv
         natural = self.dataset in ("imagenet", "catsdogs")
+        if (self.edges == "device" and natural and self.smooth_factor != 0 and isinstance(img, np.ndarray)
+                and img.dtype == np.uint8 and self.smooth_factor in (1, 3, 5)):
+            return self._edges_device(img)
+        import cv2 as cv
         if self.smooth_factor == 0:
             lo, hi = (0, 1) if natural else (np.min(img), np.max(img))
             return np.random.uniform(low=lo, high=hi, size=(img.shape[0], img.shape[1]))

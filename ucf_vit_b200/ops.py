@@ -1,6 +1,7 @@
 """Thin tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers,
 launch on torch's current stream.  No autograd here (see `functional.py`)."""
 import ctypes
+import threading
 
 import torch
 
@@ -691,3 +692,39 @@ def inorm_bwd(dy, y, a, stats_a, b=None, stats_b=None, slope=0.01):
     L.check(L.lib().ucf_inorm_bwd(dy.data_ptr(), ptr(y), a.data_ptr(), stats_a.data_ptr(), ptr(b), ptr(stats_b), da.data_ptr(),
                                   ptr(db), N, S, C, float(slope), ws.data_ptr(), coef.data_ptr(), _stream()), "inorm_bwd")
     return da, db
+
+
+# ---- SAP front end: Gaussian blur + Canny of a uint8 image on the device (bit-exact with OpenCV) ---------------------------
+def _hwc_u8(img):
+    _require_cuda(img)
+    if img.dtype != torch.uint8 or img.dim() not in (2, 3) or not img.is_contiguous():
+        raise TypeError(f"expected a contiguous uint8 [H, W] or [H, W, C] CUDA image, got {img.dtype} {tuple(img.shape)}")
+    H, W = img.shape[:2]
+    return H, W, (img.shape[2] if img.dim() == 3 else 1)
+
+
+def gaussian_blur_u8(img, ksize):
+    """cv.GaussianBlur(img, (ksize, ksize), 0) of a uint8 image, ksize in {1, 3, 5}."""
+    H, W, C = _hwc_u8(img)
+    out = torch.empty_like(img)
+    L.check(L.lib().ucf_gaussian_blur_u8(img.data_ptr(), out.data_ptr(), H, W, C, int(ksize), _stream()), "gaussian_blur_u8")
+    return out
+
+
+_canny_flags = {}
+
+
+def canny_u8(img, low, high, return_sweeps=False):
+    """cv.Canny(img, low, high) (aperture 3, L1 norm) of a uint8 [H, W(, C)] image: uint8 [H, W] of 0 / 255.
+    Synchronises the current stream (the hysteresis loop reads a convergence flag back)."""
+    H, W, C = _hwc_u8(img)
+    key = (img.device.index, threading.get_ident())
+    if key not in _canny_flags:
+        _canny_flags[key] = (torch.zeros(1, dtype=torch.int32, device=img.device), torch.zeros(1, dtype=torch.int32).pin_memory())
+    fdev, fhost = _canny_flags[key]
+    cmap = torch.empty(H, W, dtype=torch.uint8, device=img.device)
+    edges = torch.empty(H, W, dtype=torch.uint8, device=img.device)
+    sweeps = ctypes.c_int(0)
+    L.check(L.lib().ucf_canny_u8(img.data_ptr(), H, W, C, float(low), float(high), cmap.data_ptr(), edges.data_ptr(),
+                                 fdev.data_ptr(), fhost.data_ptr(), ctypes.addressof(sweeps), _stream()), "canny_u8")
+    return (edges, sweeps.value) if return_sweeps else edges
