@@ -411,10 +411,11 @@ def main():
                     help="capture the whole training step in a CUDA graph (utils/graph.py) and replay it; the GEMM roofline "
                          "is then taken from an eager pass after the timed region")
     ap.add_argument("--bf16-decoder", action="store_true",
-                    help="unetr_128: run the cuDNN conv decoder under bf16 autocast (default: fp32 like the reference)")
-    ap.add_argument("--fused-decoder", action="store_true",
-                    help="unetr_128: channels-last bf16 decoder -- cuDNN convolutions under autocast with this package's fused "
-                         "InstanceNorm + residual + LeakyReLU kernels between them (UNETR.use_fused_decoder)")
+                    help="unetr_128: PyTorch decoder under bf16 autocast (PyTorch InstanceNorm / LeakyReLU kernels; for comparison)")
+    ap.add_argument("--fp32-decoder", action="store_true",
+                    help="unetr_128: PyTorch / cuDNN decoder in fp32, the reference's arithmetic (default: channels-last bf16 decoder "
+                         "-- cuDNN convolutions under autocast with this package's fused InstanceNorm + residual + LeakyReLU "
+                         "kernels between them, UNETR.use_fused_decoder)")
     ap.add_argument("--fp32-pixels", action="store_true", help="vit configs: host batches as fp32 pixels (round-1 form) instead of uint8")
     ap.add_argument("--fp32-allreduce", action="store_true",
                     help="DDP gradient all-reduce in fp32 (round-1 form); default: bf16 (torch's bf16_compress_hook -- the "

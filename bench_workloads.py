@@ -459,7 +459,9 @@ class Unetr128(Workload):
         if getattr(args, "bf16_decoder", False):
             self.model.conv_autocast_dtype = torch.bfloat16
             self.workload = self.workload.replace("conv decoder (feature_size 16)", "conv decoder (feature_size 16) under bf16 autocast")
-        if getattr(args, "fused_decoder", False):
+        if getattr(args, "fp32_decoder", False):
+            self.workload = self.workload.replace("conv decoder (feature_size 16)", "fp32 PyTorch / cuDNN conv decoder (feature_size 16)")
+        elif not getattr(args, "bf16_decoder", False):
             self.model.use_fused_decoder()
             self.workload = self.workload.replace("conv decoder (feature_size 16)", "channels-last bf16 conv decoder (feature_size "
                                                   "16; cuDNN convolutions, fused InstanceNorm + LeakyReLU kernels)")

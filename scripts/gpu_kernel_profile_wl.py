@@ -1,5 +1,5 @@
 """Device-time table (torch.profiler, CUDA activities) of one bench workload's training step.
-   python scripts/gpu_kernel_profile_wl.py CONFIG [steps] [--bf16-decoder | --fused-decoder]"""
+   python scripts/gpu_kernel_profile_wl.py CONFIG [steps] [--bf16-decoder | --fp32-decoder]"""
 import argparse, os, sys
 import torch
 from torch.profiler import profile, ProfilerActivity
@@ -8,7 +8,7 @@ import bench_workloads
 name = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 2
 wl = bench_workloads.registry()[name]
-args = argparse.Namespace(optimizer="ucf", bf16_allreduce=False, steps=n, bf16_decoder="--bf16-decoder" in sys.argv, fused_decoder="--fused-decoder" in sys.argv,
+args = argparse.Namespace(optimizer="ucf", bf16_allreduce=False, steps=n, bf16_decoder="--bf16-decoder" in sys.argv, fp32_decoder="--fp32-decoder" in sys.argv,
                           cuda_graph=False, eager=True, fp32_pixels=False, batch=None)
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)

@@ -1,5 +1,5 @@
 """Run ONE hot kernel a few times so that ncu can capture it in isolation.
-python scripts/gpu_one_kernel.py {fc1_gelu|fc2_dgelu|fc1_plain|attn_fwd|attn_bwd|ln_fwd|ln_bwd|wgrad|sap_gather|var_attn} [B N H hd]"""
+python scripts/gpu_one_kernel.py {fc1_gelu|fc2_dgelu|fc1_plain|attn_fwd|attn_bwd|ln_fwd|ln_bwd|wgrad|sap_gather|var_attn|inorm|canny} [B N H hd]"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -51,6 +51,29 @@ elif which in ("ln_fwd", "ln_bwd"):
     dy = bf(torch.randn(M, D, device=dev)); dg = torch.zeros(D, device=dev); dbb = torch.zeros(D, device=dev)
     f = (lambda: ops.layernorm_fwd(x, g, b, 1e-6)) if which == "ln_fwd" else \
         (lambda: ops.layernorm_bwd(dy, x, g, mean, rstd, dres=dy, dgamma=dg, dbeta=dbb))
+elif which == "inorm":
+    # UNETR-128 decoder2 / encoder1 block bodies: batch 16, 16 channels, 128^3 voxels, channels-last bf16 (1.07 GB per tensor)
+    from ucf_vit_b200 import functional as UF
+    N, C, S = (int(a) for a in sys.argv[2:5]) if len(sys.argv) >= 5 else (16, 16, 128)
+    mk = lambda: bf(torch.randn(N, S, S, S, C, device=dev)).permute(0, 4, 1, 2, 3)
+    a, b, dy = mk(), mk(), mk()
+    sa, sb = ops.inorm_stats(a), ops.inorm_stats(b)
+    y = ops.inorm_apply(a, sa, b, sb, 0.01)
+    def f():
+        ops.inorm_stats(a)
+        ops.inorm_apply(a, sa, None, None, 0.01)
+        ops.inorm_apply(a, sa, b, sb, 0.01)
+        ops.inorm_bwd(dy, y, a, sa, None, None, 0.01)
+        ops.inorm_bwd(dy, y, a, sa, b, sb, 0.01)
+elif which == "canny":
+    import numpy as np
+    sys.path.insert(0, "tests")
+    from test_gpu_canny import _scene
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+    img = torch.as_tensor(_scene(n, np.random.default_rng(n))).to(dev)
+    def f():
+        ops.canny_u8(ops.gaussian_blur_u8(img, 5), 60, 110)
+        ops.gaussian_blur_u8(img, 3)
 else:
     raise SystemExit("unknown kernel " + which)
 for _ in range(4):

@@ -28,11 +28,11 @@ def _ref(a, b, mode, slope, eps=1e-5):
 
 
 # (shape, second operand: 0 none / 1 raw / 2 normalised, slope); C = 16..256 (vector 8), 12 (vector 4), 6 (vector 2),
-# 48 (6 vectors: lanes do not divide 256), S ragged against the rows a CTA covers, one 2-D case
+# 48 (6 vectors: lanes do not divide 256), 384 / 768 (more than 1024 partial columns: the finish kernel's second pass), S ragged against the rows a CTA covers, one 2-D case
 CASES = [((2, 16, 8, 8, 8), 0, 0.01), ((2, 16, 8, 8, 8), 1, 0.01), ((2, 16, 8, 8, 8), 2, 0.01),
          ((3, 32, 9, 7, 5), 2, 0.01), ((1, 128, 16, 16, 16), 1, 0.01), ((2, 256, 5, 3, 2), 0, 0.2),
          ((2, 48, 6, 6, 6), 2, 0.01), ((2, 12, 7, 5, 3), 1, 0.01), ((1, 6, 11, 3, 2), 2, 0.01),
-         ((2, 64, 33, 17), 2, 0.01), ((2, 16, 40, 40, 40), 0, 1.0), ((4, 16, 64, 64, 64), 2, 0.01)]
+         ((2, 64, 33, 17), 2, 0.01), ((2, 16, 40, 40, 40), 0, 1.0), ((2, 768, 4, 4, 4), 2, 0.01), ((1, 384, 6, 5, 4), 1, 0.01), ((4, 16, 64, 64, 64), 2, 0.01)]
 
 
 @pytest.mark.parametrize("shape,mode,slope", CASES)

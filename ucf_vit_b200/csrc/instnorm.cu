@@ -142,44 +142,58 @@ inorm_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part
 }
 
 // MODE 0: partial [N][chunks][2][C] -> out [N][2][C] = (mean, rstd);  MODE 1: partial [N][chunks][3][C] -> out [N][3][C] = sums / S
+// One CTA per sample walks the sample's partials as one flat array with a stride that is a multiple of K*C, so a thread
+// always meets the same (k, c) column and consecutive threads read consecutive floats; fp64 from here on, fixed order.
+constexpr int FIN_THREADS = 1024;
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FIN_THREADS)
 inorm_finish_kernel(const float* __restrict__ partial, float* __restrict__ out, int chunks, int C, long long S, float eps) {
   constexpr int K = MODE == 0 ? 2 : 3;
-  __shared__ double sm[8][32][K];
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  const int n = blockIdx.y, c = blockIdx.x * 32 + l;
-  double acc[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) acc[k] = 0.0;
-  if (c < C) {
-    for (int ch = w; ch < chunks; ch += 8) {
-      const float* p = partial + (static_cast<long long>(n) * chunks + ch) * K * C + c;
-#pragma unroll
-      for (int k = 0; k < K; ++k) acc[k] += static_cast<double>(p[k * C]);
+  __shared__ double sm[FIN_THREADS];
+  __shared__ double tot[FIN_THREADS];
+  const int KC = K * C;
+  const int n = blockIdx.x, t = threadIdx.x;
+  const float* p = partial + static_cast<long long>(n) * chunks * KC;
+  float* o = out + static_cast<long long>(n) * KC;
+  const double inv = 1.0 / static_cast<double>(S);
+  for (int col0 = 0; col0 < KC; col0 += FIN_THREADS) {        // one pass unless K * C > 1024
+    const int width = (KC - col0 < FIN_THREADS) ? KC - col0 : FIN_THREADS;
+    const int lanes = FIN_THREADS / width;                     // chunk lanes working side by side
+    double acc = 0.0;
+    if (t < lanes * width) {
+      const int col = col0 + t % width;
+      for (int ch = t / width; ch < chunks; ch += lanes) acc += static_cast<double>(p[static_cast<long long>(ch) * KC + col]);
     }
-  }
-#pragma unroll
-  for (int k = 0; k < K; ++k) sm[w][l][k] = acc[k];
-  __syncthreads();
-  if (w == 0 && c < C) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
+    sm[t] = acc;
+    __syncthreads();
+    if (t < width) {
       double s = 0.0;
-      for (int i = 0; i < 8; ++i) s += sm[i][l][k];
-      acc[k] = s;
+      for (int l = 0; l < lanes; ++l) s += sm[l * width + t];
+      tot[t] = s;
     }
-    float* o = out + static_cast<long long>(n) * K * C + c;
-    const double inv = 1.0 / static_cast<double>(S);
-    if (MODE == 0) {
-      const double mean = acc[0] * inv;
-      double var = acc[1] * inv - mean * mean;
-      if (var < 0.0) var = 0.0;
-      o[0] = static_cast<float>(mean);
-      o[C] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    __syncthreads();
+    if (MODE == 1) {
+      if (t < width) o[col0 + t] = static_cast<float>(tot[t] * inv);
+    } else if (KC <= FIN_THREADS) {
+      if (t < C) {
+        const double mean = tot[t] * inv;
+        double var = tot[C + t] * inv - mean * mean;
+        if (var < 0.0) var = 0.0;
+        o[t] = static_cast<float>(mean);
+        o[C + t] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      }
     } else {
-#pragma unroll
-      for (int k = 0; k < K; ++k) o[k * C] = static_cast<float>(acc[k] * inv);
+      if (t < width) o[col0 + t] = static_cast<float>(tot[t]);   // raw sums; turned into (mean, rstd) below
+    }
+    __syncthreads();
+  }
+  if (MODE == 0 && KC > FIN_THREADS) {
+    for (int c = t; c < C; c += FIN_THREADS) {
+      const double mean = static_cast<double>(o[c]) * inv;
+      double var = static_cast<double>(o[C + c]) * inv - mean * mean;
+      if (var < 0.0) var = 0.0;
+      o[c] = static_cast<float>(mean);
+      o[C + c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
     }
   }
 }
@@ -305,7 +319,7 @@ inorm_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat1
 
 // da = rstd_a (dz - c1 - a_hat c2a);  db = dz (BMODE 1) | rstd_b (dz - c1 - b_hat c2b) (BMODE 2)
 template <int VEC, int BMODE>
-__global__ void __launch_bounds__(IN_THREADS)
+__global__ void __launch_bounds__(IN_THREADS, BMODE == 2 ? 3 : 0)
 inorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                        const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                        const float* __restrict__ stats_a, const float* __restrict__ stats_b, const float* __restrict__ coef,
@@ -360,7 +374,7 @@ inorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
     if (BMODE) *reinterpret_cast<typename InVec<VEC>::T*>(db + o) = in_pack<VEC>(ob);
   };
   long long r = r0 + rl;
-  for (; r + lanes < r1; r += 2LL * lanes) {
+  for (; BMODE != 2 && r + lanes < r1; r += 2LL * lanes) {   // two operands: one row in flight, 80 registers, 3 CTAs per SM
     typename InVec<VEC>::T vd[2], vy[2], va[2], vb[2];
     long long o[2];
 #pragma unroll
@@ -428,7 +442,7 @@ extern "C" int ucf_inorm_stats(const void* x, int N, long long S, int C, float e
   UCF_IN_VEC_DISPATCH(vec, M)
 #undef M
   if (int e = check_launch("inorm_stats_kernel")) return e;
-  inorm_finish_kernel<0><<<dim3((C + 31) / 32, N), 256, 0, st>>>(workspace, stats, g.chunks, C, S, eps);
+  inorm_finish_kernel<0><<<N, FIN_THREADS, 0, st>>>(workspace, stats, g.chunks, C, S, eps);
   return check_launch("inorm_finish_kernel");
 }
 
@@ -480,7 +494,7 @@ extern "C" int ucf_inorm_bwd(const void* dy, const void* y, const void* a, const
   UCF_IN_VEC_DISPATCH(vec, M)
 #undef M
   if (int e = check_launch("inorm_bwd_reduce_kernel")) return e;
-  inorm_finish_kernel<1><<<dim3((C + 31) / 32, N), 256, 0, st>>>(workspace, coef, g.chunks, C, S, 0.f);
+  inorm_finish_kernel<1><<<N, FIN_THREADS, 0, st>>>(workspace, coef, g.chunks, C, S, 0.f);
   if (int e = check_launch("inorm_finish_kernel")) return e;
 #define M(V)                                                                                                                      \
   if (bmode == 0) inorm_bwd_apply_kernel<V, 0><<<grid, IN_THREADS, 0, st>>>(dyp, yp, ap, bp, stats_a, stats_b, coef, dap, dbp, S, C, g.vecs, g.lanes, g.rows_per_cta, slope); \
