@@ -10,6 +10,8 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 2
 wl = bench_workloads.registry()[name]
 args = argparse.Namespace(optimizer="ucf", bf16_allreduce=False, steps=n, bf16_decoder="--bf16-decoder" in sys.argv, fp32_decoder="--fp32-decoder" in sys.argv,
                           cuda_graph=False, eager=True, fp32_pixels=False, batch=None)
+if "--cudnn-benchmark" in sys.argv:
+    torch.backends.cudnn.benchmark = True
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 if wl.uses_fsdp:

@@ -132,3 +132,16 @@ def test_checkpoint_pos_embed_interpolation_and_power_of_two_match_reference():
     misc.interpolate_pos_embed_adaptive(None, ck2, new_size=12)
     assert np.array_equal(ck2["decoder_pos_embed"].numpy(), HOST["interp_dec_5to12"])
     assert [int(bool(misc.is_power_of_two(n))) for n in range(0, 70)] == HOST["pow2"].tolist()
+
+
+def test_head_dim_without_a_kernel_is_refused_at_construction():
+    """head widths the attention kernels cannot serve fail when the module is built, with the reason, instead of
+    in the first forward; the 36-wide heads of configs/basic_ct (zero-padded to 64) are accepted."""
+    import pytest
+    from ucf_vit_b200.simple.building_blocks import Attention, VariableMapping_Attention
+    with pytest.raises(ValueError, match="head_dim = 1280 // 16 = 80"):
+        Attention(1280, num_heads=16)
+    with pytest.raises(ValueError, match="head_dim"):
+        VariableMapping_Attention(1024, num_heads=8)
+    assert Attention(576, num_heads=16).head_dim == 36
+    assert Attention(1280, num_heads=20).head_dim == 64

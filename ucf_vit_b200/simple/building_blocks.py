@@ -127,6 +127,17 @@ class Mlp(nn.Module):
         return y if residual is None else y + residual
 
 
+def _checked_head_dim(dim, num_heads):
+    """dim // num_heads, refused at construction when no attention kernel serves it: the tcgen05 kernels run heads of 32 and 64
+    columns (narrower heads, e.g. the 36 of configs/basic_ct, are zero-padded to those); wider heads (ViT-H's 80, 128) would
+    need more tensor-memory columns than the backward kernel has."""
+    hd = dim // num_heads
+    if hd > 64:
+        raise ValueError(f"ucf_vit_b200: head_dim = {dim} // {num_heads} = {hd} is not supported (attention kernels serve "
+                         "head_dim <= 64; use more heads)")
+    return hd
+
+
 class Attention(nn.Module):
     """Multi-head self-attention.  Every `FusedAttn` member runs the same tcgen05 flash-attention
     kernel, reading q/k/v in place from the packed qkv projection."""
@@ -137,7 +148,7 @@ class Attention(nn.Module):
         super().__init__()
         assert dim % num_heads == 0, 'dim should be divisible by num_heads'
         self.num_heads = num_heads
-        self.head_dim = dim // num_heads
+        self.head_dim = _checked_head_dim(dim, num_heads)
         self.scale = self.head_dim ** -0.5
         self.fused_attn = fused_attn
         self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
@@ -278,7 +289,7 @@ class VariableMapping_Attention(nn.Module):
         super().__init__()
         assert dim % num_heads == 0, 'dim should be divisible by num_heads'
         self.num_heads = num_heads
-        self.head_dim = dim // num_heads
+        self.head_dim = _checked_head_dim(dim, num_heads)
         self.scale = self.head_dim ** -0.5
         self.fused_attn = fused_attn
         self.q = nn.Linear(dim, dim, bias=qkv_bias)
