@@ -463,8 +463,9 @@ class Unetr128(Workload):
             self.workload = self.workload.replace("conv decoder (feature_size 16)", "fp32 PyTorch / cuDNN conv decoder (feature_size 16)")
         elif not getattr(args, "bf16_decoder", False):
             self.model.use_fused_decoder()
+            torch.backends.cudnn.benchmark = True       # cuDNN picks its convolution kernels by timing them in the warm-up steps
             self.workload = self.workload.replace("conv decoder (feature_size 16)", "channels-last bf16 conv decoder (feature_size "
-                                                  "16; cuDNN convolutions, fused InstanceNorm + LeakyReLU kernels)")
+                                                  "16; cuDNN convolutions chosen with cudnn.benchmark, fused InstanceNorm + LeakyReLU kernels)")
         self.net = self._wrap_ddp(self.model, world, local, args)
         self.opt = configure_optimizer(self.model, 1e-5, 0.9, 0.95, 1e-5, fused=_opt_kind(args, True))
         self.lossf = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)
