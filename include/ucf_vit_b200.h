@@ -345,6 +345,17 @@ int ucf_dice_ce_fwd(const void* logits, int logits_dtype, const void* target, in
 int ucf_dice_ce_bwd(const void* logits, int logits_dtype, const void* target, int target_dtype, const float* fwd_out,
                     const float* grad_out, int B, int C, long long S, int squared_pred, void* dlogits, void* stream);
 
+/* Weight gradient of a 3x3x3 convolution (stride 1, padding 1) on channels-last bf16: replaces the wgrad half of autograd's
+ * `convolution_backward` for the nn.Conv3d layers inside the decoder blocks above at this decoder's widths.
+ *   dW[co][ci][kd][kh][kw] = sum_{n,z,y,x} dY[n,z,y,x,co] * X[n,z+kd-1,y+kh-1,x+kw-1,ci]      (zero outside the volume)
+ * x: bf16 [N, D, H, W, Ci], dy: bf16 [N, D, H, W, Co], dw: fp32 [Co, Ci, 3, 3, 3] (overwritten);
+ * workspace: fp32 [ucf_conv3d_wgrad_ctas(N, D, H, W) * 27 * Co * Ci].  Served: ucf_conv3d_wgrad_supported() != 0
+ * ((Ci, Co) in {(16,16), (32,16), (32,32), (64,32)}, D and H multiples of 4, W of 8); reproducible (fixed-order sums). */
+int ucf_conv3d_wgrad_supported(int Ci, int Co, int D, int H, int W);
+int ucf_conv3d_wgrad_ctas(int N, int D, int H, int W);
+int ucf_conv3d_wgrad(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Ci, int Co, float* workspace,
+                     void* stream);
+
 /* ---- SAP front end on the device: edge map of a natural (uint8) image -------------------------------
  * Replace `grey_img = cv.GaussianBlur(img, (k, k), 0)` and `edges = cv.Canny(grey_img, c, c + 50)`
  * (dataloaders/transform.py:33-34; opencv-python is a dependency of the reference that is not vendored in it: restated

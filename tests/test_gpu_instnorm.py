@@ -87,11 +87,44 @@ def test_instance_norm_kernels_are_loud():
         UF.instance_norm_act(torch.randn(2, 16, 4, 4, 4).to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("Ci,Co", [(16, 16), (32, 16), (32, 32), (64, 32)])
+@pytest.mark.parametrize("N,D,H,W", [(1, 4, 4, 8), (2, 8, 8, 16), (3, 12, 8, 24), (2, 16, 20, 40)])
+def test_conv3d_wgrad_matches_autograd(Ci, Co, N, D, H, W):
+    """ucf_conv3d_wgrad against autograd's weight gradient of F.conv3d evaluated in fp32 on the same bf16 values (single tile,
+    several tiles per CTA, more tiles than CTAs; every channel pair the kernel serves)."""
+    g = torch.Generator().manual_seed(Ci + Co + N + D)
+    x = torch.randn(N, Ci, D, H, W, generator=g).to(torch.bfloat16)
+    dy = torch.randn(N, Co, D, H, W, generator=g).to(torch.bfloat16)
+    assert ops.conv3d_wgrad_supported(Ci, Co, D, H, W)
+    dw = ops.conv3d_wgrad(_cl(x.to(dev)), _cl(dy.to(dev)))
+    dw2 = ops.conv3d_wgrad(_cl(x.to(dev)), _cl(dy.to(dev)))
+    assert torch.equal(dw, dw2)                                             # fixed-order reduction
+    w = torch.zeros(Co, Ci, 3, 3, 3, device=dev, requires_grad=True)
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = torch.nn.functional.conv3d(x.to(dev).float(), w, None, 1, 1)
+        y.backward(dy.to(dev).float())
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
+    ref = w.grad
+    err = (dw - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+def test_conv3d_wgrad_is_loud_about_unsupported_shapes():
+    assert not ops.conv3d_wgrad_supported(48, 16, 8, 8, 16)
+    assert not ops.conv3d_wgrad_supported(16, 16, 6, 8, 16)
+    x = _cl(torch.randn(1, 48, 8, 8, 16, device=dev).to(torch.bfloat16))
+    dy = _cl(torch.randn(1, 16, 8, 8, 16, device=dev).to(torch.bfloat16))
+    with pytest.raises(RuntimeError, match="not served"):
+        ops.conv3d_wgrad(x, dy)
+
+
 def _unetr(mode, seed=0):
     from ucf_vit_b200.simple.arch import UNETR
     torch.manual_seed(seed)
     m = UNETR(img_size=[32] * 3, patch_size=16, in_chans=2, num_classes=3, embed_dim=96, depth=4, num_heads=3, twoD=False,
-              use_varemb=True, default_vars=["a", "b"], feature_size=8, skip_connection=True, linear_decoder=False,
+              use_varemb=True, default_vars=["a", "b"], feature_size=16, skip_connection=True, linear_decoder=False,
               class_token=False).to(dev).train()
     if mode == "fused":
         m.use_fused_decoder()

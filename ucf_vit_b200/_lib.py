@@ -90,6 +90,9 @@ _SIGNATURES = {
                                  c_void_p, c_void_p]),
     "ucf_dice_bce_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, _LL, c_float, c_int,
                                  c_void_p, c_void_p]),
+    "ucf_conv3d_wgrad_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "ucf_conv3d_wgrad_ctas": (c_int, [c_int, c_int, c_int, c_int]),
+    "ucf_conv3d_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ucf_gaussian_blur_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ucf_canny_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
                      c_void_p, c_void_p]),

@@ -750,3 +750,33 @@ def instance_norm_act(a, residual=None, norm_residual=False, negative_slope=0.01
     if residual is not None:
         residual = channels_last(residual.to(torch.bfloat16))
     return _InstNormActFn.apply(a, residual, bool(norm_residual), float(negative_slope), float(eps))
+
+
+class _Conv3x3x3Fn(torch.autograd.Function):
+    """conv3d(x, w, stride 1, padding 1, no bias) on channels-last bf16 x with an fp32 (or bf16) master weight: cuDNN for the
+    forward and the data gradient, ucf_conv3d_wgrad for the weight gradient (fp32, handed to the master weight directly)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        wb = w.detach().to(torch.bfloat16)
+        ctx.save_for_backward(x, wb)
+        ctx.w_dtype = w.dtype
+        return torch.nn.functional.conv3d(x, wb, None, 1, 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wb = ctx.saved_tensors
+        dy = channels_last(dy)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.ops.aten.convolution_backward(dy, x, wb, None, [1, 1, 1], [1, 1, 1], [1, 1, 1], False, [0, 0, 0], 1,
+                                                     [True, False, False])[0]
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv3d_wgrad(x, dy).to(ctx.w_dtype)
+        return dx, dw
+
+
+def conv3x3x3(x, weight):
+    """3x3x3 convolution (stride 1, padding 1, no bias) of a channels-last bf16 CUDA tensor whose weight gradient comes from
+    this package's kernel; callers check `ops.conv3d_wgrad_supported` first."""
+    return _Conv3x3x3Fn.apply(channels_last(x), weight)

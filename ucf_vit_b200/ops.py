@@ -728,3 +728,24 @@ def canny_u8(img, low, high, return_sweeps=False):
     L.check(L.lib().ucf_canny_u8(img.data_ptr(), H, W, C, float(low), float(high), cmap.data_ptr(), edges.data_ptr(),
                                  fdev.data_ptr(), fhost.data_ptr(), ctypes.addressof(sweeps), _stream()), "canny_u8")
     return (edges, sweeps.value) if return_sweeps else edges
+
+
+# ---- UNETR decoder: weight gradient of the 3x3x3 convolutions (channels-last bf16) ------------------------------------------
+def conv3d_wgrad_supported(Ci, Co, D, H, W):
+    return bool(L.lib().ucf_conv3d_wgrad_supported(int(Ci), int(Co), int(D), int(H), int(W)))
+
+
+def conv3d_wgrad(x, dy):
+    """fp32 [Co, Ci, 3, 3, 3]: weight gradient of conv3d(x, w, stride 1, padding 1) given dy; x [N, Ci, D, H, W] and
+    dy [N, Co, D, H, W] are channels-last bf16."""
+    _require_cuda(x, dy)
+    N, S, Ci = _nsc(x)
+    N2, S2, Co = _nsc(dy)
+    assert x.dim() == 5 and dy.dim() == 5 and N == N2 and x.shape[2:] == dy.shape[2:], (tuple(x.shape), tuple(dy.shape))
+    D, H, W = x.shape[2:]
+    ctas = L.lib().ucf_conv3d_wgrad_ctas(N, D, H, W)
+    ws = torch.empty(ctas * 27 * Co * Ci, dtype=torch.float32, device=x.device)
+    dw = torch.empty(Co, Ci, 3, 3, 3, dtype=torch.float32, device=x.device)
+    L.check(L.lib().ucf_conv3d_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, D, H, W, Ci, Co, ws.data_ptr(), _stream()),
+            "conv3d_wgrad")
+    return dw

@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as UF
+from .. import ops
 
 __all__ = [
     "get_conv_layer", "UnetResBlock", "UnetBasicBlock", "UnetrBasicBlock",
@@ -70,6 +71,17 @@ class _Convolution(nn.Sequential):
             conv = _CONV[spatial_dims](
                 in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding, bias=bias)
         self.add_module("conv", conv)
+
+    ndhwc_bf16 = False        # set by UNETR.use_fused_decoder(): 3x3x3 layers take their weight gradient from ucf_conv3d_wgrad
+
+    def forward(self, x):
+        c = self.conv
+        if (self.ndhwc_bf16 and isinstance(c, nn.Conv3d) and x.is_cuda and x.dim() == 5 and c.bias is None and c.groups == 1
+                and c.kernel_size == (3, 3, 3) and c.stride == (1, 1, 1) and c.padding == (1, 1, 1) and c.dilation == (1, 1, 1)
+                and c.in_channels * c.out_channels <= 1024       # measured ahead of cuDNN there (profiles/r02_conv_wgrad.log), behind at 64 -> 32
+                and ops.conv3d_wgrad_supported(c.in_channels, c.out_channels, *x.shape[2:])):
+            return UF.conv3x3x3(x.to(torch.bfloat16), c.weight)
+        return super().forward(x)
 
 
 def get_conv_layer(spatial_dims: int, in_channels: int, out_channels: int,
