@@ -1,5 +1,5 @@
 """Run ONE hot kernel a few times so that ncu can capture it in isolation.
-python scripts/gpu_one_kernel.py {fc1_gelu|fc2_dgelu|fc1_plain|attn_fwd|attn_bwd|ln_fwd|ln_bwd|wgrad|sap_gather|var_attn|inorm|canny} [B N H hd]"""
+python scripts/gpu_one_kernel.py {fc1_gelu|fc2_dgelu|fc1_plain|attn_fwd|attn_bwd|ln_fwd|ln_bwd|wgrad|sap_gather|var_attn|inorm|canny|conv_wgrad} [B N H hd]"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -74,6 +74,11 @@ elif which == "canny":
     def f():
         ops.canny_u8(ops.gaussian_blur_u8(img, 5), 60, 110)
         ops.gaussian_blur_u8(img, 3)
+elif which == "conv_wgrad":
+    N, Ci, Co, S = (int(a) for a in sys.argv[2:6]) if len(sys.argv) >= 6 else (16, 32, 16, 128)
+    x = bf(torch.randn(N, S, S, S, Ci, device=dev)).permute(0, 4, 1, 2, 3)
+    dy = bf(torch.randn(N, S, S, S, Co, device=dev)).permute(0, 4, 1, 2, 3)
+    f = lambda: ops.conv3d_wgrad(x, dy)
 else:
     raise SystemExit("unknown kernel " + which)
 for _ in range(4):
