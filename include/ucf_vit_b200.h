@@ -334,16 +334,18 @@ int ucf_dice_bce_bwd(const void* logits, int logits_dtype, const void* targets, 
  *   p = softmax(logits, 1), t = one_hot(target); per (b, c) over the S positions: I = sum p t, Q = sum p^2 (squared_pred
  *   != 0) or sum p, T = sum t;  loss = lambda_dice * mean_{b,c}(1 - (2I + smooth_nr) / (Q + T + smooth_dr))
  *                                      + lambda_ce * mean_{b,s}(-log p[b, target[b,s], s])
- * logits [B, C, S] f32|bf16 contiguous, 2 <= C <= 8; target [B, S] class indices as u8, i64 or f32; workspace
+ * logits f32|bf16, 2 <= C <= 8: [B, C, S] contiguous (channels_last = 0) or [B, S, C] (channels_last != 0: the memory of a
+ * torch.channels_last{,_3d} tensor, what the channels-last decoder emits; dlogits in the same layout); target [B, S] class indices as u8, i64 or f32; workspace
  * B * ucf_dice_ce_blocks_per_sample(B, S) * 25 doubles; out f32 [2 + 2 B C]: out[0] = loss, the rest are the per-(b, c)
  * coefficients and the cross-entropy scale the backward call reads.  One read of both tensors; reproducible (fixed order). */
 int ucf_dice_ce_blocks_per_sample(int B, long long S);
 int ucf_dice_ce_fwd(const void* logits, int logits_dtype, const void* target, int target_dtype, int B, int C, long long S,
                     int squared_pred, float smooth_nr, float smooth_dr, float lambda_dice, float lambda_ce,
-                    double* workspace, float* out, void* stream);
+                    double* workspace, float* out, int channels_last, void* stream);
 /* dlogits [B, C, S] (dtype of logits) = grad_out * d loss / d logits; grad_out a DEVICE f32 scalar. */
 int ucf_dice_ce_bwd(const void* logits, int logits_dtype, const void* target, int target_dtype, const float* fwd_out,
-                    const float* grad_out, int B, int C, long long S, int squared_pred, void* dlogits, void* stream);
+                    const float* grad_out, int B, int C, long long S, int squared_pred, void* dlogits, int channels_last,
+                    void* stream);
 
 /* Weight gradient of a 3x3x3 convolution (stride 1, padding 1) on channels-last bf16: replaces the wgrad half of autograd's
  * `convolution_backward` for the nn.Conv3d layers inside the decoder blocks above at this decoder's widths.

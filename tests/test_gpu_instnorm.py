@@ -111,6 +111,31 @@ def test_conv3d_wgrad_matches_autograd(Ci, Co, N, D, H, W):
     assert err <= 2e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
 
 
+def test_conv3x3x3_first_layer_pads_the_input_channels():
+    """UF.conv3x3x3 with 4 input channels (the decoder's first layer): forward and dx from cuDNN, dW from ucf_conv3d_wgrad on a
+    zero-padded copy -- against autograd in fp32."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 4, 8, 8, 16, generator=g).to(torch.bfloat16).to(dev)
+    w = (torch.randn(16, 4, 3, 3, 3, generator=g) * 0.1).to(dev)
+    dy = torch.randn(2, 16, 8, 8, 16, generator=g).to(torch.bfloat16).to(dev)
+    x1 = _cl(x).requires_grad_(True)
+    w1 = w.clone().requires_grad_(True)
+    y = UF.conv3x3x3(x1, w1)
+    y.backward(_cl(dy))
+    x2 = x.float().requires_grad_(True)
+    w2 = w.to(torch.bfloat16).float().requires_grad_(True)
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y2 = torch.nn.functional.conv3d(x2, w2, None, 1, 1)
+        y2.backward(dy.float())
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
+    assert w1.grad.dtype == torch.float32 and w1.grad.shape == w.shape
+    assert (y.float() - y2).abs().max().item() <= 1e-2 * y2.abs().max().item()
+    assert (w1.grad - w2.grad).abs().max().item() <= 2e-3 * w2.grad.abs().max().item()
+    assert (x1.grad.float() - x2.grad).abs().max().item() <= 1e-2 * x2.grad.abs().max().item()
+
+
 def test_conv3d_wgrad_is_loud_about_unsupported_shapes():
     assert not ops.conv3d_wgrad_supported(48, 16, 8, 8, 16)
     assert not ops.conv3d_wgrad_supported(16, 16, 6, 8, 16)

@@ -431,3 +431,11 @@ def test_dice_ce_kernels_match_the_torch_formulation(shape, dt, tdt):
         tol = 2e-5 if dt == torch.float32 else 1e-2
         err = (a.grad.float() - b.grad).abs().max().item()
         assert err <= tol * b.grad.abs().max().item() + 1e-9, err
+        # channels-last logits (what the channels-last UNETR decoder emits) are read in place: same loss, gradient in that layout
+        mf = torch.channels_last_3d if len(shape) == 5 else torch.channels_last
+        c = logits.to(dt).contiguous(memory_format=mf).detach().requires_grad_(True)
+        lc = lossf(c, target)
+        (lc * 1.7).backward()
+        assert abs(lc.item() - la.item()) <= 1e-6 * abs(la.item()) + 1e-7, (lc.item(), la.item())
+        assert c.grad.stride() == c.stride()
+        assert (c.grad.float() - a.grad.float()).abs().max().item() <= 1e-6 * a.grad.float().abs().max().item() + 1e-12

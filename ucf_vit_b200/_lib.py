@@ -103,8 +103,9 @@ _SIGNATURES = {
                       c_float, c_void_p, c_void_p, c_void_p]),
     "ucf_dice_ce_blocks_per_sample": (c_int, [c_int, _LL]),
     "ucf_dice_ce_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, _LL, c_int, c_float, c_float, c_float, c_float,
-                                c_void_p, c_void_p, c_void_p]),
-    "ucf_dice_ce_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, _LL, c_int, c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_int, c_void_p]),
+    "ucf_dice_ce_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, _LL, c_int, c_void_p, c_int,
+                                c_void_p]),
     "ucf_adamw_multi": (c_int, [c_int] + [c_void_p] * 5 + [c_double] * 5 + [_LL, c_int, c_void_p]),
     "ucf_adamw_multi_dev": (c_int, [c_int] + [c_void_p] * 6 + [c_double] * 4 + [c_void_p, c_int, c_void_p]),
     "ucf_patchify": (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [_LL, c_int, c_void_p]),

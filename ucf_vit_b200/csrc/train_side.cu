@@ -566,7 +566,7 @@ __device__ __forceinline__ int ld_class(const float* p) { return static_cast<int
 template <typename TL, typename TT>
 __global__ void __launch_bounds__(256)
 dice_ce_fwd_kernel(const TL* __restrict__ logits, const TT* __restrict__ target, int C, long long S, int nb, int squared,
-                   double* __restrict__ partials) {
+                   double* __restrict__ partials, long long cs, long long ss) {     // logit (b, c, s) at b C S + c cs + s ss
   const int b = blockIdx.x / nb, j = blockIdx.x - b * nb;
   const long long per = (S + nb - 1) / nb;
   const long long s0 = j * per, s1 = s0 + per < S ? s0 + per : S;
@@ -579,7 +579,7 @@ dice_ce_fwd_kernel(const TL* __restrict__ logits, const TT* __restrict__ target,
     float z[kDiceCeMaxC], m = -INFINITY;
 #pragma unroll
     for (int c = 0; c < kDiceCeMaxC; ++c)
-      if (c < C) { z[c] = ldf(lg + c * S + s); m = fmaxf(m, z[c]); }
+      if (c < C) { z[c] = ldf(lg + c * cs + s * ss); m = fmaxf(m, z[c]); }
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < kDiceCeMaxC; ++c)
@@ -642,18 +642,19 @@ dice_ce_finish_kernel(const double* __restrict__ partials, int B, int C, int nb,
 template <typename TL, typename TT>
 __global__ void __launch_bounds__(256)
 dice_ce_bwd_kernel(const TL* __restrict__ logits, const TT* __restrict__ target, const float* __restrict__ fwd_out,
-                   const float* __restrict__ grad_out, int B, int C, long long S, int squared, TL* __restrict__ dlogits) {
+                   const float* __restrict__ grad_out, int B, int C, long long S, int squared, TL* __restrict__ dlogits,
+                   long long cs, long long ss) {
   const float g = *grad_out, ces = fwd_out[1 + 2 * B * C];
   const long long total = static_cast<long long>(B) * S;
   const long long stride = static_cast<long long>(gridDim.x) * 256;
   for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total; i += stride) {
     const int b = static_cast<int>(i / S);
     const long long s = i - b * S;
-    const TL* lg = logits + static_cast<long long>(b) * C * S + s;
+    const TL* lg = logits + static_cast<long long>(b) * C * S + s * ss;
     float z[kDiceCeMaxC], m = -INFINITY;
 #pragma unroll
     for (int c = 0; c < kDiceCeMaxC; ++c)
-      if (c < C) { z[c] = ldf(lg + c * S); m = fmaxf(m, z[c]); }
+      if (c < C) { z[c] = ldf(lg + c * cs); m = fmaxf(m, z[c]); }
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < kDiceCeMaxC; ++c)
@@ -669,10 +670,10 @@ dice_ce_bwd_kernel(const TL* __restrict__ logits, const TT* __restrict__ target,
         G[c] = (c == t ? a : 0.f) + (squared ? bb * z[c] : bb);         // d(dice term) / d p_c
         dot = fmaf(z[c], G[c], dot);
       }
-    TL* dl = dlogits + static_cast<long long>(b) * C * S + s;
+    TL* dl = dlogits + static_cast<long long>(b) * C * S + s * ss;
 #pragma unroll
     for (int c = 0; c < kDiceCeMaxC; ++c)
-      if (c < C) stf(dl + c * S, g * (z[c] * (G[c] - dot) + ces * (z[c] - (c == t ? 1.f : 0.f))));
+      if (c < C) stf(dl + c * cs, g * (z[c] * (G[c] - dot) + ces * (z[c] - (c == t ? 1.f : 0.f))));
   }
 }
 
@@ -933,21 +934,21 @@ extern "C" int ucf_dice_bce_bwd(const void* logits, int logits_dtype, const void
 namespace {
 template <typename TL>
 int dice_ce_dispatch_fwd(const void* logits, const void* target, int tdt, int C, long long S, int nb, int squared, double* ws,
-                         int grid, cudaStream_t st) {
+                         int grid, cudaStream_t st, long long cs, long long ss) {
   const TL* lg = static_cast<const TL*>(logits);
-  if (tdt == UCF_DTYPE_U8) dice_ce_fwd_kernel<TL, uint8_t><<<grid, 256, 0, st>>>(lg, static_cast<const uint8_t*>(target), C, S, nb, squared, ws);
-  else if (tdt == UCF_DTYPE_I64) dice_ce_fwd_kernel<TL, long long><<<grid, 256, 0, st>>>(lg, static_cast<const long long*>(target), C, S, nb, squared, ws);
-  else dice_ce_fwd_kernel<TL, float><<<grid, 256, 0, st>>>(lg, static_cast<const float*>(target), C, S, nb, squared, ws);
+  if (tdt == UCF_DTYPE_U8) dice_ce_fwd_kernel<TL, uint8_t><<<grid, 256, 0, st>>>(lg, static_cast<const uint8_t*>(target), C, S, nb, squared, ws, cs, ss);
+  else if (tdt == UCF_DTYPE_I64) dice_ce_fwd_kernel<TL, long long><<<grid, 256, 0, st>>>(lg, static_cast<const long long*>(target), C, S, nb, squared, ws, cs, ss);
+  else dice_ce_fwd_kernel<TL, float><<<grid, 256, 0, st>>>(lg, static_cast<const float*>(target), C, S, nb, squared, ws, cs, ss);
   return check_launch("dice_ce_fwd_kernel");
 }
 template <typename TL>
 int dice_ce_dispatch_bwd(const void* logits, const void* target, int tdt, const float* fwd_out, const float* grad_out, int B, int C,
-                         long long S, int squared, void* dlogits, int grid, cudaStream_t st) {
+                         long long S, int squared, void* dlogits, int grid, cudaStream_t st, long long cs, long long ss) {
   const TL* lg = static_cast<const TL*>(logits);
   TL* dl = static_cast<TL*>(dlogits);
-  if (tdt == UCF_DTYPE_U8) dice_ce_bwd_kernel<TL, uint8_t><<<grid, 256, 0, st>>>(lg, static_cast<const uint8_t*>(target), fwd_out, grad_out, B, C, S, squared, dl);
-  else if (tdt == UCF_DTYPE_I64) dice_ce_bwd_kernel<TL, long long><<<grid, 256, 0, st>>>(lg, static_cast<const long long*>(target), fwd_out, grad_out, B, C, S, squared, dl);
-  else dice_ce_bwd_kernel<TL, float><<<grid, 256, 0, st>>>(lg, static_cast<const float*>(target), fwd_out, grad_out, B, C, S, squared, dl);
+  if (tdt == UCF_DTYPE_U8) dice_ce_bwd_kernel<TL, uint8_t><<<grid, 256, 0, st>>>(lg, static_cast<const uint8_t*>(target), fwd_out, grad_out, B, C, S, squared, dl, cs, ss);
+  else if (tdt == UCF_DTYPE_I64) dice_ce_bwd_kernel<TL, long long><<<grid, 256, 0, st>>>(lg, static_cast<const long long*>(target), fwd_out, grad_out, B, C, S, squared, dl, cs, ss);
+  else dice_ce_bwd_kernel<TL, float><<<grid, 256, 0, st>>>(lg, static_cast<const float*>(target), fwd_out, grad_out, B, C, S, squared, dl, cs, ss);
   return check_launch("dice_ce_bwd_kernel");
 }
 int dice_ce_check(const char* who, int ldt, int tdt, int B, int C, long long S) {
@@ -967,14 +968,15 @@ extern "C" int ucf_dice_ce_blocks_per_sample(int B, long long S) {
 
 extern "C" int ucf_dice_ce_fwd(const void* logits, int logits_dtype, const void* target, int target_dtype, int B, int C,
                                long long S, int squared_pred, float smooth_nr, float smooth_dr, float lambda_dice,
-                               float lambda_ce, double* workspace, float* out, void* stream) {
+                               float lambda_ce, double* workspace, float* out, int channels_last, void* stream) {
   int rc = dice_ce_check("dice_ce_fwd", logits_dtype, target_dtype, B, C, S);
+  const long long cs = channels_last ? 1 : S, ss = channels_last ? C : 1;
   if (rc != UCF_OK) return rc;
   if (!logits || !target || !workspace || !out) { set_last_error("dice_ce_fwd: null pointer"); return UCF_ERR_BAD_ARG; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nb = ucf_dice_ce_blocks_per_sample(B, S);
-  rc = logits_dtype == UCF_DTYPE_F32 ? dice_ce_dispatch_fwd<float>(logits, target, target_dtype, C, S, nb, squared_pred, workspace, B * nb, st)
-                                     : dice_ce_dispatch_fwd<__nv_bfloat16>(logits, target, target_dtype, C, S, nb, squared_pred, workspace, B * nb, st);
+  rc = logits_dtype == UCF_DTYPE_F32 ? dice_ce_dispatch_fwd<float>(logits, target, target_dtype, C, S, nb, squared_pred, workspace, B * nb, st, cs, ss)
+                                     : dice_ce_dispatch_fwd<__nv_bfloat16>(logits, target, target_dtype, C, S, nb, squared_pred, workspace, B * nb, st, cs, ss);
   if (rc != UCF_OK) return rc;
   dice_ce_finish_kernel<<<1, 256, 0, st>>>(workspace, B, C, nb, static_cast<double>(S), squared_pred, smooth_nr, smooth_dr, lambda_dice,
                                            lambda_ce, out);
@@ -982,13 +984,15 @@ extern "C" int ucf_dice_ce_fwd(const void* logits, int logits_dtype, const void*
 }
 
 extern "C" int ucf_dice_ce_bwd(const void* logits, int logits_dtype, const void* target, int target_dtype, const float* fwd_out,
-                               const float* grad_out, int B, int C, long long S, int squared_pred, void* dlogits, void* stream) {
+                               const float* grad_out, int B, int C, long long S, int squared_pred, void* dlogits, int channels_last,
+                               void* stream) {
   int rc = dice_ce_check("dice_ce_bwd", logits_dtype, target_dtype, B, C, S);
+  const long long cs = channels_last ? 1 : S, ss = channels_last ? C : 1;
   if (rc != UCF_OK) return rc;
   if (!logits || !target || !fwd_out || !grad_out || !dlogits) { set_last_error("dice_ce_bwd: null pointer"); return UCF_ERR_BAD_ARG; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = dice_grid(static_cast<long long>(B) * S);
   return logits_dtype == UCF_DTYPE_F32
-             ? dice_ce_dispatch_bwd<float>(logits, target, target_dtype, fwd_out, grad_out, B, C, S, squared_pred, dlogits, grid, st)
-             : dice_ce_dispatch_bwd<__nv_bfloat16>(logits, target, target_dtype, fwd_out, grad_out, B, C, S, squared_pred, dlogits, grid, st);
+             ? dice_ce_dispatch_bwd<float>(logits, target, target_dtype, fwd_out, grad_out, B, C, S, squared_pred, dlogits, grid, st, cs, ss)
+             : dice_ce_dispatch_bwd<__nv_bfloat16>(logits, target, target_dtype, fwd_out, grad_out, B, C, S, squared_pred, dlogits, grid, st, cs, ss);
 }

@@ -772,7 +772,13 @@ class _Conv3x3x3Fn(torch.autograd.Function):
             dx = torch.ops.aten.convolution_backward(dy, x, wb, None, [1, 1, 1], [1, 1, 1], [1, 1, 1], False, [0, 0, 0], 1,
                                                      [True, False, False])[0]
         if ctx.needs_input_grad[1]:
-            dw = ops.conv3d_wgrad(x, dy).to(ctx.w_dtype)
+            Ci = x.shape[1]
+            if Ci < 16:       # the decoder's first layer (in_chans -> 16): zero channels appended, their gradient rows dropped
+                xp = x.new_zeros(x.shape[0], *x.shape[2:], 16).movedim(-1, 1)
+                xp[:, :Ci] = x
+                dw = ops.conv3d_wgrad(xp, dy)[:, :Ci].to(ctx.w_dtype)
+            else:
+                dw = ops.conv3d_wgrad(x, dy).to(ctx.w_dtype)
         return dx, dw
 
 

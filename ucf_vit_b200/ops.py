@@ -613,10 +613,20 @@ def _class_dtype(t):
     raise TypeError(f"dice_ce: class indices must be uint8, int64 or float32, got {t.dtype}")
 
 
+def _dice_layout(logits):
+    """0: [B, C, S] contiguous; 1: channels-last memory ([B, S, C]).  Anything else is refused (callers make it contiguous)."""
+    if logits.is_contiguous():
+        return 0
+    if logits.dim() >= 3 and logits.movedim(1, -1).is_contiguous():
+        return 1
+    raise TypeError("dice_ce: logits must be contiguous or channels-last")
+
+
 def dice_ce_fwd(logits, target, squared_pred, smooth_nr, smooth_dr, lambda_dice, lambda_ce):
     """fp32 [2 + 2 B C]: [0] = DiceCE loss of logits [B, C, ...] against class indices target [B, ...]; the rest feeds dice_ce_bwd."""
     _require_cuda(logits, target)
-    assert logits.is_contiguous() and target.is_contiguous()
+    assert target.is_contiguous()
+    cl = _dice_layout(logits)
     B, C = logits.shape[:2]
     S = logits[0, 0].numel()
     assert target.numel() == B * S, (tuple(logits.shape), tuple(target.shape))
@@ -625,18 +635,19 @@ def dice_ce_fwd(logits, target, squared_pred, smooth_nr, smooth_dr, lambda_dice,
     out = torch.empty(2 + 2 * B * C, dtype=torch.float32, device=logits.device)
     L.check(L.lib().ucf_dice_ce_fwd(logits.data_ptr(), _dt(logits), target.data_ptr(), _class_dtype(target), B, C, S,
                                     int(bool(squared_pred)), float(smooth_nr), float(smooth_dr), float(lambda_dice),
-                                    float(lambda_ce), ws.data_ptr(), out.data_ptr(), _stream()), "dice_ce_fwd")
+                                    float(lambda_ce), ws.data_ptr(), out.data_ptr(), cl, _stream()), "dice_ce_fwd")
     return out
 
 
 def dice_ce_bwd(logits, target, fwd_out, grad_out, squared_pred):
     _require_cuda(logits, target, fwd_out, grad_out)
+    cl = _dice_layout(logits)
     B, C = logits.shape[:2]
     S = logits[0, 0].numel()
     assert grad_out.dtype == torch.float32 and grad_out.numel() == 1
-    dlogits = torch.empty_like(logits)
+    dlogits = torch.empty_like(logits, memory_format=torch.preserve_format)
     L.check(L.lib().ucf_dice_ce_bwd(logits.data_ptr(), _dt(logits), target.data_ptr(), _class_dtype(target), fwd_out.data_ptr(),
-                                    grad_out.data_ptr(), B, C, S, int(bool(squared_pred)), dlogits.data_ptr(), _stream()),
+                                    grad_out.data_ptr(), B, C, S, int(bool(squared_pred)), dlogits.data_ptr(), cl, _stream()),
             "dice_ce_bwd")
     return dlogits
 

@@ -152,7 +152,9 @@ class DiceCELoss(nn.Module):
             target = target[:, 0]
         if logits.is_cuda and 2 <= C <= 8 and logits.dtype in (torch.float32, torch.bfloat16):
             t = target if target.dtype in (torch.uint8, torch.int64, torch.float32) else target.long()
-            return _DiceCEFn.apply(logits.contiguous(), t.contiguous(), self.squared_pred, self.smooth_nr, self.smooth_dr,
+            if not (logits.is_contiguous() or logits.movedim(1, -1).is_contiguous()):     # channels-last logits are read in place
+                logits = logits.contiguous()
+            return _DiceCEFn.apply(logits, t.contiguous(), self.squared_pred, self.smooth_nr, self.smooth_dr,
                                    self.lambda_dice, self.lambda_ce)
         return self.forward_torch(logits, target)
 

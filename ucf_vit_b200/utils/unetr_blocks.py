@@ -79,7 +79,7 @@ class _Convolution(nn.Sequential):
         if (self.ndhwc_bf16 and isinstance(c, nn.Conv3d) and x.is_cuda and x.dim() == 5 and c.bias is None and c.groups == 1
                 and c.kernel_size == (3, 3, 3) and c.stride == (1, 1, 1) and c.padding == (1, 1, 1) and c.dilation == (1, 1, 1)
                 and c.in_channels * c.out_channels <= 1024       # measured ahead of cuDNN there (profiles/r02_conv_wgrad.log), behind at 64 -> 32
-                and ops.conv3d_wgrad_supported(c.in_channels, c.out_channels, *x.shape[2:])):
+                and ops.conv3d_wgrad_supported(max(c.in_channels, 16), c.out_channels, *x.shape[2:])):   # < 16 inputs: zero-padded
             return UF.conv3x3x3(x.to(torch.bfloat16), c.weight)
         return super().forward(x)
 
