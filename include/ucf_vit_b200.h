@@ -358,6 +358,18 @@ int ucf_conv3d_wgrad_ctas(int N, int D, int H, int W);
 int ucf_conv3d_wgrad(const void* x, const void* dy, float* dw, int N, int D, int H, int W, int Ci, int Co, float* workspace,
                      void* stream);
 
+/* 1x1x1 convolutions of the same decoder (UnetResBlock.conv3 residual projections, UnetOutBlock head; arch.py:808-940,960-993)
+ * on channels-last bf16: replace `nn.Conv3d(kernel_size=1)` forward, the data gradient (the same call on the transposed
+ * weight) and the weight / bias gradient of autograd's `convolution_backward`.
+ *   y[v, co] = sum_ci x[v, ci] * w[co, ci] (+ bias[co]);   dw[co, ci] = sum_v dy[v, co] * x[v, ci];   dbias[co] = sum_v dy[v, co]
+ * x: bf16 [V, Ci], y / dy: bf16 [V, Co] (V = all voxels of the batch), w / dw: fp32 [Co, Ci], bias / dbias: fp32 [Co] or NULL;
+ * workspace: fp32 [ucf_pointwise_conv_ctas(V) * (Co * Ci + Co)].  Ci, Co each one of 4, 8, 16, 32; fixed-order sums. */
+int ucf_pointwise_conv_supported(int Ci, int Co);
+int ucf_pointwise_conv_ctas(long long V);
+int ucf_pointwise_conv(const void* x, const float* w, const float* bias, void* y, long long V, int Ci, int Co, void* stream);
+int ucf_pointwise_conv_wgrad(const void* x, const void* dy, float* dw, float* dbias, long long V, int Ci, int Co,
+                             float* workspace, void* stream);
+
 /* ---- SAP front end on the device: edge map of a natural (uint8) image -------------------------------
  * Replace `grey_img = cv.GaussianBlur(img, (k, k), 0)` and `edges = cv.Canny(grey_img, c, c + 50)`
  * (dataloaders/transform.py:33-34; opencv-python is a dependency of the reference that is not vendored in it: restated

@@ -41,7 +41,7 @@ for k, t, c in rows[:45]:
     print(f"{t/1e3:9.3f} ms {100*t/tot:5.1f}% x{c:5.0f}  {k[:150]}")
 print("--- by operator (shapes)")
 ops_ = [(e.key, str(e.input_shapes)[:120], e.device_time_total / n, e.count / n) for e in prof.key_averages(group_by_input_shape=True)
-        if e.device_time_total > 0 and ("conv" in e.key.lower() or "norm" in e.key.lower() or "leaky" in e.key.lower())]
+        if e.device_time_total > 0 and any(w in e.key.lower() for w in ("conv", "norm", "leaky", "copy", "contiguous", "cat", "to_copy", "fill", "zero"))]
 ops_.sort(key=lambda r: -r[2])
 for k, s, t, c in ops_[:40]:
     print(f"{t/1e3:9.3f} ms x{c:4.0f} {k[:40]:40s} {s}")

@@ -136,6 +136,39 @@ def test_conv3x3x3_first_layer_pads_the_input_channels():
     assert (x1.grad.float() - x2.grad).abs().max().item() <= 1e-2 * x2.grad.abs().max().item()
 
 
+@pytest.mark.parametrize("Ci,Co,bias", [(4, 16, False), (16, 4, True), (32, 16, False), (16, 32, False), (8, 8, True), (32, 32, True),
+                                        (4, 4, False)])
+@pytest.mark.parametrize("shape", [(2, 5, 7, 3), (1, 16, 16, 16), (3, 9, 8, 11)])
+def test_conv1x1x1_matches_autograd(Ci, Co, bias, shape):
+    """UF.conv1x1x1 (ucf_pointwise_conv / _wgrad) against nn.functional.conv3d in fp32 on the same bf16 values: output, data
+    gradient, weight and bias gradients; voxel counts that leave partial tiles."""
+    N, D, H, W = shape
+    g = torch.Generator().manual_seed(Ci * 100 + Co + N)
+    x = torch.randn(N, Ci, D, H, W, generator=g).to(torch.bfloat16).to(dev)
+    w = (torch.randn(Co, Ci, 1, 1, 1, generator=g) * 0.3).to(dev)
+    b = torch.randn(Co, generator=g).to(dev) if bias else None
+    dy = torch.randn(N, Co, D, H, W, generator=g).to(torch.bfloat16).to(dev)
+    x1 = _cl(x).requires_grad_(True)
+    w1 = w.clone().requires_grad_(True)
+    b1 = b.clone().requires_grad_(True) if bias else None
+    y = UF.conv1x1x1(x1, w1, b1)
+    assert y.dtype == torch.bfloat16 and y.movedim(1, -1).is_contiguous()
+    y.backward(_cl(dy))
+    x2 = x.float().requires_grad_(True)
+    w2 = w.clone().requires_grad_(True)
+    b2 = b.clone().requires_grad_(True) if bias else None
+    y2 = torch.nn.functional.conv3d(x2, w2, b2)
+    y2.backward(dy.float())
+    assert (y.float() - y2).abs().max().item() <= 8e-3 * y2.abs().max().item() + 1e-6
+    assert (x1.grad.float() - x2.grad).abs().max().item() <= 8e-3 * x2.grad.abs().max().item() + 1e-6
+    assert (w1.grad - w2.grad).abs().max().item() <= 1e-4 * w2.grad.abs().max().item() + 1e-5
+    if bias:
+        assert (b1.grad - b2.grad).abs().max().item() <= 1e-4 * b2.grad.abs().max().item() + 1e-5
+    dw_a, _ = ops.pointwise_conv_wgrad(x1.detach(), _cl(dy))
+    dw_b, _ = ops.pointwise_conv_wgrad(x1.detach(), _cl(dy))
+    assert torch.equal(dw_a, dw_b)
+
+
 def test_conv3d_wgrad_is_loud_about_unsupported_shapes():
     assert not ops.conv3d_wgrad_supported(48, 16, 8, 8, 16)
     assert not ops.conv3d_wgrad_supported(16, 16, 6, 8, 16)

@@ -93,6 +93,10 @@ _SIGNATURES = {
     "ucf_conv3d_wgrad_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "ucf_conv3d_wgrad_ctas": (c_int, [c_int, c_int, c_int, c_int]),
     "ucf_conv3d_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ucf_pointwise_conv_supported": (c_int, [c_int, c_int]),
+    "ucf_pointwise_conv_ctas": (c_int, [_LL]),
+    "ucf_pointwise_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _LL, c_int, c_int, c_void_p]),
+    "ucf_pointwise_conv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _LL, c_int, c_int, c_void_p, c_void_p]),
     "ucf_gaussian_blur_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ucf_canny_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
                      c_void_p, c_void_p]),

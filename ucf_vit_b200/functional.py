@@ -786,3 +786,34 @@ def conv3x3x3(x, weight):
     """3x3x3 convolution (stride 1, padding 1, no bias) of a channels-last bf16 CUDA tensor whose weight gradient comes from
     this package's kernel; callers check `ops.conv3d_wgrad_supported` first."""
     return _Conv3x3x3Fn.apply(channels_last(x), weight)
+
+
+class _Conv1x1x1Fn(torch.autograd.Function):
+    """nn.Conv{2,3}d(kernel_size=1, stride=1) on channels-last bf16 x with fp32 (or bf16) master weight [Co, Ci, 1, ...] and
+    optional bias: forward, data gradient and weight / bias gradient through ucf_pointwise_conv*."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        w2 = w.detach().reshape(w.shape[0], w.shape[1]).float().contiguous()
+        ctx.save_for_backward(x, w2)
+        ctx.w_shape, ctx.w_dtype, ctx.has_bias = w.shape, w.dtype, b is not None
+        ctx.b_dtype = b.dtype if b is not None else None
+        return ops.pointwise_conv(x, w2, b.detach().float().contiguous() if b is not None else None)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w2 = ctx.saved_tensors
+        dy = channels_last(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.pointwise_conv(dy, w2.t().contiguous())
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.pointwise_conv_wgrad(x, dy, with_bias=ctx.has_bias)
+            dw = dw.reshape(ctx.w_shape).to(ctx.w_dtype)
+            db = db.to(ctx.b_dtype) if db is not None else None
+        return dx, dw, db
+
+
+def conv1x1x1(x, weight, bias=None):
+    """1x1 convolution (stride 1) of a channels-last bf16 CUDA tensor; callers check `ops.pointwise_conv_supported` first."""
+    return _Conv1x1x1Fn.apply(channels_last(x), weight, bias)

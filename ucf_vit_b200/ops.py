@@ -760,3 +760,36 @@ def conv3d_wgrad(x, dy):
     L.check(L.lib().ucf_conv3d_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, D, H, W, Ci, Co, ws.data_ptr(), _stream()),
             "conv3d_wgrad")
     return dw
+
+
+# ---- UNETR decoder: 1x1x1 convolutions (channels-last bf16) -----------------------------------------------------------------
+def pointwise_conv_supported(Ci, Co):
+    return bool(L.lib().ucf_pointwise_conv_supported(int(Ci), int(Co)))
+
+
+def pointwise_conv(x, w, bias=None):
+    """y [N, Co, ...] (channels-last bf16) = 1x1 convolution of channels-last bf16 x [N, Ci, ...] with fp32 w [Co, Ci]."""
+    _require_cuda(x, w)
+    N, S, Ci = _nsc(x)
+    Co = w.shape[0]
+    assert w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape) == (Co, Ci)
+    assert bias is None or (bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == Co)
+    y = torch.empty((N, *x.shape[2:], Co), dtype=torch.bfloat16, device=x.device).movedim(-1, 1)
+    L.check(L.lib().ucf_pointwise_conv(x.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None, y.data_ptr(),
+                                       N * S, Ci, Co, _stream()), "pointwise_conv")
+    return y
+
+
+def pointwise_conv_wgrad(x, dy, with_bias=False):
+    """(dw fp32 [Co, Ci], dbias fp32 [Co] | None) of pointwise_conv for channels-last bf16 x [N, Ci, ...], dy [N, Co, ...]."""
+    _require_cuda(x, dy)
+    N, S, Ci = _nsc(x)
+    N2, S2, Co = _nsc(dy)
+    assert (N, S) == (N2, S2)
+    V = N * S
+    ws = torch.empty(L.lib().ucf_pointwise_conv_ctas(V) * (Co * Ci + Co), dtype=torch.float32, device=x.device)
+    dw = torch.empty(Co, Ci, dtype=torch.float32, device=x.device)
+    db = torch.empty(Co, dtype=torch.float32, device=x.device) if with_bias else None
+    L.check(L.lib().ucf_pointwise_conv_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr() if with_bias else None, V,
+                                             Ci, Co, ws.data_ptr(), _stream()), "pointwise_conv_wgrad")
+    return dw, db

@@ -72,7 +72,9 @@ class _Convolution(nn.Sequential):
                 in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding, bias=bias)
         self.add_module("conv", conv)
 
-    ndhwc_bf16 = False        # set by UNETR.use_fused_decoder(): 3x3x3 layers take their weight gradient from ucf_conv3d_wgrad
+    # set by UNETR.use_fused_decoder(): 3x3x3 layers take their weight gradient from ucf_conv3d_wgrad, 1x1x1 layers run on
+    # ucf_pointwise_conv* in all three directions
+    ndhwc_bf16 = False
 
     def forward(self, x):
         c = self.conv
@@ -81,6 +83,10 @@ class _Convolution(nn.Sequential):
                 and c.in_channels * c.out_channels <= 1024       # measured ahead of cuDNN there (profiles/r02_conv_wgrad.log), behind at 64 -> 32
                 and ops.conv3d_wgrad_supported(max(c.in_channels, 16), c.out_channels, *x.shape[2:])):   # < 16 inputs: zero-padded
             return UF.conv3x3x3(x.to(torch.bfloat16), c.weight)
+        if (self.ndhwc_bf16 and isinstance(c, (nn.Conv2d, nn.Conv3d)) and x.is_cuda and c.groups == 1
+                and all(k == 1 for k in c.kernel_size) and all(v == 1 for v in c.stride) and all(v == 0 for v in c.padding)
+                and ops.pointwise_conv_supported(c.in_channels, c.out_channels)):
+            return UF.conv1x1x1(x.to(torch.bfloat16), c.weight, c.bias)
         return super().forward(x)
 
 
