@@ -526,7 +526,9 @@ class Unetr128(Workload):
         return {"encoder_ms_per_step": enc_ms, "encoder_tflops": 3 * enc * self.batch / (enc_ms * 1e-3) / 1e12,
                 "encoder_attn_mlp_tflops": 3 * blocks * self.batch / (enc_ms * 1e-3) / 1e12,
                 "decoder_fwd_gflops_per_volume": self.decoder_fwd_flops / 1e9,
-                "decoder_note": "conv decoder runs on cuDNN (SURVEY §8f rank 1, not rebuilt); its parity is unpinned (MONAI absent)"}
+                "decoder_note": "default decoder: channels-last bf16 with this package's InstanceNorm / LeakyReLU, 3x3x3 weight-gradient and "
+                                "1x1x1 convolution kernels, cuDNN for the 3x3x3 forward / data-gradient and transposed convolutions; the "
+                                "block structure is MONAI's restated (MONAI absent: parity unpinned)"}
 
     def cpu_step_fn(self):
         from oracle import vit_ref as R

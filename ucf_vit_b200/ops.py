@@ -722,17 +722,18 @@ def gaussian_blur_u8(img, ksize):
     return out
 
 
-_canny_flags = {}
+_canny_tls = threading.local()      # per host thread: {device index: (device flag, pinned host flag)}
 
 
 def canny_u8(img, low, high, return_sweeps=False):
     """cv.Canny(img, low, high) (aperture 3, L1 norm) of a uint8 [H, W(, C)] image: uint8 [H, W] of 0 / 255.
     Synchronises the current stream (the hysteresis loop reads a convergence flag back)."""
     H, W, C = _hwc_u8(img)
-    key = (img.device.index, threading.get_ident())
-    if key not in _canny_flags:
-        _canny_flags[key] = (torch.zeros(1, dtype=torch.int32, device=img.device), torch.zeros(1, dtype=torch.int32).pin_memory())
-    fdev, fhost = _canny_flags[key]
+    flags = _canny_tls.__dict__.setdefault("flags", {})
+    if img.device.index not in flags:
+        flags[img.device.index] = (torch.zeros(1, dtype=torch.int32, device=img.device),
+                                   torch.zeros(1, dtype=torch.int32).pin_memory())
+    fdev, fhost = flags[img.device.index]
     cmap = torch.empty(H, W, dtype=torch.uint8, device=img.device)
     edges = torch.empty(H, W, dtype=torch.uint8, device=img.device)
     sweeps = ctypes.c_int(0)
