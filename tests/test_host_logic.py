@@ -145,3 +145,28 @@ def test_head_dim_without_a_kernel_is_refused_at_construction():
         VariableMapping_Attention(1024, num_heads=8)
     assert Attention(576, num_heads=16).head_dim == 36
     assert Attention(1280, num_heads=20).head_dim == 64
+
+
+def test_dense_layout_check_and_fused_decoder_switch():
+    """Host logic of round 2's decoder work: the dense-layout predicate FusedAdamW uses for channels-last parameters, the
+    decoder-mode switch reaching every block and convolution wrapper, and argument validation of the device edge front end."""
+    import pytest
+    import torch
+    from ucf_vit_b200 import ops
+    from ucf_vit_b200.simple.arch import UNETR
+    from ucf_vit_b200.dataloaders.transform import Patchify
+    t = torch.zeros(2, 4, 3, 5, 6)
+    assert ops._is_dense(t) and ops._is_dense(t.contiguous(memory_format=torch.channels_last_3d))
+    assert ops._is_dense(t.permute(4, 0, 2, 1, 3)) and not ops._is_dense(t[:, :2]) and not ops._is_dense(t[..., ::2])
+    assert ops._is_dense(torch.zeros(4, 1, 1, 1, 1).contiguous(memory_format=torch.channels_last_3d))
+    m = UNETR(img_size=[32] * 3, patch_size=16, in_chans=2, num_classes=3, embed_dim=96, depth=4, num_heads=3, twoD=False,
+              use_varemb=True, default_vars=["a", "b"], feature_size=8, skip_connection=True, linear_decoder=False,
+              class_token=False)
+    flagged = [x for x in m.modules() if hasattr(x, "ndhwc_bf16")]
+    assert len(flagged) > 20 and not any(x.ndhwc_bf16 for x in flagged) and m.conv_autocast_dtype is None
+    assert m.use_fused_decoder() is m
+    assert all(x.ndhwc_bf16 for x in flagged) and m.conv_autocast_dtype == torch.bfloat16
+    m.use_fused_decoder(False)
+    assert not any(x.ndhwc_bf16 for x in flagged) and m.conv_autocast_dtype is None
+    with pytest.raises(ValueError, match="edges"):
+        Patchify(edges="gpu")
