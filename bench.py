@@ -416,6 +416,9 @@ def main():
                     help="unetr_128: PyTorch / cuDNN decoder in fp32, the reference's arithmetic (default: channels-last bf16 decoder "
                          "-- cuDNN convolutions under autocast with this package's fused InstanceNorm + residual + LeakyReLU "
                          "kernels between them, UNETR.use_fused_decoder)")
+    ap.add_argument("--device-edges", action="store_true",
+                    help="sap_4096_*: run the edge detector (ucf_gaussian_blur_u8 + ucf_canny_u8) of every image inside the step, on "
+                         "a side stream one batch ahead, instead of building the trees from fixed synthetic edge maps")
     ap.add_argument("--fp32-pixels", action="store_true", help="vit configs: host batches as fp32 pixels (round-1 form) instead of uint8")
     ap.add_argument("--fp32-allreduce", action="store_true",
                     help="DDP gradient all-reduce in fp32 (round-1 form); default: bf16 (torch's bf16_compress_hook -- the "

@@ -567,7 +567,8 @@ class Sap4096(Workload):
         self.batch = 16 if L <= 1024 else 8
         self.workload = (f"SAP adaptive-patching ViT-B segmentation train step on 4096x4096x3 uint8 images: quadtree of {L} leaves "
                          f"per image (host C++ build) + device cubic gather to {self.p}x{self.p} patches + fwd + DiceBCE + bwd + AdamW, "
-                         f"batch {self.batch}/GPU; edge maps are synthetic (OpenCV is not in the image)")
+                         f"batch {self.batch}/GPU; the trees come from fixed synthetic edge maps (the edge detector is timed in "
+                         f"`extras`; --device-edges puts ucf_gaussian_blur_u8 + ucf_canny_u8 of every image into the step)")
         self.cfg = dict(patch_size=self.p, in_chans=3, num_classes=4, embed_dim=768, depth=12, num_heads=12, fixed_length=L,
                         sqrt_len=self.s, class_token=False, use_adaptive_pos_emb=True)
 
@@ -590,6 +591,15 @@ class Sap4096(Workload):
         self.lossf = DiceBLoss(num_class=self.cfg["num_classes"])
         g = torch.Generator().manual_seed(77 + rank)
         self.edges = [self._edge_map(g) for _ in range(self.batch)]
+        self.device_edges = bool(getattr(args, "device_edges", False))
+        if self.device_edges:
+            from concurrent.futures import ThreadPoolExecutor
+            self._edge_pool = ThreadPoolExecutor(max_workers=1)
+            self._edge_stream = torch.cuda.Stream(device=dev)
+            self.workload = self.workload.split("; the trees come from")[0] + (
+                "; every step runs the reference's edge detector on the device for the next batch (cv.GaussianBlur 5x5 + cv.Canny "
+                "60/110 as ucf_gaussian_blur_u8 + ucf_canny_u8 on a side stream, byte-identical to OpenCV), copies the edge maps to "
+                "the host and builds the trees there, all under the current step's GPU work")
         self.label = (torch.rand(self.batch, self.cfg["num_classes"], self.side, self.side, generator=g) > 0.5).float().to(dev)
 
     @staticmethod
@@ -610,14 +620,40 @@ class Sap4096(Workload):
         g = torch.Generator().manual_seed(1234 + rank)
         return (_pin(torch.randint(0, 256, (self.batch, 4096, 4096, 3), generator=g, dtype=torch.uint8)),)
 
-    def front_end(self, imgs):
-        """Patchify.forward_batch minus the OpenCV edge detection: trees on host threads, gather on the device."""
+    def _trees_from_device_edges(self, imgs):
+        """Future of the batch's trees: blur + Canny of every image on a side stream (worker thread: the hysteresis loop
+        synchronises that stream only), edge maps to the host, C++ tree build on host threads."""
+        from ucf_vit_b200 import ops
         from ucf_vit_b200.dataloaders.quadtree import FixedQuadTree
+        ready = torch.cuda.Event()
+        ready.record()
+
+        def work():
+            with torch.cuda.device(self.dev), torch.cuda.stream(self._edge_stream):
+                self._edge_stream.wait_event(ready)
+                maps = [ops.canny_u8(ops.gaussian_blur_u8(imgs[i], 5), 60, 110) for i in range(imgs.shape[0])]
+                host = [m.cpu().numpy() for m in maps]
+            return FixedQuadTree.build_many(host, self.L, device=self.dev)
+        return self._edge_pool.submit(work)
+
+    def front_end(self, imgs):
+        """Patchify.forward_batch: trees on host threads, gather on the device (edge maps: fixed synthetic ones, or with
+        --device-edges the device blur + Canny of the images)."""
+        from ucf_vit_b200.dataloaders.quadtree import FixedQuadTree
+        if self.device_edges:
+            # the next batch is on the device one step ahead (DevicePrefetcher); the synthetic batches are identical, so the
+            # current images stand in for it
+            trees = (getattr(self, "_next_trees", None) or self._trees_from_device_edges(imgs)).result()
+            self._next_trees = self._trees_from_device_edges(imgs)
+            return self._gather(trees, imgs)
         # the trees of THIS batch were submitted during the previous step (a loader knows batch k+1 while the GPU works on
         # batch k); the trees of the next batch are submitted now and built on a host thread under this step's GPU work
         fut = getattr(self, "_next_trees", None) or FixedQuadTree.build_many_async(self.edges, self.L, device=self.dev)
         trees = fut.result()
         self._next_trees = FixedQuadTree.build_many_async(self.edges, self.L, device=self.dev)
+        return self._gather(trees, imgs)
+
+    def _gather(self, trees, imgs):
         p = self.p
         seqs, ps = [], []
         for i, qdt in enumerate(trees):
